@@ -1,0 +1,442 @@
+// Memory-bound kernels of the hot path: 128-bit vectorised, coalesced HBM access with warp-shuffle reductions.
+//   K2  layernorm_bf16           (ln_pre / ln_1 / ln_2; reference twin aligner/encoder/slip.py:350-356)
+//   K1a im2col_patches + cls row (feeds the patch-embed GEMM; [3P] VisionTransformer.forward)
+//   K9  text_embed               (token_embedding(text) + positional_embedding; slip.py:469-470)
+//   K7/K10 head                  (ln_post(x[:,0]) @ proj  /  ln_final(x)[eot] @ text_projection; slip.py:475-478)
+//   K8  pool_normalize           (x / ||x|| per frame, mean over frames; clip_video_text_encoder.py:85-89,93-94)
+//   K14 wise_lerp                ((1-w) p1 + w p2, no FMA contraction; aligner/wise.py:16)
+#include "kernels.cuh"
+
+namespace fc {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------- LayerNorm (K2)
+// One warp per row; the row lives in registers (D <= 1024): one HBM read, one HBM write. fp32 statistics, eps inside
+// the sqrt, two-pass (mean, then centred variance) like ATen's CPU kernel within rounding.
+constexpr int LN_MAX_CHUNKS = 4;  // 4 x 32 lanes x 8 bf16 = 1024
+
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* x, bf16* y,  // may alias (ln_pre runs in place)
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, int64_t rows, int D,
+                                                             int64_t ldx, int64_t ldy, float eps) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int chunks = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+  float v[LN_MAX_CHUNKS][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    const int c = lane + 32 * i;
+    if (c < chunks) {
+      const uint4 u = xr[c];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_bf16x2(w[t]);
+        v[i][2 * t] = f.x;
+        v[i][2 * t + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    if (lane + 32 * i < chunks) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = v[i][t] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    const int c = lane + 32 * i;
+    if (c < chunks) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
+      uint4 o;
+      o.x = pack_bf16x2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
+      o.y = pack_bf16x2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
+      o.z = pack_bf16x2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
+      o.w = pack_bf16x2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+      yr[c] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- im2col (K1a)
+// frames (F,3,R,R) -> patches (F*G*G, 3*P*P) bf16, column order (c, ky, kx) = conv1.weight.reshape(width, -1).
+// One thread moves 8 consecutive kx: a 32-byte (fp32) read and a 16-byte write; consecutive threads walk the image row.
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = unpack_bf16x2(w[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(h[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ frames, bf16* __restrict__ patches,
+                                                     int64_t total_vec, int R, int P) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int vec_per_row = R >> 3;
+  const int xv = static_cast<int>(idx % vec_per_row);
+  int64_t t = idx / vec_per_row;
+  const int y = static_cast<int>(t % R);
+  t /= R;
+  const int c = static_cast<int>(t % 3);
+  const int64_t f = t / 3;
+  float v[8];
+  load8<T>(frames + ((f * 3 + c) * R + y) * static_cast<int64_t>(R) + xv * 8, v);
+  const int G = R / P;
+  const int x = xv * 8;
+  const int py = y / P, ky = y - py * P, px = x / P, kx = x - px * P;
+  const int64_t row = (f * G + py) * G + px;
+  const int64_t col = (static_cast<int64_t>(c) * P + ky) * P + kx;
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(patches + row * (3 * P * P) + col) = o;
+}
+
+// class-token row: x[f*L + 0, :] = class_embedding + positional_embedding[0]
+__global__ void cls_row_kernel(bf16* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                               int64_t frames, int L, int D) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= frames * D) return;
+  const int64_t f = idx / D;
+  const int d = static_cast<int>(idx - f * D);
+  x[f * L * D + d] = __float2bfloat16(cls[d] + pos[d]);
+}
+
+// ------------------------------------------------------------------------------------------- text embed (K9)
+__global__ void __launch_bounds__(256) text_embed_kernel(const int32_t* __restrict__ ids,
+                                                         const float* __restrict__ tok, const float* __restrict__ pos,
+                                                         bf16* __restrict__ x, int64_t tokens, int L, int D,
+                                                         int vocab, int* __restrict__ err_flag) {
+  const int vec_per_row = D >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= tokens * vec_per_row) return;
+  const int64_t row = idx / vec_per_row;
+  const int dv = static_cast<int>(idx - row * vec_per_row) * 8;
+  int id = ids[row];
+  if (id < 0 || id >= vocab) {  // torch would raise an index error; flag it and clamp so we never read out of bounds
+    atomicExch(err_flag, 1);
+    id = 0;
+  }
+  const int l = static_cast<int>(row % L);
+  float a[8], b[8];
+  load8<float>(tok + static_cast<int64_t>(id) * D + dv, a);
+  load8<float>(pos + static_cast<int64_t>(l) * D + dv, b);
+  uint4 o;
+  o.x = pack_bf16x2(a[0] + b[0], a[1] + b[1]);
+  o.y = pack_bf16x2(a[2] + b[2], a[3] + b[3]);
+  o.z = pack_bf16x2(a[4] + b[4], a[5] + b[5]);
+  o.w = pack_bf16x2(a[6] + b[6], a[7] + b[7]);
+  *reinterpret_cast<uint4*>(x + row * D + dv) = o;
+}
+
+// ------------------------------------------------------------------------------------------- heads (K7 / K10)
+// One CTA per sequence: pick the pooled token row (class token, or the EOT position = first argmax of the ids),
+// LayerNorm it in fp32, multiply by the fp32 projection (W, E) and write the un-normalised embedding.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ ids,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   const float* __restrict__ proj, float* __restrict__ out, int L,
+                                                   int W, int E, float eps) {
+  extern __shared__ float sh[];  // W normalised values + 32 reduction slots
+  float* y = sh;
+  float* red = sh + W;
+  __shared__ int s_pos;
+  const int64_t seq = blockIdx.x;
+  if (threadIdx.x < 32) {
+    int pos = 0;
+    if (ids != nullptr) {  // first index of the maximum id (torch.argmax semantics)
+      int best = INT_MIN, best_i = 0;
+      for (int l = threadIdx.x; l < L; l += 32) {
+        const int v = ids[seq * L + l];
+        if (v > best) {
+          best = v;
+          best_i = l;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ob > best || (ob == best && oi < best_i)) {
+          best = ob;
+          best_i = oi;
+        }
+      }
+      pos = best_i;
+    }
+    if (threadIdx.x == 0) s_pos = pos;
+  }
+  __syncthreads();
+  const bf16* row = x + (seq * L + s_pos) * static_cast<int64_t>(W);
+  float part = 0.f;
+  for (int k = threadIdx.x; k < W; k += blockDim.x) {
+    const float v = __bfloat162float(row[k]);
+    y[k] = v;
+    part += v;
+  }
+  const float mean = block_sum(part, red) / static_cast<float>(W);
+  part = 0.f;
+  for (int k = threadIdx.x; k < W; k += blockDim.x) {
+    const float d = y[k] - mean;
+    part += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(part, red) / static_cast<float>(W) + eps);
+  for (int k = threadIdx.x; k < W; k += blockDim.x) y[k] = (y[k] - mean) * rstd * gamma[k] + beta[k];
+  __syncthreads();
+  for (int n = threadIdx.x; n < E; n += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < W; ++k) acc = fmaf(y[k], __ldg(proj + static_cast<int64_t>(k) * E + n), acc);
+    out[seq * E + n] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- pool + normalise (K8)
+// out[b,:] = scale * mean_t( x[b*T+t,:] / ||x[b*T+t,:]||_2 ).  One CTA per output row, one warp per frame slot.
+__global__ void __launch_bounds__(256) pool_normalize_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                             bf16* __restrict__ out_bf16, int T, int D, float scale) {
+  extern __shared__ float sh[];  // T inverse norms
+  const int64_t b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = warp; t < T; t += nw) {
+    const float* r = x + (b * T + t) * static_cast<int64_t>(D);
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) ss += r[d] * r[d];
+    ss = warp_sum(ss);
+    if (lane == 0) sh[t] = sqrtf(ss);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc += x[(b * T + t) * static_cast<int64_t>(D) + d] / sh[t];
+    const float v = (T == 1 ? acc : acc / static_cast<float>(T)) * scale;
+    out[b * D + d] = v;
+    if (out_bf16) out_bf16[b * D + d] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- WiSE lerp (K14)
+// out = c1 * p1 + c2 * p2 with two rounded products and a rounded add -- exactly what torch evaluates for
+// `(1 - w) * p1 + w * p2` (aligner/wise.py:16); __fmul_rn/__fadd_rn forbid FMA contraction.
+__global__ void __launch_bounds__(256) wise_lerp_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                                        float* __restrict__ out, bf16* __restrict__ out_bf16,
+                                                        int64_t n, float c1, float c2) {
+  const int64_t nvec = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 ua = ld_nc_v4(reinterpret_cast<const uint4*>(p1) + i);
+    const uint4 ub = ld_nc_v4(reinterpret_cast<const uint4*>(p2) + i);
+    float4 r;
+    r.x = __fadd_rn(__fmul_rn(c1, __uint_as_float(ua.x)), __fmul_rn(c2, __uint_as_float(ub.x)));
+    r.y = __fadd_rn(__fmul_rn(c1, __uint_as_float(ua.y)), __fmul_rn(c2, __uint_as_float(ub.y)));
+    r.z = __fadd_rn(__fmul_rn(c1, __uint_as_float(ua.z)), __fmul_rn(c2, __uint_as_float(ub.z)));
+    r.w = __fadd_rn(__fmul_rn(c1, __uint_as_float(ua.w)), __fmul_rn(c2, __uint_as_float(ub.w)));
+    uint4 o;
+    o.x = __float_as_uint(r.x); o.y = __float_as_uint(r.y); o.z = __float_as_uint(r.z); o.w = __float_as_uint(r.w);
+    st_na_v4(reinterpret_cast<uint4*>(out) + i, o);
+    if (out_bf16) {
+      uint2 h;
+      h.x = pack_bf16x2(r.x, r.y);
+      h.y = pack_bf16x2(r.z, r.w);
+      reinterpret_cast<uint2*>(out_bf16)[i] = h;
+    }
+  }
+  // tail (n % 4 elements)
+  const int64_t tail0 = nvec << 2;
+  const int64_t i = tail0 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float r = __fadd_rn(__fmul_rn(c1, p1[i]), __fmul_rn(c2, p2[i]));
+    out[i] = r;
+    if (out_bf16) out_bf16[i] = __float2bfloat16(r);
+  }
+}
+
+// fp32 -> bf16 weight conversion at load time
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
+                                                          int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+// split an fp32 matrix (rows, D) into bf16 hi / lo parts laid out for the 3-term similarity GEMM:
+//   mode 0 (A side): [hi | hi | lo]     mode 1 (B side): [hi | lo | hi]      -> (rows, 3D)
+// so that A'.B'^T = hi.hi + hi.lo + lo.hi  ~  fp32 dot product to ~2^-16.   terms == 1 writes [hi] only.
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
+                                                         int64_t rows, int D, int mode, int terms) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= rows * D) return;
+  const int64_t r = idx / D;
+  const int d = static_cast<int>(idx - r * D);
+  const float v = in[idx];
+  const bf16 hi = __float2bfloat16(v);
+  if (terms == 1) {
+    out[idx] = hi;
+    return;
+  }
+  const bf16 lo = __float2bfloat16(v - __bfloat162float(hi));
+  bf16* o = out + r * 3 * D;
+  o[d] = hi;
+  o[D + d] = mode == 0 ? hi : lo;
+  o[2 * D + d] = mode == 0 ? lo : hi;
+}
+
+inline int grid_for(int64_t n, int block, int cap_mult = 32) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * cap_mult;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float* gamma, const float* beta,
+                   int64_t rows, int D, float eps, cudaStream_t s) {
+  FC_REQUIRE(x && y && gamma && beta, "layernorm: null pointer");
+  FC_REQUIRE(D % 8 == 0 && D <= 8 * 32 * LN_MAX_CHUNKS && ldx % 8 == 0 && ldy % 8 == 0,
+             "layernorm: D=%d must be a multiple of 8 and <= 1024", D);
+  if (rows == 0) return FC_OK;
+  const int wpb = 8;
+  layernorm_bf16_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(x, y, gamma, beta, rows, D,
+                                                                                          ldx, ldy, eps);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int im2col_patches(const void* frames, int dtype, bf16* patches, int64_t F, int R, int P, cudaStream_t s) {
+  FC_REQUIRE(frames && patches, "im2col: null pointer");
+  FC_REQUIRE(R % P == 0 && P % 8 == 0, "im2col: resolution %d / patch %d unsupported (patch must be a multiple of 8)",
+             R, P);
+  if (F == 0) return FC_OK;
+  const int64_t total = F * 3 * R * (R / 8);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == FC_DTYPE_F32)
+    im2col_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(frames), patches, total, R, P);
+  else if (dtype == FC_DTYPE_BF16)
+    im2col_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(frames), patches, total, R, P);
+  else if (dtype == FC_DTYPE_F16)
+    im2col_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(frames), patches, total, R, P);
+  else
+    FC_REQUIRE(false, "im2col: unsupported frame dtype %d", dtype);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int cls_rows(bf16* x, const float* cls, const float* pos, int64_t F, int L, int D, cudaStream_t s) {
+  if (F == 0) return FC_OK;
+  cls_row_kernel<<<static_cast<unsigned>((F * D + 255) / 256), 256, 0, s>>>(x, cls, pos, F, L, D);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int text_embed(const int32_t* ids, const float* tok, const float* pos, bf16* x, int64_t C, int L, int D, int vocab,
+               int* err_flag, cudaStream_t s) {
+  FC_REQUIRE(D % 8 == 0, "text_embed: width must be a multiple of 8");
+  if (C == 0) return FC_OK;
+  const int64_t total = C * L * (D / 8);
+  text_embed_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(ids, tok, pos, x, C * L, L, D, vocab,
+                                                                              err_flag);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int head_project(const bf16* x, const int32_t* ids, const float* gamma, const float* beta, const float* proj,
+                 float* out, int64_t seqs, int L, int W, int E, float eps, cudaStream_t s) {
+  if (seqs == 0) return FC_OK;
+  const size_t smem = (W + 32) * sizeof(float);
+  head_kernel<<<static_cast<unsigned>(seqs), 256, smem, s>>>(x, ids, gamma, beta, proj, out, L, W, E, eps);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int pool_normalize(const float* x, float* out, bf16* out_bf16, int64_t B, int T, int D, float scale, cudaStream_t s) {
+  FC_REQUIRE(x && out, "pool_normalize: null pointer");
+  FC_REQUIRE(T >= 1 && T <= 4096 && D >= 1, "pool_normalize: bad T=%d D=%d", T, D);
+  if (B == 0) return FC_OK;
+  pool_normalize_kernel<<<static_cast<unsigned>(B), 256, T * sizeof(float), s>>>(x, out, out_bf16, T, D, scale);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int wise_lerp(const float* p1, const float* p2, float* out, bf16* out_bf16, int64_t n, double w, cudaStream_t s) {
+  FC_REQUIRE(p1 && p2 && out, "wise_lerp: null pointer");
+  FC_REQUIRE(((reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) | reinterpret_cast<uintptr_t>(out)) &
+              15) == 0,
+             "wise_lerp: pointers must be 16-byte aligned");
+  if (n == 0) return FC_OK;
+  // python evaluates (1 - w) in double; torch then multiplies the fp32 tensor by the scalar cast to fp32
+  const float c1 = static_cast<float>(1.0 - w), c2 = static_cast<float>(w);
+  wise_lerp_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, s>>>(p1, p2, out, out_bf16, n, c1, c2);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int f32_to_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return FC_OK;
+  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int split_bf16(const float* in, bf16* out, int64_t rows, int D, int mode, int terms, cudaStream_t s) {
+  if (rows == 0) return FC_OK;
+  split_bf16_kernel<<<static_cast<unsigned>((rows * D + 255) / 256), 256, 0, s>>>(in, out, rows, D, mode, terms);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+}  // namespace fc

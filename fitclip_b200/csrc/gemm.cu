@@ -1,0 +1,361 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * B[N,K]^T), bf16 in, fp32 acc.
+//
+//   warp 0   TMA producer   : cp.async.bulk.tensor (128B-swizzled 128x64 A tile + 256x64 B tile per stage)
+//   warp 1   MMA issuer     : one elected thread issues tcgen05.mma 128x256x16, accumulators in TMEM
+//   warp 2   TMEM allocator : 512 columns = 2 accumulator stages of 256 fp32 columns
+//   warp 3   idle
+//   warps 4-7 epilogue      : tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
+//
+// Three pipelines: smem full/empty (TMA<->MMA, 4 stages of 48 KiB), TMEM full/empty (MMA<->epilogue, 2 stages), and a
+// static persistent tile scheduler (tile = blockIdx.x + i*gridDim.x, N fastest so the CTAs of one wave share A
+// tiles in L2 while the weight matrix B stays L2-resident).
+//
+// This one kernel serves every dense contraction of the hot path (reference call sites in SURVEY.md 2.2):
+//   K1 patch-embed, K3 QKV, K5 out-proj(+residual), K6 MLP fc1(+QuickGELU)/fc2(+residual), K11/K12 similarity,
+//   K13 rank counting fused into the similarity epilogue (the similarity matrix is never materialised).
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace fc {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+__device__ __forceinline__ float quick_gelu(float v) {
+  // x * sigmoid(1.702 x)  (reference twin: aligner/encoder/slip.py:359-361)
+  return __fdividef(v, 1.f + __expf(-1.702f * v));
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m_tiles = (p.M + BM - 1) / BM;
+  const int num_n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_k = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance along K inside the 128-byte swizzle atom: +32 bytes per UMMA_K
+            umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2), umma_desc_k_sw128(b_addr + k * UMMA_K * 2),
+                         idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+      const int row = m_blk * BM + row_in_tile;
+      const int n0 = n_blk * BN;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+
+      // per-row constants of the fused epilogues
+      int64_t out_row = row;
+      const float* pos_row = nullptr;
+      int tgt = 0;
+      float tsc = 0.f;
+      int cnt = 0;
+      if (EPI == EPI_PATCH && row_ok) {
+        const int f = row / p.patches_per_frame, pp = row - f * p.patches_per_frame;
+        out_row = static_cast<int64_t>(row) + f + 1;  // skip one class-token row per frame
+        pos_row = p.pos + static_cast<int64_t>(pp + 1) * p.N;
+      }
+      if ((EPI == EPI_TARGET || EPI == EPI_COUNT) && row_ok) {
+        tgt = p.target[row];
+        if (EPI == EPI_COUNT) tsc = p.target_score[row];
+      }
+
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (!row_ok) continue;
+
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || EPI == EPI_BIAS_RESID || EPI == EPI_PATCH) {
+          // N is a multiple of 32 on these paths (checked on the host): full, 16-byte aligned chunks.
+          float v[32];
+          const float4* add4 = reinterpret_cast<const float4*>((EPI == EPI_PATCH ? pos_row : p.bias) + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(add4 + j);
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+          }
+          if (EPI == EPI_BIAS_QGELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+          }
+          if (EPI == EPI_BIAS_RESID) {
+            const uint4* res4 = reinterpret_cast<const uint4*>(p.resid + static_cast<int64_t>(row) * p.ldr + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = res4[j];
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(w[t]);
+                v[8 * j + 2 * t] += f.x;
+                v[8 * j + 2 * t + 1] += f.y;
+              }
+            }
+          }
+          uint4* out4 = reinterpret_cast<uint4*>(static_cast<bf16*>(p.C) + out_row * p.ldc + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            out4[j] = u;
+          }
+        } else if (EPI == EPI_F32) {
+          float* out = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
+          if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              o.x = p.alpha * __uint_as_float(r[4 * j + 0]);
+              o.y = p.alpha * __uint_as_float(r[4 * j + 1]);
+              o.z = p.alpha * __uint_as_float(r[4 * j + 2]);
+              o.w = p.alpha * __uint_as_float(r[4 * j + 3]);
+              reinterpret_cast<float4*>(out)[j] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) out[j] = p.alpha * __uint_as_float(r[j]);
+          }
+        } else if (EPI == EPI_TARGET) {
+          const int local = tgt - p.col_offset - col0;
+          if (local >= 0 && local < 32 && col0 + local < p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j == local) p.tscore_out[row] = __uint_as_float(r[j]);
+          }
+        } else if (EPI == EPI_COUNT) {
+          const int gcol0 = p.col_offset + col0;
+          const int nvalid = min(32, p.N - col0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(r[j]);
+            const bool hit = (s > tsc) || (s == tsc && (gcol0 + j) < tgt);
+            cnt += (j < nvalid && hit) ? 1 : 0;
+          }
+        }
+      }
+      if (EPI == EPI_COUNT && row_ok && cnt) atomicAdd(p.counts + row, cnt);
+
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- host side: tensor maps + launch ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// rows x K bf16 matrix, K contiguous, row stride ld elements; box = box_rows x 64 elements, 128B swizzle.
+int make_tmap(CUtensorMap* tm, const bf16* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return FC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(bf16)};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld K=%lld ld=%lld", static_cast<int>(r),
+              static_cast<long long>(rows), static_cast<long long>(K), static_cast<long long>(ld));
+    return FC_ERR_CUDA;
+  }
+  return FC_OK;
+}
+
+template <int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    FC_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tn_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+}  // namespace
+
+int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, const GemmParams& p,
+                 cudaStream_t stream) {
+  FC_REQUIRE(A && B, "gemm: null operand");
+  FC_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  FC_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm: K/lda/ldb must be multiples of 8 (K=%d)", p.K);
+  FC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             "gemm: operands must be 16-byte aligned");
+  if (epilogue <= EPI_PATCH) {
+    FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0, "gemm: bf16 epilogues need N %% 32 == 0 and ldc %% 8 == 0");
+    FC_REQUIRE((reinterpret_cast<uintptr_t>(p.C) & 15) == 0, "gemm: C must be 16-byte aligned");
+    if (epilogue == EPI_PATCH)
+      FC_REQUIRE(p.pos && p.patches_per_frame > 0, "gemm: patch epilogue needs pos and patches_per_frame");
+    else
+      FC_REQUIRE(p.bias, "gemm: bias epilogue needs a bias vector");
+    if (epilogue == EPI_BIAS_RESID)
+      FC_REQUIRE(p.resid && p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 15) == 0,
+                 "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
+  } else if (epilogue == EPI_F32) {
+    FC_REQUIRE(p.C, "gemm: null C");
+  } else if (epilogue == EPI_TARGET) {
+    FC_REQUIRE(p.target && p.tscore_out, "gemm: target epilogue needs target and tscore_out");
+  } else if (epilogue == EPI_COUNT) {
+    FC_REQUIRE(p.target && p.target_score && p.counts, "gemm: count epilogue needs target, target_score, counts");
+  } else {
+    FC_REQUIRE(false, "gemm: unknown epilogue %d", epilogue);
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tb, B, p.N, p.K, ldb, BN);
+  if (rc) return rc;
+  switch (epilogue) {
+    case EPI_BIAS: return launch<EPI_BIAS>(ta, tb, p, stream);
+    case EPI_BIAS_QGELU: return launch<EPI_BIAS_QGELU>(ta, tb, p, stream);
+    case EPI_BIAS_RESID: return launch<EPI_BIAS_RESID>(ta, tb, p, stream);
+    case EPI_PATCH: return launch<EPI_PATCH>(ta, tb, p, stream);
+    case EPI_F32: return launch<EPI_F32>(ta, tb, p, stream);
+    case EPI_TARGET: return launch<EPI_TARGET>(ta, tb, p, stream);
+    default: return launch<EPI_COUNT>(ta, tb, p, stream);
+  }
+}
+
+}  // namespace fc

@@ -1,0 +1,161 @@
+/* libfitclip_b200 -- C ABI of the B200-native FitCLIP evaluation hot path.
+ *
+ * The reference (bryant1410/fitclip) is pure Python: its boundary for this path is the `VideoTextEncoder` plugin ABC
+ * (aligner/encoder/video_encoder.py:14-52, aligner/encoder/video_text_encoder.py:15-31), not an FFI.  This header is
+ * what the Python drop-in (`fitclip_b200.encoder.B200ClipVideoTextEncoder`, bound with ctypes -- see INTEGRATION.md)
+ * calls underneath; each entry point cites the reference call it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative fc_status; fc_last_error() gives the text (thread-local).
+ *     Nothing throws or aborts across the boundary.
+ *   - every pointer is CALLER-OWNED CUDA DEVICE memory unless it says "host"; no ownership is transferred.
+ *   - work is enqueued on the caller's `stream` (a cudaStream_t passed as void*) and is asynchronous.
+ *   - no hidden allocation after fc_model_create(); a handle is bound to the device current at creation,
+ *     is not thread-safe, and needs compute capability 10.x (FC_ERR_ARCH otherwise -- there is no CPU fallback).
+ *   - matrices are row-major; "ld" is the row stride in elements.
+ */
+#ifndef FITCLIP_B200_H_
+#define FITCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FC_API __attribute__((visibility("default")))
+
+typedef enum fc_status {
+  FC_STATUS_OK = 0,
+  FC_STATUS_INVALID = -1, /* bad argument: null pointer, shape, alignment */
+  FC_STATUS_CUDA = -2,    /* a CUDA call failed (message has the CUDA error string) */
+  FC_STATUS_ARCH = -3,    /* device is not sm_100 */
+  FC_STATUS_STATE = -4,   /* e.g. encode before every parameter was loaded */
+  FC_STATUS_NOMEM = -5
+} fc_status;
+
+typedef enum fc_dtype { FC_F32 = 0, FC_BF16 = 1, FC_F16 = 2 } fc_dtype;
+
+/* GEMM epilogues exposed for kernel-level parity tests (fc_gemm_bf16). */
+typedef enum fc_epilogue {
+  FC_EPI_BIAS = 0,       /* C(bf16) = A.B^T + bias                                  (K3)  */
+  FC_EPI_BIAS_QGELU = 1, /* C(bf16) = quickgelu(A.B^T + bias), x*sigmoid(1.702x)    (K6)  */
+  FC_EPI_BIAS_RESID = 2, /* C(bf16) = resid + A.B^T + bias                          (K5)  */
+  FC_EPI_F32 = 4         /* C(fp32) = alpha * A.B^T                                 (K11/K12) */
+} fc_epilogue;
+
+/* Geometry of clip.model.CLIP(**kwargs): config/encoder/clip_from_scratch_vit_b_16.yaml:5-16. */
+typedef struct fc_config {
+  int32_t embed_dim;
+  int32_t image_resolution;
+  int32_t vision_layers;
+  int32_t vision_width;
+  int32_t vision_patch_size;
+  int32_t context_length;
+  int32_t vocab_size;
+  int32_t transformer_width;
+  int32_t transformer_heads;
+  int32_t transformer_layers;
+  int32_t max_frames_per_pass; /* frames encoded per internal pass (workspace is sized for it); 0 = 256 */
+  int32_t max_texts_per_pass;  /* captions encoded per internal pass; 0 = 984 */
+} fc_config;
+
+typedef struct fc_model fc_model;
+
+FC_API int fc_version(void);
+/* Copies the last error message of the calling thread into buf (NUL-terminated); returns its full length. */
+FC_API size_t fc_last_error(char* buf, size_t cap);
+/* Number of kernel launches issued by this library in this process so far (bench.py's gpu_launches). */
+FC_API int64_t fc_launch_count(void);
+
+/* ---- model lifetime and weights --------------------------------------------------------------------------------
+ * Replaces clip.load / build_model as used by load_clip_model (aligner/encoder/clip_video_text_encoder.py:22-61):
+ * the Python side owns the fp32 nn.Parameters (OpenAI state-dict names); the library keeps its own bf16 copies of
+ * the GEMM weights and fp32 copies of biases / LayerNorm / embeddings / projections. */
+FC_API int fc_model_create(const fc_config* cfg, fc_model** out);
+FC_API int fc_model_destroy(fc_model* m);
+/* `name` is an OpenAI-CLIP parameter name ("visual.conv1.weight", "transformer.resblocks.3.attn.in_proj_weight",
+ * "token_embedding.weight", ...; "logit_scale" is accepted and ignored, clip_video_text_encoder.py:75-77).
+ * `data` is a contiguous fp32 device tensor of `numel` elements. */
+FC_API int fc_model_set_param(fc_model* m, const char* name, const float* data, int64_t numel, void* stream);
+/* 1 when every parameter has been set, else 0 (and the first missing name in fc_last_error). */
+FC_API int fc_model_ready(fc_model* m);
+FC_API int64_t fc_model_workspace_bytes(const fc_model* m);
+
+/* ---- encoders ---------------------------------------------------------------------------------------------------
+ * ClipVideoTextEncoder.encode_video (clip_video_text_encoder.py:80-89): frames (videos*frames_per_video, 3, R, R) of
+ * `dtype`, CLIP-normalised pixels -> CLIP.encode_image -> x/||x|| per FRAME -> mean over the frames of each video
+ * (not re-normalised).  out_video: fp32 (videos, embed_dim).  out_frames (optional, may be NULL): the un-normalised
+ * per-frame image features, fp32 (videos*frames_per_video, embed_dim). */
+FC_API int fc_encode_video(fc_model* m, const void* frames, int dtype, int64_t videos, int32_t frames_per_video,
+                           float* out_video, float* out_frames, void* stream);
+/* ClipVideoTextEncoder.encode_text (clip_video_text_encoder.py:92-94): int32 token ids (texts, context_length) ->
+ * CLIP.encode_text (EOT = first argmax of the ids) -> x/||x||.  out_text: fp32 (texts, embed_dim).
+ * Out-of-vocabulary ids are reported as FC_STATUS_INVALID by fc_model_check() after the stream has run. */
+FC_API int fc_encode_text(fc_model* m, const int32_t* ids, int64_t texts, float* out_text, void* stream);
+/* Synchronises `stream` and reports deferred device-side input errors (bad token ids). */
+FC_API int fc_model_check(fc_model* m, void* stream);
+
+/* ---- pooling / WiSE ---------------------------------------------------------------------------------------------
+ * out[b] = scale * mean_t( x[b*T+t] / ||x[b*T+t]||_2 ), fp32 (clip_video_text_encoder.py:85-89; T = 1 is the text
+ * normalisation of :94).  out_bf16 may be NULL. */
+FC_API int fc_pool_normalize(const float* x, float* out, void* out_bf16, int64_t rows_out, int32_t T, int32_t D,
+                             float scale, void* stream);
+/* wise_state_dict (aligner/wise.py:10-16): out = (1 - w) * p1 + w * p2 elementwise over n fp32 values, evaluated as
+ * two rounded products and a rounded sum (bit-exact with torch).  out may alias p1 or p2; out_bf16 may be NULL. */
+FC_API int fc_wise_lerp(const float* p1, const float* p2, float* out, void* out_bf16, int64_t n, double w,
+                        void* stream);
+
+/* ---- similarity + rank (rows = texts / queries, columns = videos / classes) ------------------------------------
+ * TextVideoRetrievalLightningModule._validate_dataset (aligner/text_video_retrieval.py:67-83) without materialising
+ * the Nt x Nv matrix.  `terms` = 1: operands rounded to bf16; 3: split-bf16 (hi.hi + hi.lo + lo.hi ~ fp32 product).
+ * The column slab may be a shard: `col_offset` is the global index of local column 0, `target[i]` the GLOBAL target
+ * column of row i.  Protocol: prepare -> target_scores (tscore zeroed by caller; all-reduce(sum) across shards)
+ *                                   -> count (counts zeroed by caller; all-reduce(sum) across shards) = 0-based ranks.
+ * Tie rule: rank_i = #{j: s_ij > s_it} + #{j < t: s_ij == s_it}. */
+FC_API int64_t fc_sim_workspace_bytes(int64_t nt, int64_t nv, int32_t dim, int32_t terms);
+FC_API int fc_sim_prepare(const float* text_emb, const float* video_emb, int64_t nt, int64_t nv, int32_t dim,
+                          int32_t terms, void* workspace, void* stream);
+FC_API int fc_sim_target_scores(const void* workspace, int64_t nt, int64_t nv, int32_t dim, int32_t terms,
+                                const int32_t* target, int32_t col_offset, float* tscore, void* stream);
+FC_API int fc_sim_count(const void* workspace, int64_t nt, int64_t nv, int32_t dim, int32_t terms,
+                        const int32_t* target, int32_t col_offset, const float* tscore, int32_t* counts, void* stream);
+/* Materialise S = alpha * text . video^T as fp32 (nt, ld) -- `scores = encoded_texts @ encoded_videos.T`
+ * (text_video_retrieval.py:74) and the scaled per-batch scores of :49-50 / video_text_module.py:62-63. */
+FC_API int fc_sim_scores(const void* workspace, int64_t nt, int64_t nv, int32_t dim, int32_t terms, float alpha,
+                         float* scores, int64_t ld, void* stream);
+
+/* Rank.update on a materialised matrix (aligner/metrics.py:16-19): ranks[i] (int64, 0-based), same tie rule. */
+FC_API int fc_rank_from_scores(const float* scores, int64_t ld, int64_t rows, int64_t cols, const int32_t* target,
+                               int64_t* ranks, void* stream);
+FC_API int fc_counts_to_ranks(const int32_t* counts, int64_t* ranks, int64_t n, void* stream);
+/* Recall(top_k=1|5|10) as hits/n (fp32 x3), MedianRank = lower median + 1 (int64; aligner/metrics.py:33-36),
+ * MeanRank = mean + 1 (fp32, may be NULL; :27-30).  num_candidates = number of columns ranked against. */
+FC_API int fc_metrics_from_ranks(const int64_t* ranks, int64_t n, int64_t num_candidates, float* recall_1_5_10,
+                                 int64_t* median_rank, float* mean_rank, void* stream);
+/* Per-row top-k (k <= 16), value descending then index ascending. */
+FC_API int fc_topk_rows(const float* scores, int64_t ld, int64_t rows, int64_t cols, int32_t k, float* values,
+                        int32_t* indices, void* stream);
+
+/* ---- per-batch losses, forward only (aligner/loss.py:13-39); scores are (B, ld) fp32; workspace >= 2*B floats ---- */
+FC_API int fc_nce_loss(const float* scores, int64_t ld, int32_t B, float* workspace, float* out, void* stream);
+/* TeacherStudentNCELoss(reduction="batchmean") (aligner/teacher_student.py:73). */
+FC_API int fc_ts_nce_loss(const float* scores, const float* teacher_scores, int64_t ld, int32_t B, float* workspace,
+                          float* out, void* stream);
+
+/* ---- kernel-level entry points (parity tests, microbenchmarks) -------------------------------------------------- */
+/* C[M,N] = epilogue(A[M,K] . B[N,K]^T): bf16 operands, K contiguous, fp32 accumulation in TMEM (tcgen05.mma). */
+FC_API int fc_gemm_bf16(int epilogue, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                        const float* bias, const void* resid, int64_t ldr, float alpha, int32_t M, int32_t N,
+                        int32_t K, void* stream);
+FC_API int fc_layernorm_bf16(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int32_t D,
+                             float eps, void* stream);
+/* qkv: bf16 (seqs*L, 3*heads*64) rows [q|k|v]; out: bf16 (seqs*L, heads*64). */
+FC_API int fc_attention_bf16(const void* qkv, void* out, int64_t seqs, int32_t L, int32_t heads, int32_t causal,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FITCLIP_B200_H_ */

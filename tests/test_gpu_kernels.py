@@ -1,0 +1,77 @@
+"""Parity of the memory-bound kernels and the fused attention against PyTorch fp32 references (via the C ABI)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,D", [(1, 768), (197 * 3 + 5, 768), (77 * 7, 512), (33, 1024), (10, 64)])
+def test_layernorm(dev, rows, D):
+    from fitclip_b200 import ops
+    torch.manual_seed(0)
+    x = (torch.randn(rows, D, device=dev) * 3 + 1).bfloat16()
+    g = torch.randn(D, device=dev)
+    b = torch.randn(D, device=dev)
+    out = ops.layernorm_bf16(x, g, b)
+    ref = F.layer_norm(x.float(), (D,), g, b, 1e-5)
+    # output rounding to bf16 dominates: 2^-9 relative
+    assert torch.allclose(out.float(), ref, atol=2e-2, rtol=8e-3), (out.float() - ref).abs().max().item()
+    # in place (ln_pre)
+    y = x.clone()
+    ops.layernorm_bf16(y, g, b, out=y)
+    assert torch.equal(y, out)
+
+
+def _ref_attention(qkv, seqs, L, heads, causal):
+    D = heads * 64
+    q, k, v = qkv.float().view(seqs, L, 3, heads, 64).permute(2, 0, 3, 1, 4)  # (3, S, H, L, 64)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device=qkv.device).triu_(1)
+    o = torch.softmax(s, dim=-1) @ v
+    return o.permute(0, 2, 1, 3).reshape(seqs * L, D)
+
+
+@pytest.mark.parametrize("seqs,L,heads,causal", [
+    (3, 197, 12, False), (5, 77, 8, True), (2, 77, 8, False), (4, 16, 2, True), (3, 50, 4, False),
+    (2, 130, 3, True), (1, 208, 1, False), (7, 1, 2, True)])
+def test_attention(dev, seqs, L, heads, causal):
+    from fitclip_b200 import ops
+    torch.manual_seed(1)
+    qkv = torch.randn(seqs * L, 3 * heads * 64, device=dev).bfloat16()
+    out = ops.attention_bf16(qkv, seqs, L, heads, causal)
+    ref = _ref_attention(qkv, seqs, L, heads, causal)
+    # P is rounded to bf16 before PV and the output is bf16: ~1e-2 absolute on O(1) values
+    assert torch.allclose(out.float(), ref, atol=3e-2, rtol=2e-2), (out.float() - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("B,T,D", [(1, 1, 512), (32, 4, 512), (7, 8, 512), (1000, 1, 512), (3, 5, 100)])
+def test_pool_normalize(dev, B, T, D):
+    from fitclip_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn(B * T, D, device=dev) * 5
+    out = ops.pool_normalize(x, T)
+    ref = (x / x.norm(dim=-1, keepdim=True)).view(B, T, D).mean(dim=1)  # clip_video_text_encoder.py:85-89
+    assert (out - ref).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1000, 768 * 3072 + 3, 49408 * 512])
+@pytest.mark.parametrize("w", [0.4, 0.5, 0.0, 1.0, 0.123456789])
+def test_wise_lerp_bit_exact(dev, n, w):
+    from fitclip_b200 import ops
+    torch.manual_seed(3)
+    p1 = torch.randn(n, device=dev)
+    p2 = torch.randn(n, device=dev)
+    out = ops.wise_lerp(p1, p2, w)
+    ref = (1 - w) * p1.cpu() + w * p2.cpu()  # aligner/wise.py:16 evaluated by torch on the CPU
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_wise_lerp_bf16_copy(dev):
+    from fitclip_b200 import ops
+    p1 = torch.randn(1001, device=dev)
+    p2 = torch.randn(1001, device=dev)
+    ob = torch.empty(1001, device=dev, dtype=torch.bfloat16)
+    out = ops.wise_lerp(p1, p2, 0.4, out_bf16=ob)
+    assert torch.equal(ob, out.bfloat16())
