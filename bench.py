@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the FitCLIP evaluation hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one complete retrieval evaluation of the synthetic MSR-VTT-1kA-shaped workload (BASELINE.json configs[1]):
+per GPU 1000 videos x 4 frames x 3x224x224 fp32 + 1000 captions x 77 tokens -> CLIP ViT-B/16 encode (bf16 tensor
+cores, random-init weights) -> per-frame L2 norm + frame mean-pool -> text x video similarity -> ranks -> R@1/5/10/MdR.
+With N > 1 every rank owns 1000 videos/captions of an N*1000 gallery (weak scaling): video-sharded encode, NCCL
+all-gather of text embeddings, column-sharded fused similarity+rank count, all-reduce of target scores and counts.
+
+`value`   videos/s, inputs resident in HBM when the timed region starts (inputs are 2.4 GB/GPU > the 126 MB L2).
+`e2e`     videos/s through the public plugin API from pinned HOST buffers (H2D of every frame/token batch and the
+          D2H read of the metrics are inside the timed region).
+`roofline` the tcgen05 GEMM kernel, timed per launch with CUDA events on its stream during the timed steps.
+`cpu_baseline` the oracle (restated reference path, fp32 torch CPU) on a bounded sample, on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_FRAME = 35_126_906_880      # SURVEY.md 8d / BASELINE.md section 2
+FLOP_PER_CAPTION = 5_959_540_736
+VIDEOS_PER_GPU, FRAMES, CAPTIONS_PER_GPU, CTX = 1000, 4, 1000, 77
+WORKLOAD = "msrvtt_1ka_shape: 1000 videos x 4 frames x 3x224x224 fp32 + 1000 captions x 77 tok per GPU, ViT-B/16"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), d["hbm_gbs"], "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"  # B200_PROFILING.md fallback figures
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.rows = []
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self) -> None:
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, r[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_inputs(rank: int, device, pinned: bool):
+    """frames ~ N(0,1) (post-Normalize statistics), captions = [SOT] + random ids + [EOT], dense 77."""
+    import torch
+
+    import oracle
+    g = torch.Generator().manual_seed(1234 + rank)
+    ids = oracle.tokenize_synthetic(CAPTIONS_PER_GPU, CTX, seed=4321 + rank)
+    if pinned:
+        frames = torch.empty(VIDEOS_PER_GPU, FRAMES, 3, 224, 224, dtype=torch.float32, pin_memory=True)
+        frames.normal_(generator=g)
+        return frames, ids.pin_memory()
+    gd = torch.Generator(device=device).manual_seed(1234 + rank)
+    frames = torch.randn(VIDEOS_PER_GPU, FRAMES, 3, 224, 224, device=device, generator=gd)
+    return frames, ids.to(device)
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder, _lib, metrics_from_ranks, retrieval_ranks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+
+    # random-init ViT-B/16, identical on every rank (config/encoder/clip_from_scratch_vit_b_16.yaml)
+    model = oracle.clip_vit_b_16(seed=0)
+    encoder = B200ClipVideoTextEncoder(model.state_dict(), num_frames=FRAMES).to(device)
+    del model
+    frames, ids = synthetic_inputs(rank, device, pinned=False)
+    n_total = VIDEOS_PER_GPU * world
+
+    def step_resident():
+        v = encoder.encode_video(frames)
+        t = encoder.encode_text({"input_ids": ids})
+        ranks = retrieval_ranks(t, v, group=group)
+        return metrics_from_ranks(ranks, n_total)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.inference_mode():
+        for _ in range(max(args.warmup, 3)):
+            metrics = step_resident()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = _lib.launch_count()
+        _lib.profile_start(1 << 16)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            metrics = step_resident()
+        e1.record()
+        barrier()
+        records = _lib.profile_stop()
+        launches = _lib.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_per_step = ms.item() / args.steps
+
+        # ---- end to end through the public API from pinned host memory ----
+        h_frames, h_ids = synthetic_inputs(rank, device, pinned=True)
+        chunk = 250  # videos per H2D chunk; copies run on a side stream and overlap the previous chunk's encode
+        copy_stream = torch.cuda.Stream(device)
+        bufs = [torch.empty(chunk, FRAMES, 3, 224, 224, device=device) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def step_e2e():
+            main = torch.cuda.current_stream(device)
+            outs = []
+            n_chunks = VIDEOS_PER_GPU // chunk
+            for i in range(n_chunks + 1):
+                if i < n_chunks:
+                    b = i % 2
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(freed[b])
+                        bufs[b].copy_(h_frames[i * chunk:(i + 1) * chunk], non_blocking=True)
+                        ready[b].record(copy_stream)
+                if i > 0:
+                    b = (i - 1) % 2
+                    main.wait_event(ready[b])
+                    outs.append(encoder.encode_video(bufs[b]))
+                    freed[b].record(main)
+            d_ids = h_ids.to(device, non_blocking=True)
+            t = encoder.encode_text({"input_ids": d_ids})
+            ranks = retrieval_ranks(t, torch.cat(outs), group=group)
+            m = metrics_from_ranks(ranks, n_total)
+            return {k: x.cpu() for k, x in m.items()}  # D2H read of the step's result
+
+        for b in range(2):
+            freed[b].record(torch.cuda.current_stream(device))
+        for _ in range(2):
+            m_e2e = step_e2e()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            m_e2e = step_e2e()
+        e1.record()
+        barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e_ms = ms2.item() / args.steps
+
+    if rank == 0:
+        peak, sustained, hbm, src = measured_peaks()
+        gemm = [r for r in records if r["kind"] == 0]
+        g_ms = sum(r["ms"] for r in gemm)
+        g_flops = sum(r["flops"] for r in gemm)
+        total_ms = sum(r["ms"] for r in records)
+        achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
+        by_kind = {}
+        for r in records:
+            name = {0: "gemm_tcgen05", 1: "attention", 2: "layernorm", 3: "other"}[r["kind"]]
+            by_kind[name] = by_kind.get(name, 0.0) + r["ms"]
+        shapes = sorted(gemm, key=lambda r: -r["ms"])
+        step_flops = VIDEOS_PER_GPU * FRAMES * FLOP_PER_FRAME + CAPTIONS_PER_GPU * FLOP_PER_CAPTION \
+            + 2.0 * n_total * VIDEOS_PER_GPU * 512
+        line = {
+            "metric": "videos/sec (ViT-B/16 encode+sim+rank)", "value": n_total / (ms_per_step * 1e-3),
+            "unit": "videos/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (random-init CLIP ViT-B/16, N(0,1) frames, random token ids)",
+            "config": {"workload": WORKLOAD, "videos_per_gpu": VIDEOS_PER_GPU, "frames_per_video": FRAMES,
+                       "captions_per_gpu": CAPTIONS_PER_GPU, "gallery": n_total, "similarity": "split-bf16 x3",
+                       "l2": "inputs (2.4 GB/GPU) exceed L2; no explicit flush", "parallelism": f"dp{world}"},
+            "queries_per_sec": n_total / (ms_per_step * 1e-3),
+            "e2e_roofline_frac": step_flops / (ms_per_step * 1e-3) / (peak * 1e12),
+            "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "videos/s",
+                    "h2d_bytes_per_step": int(h_frames.numel() * 4 + h_ids.numel() * 4),
+                    "d2h_bytes_per_step": 3 * 4 + 8, "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": src,
+                         "frac_of_sustained": achieved / sustained, "kernel": "gemm_bf16_tn_kernel (all shapes)",
+                         "kernel_share_of_step": g_ms / total_ms if total_ms else None,
+                         "ms_by_kernel_class": by_kind,
+                         "top_shapes": [{"epi": r["tag"], "N": r["n"], "K": r["k"], "launches": r["launches"],
+                                         "ms": round(r["ms"], 3),
+                                         "tflops": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 1)}
+                                        for r in shapes[:8]]},
+            "metrics": {k: float(v) for k, v in metrics.items()},
+        }
+        line["cpu_baseline"] = cpu_baseline(sample_videos=args.cpu_sample)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample_videos: int = 16, steps: int = 1) -> dict:
+    """The oracle (the reference's path restated: fp32 torch on the host cores) on a bounded sample of the workload:
+    `sample_videos` videos x 4 frames + as many captions in batches of 32 (aligner/data/video_data_module.py:32),
+    plus the full 1000 x 1000 similarity + argsort rank + metrics; encode time is extrapolated linearly to 1000."""
+    import torch
+
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = oracle.RefClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0))
+    g = torch.Generator().manual_seed(1234)
+    video = torch.randn(sample_videos, FRAMES, 3, 224, 224, generator=g)
+    ids = oracle.tokenize_synthetic(sample_videos, CTX, seed=4321)
+    with torch.inference_mode():
+        ref(video[:2], {"input_ids": ids[:2]})  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for i in range(0, sample_videos, 32):
+                ref(video[i:i + 32], {"input_ids": ids[i:i + 32]})
+        t_enc = (time.perf_counter() - t0) / steps
+        tv = torch.nn.functional.normalize(torch.randn(VIDEOS_PER_GPU, 512, generator=g), dim=-1)
+        tt = torch.nn.functional.normalize(torch.randn(CAPTIONS_PER_GPU, 512, generator=g), dim=-1)
+        t0 = time.perf_counter()
+        oracle.ref_retrieval_metrics(tt @ tv.T)
+        t_rank = time.perf_counter() - t0
+    total = t_enc * (VIDEOS_PER_GPU / sample_videos) + t_rank
+    return {"value": VIDEOS_PER_GPU / total, "unit": "videos/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_videos} videos x {FRAMES} frames + {sample_videos} captions encoded in {t_enc:.2f} s "
+                      f"(extrapolated x{VIDEOS_PER_GPU / sample_videos:.1f}) + full 1000x1000 sim+rank {t_rank:.3f} s"}
+
+
+def run_reference(args) -> None:
+    """Reference arm: the reference's own CPU implementation of the path.  The reference package cannot be imported
+    (clip / pytorch_lightning / torchmetrics / overrides absent, no network), so this times the oracle port on all
+    host threads.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    base = cpu_baseline(sample_videos=args.cpu_sample, steps=1)
+    for _ in range(steps - 1):
+        if time.perf_counter() - t0 > 150:
+            break
+        base = cpu_baseline(sample_videos=args.cpu_sample, steps=1)
+    v = base["value"]
+    print(json.dumps({
+        "impl": "reference", "metric": "videos/sec (ViT-B/16 encode+sim+rank)", "value": v, "unit": "videos/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * VIDEOS_PER_GPU / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference path; bounded sample per step"},
+        "cpu_baseline": base, "gpu_launches": 0,
+        "e2e": {"value": v, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=16, help="videos in the bounded CPU-baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,12 @@ class fc_config(C.Structure):
         "max_texts_per_pass")]
 
 
+class fc_profile_record(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("tag", C.c_int32), ("n", C.c_int64), ("k", C.c_int64),
+                ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double),
+                ("rows", C.c_double)]
+
+
 _p, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); must list every FC_API symbol of include/fitclip_b200.h (tests/test_abi.py checks it)
@@ -34,6 +40,8 @@ SIGNATURES = {
     "fc_version": (C.c_int, []),
     "fc_last_error": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "fc_launch_count": (_i64, []),
+    "fc_profile_start": (C.c_int, [_i32]),
+    "fc_profile_stop": (C.c_int, [_p, _i32]),
     "fc_model_create": (C.c_int, [C.POINTER(fc_config), C.POINTER(_p)]),
     "fc_model_destroy": (C.c_int, [_p]),
     "fc_model_set_param": (C.c_int, [_p, C.c_char_p, _p, _i64, _p]),
@@ -104,6 +112,19 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def stream_ptr(device: Optional[torch.device] = None) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def profile_start(max_records: int = 65536) -> None:
+    check(load().fc_profile_start(max_records))
+
+
+def profile_stop(cap: int = 256):
+    """-> list of dict records aggregated by (kind, tag, n, k); synchronises the device."""
+    arr = (fc_profile_record * cap)()
+    n = load().fc_profile_stop(C.cast(arr, C.c_void_p), cap)
+    if n < 0:
+        check(n)
+    return [{f: getattr(arr[i], f) for f, _ in fc_profile_record._fields_} for i in range(n)]
 
 
 def launch_count() -> int:

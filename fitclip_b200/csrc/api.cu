@@ -28,6 +28,29 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---------------------------------------------------------------- profiler
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  int kind, tag;
+  int64_t m, n, k;
+  double flops, bytes;
+};
+static std::vector<ProfRec> g_prof;
+static int g_prof_used = 0;
+static bool g_prof_on = false;
+
+ProfScope::ProfScope(cudaStream_t s, int kind, int tag, int64_t m, int64_t n, int64_t k, double flops, double bytes)
+    : slot(-1), stream(s) {
+  if (!g_prof_on || g_prof_used >= static_cast<int>(g_prof.size())) return;
+  slot = g_prof_used++;
+  ProfRec& r = g_prof[slot];
+  r.kind = kind; r.tag = tag; r.m = m; r.n = n; r.k = k; r.flops = flops; r.bytes = bytes;
+  cudaEventRecord(r.e0, stream);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].e1, stream);
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -262,6 +285,46 @@ size_t fc_last_error(char* buf, size_t cap) {
 
 int64_t fc_launch_count(void) { return g_launches.load(); }
 
+int fc_profile_start(int32_t max_records) {
+  FC_REQUIRE(max_records > 0 && max_records <= (1 << 20), "fc_profile_start: bad capacity");
+  while (static_cast<int>(g_prof.size()) < max_records) {
+    ProfRec r{};
+    FC_CUDA(cudaEventCreate(&r.e0));
+    FC_CUDA(cudaEventCreate(&r.e1));
+    g_prof.push_back(r);
+  }
+  g_prof_used = 0;
+  g_prof_on = true;
+  return FC_OK;
+}
+
+int fc_profile_stop(fc_profile_record* out, int32_t cap) {
+  g_prof_on = false;
+  FC_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (int i = 0; i < g_prof_used; ++i) {
+    const ProfRec& r = g_prof[i];
+    float ms = 0.f;
+    FC_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    // aggregate by (kind, tag, n, k)
+    int j = 0;
+    for (; j < n; ++j)
+      if (out[j].kind == r.kind && out[j].tag == r.tag && out[j].n == r.n && out[j].k == r.k) break;
+    if (j == n) {
+      if (n >= cap) continue;
+      out[n] = fc_profile_record{r.kind, r.tag, r.n, r.k, 0, 0.0, 0.0, 0.0, 0.0};
+      ++n;
+    }
+    out[j].launches += 1;
+    out[j].ms += ms;
+    out[j].flops += r.flops;
+    out[j].bytes += r.bytes;
+    out[j].rows += static_cast<double>(r.m);
+  }
+  g_prof_used = 0;
+  return n;
+}
+
 int fc_model_create(const fc_config* cfg, fc_model** out) {
   FC_REQUIRE(cfg && out, "fc_model_create: null argument");
   int rc = check_arch();
@@ -351,7 +414,7 @@ int64_t fc_model_workspace_bytes(const fc_model* m) { return m ? m->workspace_by
 
 int fc_encode_video(fc_model* m, const void* frames, int dtype, int64_t videos, int32_t T, float* out_video,
                     float* out_frames, void* stream) {
-  FC_REQUIRE(m && out_video && (frames || videos == 0), "fc_encode_video: null argument");
+  FC_REQUIRE(m && ((out_video && frames) || videos == 0), "fc_encode_video: null argument");
   FC_REQUIRE(videos >= 0 && T >= 1, "fc_encode_video: bad shape videos=%lld frames_per_video=%d",
              static_cast<long long>(videos), T);
   FC_REQUIRE(T <= m->maxF, "fc_encode_video: frames_per_video=%d exceeds max_frames_per_pass=%d", T, m->maxF);
@@ -376,7 +439,7 @@ int fc_encode_video(fc_model* m, const void* frames, int dtype, int64_t videos, 
 }
 
 int fc_encode_text(fc_model* m, const int32_t* ids, int64_t texts, float* out_text, void* stream) {
-  FC_REQUIRE(m && out_text && (ids || texts == 0), "fc_encode_text: null argument");
+  FC_REQUIRE(m && ((out_text && ids) || texts == 0), "fc_encode_text: null argument");
   FC_REQUIRE(texts >= 0, "fc_encode_text: negative count");
   if (!fc_model_ready(m)) return FC_ERR_STATE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -45,6 +45,15 @@ void note_launch();
 
 int num_sms();
 
+// ---- optional per-launch CUDA-event profiler (fc_profile_start / fc_profile_stop); off by default ----
+enum ProfKind : int { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_OTHER = 3 };
+struct ProfScope {
+  int slot;
+  cudaStream_t stream;
+  ProfScope(cudaStream_t s, int kind, int tag, int64_t m, int64_t n, int64_t k, double flops, double bytes);
+  ~ProfScope();
+};
+
 // ---- device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

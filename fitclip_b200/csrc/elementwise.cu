@@ -350,6 +350,7 @@ int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float
   FC_REQUIRE(D % 8 == 0 && D <= 8 * 32 * LN_MAX_CHUNKS && ldx % 8 == 0 && ldy % 8 == 0,
              "layernorm: D=%d must be a multiple of 8 and <= 1024", D);
   if (rows == 0) return FC_OK;
+  ProfScope prof(s, PROF_LAYERNORM, 0, rows, D, 0, 0.0, 4.0 * rows * D);
   const int wpb = 8;
   layernorm_bf16_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(x, y, gamma, beta, rows, D,
                                                                                           ldx, ldy, eps);
@@ -362,6 +363,7 @@ int im2col_patches(const void* frames, int dtype, bf16* patches, int64_t F, int 
   FC_REQUIRE(R % P == 0 && P % 8 == 0, "im2col: resolution %d / patch %d unsupported (patch must be a multiple of 8)",
              R, P);
   if (F == 0) return FC_OK;
+  ProfScope prof(s, PROF_OTHER, 0, F, R, P, 0.0, static_cast<double>(F) * 3 * R * R * ((dtype == FC_DTYPE_F32 ? 4 : 2) + 2));
   const int64_t total = F * 3 * R * (R / 8);
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (dtype == FC_DTYPE_F32)
@@ -387,6 +389,7 @@ int text_embed(const int32_t* ids, const float* tok, const float* pos, bf16* x, 
                int* err_flag, cudaStream_t s) {
   FC_REQUIRE(D % 8 == 0, "text_embed: width must be a multiple of 8");
   if (C == 0) return FC_OK;
+  ProfScope prof(s, PROF_OTHER, 2, C, L, D, 0.0, static_cast<double>(C) * L * D * (4 + 2));
   const int64_t total = C * L * (D / 8);
   text_embed_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(ids, tok, pos, x, C * L, L, D, vocab,
                                                                               err_flag);
@@ -397,6 +400,7 @@ int text_embed(const int32_t* ids, const float* tok, const float* pos, bf16* x, 
 int head_project(const bf16* x, const int32_t* ids, const float* gamma, const float* beta, const float* proj,
                  float* out, int64_t seqs, int L, int W, int E, float eps, cudaStream_t s) {
   if (seqs == 0) return FC_OK;
+  ProfScope prof(s, PROF_OTHER, 3, seqs, W, E, 2.0 * seqs * W * E, 4.0 * seqs * W * E);
   const size_t smem = (W + 32) * sizeof(float);
   head_kernel<<<static_cast<unsigned>(seqs), 256, smem, s>>>(x, ids, gamma, beta, proj, out, L, W, E, eps);
   FC_CHECK_LAUNCH();
@@ -407,6 +411,7 @@ int pool_normalize(const float* x, float* out, bf16* out_bf16, int64_t B, int T,
   FC_REQUIRE(x && out, "pool_normalize: null pointer");
   FC_REQUIRE(T >= 1 && T <= 4096 && D >= 1, "pool_normalize: bad T=%d D=%d", T, D);
   if (B == 0) return FC_OK;
+  ProfScope prof(s, PROF_OTHER, 4, B, T, D, 0.0, 4.0 * B * D * (2.0 * T + 1));
   pool_normalize_kernel<<<static_cast<unsigned>(B), 256, T * sizeof(float), s>>>(x, out, out_bf16, T, D, scale);
   FC_CHECK_LAUNCH();
   return FC_OK;
@@ -420,6 +425,7 @@ int wise_lerp(const float* p1, const float* p2, float* out, bf16* out_bf16, int6
   if (n == 0) return FC_OK;
   // python evaluates (1 - w) in double; torch then multiplies the fp32 tensor by the scalar cast to fp32
   const float c1 = static_cast<float>(1.0 - w), c2 = static_cast<float>(w);
+  ProfScope prof(s, PROF_OTHER, 5, n, 0, 0, 3.0 * n, 12.0 * n + (out_bf16 ? 2.0 * n : 0.0));
   wise_lerp_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, s>>>(p1, p2, out, out_bf16, n, c1, c2);
   FC_CHECK_LAUNCH();
   return FC_OK;

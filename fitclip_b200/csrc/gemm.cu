@@ -342,6 +342,11 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   } else {
     FC_REQUIRE(false, "gemm: unknown epilogue %d", epilogue);
   }
+  const double mn = static_cast<double>(p.M) * p.N;
+  ProfScope prof(stream, PROF_GEMM, epilogue, p.M, p.N, p.K, 2.0 * mn * p.K,
+                 2.0 * (static_cast<double>(p.M) + p.N) * p.K +
+                     (epilogue <= EPI_PATCH ? 2.0 * mn : 0.0) * (epilogue == EPI_BIAS_RESID ? 2.0 : 1.0) +
+                     (epilogue == EPI_F32 ? 4.0 * mn : 0.0));
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
   if (rc) return rc;

@@ -69,6 +69,21 @@ FC_API size_t fc_last_error(char* buf, size_t cap);
 /* Number of kernel launches issued by this library in this process so far (bench.py's gpu_launches). */
 FC_API int64_t fc_launch_count(void);
 
+/* Optional per-launch timing with CUDA events on the launching stream (bench.py's roofline numbers). Records are
+ * aggregated by (kind, tag, n, k): kind 0 = tcgen05 GEMM (tag = epilogue), 1 = attention (tag = causal),
+ * 2 = LayerNorm, 3 = other memory-bound kernels.  fc_profile_stop synchronises the device and returns the record count. */
+typedef struct fc_profile_record {
+  int32_t kind, tag;
+  int64_t n, k;
+  int64_t launches;
+  double ms;    /* summed launch durations */
+  double flops; /* summed algorithmic FLOPs */
+  double bytes; /* summed algorithmic HBM bytes */
+  double rows;  /* summed M */
+} fc_profile_record;
+FC_API int fc_profile_start(int32_t max_records);
+FC_API int fc_profile_stop(fc_profile_record* out, int32_t cap);
+
 /* ---- model lifetime and weights --------------------------------------------------------------------------------
  * Replaces clip.load / build_model as used by load_clip_model (aligner/encoder/clip_video_text_encoder.py:22-61):
  * the Python side owns the fp32 nn.Parameters (OpenAI state-dict names); the library keeps its own bf16 copies of
