@@ -1,14 +1,23 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * B[N,K]^T), bf16 in, fp32 acc.
 //
-//   warp 0   TMA producer   : cp.async.bulk.tensor (128B-swizzled 128x64 A tile + 256x64 B tile per stage)
-//   warp 1   MMA issuer     : one elected thread issues tcgen05.mma 128x256x16, accumulators in TMEM
-//   warp 2   TMEM allocator : 512 columns = 2 accumulator stages of 256 fp32 columns
-//   warp 3   idle
-//   warps 4-7 epilogue      : tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
+//   warp 0    TMA producer   : cp.async.bulk.tensor (128B-swizzled 128x64 A tile + 256x64 B tile per stage)
+//   warp 1    MMA issuer     : one elected thread issues tcgen05.mma 128x256x16, accumulators in TMEM
+//   warp 2    TMEM allocator : 512 columns = 2 accumulator stages of 256 fp32 columns
+//   warp 3    idle
+//   warps 4-11 epilogue      : two groups of 4 warps (one warp per TMEM lane quarter)
 //
 // Three pipelines: smem full/empty (TMA<->MMA, 4 stages of 48 KiB), TMEM full/empty (MMA<->epilogue, 2 stages), and a
 // static persistent tile scheduler (tile = blockIdx.x + i*gridDim.x, N fastest so the CTAs of one wave share A
 // tiles in L2 while the weight matrix B stays L2-resident).
+//
+// Epilogues
+//   staged (bias / bias+QuickGELU / bias+residual, bf16 out): each warp group owns the 64-column sub-tiles
+//     {g, g+2} of the 128x256 tile.  tcgen05.ld -> registers -> bias (smem) / activation / residual -> bf16 ->
+//     128B-swizzled 128x64 staging tile in smem -> ONE TMA store per sub-tile (full 128-byte lines, rows beyond M
+//     clipped by the hardware).  The residual sub-tile is TMA-LOADED into the same staging tile first and updated in
+//     place, so the epilogue issues no per-thread global loads or stores at all.
+//   direct (patch-embed scatter, fp32 scores, target-score extraction, rank counting): registers -> global, with the
+//     TMEM load of the next 32-column chunk in flight while the current one is consumed.
 //
 // This one kernel serves every dense contraction of the hot path (reference call sites in SURVEY.md 2.2):
 //   K1 patch-embed, K3 QKV, K5 out-proj(+residual), K6 MLP fc1(+QuickGELU)/fc2(+residual), K11/K12 similarity,
@@ -24,26 +33,38 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 256;               // 8 epilogue warps = 2 groups of 128
+constexpr int SUB_N = 64;                      // staged sub-tile width (64 bf16 = one 128-byte swizzle row)
+constexpr int STAGING_BYTES = BM * SUB_N * 2;  // 16 KiB per warp group
+constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
+constexpr int OFF_BIAS = OFF_STAGING + 2 * STAGING_BYTES;
+constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4;
+constexpr int SMEM_BYTES = OFF_BARS + 128;
+constexpr int NUM_THREADS = 128 + EPI_THREADS;
 constexpr uint32_t TMEM_COLS = 512;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
 __device__ __forceinline__ float quick_gelu(float v) {
-  // x * sigmoid(1.702 x)  (reference twin: aligner/encoder/slip.py:359-361)
-  return __fdividef(v, 1.f + __expf(-1.702f * v));
+  // x * sigmoid(1.702 x)  (reference twin: aligner/encoder/slip.py:359-361), written with one MUFU op:
+  // sigmoid(y) = 0.5 + 0.5 tanh(y/2); tanh.approx is ~2^-11 accurate, far inside the bf16 output rounding (2^-9).
+  const float h = 0.5f * v;
+  return fmaf(h, tanh_approx(0.851f * v), h);
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  constexpr bool kStaged = (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || EPI == EPI_BIAS_RESID);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* resid_bar = tmem_empty + 2;  // [2], one per epilogue warp group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 2);
+  float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -52,9 +73,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_k = (p.K + BK - 1) / BK;
 
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (kStaged) tma_prefetch_desc(&tmC);
+    if (EPI == EPI_BIAS_RESID) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -63,7 +87,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], EPI_THREADS);
+      mbar_init(&resid_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -129,127 +154,206 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps) =====================
+    // Warp w may only read TMEM lanes [32*(w%4), +32); thread -> one output row of the tile.
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;  // warp group 0 / 1
     const int row_in_tile = q * 32 + lane;
+    const int etid = threadIdx.x - 128;  // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t resid_phase = 0;
+    const bool issuer = (etid & 127) == 0;  // one thread per warp group drives its TMA traffic
+    uint8_t* stg_ptr = smem + OFF_STAGING + grp * STAGING_BYTES;
+    const uint32_t stg_row = smem_u32(stg_ptr) + row_in_tile * 128;
+    const int sw = row_in_tile & 7;
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
       const int row = m_blk * BM + row_in_tile;
       const int n0 = n_blk * BN;
       const bool row_ok = row < p.M;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-      // per-row constants of the fused epilogues
-      int64_t out_row = row;
-      const float* pos_row = nullptr;
-      int tgt = 0;
-      float tsc = 0.f;
-      int cnt = 0;
-      if (EPI == EPI_PATCH && row_ok) {
-        const int f = row / p.patches_per_frame, pp = row - f * p.patches_per_frame;
-        out_row = static_cast<int64_t>(row) + f + 1;  // skip one class-token row per frame
-        pos_row = p.pos + static_cast<int64_t>(pp + 1) * p.N;
-      }
-      if ((EPI == EPI_TARGET || EPI == EPI_COUNT) && row_ok) {
-        tgt = p.target[row];
-        if (EPI == EPI_COUNT) tsc = p.target_score[row];
-      }
-
+      if (kStaged) {
+        // stage this tile's 256 bias values once (double-buffered by accumulator stage)
+        const int n = n0 + etid;
+        sbias[acc * BN + etid] = n < p.N ? __ldg(p.bias + n) : 0.f;
+        named_bar_sync(1, EPI_THREADS);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        bool released = false;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (n0 + c >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_addr + c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (!row_ok) continue;
-
-        if (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || EPI == EPI_BIAS_RESID || EPI == EPI_PATCH) {
-          // N is a multiple of 32 on these paths (checked on the host): full, 16-byte aligned chunks.
-          float v[32];
-          const float4* add4 = reinterpret_cast<const float4*>((EPI == EPI_PATCH ? pos_row : p.bias) + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(add4 + j);
-            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+        for (int si = 0; si < 2; ++si) {
+          const int sub = grp + 2 * si;  // 64-column sub-tile of this warp group
+          const int col0 = n0 + sub * SUB_N;
+          if (col0 >= p.N) break;  // uniform across the group
+          // (a) the staging tile is free once the group's previous TMA store has finished reading it
+          if (issuer) {
+            bulk_wait_group_read<0>();
+            if (EPI == EPI_BIAS_RESID) {
+              mbar_expect_tx(&resid_bar[grp], STAGING_BYTES);
+              tma_load_2d(stg_ptr, &tmR, &resid_bar[grp], col0, m_blk * BM);
+            }
           }
-          if (EPI == EPI_BIAS_QGELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+          named_bar_sync(2 + grp, 128);
+          // (b) accumulators: 64 fp32 columns of this thread's row
+          uint32_t r0[32], r1[32];
+          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + sub * SUB_N;
+          tmem_ld_32x32b_x32(t_addr, r0);
+          tmem_ld_32x32b_x32(t_addr + 32, r1);
+          tmem_ld_wait_fence(r0);
+          tmem_ld_wait_fence(r1);
+          if (si == 1 || col0 + 2 * SUB_N >= p.N) {  // last TMEM read of this tile by this thread
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            released = true;
           }
           if (EPI == EPI_BIAS_RESID) {
-            const uint4* res4 = reinterpret_cast<const uint4*>(p.resid + static_cast<int64_t>(row) * p.ldr + col0);
+            mbar_wait(&resid_bar[grp], resid_phase);
+            resid_phase ^= 1;
+          }
+          const float* bias_s = sbias + acc * BN + sub * SUB_N;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = res4[j];
+          for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 columns = 16 bytes of bf16 each
+            const uint32_t(&rr)[32] = c < 4 ? r0 : r1;
+            const int o = (c & 3) * 8;
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c * 8 + 4);
+            float v[8] = {__uint_as_float(rr[o + 0]) + b0.x, __uint_as_float(rr[o + 1]) + b0.y,
+                          __uint_as_float(rr[o + 2]) + b0.z, __uint_as_float(rr[o + 3]) + b0.w,
+                          __uint_as_float(rr[o + 4]) + b1.x, __uint_as_float(rr[o + 5]) + b1.y,
+                          __uint_as_float(rr[o + 6]) + b1.z, __uint_as_float(rr[o + 7]) + b1.w};
+            if (EPI == EPI_BIAS_QGELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = quick_gelu(v[j]);
+            }
+            const uint32_t addr = stg_row + ((c ^ sw) << 4);
+            if (EPI == EPI_BIAS_RESID) {
+              const uint4 u = ld_shared_v4(addr);
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float2 f = unpack_bf16x2(w[t]);
-                v[8 * j + 2 * t] += f.x;
-                v[8 * j + 2 * t + 1] += f.y;
+                v[2 * t] += f.x;
+                v[2 * t + 1] += f.y;
               }
             }
-          }
-          uint4* out4 = reinterpret_cast<uint4*>(static_cast<bf16*>(p.C) + out_row * p.ldc + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
             uint4 u;
-            u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            out4[j] = u;
+            u.x = pack_bf16x2(v[0], v[1]);
+            u.y = pack_bf16x2(v[2], v[3]);
+            u.z = pack_bf16x2(v[4], v[5]);
+            u.w = pack_bf16x2(v[6], v[7]);
+            st_shared_v4(addr, u);
           }
-        } else if (EPI == EPI_F32) {
-          float* out = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
-          if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o;
-              o.x = p.alpha * __uint_as_float(r[4 * j + 0]);
-              o.y = p.alpha * __uint_as_float(r[4 * j + 1]);
-              o.z = p.alpha * __uint_as_float(r[4 * j + 2]);
-              o.w = p.alpha * __uint_as_float(r[4 * j + 3]);
-              reinterpret_cast<float4*>(out)[j] = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) out[j] = p.alpha * __uint_as_float(r[j]);
-          }
-        } else if (EPI == EPI_TARGET) {
-          const int local = tgt - p.col_offset - col0;
-          if (local >= 0 && local < 32 && col0 + local < p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j == local) p.tscore_out[row] = __uint_as_float(r[j]);
-          }
-        } else if (EPI == EPI_COUNT) {
-          const int gcol0 = p.col_offset + col0;
-          const int nvalid = min(32, p.N - col0);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(r[j]);
-            const bool hit = (s > tsc) || (s == tsc && (gcol0 + j) < tgt);
-            cnt += (j < nvalid && hit) ? 1 : 0;
+          // (c) hand the finished sub-tile to the TMA engine
+          fence_proxy_async_smem();
+          named_bar_sync(2 + grp, 128);
+          if (issuer) {
+            tma_store_2d(&tmC, stg_ptr, col0, m_blk * BM);
+            bulk_commit_group();
           }
         }
-      }
-      if (EPI == EPI_COUNT && row_ok && cnt) atomicAdd(p.counts + row, cnt);
+        if (!released) {  // group had no sub-tile inside N (ragged N): it still owes the accumulator release
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+      } else {
+        // ---------------- direct epilogues ----------------
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const int half = grp;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * (BN / 2);
+        int64_t out_row = row;
+        const float* pos_row = nullptr;
+        int tgt = 0;
+        float tsc = 0.f;
+        int cnt = 0;
+        if (EPI == EPI_PATCH && row_ok) {
+          const int f = row / p.patches_per_frame, pp = row - f * p.patches_per_frame;
+          out_row = static_cast<int64_t>(row) + f + 1;  // skip one class-token row per frame
+          pos_row = p.pos + static_cast<int64_t>(pp + 1) * p.N;
+        }
+        if ((EPI == EPI_TARGET || EPI == EPI_COUNT) && row_ok) {
+          tgt = p.target[row];
+          if (EPI == EPI_COUNT) tsc = p.target_score[row];
+        }
+        const int cbase = n0 + half * (BN / 2);
+        constexpr int NCH = BN / 2 / 32;  // 4 chunks of 32 columns per thread
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(t_addr, r[0]);
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          uint32_t(&rc)[32] = r[i & 1];
+          tmem_ld_wait_fence(rc);
+          if (i + 1 < NCH) tmem_ld_32x32b_x32(t_addr + (i + 1) * 32, r[(i + 1) & 1]);
+          const int col0 = cbase + i * 32;
+          if (!row_ok || col0 >= p.N) continue;
 
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+          if (EPI == EPI_PATCH) {
+            // N is a multiple of 32 on this path (checked on the host): full, 16-byte aligned chunks.
+            float v[32];
+            const float4* add4 = reinterpret_cast<const float4*>(pos_row + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(add4 + j);
+              v[4 * j + 0] = __uint_as_float(rc[4 * j + 0]) + b.x;
+              v[4 * j + 1] = __uint_as_float(rc[4 * j + 1]) + b.y;
+              v[4 * j + 2] = __uint_as_float(rc[4 * j + 2]) + b.z;
+              v[4 * j + 3] = __uint_as_float(rc[4 * j + 3]) + b.w;
+            }
+            uint4* out4 = reinterpret_cast<uint4*>(static_cast<bf16*>(p.C) + out_row * p.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              out4[j] = u;
+            }
+          } else if (EPI == EPI_F32) {
+            float* out = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
+            if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o;
+                o.x = p.alpha * __uint_as_float(rc[4 * j + 0]);
+                o.y = p.alpha * __uint_as_float(rc[4 * j + 1]);
+                o.z = p.alpha * __uint_as_float(rc[4 * j + 2]);
+                o.w = p.alpha * __uint_as_float(rc[4 * j + 3]);
+                reinterpret_cast<float4*>(out)[j] = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) out[j] = p.alpha * __uint_as_float(rc[j]);
+            }
+          } else if (EPI == EPI_TARGET) {
+            const int local = tgt - p.col_offset - col0;
+            if (local >= 0 && local < 32 && col0 + local < p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j == local) p.tscore_out[row] = __uint_as_float(rc[j]);
+            }
+          } else if (EPI == EPI_COUNT) {
+            const int gcol0 = p.col_offset + col0;
+            const int nvalid = min(32, p.N - col0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(rc[j]);
+              const bool hit = (s > tsc) || (s == tsc && (gcol0 + j) < tgt);
+              cnt += (j < nvalid && hit) ? 1 : 0;
+            }
+          }
+        }
+        if (EPI == EPI_COUNT && row_ok && cnt) atomicAdd(p.counts + row, cnt);
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (kStaged && issuer) bulk_wait_group<0>();  // smem must outlive the last TMA store's reads
   }
 
   tc_fence_before();
@@ -278,14 +382,14 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// rows x K bf16 matrix, K contiguous, row stride ld elements; box = box_rows x 64 elements, 128B swizzle.
-int make_tmap(CUtensorMap* tm, const bf16* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+// rows x cols bf16 matrix, cols contiguous, row stride ld elements; box = box_rows x 64 elements, 128B swizzle.
+int make_tmap(CUtensorMap* tm, const bf16* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return FC_ERR_CUDA;
   }
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(bf16)};
   cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
@@ -293,15 +397,16 @@ int make_tmap(CUtensorMap* tm, const bf16* base, int64_t rows, int64_t K, int64_
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld K=%lld ld=%lld", static_cast<int>(r),
-              static_cast<long long>(rows), static_cast<long long>(K), static_cast<long long>(ld));
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld ld=%lld", static_cast<int>(r),
+              static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld));
     return FC_ERR_CUDA;
   }
   return FC_OK;
 }
 
 template <int EPI>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+           const GemmParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     FC_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -309,7 +414,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tn_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_bf16_tn_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, tr, p);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
@@ -323,6 +428,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   FC_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm: K/lda/ldb must be multiples of 8 (K=%d)", p.K);
   FC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
              "gemm: operands must be 16-byte aligned");
+  const bool staged = epilogue == EPI_BIAS || epilogue == EPI_BIAS_QGELU || epilogue == EPI_BIAS_RESID;
   if (epilogue <= EPI_PATCH) {
     FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0, "gemm: bf16 epilogues need N %% 32 == 0 and ldc %% 8 == 0");
     FC_REQUIRE((reinterpret_cast<uintptr_t>(p.C) & 15) == 0, "gemm: C must be 16-byte aligned");
@@ -347,19 +453,30 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
                  2.0 * (static_cast<double>(p.M) + p.N) * p.K +
                      (epilogue <= EPI_PATCH ? 2.0 * mn : 0.0) * (epilogue == EPI_BIAS_RESID ? 2.0 : 1.0) +
                      (epilogue == EPI_F32 ? 4.0 * mn : 0.0));
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc, tr;
   int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
   if (rc) return rc;
   rc = make_tmap(&tb, B, p.N, p.K, ldb, BN);
   if (rc) return rc;
+  tc = ta;
+  tr = ta;
+  if (staged) {
+    rc = make_tmap(&tc, static_cast<const bf16*>(p.C), p.M, p.N, p.ldc, BM);
+    if (rc) return rc;
+    tr = tc;
+    if (epilogue == EPI_BIAS_RESID) {
+      rc = make_tmap(&tr, p.resid, p.M, p.N, p.ldr, BM);
+      if (rc) return rc;
+    }
+  }
   switch (epilogue) {
-    case EPI_BIAS: return launch<EPI_BIAS>(ta, tb, p, stream);
-    case EPI_BIAS_QGELU: return launch<EPI_BIAS_QGELU>(ta, tb, p, stream);
-    case EPI_BIAS_RESID: return launch<EPI_BIAS_RESID>(ta, tb, p, stream);
-    case EPI_PATCH: return launch<EPI_PATCH>(ta, tb, p, stream);
-    case EPI_F32: return launch<EPI_F32>(ta, tb, p, stream);
-    case EPI_TARGET: return launch<EPI_TARGET>(ta, tb, p, stream);
-    default: return launch<EPI_COUNT>(ta, tb, p, stream);
+    case EPI_BIAS: return launch<EPI_BIAS>(ta, tb, tc, tr, p, stream);
+    case EPI_BIAS_QGELU: return launch<EPI_BIAS_QGELU>(ta, tb, tc, tr, p, stream);
+    case EPI_BIAS_RESID: return launch<EPI_BIAS_RESID>(ta, tb, tc, tr, p, stream);
+    case EPI_PATCH: return launch<EPI_PATCH>(ta, tb, tc, tr, p, stream);
+    case EPI_F32: return launch<EPI_F32>(ta, tb, tc, tr, p, stream);
+    case EPI_TARGET: return launch<EPI_TARGET>(ta, tb, tc, tr, p, stream);
+    default: return launch<EPI_COUNT>(ta, tb, tc, tr, p, stream);
   }
 }
 
