@@ -1,0 +1,78 @@
+"""world_size-2 (and 3) gloo runs of the N>1 host logic on CPU: contiguous uneven shards, all-gather of text
+embeddings, all-reduce of target scores and rank counts.  The similarity kernel itself needs a GPU, so the sharding
+code is driven with a CPU stand-in that implements the same (target_scores, counts) contract with the oracle's tie
+rule -- this file tests the protocol, tests/test_gpu_rank.py tests the kernel."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from fitclip_b200 import shard_bounds
+from fitclip_b200.retrieval import all_gather_rows, retrieval_ranks
+
+
+class CpuSimilarity:
+    """Test double for fitclip_b200.ops.Similarity (same contract, plain torch fp32)."""
+
+    def __init__(self, text_emb, video_emb, terms=3):
+        self.s = text_emb @ video_emb.T
+        self.nv = video_emb.shape[0]
+
+    def target_scores(self, target, col_offset=0):
+        local = target.long() - col_offset
+        ok = (local >= 0) & (local < self.nv)
+        out = torch.zeros(self.s.shape[0])
+        out[ok] = self.s[ok, local[ok]]
+        return out
+
+    def counts(self, target, tscore, col_offset=0):
+        gcol = torch.arange(self.nv).unsqueeze(0) + col_offset
+        hit = (self.s > tscore.unsqueeze(1)) | ((self.s == tscore.unsqueeze(1)) & (gcol < target.long().unsqueeze(1)))
+        return hit.sum(dim=1).to(torch.int32)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, ties, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        t = torch.nn.functional.normalize(torch.randn(n, 32, generator=g), dim=-1)
+        v = torch.nn.functional.normalize(torch.randn(n, 32, generator=g), dim=-1)
+        if ties:
+            v[1::3] = v[0::3][: len(v[1::3])]  # duplicated videos -> exact score ties across shards
+        lo, hi = shard_bounds(n, world, rank)
+        ranks = retrieval_ranks(t[lo:hi], v[lo:hi], similarity_factory=CpuSimilarity)
+        gathered, sizes = all_gather_rows(t[lo:hi])
+        assert torch.equal(gathered, t) and sum(sizes) == n
+        expect = oracle.ref_stable_rank(t @ v.T, torch.arange(n))
+        assert torch.equal(ranks, expect), (rank, ranks.tolist(), expect.tolist())
+        torch.save(ranks, os.path.join(out_dir, f"ranks_{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,ties", [(2, 101, False), (2, 64, True), (3, 7, False), (2, 1, False)])
+def test_sharded_ranks_equal_single_process(tmp_path, world, n, ties):
+    mp.spawn(_worker, args=(world, _free_port(), n, ties, str(tmp_path)), nprocs=world, join=True)
+    ranks = [torch.load(tmp_path / f"ranks_{r}.pt") for r in range(world)]
+    assert all(torch.equal(ranks[0], r) for r in ranks)  # identical on every rank
+
+
+def test_single_process_path_needs_no_process_group():
+    g = torch.Generator().manual_seed(1)
+    t, v = torch.randn(20, 16, generator=g), torch.randn(20, 16, generator=g)
+    ranks = retrieval_ranks(t, v, similarity_factory=CpuSimilarity)
+    assert torch.equal(ranks, oracle.ref_stable_rank(t @ v.T, torch.arange(20)))
+    target = torch.randint(0, 20, (20,))
+    ranks = retrieval_ranks(t, v, target_local=target, similarity_factory=CpuSimilarity)
+    assert torch.equal(ranks, oracle.ref_stable_rank(t @ v.T, target))
