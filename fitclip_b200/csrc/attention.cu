@@ -214,6 +214,11 @@ int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, i
   // dense count (QK^T + PV = 4 L^2 64 per head), the figure SURVEY.md 8d uses for both towers
   ProfScope prof(s, PROF_ATTENTION, causal, seqs, L, heads, 4.0 * L * L * HD * heads * static_cast<double>(seqs),
                  static_cast<double>(seqs) * L * heads * HD * 2.0 * 4.0);
+  {
+    int handled = 0;
+    const int rc = attention_bf16_tc(qkv, out, seqs, L, heads, causal, s, &handled);
+    if (rc || handled) return rc;
+  }
   if (L <= 16) return launch<16, 2, 0, 1>(qkv, out, seqs, L, heads, causal, s);
   if (L <= 32) return launch<32, 4, 0, 2>(qkv, out, seqs, L, heads, causal, s);
   if (L <= 48) return launch<48, 6, 0, 3>(qkv, out, seqs, L, heads, causal, s);

@@ -24,6 +24,9 @@ int split_bf16(const float* in, bf16* out, int64_t rows, int D, int mode, int te
 
 // attention.cu : out[s*L + l, h*64 + d] = softmax(q k^T / 8 [+ causal mask]) v, qkv rows are [q | k | v] of width 3*D
 int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s);
+// attention_tc.cu : tcgen05 path for the un-masked 193..208-token case; *handled = 1 when it took the call
+int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
+                      int* handled);
 
 // rank.cu
 int rank_from_scores(const float* S, int64_t ld, int64_t rows, int64_t cols, const int32_t* target, int64_t* ranks,
