@@ -80,7 +80,12 @@ static int check_arch() {
 // ---------------------------------------------------------------- model
 struct Block {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *qkv_b, *out_b, *fc_b, *proj_b;
-  bf16 *qkv_w, *out_w, *fc_w, *proj_w;
+  bf16 *out_w, *proj_w;
+  // ln_1 is folded into in_proj and ln_2 into c_fc (fold_ln_weights): fp32 masters as loaded, then the folded bf16
+  // weight, its per-output column sums and the folded bias, rebuilt by finalize() whenever a parameter changes.
+  float *qkv_w32, *fc_w32;
+  bf16 *qkv_w, *fc_w;
+  float *qkv_cs, *qkv_bf, *fc_cs, *fc_bf;
 };
 
 struct Slot {
@@ -111,9 +116,10 @@ struct fc_model {
   // text params
   float *tok = nullptr, *tpos = nullptr, *ln_final_g = nullptr, *ln_final_b = nullptr, *tproj = nullptr;
   std::vector<fc::Block> tblocks;
+  bool dirty = true;  // folded weights need (re)building
   // workspace
   fc::bf16 *x = nullptr, *y = nullptr, *big = nullptr;
-  float* feat = nullptr;
+  float *feat = nullptr, *stats_a = nullptr, *stats_b = nullptr;
   int* err_flag = nullptr;
   int64_t workspace_bytes = 0;
 };
@@ -143,7 +149,7 @@ static void plan_blocks(fc_model* m, ArenaPlan& plan, std::vector<Block>& blocks
       int64_t numel;
       bool bf;
     } items[] = {
-        {"attn.in_proj_weight", reinterpret_cast<void**>(&b.qkv_w), int64_t(3) * W * W, true},
+        {"attn.in_proj_weight", reinterpret_cast<void**>(&b.qkv_w32), int64_t(3) * W * W, false},
         {"attn.in_proj_bias", reinterpret_cast<void**>(&b.qkv_b), int64_t(3) * W, false},
         {"attn.out_proj.weight", reinterpret_cast<void**>(&b.out_w), int64_t(W) * W, true},
         {"attn.out_proj.bias", reinterpret_cast<void**>(&b.out_b), W, false},
@@ -151,7 +157,7 @@ static void plan_blocks(fc_model* m, ArenaPlan& plan, std::vector<Block>& blocks
         {"ln_1.bias", reinterpret_cast<void**>(&b.ln1_b), W, false},
         {"ln_2.weight", reinterpret_cast<void**>(&b.ln2_g), W, false},
         {"ln_2.bias", reinterpret_cast<void**>(&b.ln2_b), W, false},
-        {"mlp.c_fc.weight", reinterpret_cast<void**>(&b.fc_w), int64_t(4) * W * W, true},
+        {"mlp.c_fc.weight", reinterpret_cast<void**>(&b.fc_w32), int64_t(4) * W * W, false},
         {"mlp.c_fc.bias", reinterpret_cast<void**>(&b.fc_b), int64_t(4) * W, false},
         {"mlp.c_proj.weight", reinterpret_cast<void**>(&b.proj_w), int64_t(4) * W * W, true},
         {"mlp.c_proj.bias", reinterpret_cast<void**>(&b.proj_b), W, false},
@@ -163,7 +169,29 @@ static void plan_blocks(fc_model* m, ArenaPlan& plan, std::vector<Block>& blocks
         m->slots.push_back({p + it.name, *it.dst, it.numel, it.bf, false});
       }
     }
+    struct Derived {
+      void** dst;
+      int64_t bytes;
+    } derived[] = {
+        {reinterpret_cast<void**>(&b.qkv_w), int64_t(3) * W * W * 2}, {reinterpret_cast<void**>(&b.qkv_cs), int64_t(3) * W * 4},
+        {reinterpret_cast<void**>(&b.qkv_bf), int64_t(3) * W * 4},    {reinterpret_cast<void**>(&b.fc_w), int64_t(4) * W * W * 2},
+        {reinterpret_cast<void**>(&b.fc_cs), int64_t(4) * W * 4},     {reinterpret_cast<void**>(&b.fc_bf), int64_t(4) * W * 4},
+    };
+    for (auto& d : derived) {
+      const int64_t o = plan.take(d.bytes);
+      if (assign) *d.dst = m->arena + o;
+    }
   }
+}
+
+// (Re)build the LayerNorm-folded weights of every block; called lazily by the encoders after parameters changed.
+static int finalize_blocks(const std::vector<Block>& blocks, int W, cudaStream_t s) {
+  int rc;
+  for (const Block& b : blocks) {
+    if ((rc = fold_ln_weights(b.qkv_w32, b.ln1_g, b.ln1_b, b.qkv_b, b.qkv_w, b.qkv_cs, b.qkv_bf, 3 * W, W, s))) return rc;
+    if ((rc = fold_ln_weights(b.fc_w32, b.ln2_g, b.ln2_b, b.fc_b, b.fc_w, b.fc_cs, b.fc_bf, 4 * W, W, s))) return rc;
+  }
+  return FC_OK;
 }
 
 // Two passes over the same plan: first to size the arena, then (assign) to hand out pointers.
@@ -206,35 +234,49 @@ static void plan_model(fc_model* m, ArenaPlan& plan, bool assign) {
   ws(reinterpret_cast<void**>(&m->y), x_el * 2);
   ws(reinterpret_cast<void**>(&m->big), big_el * 2);
   ws(reinterpret_cast<void**>(&m->feat), int64_t(std::max(m->maxF, m->maxC)) * E * 4);
+  const int64_t stats_bytes = std::max(vtok * (W / 64), ttok * (Wt / 64)) * 2 * 4;
+  ws(reinterpret_cast<void**>(&m->stats_a), stats_bytes);
+  ws(reinterpret_cast<void**>(&m->stats_b), stats_bytes);
   ws(reinterpret_cast<void**>(&m->err_flag), 256);
   m->workspace_bytes = plan.off - ws0;
 }
 
-static int run_blocks(const std::vector<Block>& blocks, bf16* x, bf16* y, bf16* big, int64_t seqs, int L, int W,
-                      int heads, int causal, cudaStream_t s) {
+// The residual stream x arrives with its row statistics in `stats_a` ([rows, W/64, 2] partial sums / sums of squares).
+static int run_blocks(const std::vector<Block>& blocks, bf16* x, bf16* y, bf16* big, float* stats_a, float* stats_b,
+                      int64_t seqs, int L, int W, int heads, int causal, cudaStream_t s) {
   const int64_t rows64 = seqs * L;
   FC_REQUIRE(rows64 < (int64_t(1) << 31), "too many tokens in one pass");
   const int rows = static_cast<int>(rows64);
+  const int parts = W / 64;
   int rc;
   for (const Block& b : blocks) {
-    // x = x + out_proj(attention(ln_1(x)))                      (slip.py:383)
-    if ((rc = layernorm_bf16(x, W, y, W, b.ln1_g, b.ln1_b, rows, W, 1e-5f, s))) return rc;
+    // x = x + out_proj(attention(ln_1(x)))                      (slip.py:383); ln_1 folded into the QKV GEMM
     GemmParams p;
-    p.M = rows; p.N = 3 * W; p.K = W; p.C = big; p.ldc = 3 * W; p.bias = b.qkv_b;
-    if ((rc = gemm_bf16_tn(EPI_BIAS, y, W, b.qkv_w, W, p, s))) return rc;
+    p.M = rows; p.N = 3 * W; p.K = W; p.C = big; p.ldc = 3 * W; p.bias = b.qkv_bf;
+    p.ln_stats = stats_a; p.ln_parts = parts; p.colsum = b.qkv_cs;
+    if ((rc = gemm_bf16_tn(EPI_LN_BIAS, x, W, b.qkv_w, W, p, s))) return rc;
     if ((rc = attention_bf16(big, y, seqs, L, heads, causal, s))) return rc;
     p = GemmParams();
-    p.M = rows; p.N = W; p.K = W; p.C = x; p.ldc = W; p.bias = b.out_b; p.resid = x; p.ldr = W;
+    p.M = rows; p.N = W; p.K = W; p.C = x; p.ldc = W; p.bias = b.out_b; p.resid = x; p.ldr = W; p.stats_out = stats_b;
     if ((rc = gemm_bf16_tn(EPI_BIAS_RESID, y, W, b.out_w, W, p, s))) return rc;
-    // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                  (slip.py:384)
-    if ((rc = layernorm_bf16(x, W, y, W, b.ln2_g, b.ln2_b, rows, W, 1e-5f, s))) return rc;
+    // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                  (slip.py:384); ln_2 folded into the fc1 GEMM
     p = GemmParams();
-    p.M = rows; p.N = 4 * W; p.K = W; p.C = big; p.ldc = 4 * W; p.bias = b.fc_b;
-    if ((rc = gemm_bf16_tn(EPI_BIAS_QGELU, y, W, b.fc_w, W, p, s))) return rc;
+    p.M = rows; p.N = 4 * W; p.K = W; p.C = big; p.ldc = 4 * W; p.bias = b.fc_bf;
+    p.ln_stats = stats_b; p.ln_parts = parts; p.colsum = b.fc_cs;
+    if ((rc = gemm_bf16_tn(EPI_LN_BIAS_QGELU, x, W, b.fc_w, W, p, s))) return rc;
     p = GemmParams();
-    p.M = rows; p.N = W; p.K = 4 * W; p.C = x; p.ldc = W; p.bias = b.proj_b; p.resid = x; p.ldr = W;
+    p.M = rows; p.N = W; p.K = 4 * W; p.C = x; p.ldc = W; p.bias = b.proj_b; p.resid = x; p.ldr = W; p.stats_out = stats_a;
     if ((rc = gemm_bf16_tn(EPI_BIAS_RESID, big, 4 * W, b.proj_w, 4 * W, p, s))) return rc;
   }
+  return FC_OK;
+}
+
+static int finalize(fc_model* m, cudaStream_t s) {
+  if (!m->dirty) return FC_OK;
+  int rc;
+  if ((rc = finalize_blocks(m->vblocks, m->cfg.vision_width, s))) return rc;
+  if ((rc = finalize_blocks(m->tblocks, m->cfg.transformer_width, s))) return rc;
+  m->dirty = false;
   return FC_OK;
 }
 
@@ -249,8 +291,8 @@ static int vision_pass(fc_model* m, const void* frames, int dtype, int64_t F, fl
   p.pos = m->vpos; p.patches_per_frame = G * G;
   if ((rc = gemm_bf16_tn(EPI_PATCH, m->big, m->patch_dim, m->conv_w, m->patch_dim, p, s))) return rc;
   if ((rc = cls_rows(m->x, m->cls, m->vpos, F, L, W, s))) return rc;
-  if ((rc = layernorm_bf16(m->x, W, m->x, W, m->ln_pre_g, m->ln_pre_b, F * L, W, 1e-5f, s))) return rc;
-  if ((rc = run_blocks(m->vblocks, m->x, m->y, m->big, F, L, W, W / 64, 0, s))) return rc;
+  if ((rc = layernorm_bf16(m->x, W, m->x, W, m->ln_pre_g, m->ln_pre_b, F * L, W, 1e-5f, m->stats_a, s))) return rc;
+  if ((rc = run_blocks(m->vblocks, m->x, m->y, m->big, m->stats_a, m->stats_b, F, L, W, W / 64, 0, s))) return rc;
   return head_project(m->x, nullptr, m->ln_post_g, m->ln_post_b, m->vproj, feat, F, L, W, c.embed_dim, 1e-5f, s);
 }
 
@@ -259,8 +301,9 @@ static int text_pass(fc_model* m, const int32_t* ids, int64_t C, float* feat, cu
   const fc_config& c = m->cfg;
   const int W = c.transformer_width, L = c.context_length;
   int rc;
-  if ((rc = text_embed(ids, m->tok, m->tpos, m->x, C, L, W, c.vocab_size, m->err_flag, s))) return rc;
-  if ((rc = run_blocks(m->tblocks, m->x, m->y, m->big, C, L, W, c.transformer_heads, 1, s))) return rc;
+  if ((rc = text_embed(ids, m->tok, m->tpos, m->x, C, L, W, c.vocab_size, m->err_flag, m->stats_a, s))) return rc;
+  if ((rc = run_blocks(m->tblocks, m->x, m->y, m->big, m->stats_a, m->stats_b, C, L, W, c.transformer_heads, 1, s)))
+    return rc;
   return head_project(m->x, ids, m->ln_final_g, m->ln_final_b, m->tproj, feat, C, L, W, c.embed_dim, 1e-5f, s);
 }
 
@@ -393,6 +436,7 @@ int fc_model_set_param(fc_model* m, const char* name, const float* data, int64_t
         FC_CUDA(cudaMemcpyAsync(sl.dst, data, numel * 4, cudaMemcpyDeviceToDevice, s));
       }
       sl.loaded = true;
+      m->dirty = true;
       return FC_OK;
     }
   }
@@ -420,6 +464,7 @@ int fc_encode_video(fc_model* m, const void* frames, int dtype, int64_t videos, 
   FC_REQUIRE(T <= m->maxF, "fc_encode_video: frames_per_video=%d exceeds max_frames_per_pass=%d", T, m->maxF);
   if (!fc_model_ready(m)) return FC_ERR_STATE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int frc = finalize(m, s)) return frc;
   const fc_config& c = m->cfg;
   const int64_t frame_elems = int64_t(3) * c.image_resolution * c.image_resolution;
   const int64_t esz = dtype == FC_F32 ? 4 : 2;
@@ -443,6 +488,7 @@ int fc_encode_text(fc_model* m, const int32_t* ids, int64_t texts, float* out_te
   FC_REQUIRE(texts >= 0, "fc_encode_text: negative count");
   if (!fc_model_ready(m)) return FC_ERR_STATE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int frc = finalize(m, s)) return frc;
   const fc_config& c = m->cfg;
   for (int64_t c0 = 0; c0 < texts; c0 += m->maxC) {
     const int64_t n = std::min<int64_t>(m->maxC, texts - c0);
@@ -587,7 +633,7 @@ int fc_gemm_bf16(int epilogue, const void* A, int64_t lda, const void* B, int64_
 
 int fc_layernorm_bf16(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int32_t D,
                       float eps, void* stream) {
-  return layernorm_bf16(static_cast<const bf16*>(x), D, static_cast<bf16*>(y), D, gamma, beta, rows, D, eps,
+  return layernorm_bf16(static_cast<const bf16*>(x), D, static_cast<bf16*>(y), D, gamma, beta, rows, D, eps, nullptr,
                         static_cast<cudaStream_t>(stream));
 }
 

@@ -19,7 +19,8 @@ constexpr int LN_MAX_CHUNKS = 4;  // 4 x 32 lanes x 8 bf16 = 1024
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* x, bf16* y,  // may alias (ln_pre runs in place)
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, int64_t rows, int D,
-                                                             int64_t ldx, int64_t ldy, float eps) {
+                                                             int64_t ldx, int64_t ldy, float eps,
+                                                             float* __restrict__ stats_out) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* x, bf16
   }
   const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
   uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
+  float o1 = 0.f, o2 = 0.f;  // sum / sum of squares of the OUTPUT row (consumed by a folded-LayerNorm GEMM)
 #pragma unroll
   for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
     const int c = lane + 32 * i;
@@ -64,13 +66,29 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* x, bf16
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float r[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        r[t] = (v[i][t] - mean) * rstd * gg[t] + bb[t];
+        o1 += r[t];
+        o2 = fmaf(r[t], r[t], o2);
+      }
       uint4 o;
-      o.x = pack_bf16x2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
-      o.y = pack_bf16x2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
-      o.z = pack_bf16x2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
-      o.w = pack_bf16x2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+      o.x = pack_bf16x2(r[0], r[1]);
+      o.y = pack_bf16x2(r[2], r[3]);
+      o.z = pack_bf16x2(r[4], r[5]);
+      o.w = pack_bf16x2(r[6], r[7]);
       yr[c] = o;
     }
+  }
+  if (stats_out != nullptr) {  // layout [rows, D/64, 2]: everything in part 0, zeros elsewhere
+    o1 = warp_sum(o1);
+    o2 = warp_sum(o2);
+    const int parts = D >> 6;
+    float2* so = reinterpret_cast<float2*>(stats_out) + row * parts;
+    for (int pi = lane; pi < parts; pi += 32) so[pi] = pi == 0 ? make_float2(o1, o2) : make_float2(0.f, 0.f);
   }
 }
 
@@ -149,10 +167,11 @@ __global__ void cls_row_kernel(bf16* __restrict__ x, const float* __restrict__ c
 __global__ void __launch_bounds__(256) text_embed_kernel(const int32_t* __restrict__ ids,
                                                          const float* __restrict__ tok, const float* __restrict__ pos,
                                                          bf16* __restrict__ x, int64_t tokens, int L, int D,
-                                                         int vocab, int* __restrict__ err_flag) {
+                                                         int vocab, int* __restrict__ err_flag,
+                                                         float* __restrict__ stats_out) {
   const int vec_per_row = D >> 3;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= tokens * vec_per_row) return;
+  if (idx >= tokens * vec_per_row) return;  // whole 8-thread groups drop out together (vec_per_row % 8 == 0)
   const int64_t row = idx / vec_per_row;
   const int dv = static_cast<int>(idx - row * vec_per_row) * 8;
   int id = ids[row];
@@ -170,6 +189,49 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const int32_t* __restri
   o.z = pack_bf16x2(a[4] + b[4], a[5] + b[5]);
   o.w = pack_bf16x2(a[6] + b[6], a[7] + b[7]);
   *reinterpret_cast<uint4*>(x + row * D + dv) = o;
+  if (stats_out != nullptr) {
+    // 8 consecutive threads cover one 64-column part of a row (D % 64 == 0 keeps them in one warp and one row)
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float r = a[t] + b[t];
+      s1 += r;
+      s2 = fmaf(r, r, s2);
+    }
+#pragma unroll
+    for (int o2 = 4; o2 > 0; o2 >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o2);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
+    }
+    if ((threadIdx.x & 7) == 0)
+      reinterpret_cast<float2*>(stats_out)[row * (D >> 6) + (dv >> 6)] = make_float2(s1, s2);
+  }
+}
+
+// Fold a LayerNorm (gamma, beta) into the Linear that consumes it:  LN(x) W^T + b  =  rstd (x W'^T - mean colsum) + b'
+//   W'[n,k] = bf16(gamma[k] W[n,k]),  colsum[n] = sum_k float(W'[n,k]),  b'[n] = b[n] + sum_k beta[k] W[n,k].
+// One warp per output feature n.
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      bf16* __restrict__ Wf, float* __restrict__ colsum,
+                                                      float* __restrict__ bias_f, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[static_cast<int64_t>(n) * K + k];
+    const bf16 wf = __float2bfloat16(gamma[k] * w);
+    Wf[static_cast<int64_t>(n) * K + k] = wf;
+    cs += __bfloat162float(wf);
+    bs = fmaf(beta[k], w, bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_f[n] = bias[n] + bs;
+  }
 }
 
 // ------------------------------------------------------------------------------------------- heads (K7 / K10)
@@ -345,7 +407,8 @@ inline int grid_for(int64_t n, int block, int cap_mult = 32) {
 }  // namespace
 
 int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float* gamma, const float* beta,
-                   int64_t rows, int D, float eps, cudaStream_t s) {
+                   int64_t rows, int D, float eps, float* stats_out, cudaStream_t s) {
+  FC_REQUIRE(stats_out == nullptr || D % 64 == 0, "layernorm: stats_out needs D %% 64 == 0");
   FC_REQUIRE(x && y && gamma && beta, "layernorm: null pointer");
   FC_REQUIRE(D % 8 == 0 && D <= 8 * 32 * LN_MAX_CHUNKS && ldx % 8 == 0 && ldy % 8 == 0,
              "layernorm: D=%d must be a multiple of 8 and <= 1024", D);
@@ -353,7 +416,7 @@ int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float
   ProfScope prof(s, PROF_LAYERNORM, 0, rows, D, 0, 0.0, 4.0 * rows * D);
   const int wpb = 8;
   layernorm_bf16_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(x, y, gamma, beta, rows, D,
-                                                                                          ldx, ldy, eps);
+                                                                                          ldx, ldy, eps, stats_out);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
@@ -386,13 +449,13 @@ int cls_rows(bf16* x, const float* cls, const float* pos, int64_t F, int L, int 
 }
 
 int text_embed(const int32_t* ids, const float* tok, const float* pos, bf16* x, int64_t C, int L, int D, int vocab,
-               int* err_flag, cudaStream_t s) {
-  FC_REQUIRE(D % 8 == 0, "text_embed: width must be a multiple of 8");
+               int* err_flag, float* stats_out, cudaStream_t s) {
+  FC_REQUIRE(D % 64 == 0, "text_embed: width must be a multiple of 64");
   if (C == 0) return FC_OK;
   ProfScope prof(s, PROF_OTHER, 2, C, L, D, 0.0, static_cast<double>(C) * L * D * (4 + 2));
   const int64_t total = C * L * (D / 8);
   text_embed_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(ids, tok, pos, x, C * L, L, D, vocab,
-                                                                              err_flag);
+                                                                              err_flag, stats_out);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
@@ -427,6 +490,13 @@ int wise_lerp(const float* p1, const float* p2, float* out, bf16* out_bf16, int6
   const float c1 = static_cast<float>(1.0 - w), c2 = static_cast<float>(w);
   ProfScope prof(s, PROF_OTHER, 5, n, 0, 0, 3.0 * n, 12.0 * n + (out_bf16 ? 2.0 * n : 0.0));
   wise_lerp_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, s>>>(p1, p2, out, out_bf16, n, c1, c2);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int fold_ln_weights(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* colsum,
+                    float* bias_f, int N, int K, cudaStream_t s) {
+  fold_ln_kernel<<<(N + 7) / 8, 256, 0, s>>>(W, gamma, beta, bias, Wf, colsum, bias_f, N, K);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }

@@ -11,7 +11,8 @@
 // tiles in L2 while the weight matrix B stays L2-resident).
 //
 // Epilogues
-//   staged (bias / bias+QuickGELU / bias+residual, bf16 out): each warp group owns the 64-column sub-tiles
+//   staged (bias / bias+QuickGELU / bias+residual / folded-LayerNorm variants, bf16 out): each warp group owns the
+//     64-column sub-tiles
 //     {g, g+2} of the 128x256 tile.  tcgen05.ld -> registers -> bias (smem) / activation / residual -> bf16 ->
 //     128B-swizzled 128x64 staging tile in smem -> ONE TMA store per sub-tile (full 128-byte lines, rows beyond M
 //     clipped by the hardware).  The residual sub-tile is TMA-LOADED into the same staging tile first and updated in
@@ -38,7 +39,7 @@ constexpr int SUB_N = 64;                      // staged sub-tile width (64 bf16
 constexpr int STAGING_BYTES = BM * SUB_N * 2;  // 16 KiB per warp group
 constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
 constexpr int OFF_BIAS = OFF_STAGING + 2 * STAGING_BYTES;
-constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4;
+constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4;  // bias[256] + colsum[256]
 constexpr int SMEM_BYTES = OFF_BARS + 128;
 constexpr int NUM_THREADS = 128 + EPI_THREADS;
 constexpr uint32_t TMEM_COLS = 512;
@@ -56,7 +57,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmParams p) {
-  constexpr bool kStaged = (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || EPI == EPI_BIAS_RESID);
+  constexpr bool kLn = (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_QGELU);
+  constexpr bool kGelu = (EPI == EPI_BIAS_QGELU || EPI == EPI_LN_BIAS_QGELU);
+  constexpr bool kStaged = (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || EPI == EPI_BIAS_RESID || kLn);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -164,9 +167,35 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     uint32_t resid_phase = 0;
     const bool issuer = (etid & 127) == 0;  // one thread per warp group drives its TMA traffic
+    bool resid_prefetched = false;          // (issuer only) the residual of the coming sub-tile is already in flight
     uint8_t* stg_ptr = smem + OFF_STAGING + grp * STAGING_BYTES;
     const uint32_t stg_row = smem_u32(stg_ptr) + row_in_tile * 128;
     const int sw = row_in_tile & 7;
+
+    // Values the next tile's epilogue needs from global memory (bias / column sums of its 256 columns, the LayerNorm
+    // partial sums of this thread's row) are fetched one tile ahead, so their latency hides behind the current tile.
+    float nxt_bias = 0.f, nxt_cs = 0.f, nxt_s1 = 0.f, nxt_s2 = 0.f;
+    auto prefetch_tile = [&](int t) {
+      if (!kStaged || t >= num_tiles) return;
+      const int mb = t / num_n_tiles, nb = t % num_n_tiles;
+      const int n = nb * BN + etid;
+      nxt_bias = n < p.N ? __ldg(p.bias + n) : 0.f;
+      if (kLn) {
+        nxt_cs = n < p.N ? __ldg(p.colsum + n) : 0.f;
+        nxt_s1 = 0.f;
+        nxt_s2 = 0.f;
+        const int r = mb * BM + row_in_tile;
+        if (r < p.M) {
+          const float2* ps = reinterpret_cast<const float2*>(p.ln_stats) + static_cast<int64_t>(r) * p.ln_parts;
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 v = __ldg(ps + i);
+            nxt_s1 += v.x;
+            nxt_s2 += v.y;
+          }
+        }
+      }
+    };
+    prefetch_tile(blockIdx.x);
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
@@ -175,10 +204,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = row < p.M;
 
       if (kStaged) {
-        // stage this tile's 256 bias values once (double-buffered by accumulator stage)
-        const int n = n0 + etid;
-        sbias[acc * BN + etid] = n < p.N ? __ldg(p.bias + n) : 0.f;
+        // stage this tile's 256 bias (and folded-LayerNorm column-sum) values once
+        named_bar_sync(1, EPI_THREADS);  // everyone is done with the previous tile's values
+        sbias[etid] = nxt_bias;
+        if (kLn) sbias[BN + etid] = nxt_cs;
         named_bar_sync(1, EPI_THREADS);
+        // folded LayerNorm: this row's mean / rstd from the producer's partial sums
+        float ln_rstd = 1.f, ln_shift = 0.f;  // out = rstd * acc + shift * colsum + bias,  shift = -rstd * mean
+        if (kLn) {
+          const float inv_k = 1.f / static_cast<float>(p.K);
+          const float mean = nxt_s1 * inv_k;
+          const float var = fmaxf(nxt_s2 * inv_k - mean * mean, 0.f);
+          ln_rstd = rsqrtf(var + p.ln_eps);
+          ln_shift = -ln_rstd * mean;
+        }
+        prefetch_tile(tile + gridDim.x);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         bool released = false;
@@ -188,7 +228,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int col0 = n0 + sub * SUB_N;
           if (col0 >= p.N) break;  // uniform across the group
           // (a) the staging tile is free once the group's previous TMA store has finished reading it
-          if (issuer) {
+          if (issuer && !(si == 0 && resid_prefetched)) {
             bulk_wait_group_read<0>();
             if (EPI == EPI_BIAS_RESID) {
               mbar_expect_tx(&resid_bar[grp], STAGING_BYTES);
@@ -212,18 +252,37 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&resid_bar[grp], resid_phase);
             resid_phase ^= 1;
           }
-          const float* bias_s = sbias + acc * BN + sub * SUB_N;
+          const float* bias_s = sbias + sub * SUB_N;
+          float st1 = 0.f, st2 = 0.f;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 columns = 16 bytes of bf16 each
             const uint32_t(&rr)[32] = c < 4 ? r0 : r1;
             const int o = (c & 3) * 8;
             const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c * 8 + 4);
-            float v[8] = {__uint_as_float(rr[o + 0]) + b0.x, __uint_as_float(rr[o + 1]) + b0.y,
-                          __uint_as_float(rr[o + 2]) + b0.z, __uint_as_float(rr[o + 3]) + b0.w,
-                          __uint_as_float(rr[o + 4]) + b1.x, __uint_as_float(rr[o + 5]) + b1.y,
-                          __uint_as_float(rr[o + 6]) + b1.z, __uint_as_float(rr[o + 7]) + b1.w};
-            if (EPI == EPI_BIAS_QGELU) {
+            float v[8];
+            if (kLn) {
+              const float4 c0 = *reinterpret_cast<const float4*>(bias_s + BN + c * 8);
+              const float4 c1 = *reinterpret_cast<const float4*>(bias_s + BN + c * 8 + 4);
+              v[0] = fmaf(ln_rstd, __uint_as_float(rr[o + 0]), fmaf(ln_shift, c0.x, b0.x));
+              v[1] = fmaf(ln_rstd, __uint_as_float(rr[o + 1]), fmaf(ln_shift, c0.y, b0.y));
+              v[2] = fmaf(ln_rstd, __uint_as_float(rr[o + 2]), fmaf(ln_shift, c0.z, b0.z));
+              v[3] = fmaf(ln_rstd, __uint_as_float(rr[o + 3]), fmaf(ln_shift, c0.w, b0.w));
+              v[4] = fmaf(ln_rstd, __uint_as_float(rr[o + 4]), fmaf(ln_shift, c1.x, b1.x));
+              v[5] = fmaf(ln_rstd, __uint_as_float(rr[o + 5]), fmaf(ln_shift, c1.y, b1.y));
+              v[6] = fmaf(ln_rstd, __uint_as_float(rr[o + 6]), fmaf(ln_shift, c1.z, b1.z));
+              v[7] = fmaf(ln_rstd, __uint_as_float(rr[o + 7]), fmaf(ln_shift, c1.w, b1.w));
+            } else {
+              v[0] = __uint_as_float(rr[o + 0]) + b0.x;
+              v[1] = __uint_as_float(rr[o + 1]) + b0.y;
+              v[2] = __uint_as_float(rr[o + 2]) + b0.z;
+              v[3] = __uint_as_float(rr[o + 3]) + b0.w;
+              v[4] = __uint_as_float(rr[o + 4]) + b1.x;
+              v[5] = __uint_as_float(rr[o + 5]) + b1.y;
+              v[6] = __uint_as_float(rr[o + 6]) + b1.z;
+              v[7] = __uint_as_float(rr[o + 7]) + b1.w;
+            }
+            if (kGelu) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = quick_gelu(v[j]);
             }
@@ -244,7 +303,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             u.z = pack_bf16x2(v[4], v[5]);
             u.w = pack_bf16x2(v[6], v[7]);
             st_shared_v4(addr, u);
+            if (EPI == EPI_BIAS_RESID) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                st1 += v[j];
+                st2 = fmaf(v[j], v[j], st2);
+              }
+            }
           }
+          if (EPI == EPI_BIAS_RESID && p.stats_out != nullptr && row_ok)  // row statistics for the next folded LayerNorm
+            *reinterpret_cast<float2*>(p.stats_out + (static_cast<int64_t>(row) * (p.N / SUB_N) + (col0 / SUB_N)) * 2) =
+                make_float2(st1, st2);
           // (c) hand the finished sub-tile to the TMA engine
           fence_proxy_async_smem();
           named_bar_sync(2 + grp, 128);
@@ -256,6 +325,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (!released) {  // group had no sub-tile inside N (ragged N): it still owes the accumulator release
           tc_fence_before();
           mbar_arrive(&tmem_empty[acc]);
+        }
+        if (EPI == EPI_BIAS_RESID && issuer) {
+          // start fetching the residual of the next tile's first sub-tile now: its latency overlaps the tile hand-over
+          resid_prefetched = false;
+          const int nt = tile + gridDim.x;
+          if (nt < num_tiles) {
+            const int nm = nt / num_n_tiles, nn = nt % num_n_tiles;
+            const int ncol0 = nn * BN + grp * SUB_N;
+            if (ncol0 < p.N) {
+              bulk_wait_group_read<0>();
+              mbar_expect_tx(&resid_bar[grp], STAGING_BYTES);
+              tma_load_2d(stg_ptr, &tmR, &resid_bar[grp], ncol0, nm * BM);
+              resid_prefetched = true;
+            }
+          }
         }
       } else {
         // ---------------- direct epilogues ----------------
@@ -428,17 +512,25 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   FC_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm: K/lda/ldb must be multiples of 8 (K=%d)", p.K);
   FC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
              "gemm: operands must be 16-byte aligned");
-  const bool staged = epilogue == EPI_BIAS || epilogue == EPI_BIAS_QGELU || epilogue == EPI_BIAS_RESID;
-  if (epilogue <= EPI_PATCH) {
+  const bool ln = epilogue == EPI_LN_BIAS || epilogue == EPI_LN_BIAS_QGELU;
+  const bool staged = epilogue == EPI_BIAS || epilogue == EPI_BIAS_QGELU || epilogue == EPI_BIAS_RESID || ln;
+  if (ln) {
+    FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.bias,
+               "gemm: folded-LayerNorm epilogue needs bf16 C (N %% 32 == 0, ldc %% 8 == 0) and a bias");
+    FC_REQUIRE(p.ln_stats && p.colsum && p.ln_parts > 0 && (reinterpret_cast<uintptr_t>(p.ln_stats) & 7) == 0,
+               "gemm: folded-LayerNorm epilogue needs row statistics and column sums");
+  } else if (epilogue <= EPI_PATCH) {
     FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0, "gemm: bf16 epilogues need N %% 32 == 0 and ldc %% 8 == 0");
     FC_REQUIRE((reinterpret_cast<uintptr_t>(p.C) & 15) == 0, "gemm: C must be 16-byte aligned");
     if (epilogue == EPI_PATCH)
       FC_REQUIRE(p.pos && p.patches_per_frame > 0, "gemm: patch epilogue needs pos and patches_per_frame");
     else
       FC_REQUIRE(p.bias, "gemm: bias epilogue needs a bias vector");
-    if (epilogue == EPI_BIAS_RESID)
+    if (epilogue == EPI_BIAS_RESID) {
       FC_REQUIRE(p.resid && p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 15) == 0,
                  "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
+      FC_REQUIRE(p.stats_out == nullptr || p.N % SUB_N == 0, "gemm: stats_out needs N %% 64 == 0");
+    }
   } else if (epilogue == EPI_F32) {
     FC_REQUIRE(p.C, "gemm: null C");
   } else if (epilogue == EPI_TARGET) {
@@ -451,7 +543,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   const double mn = static_cast<double>(p.M) * p.N;
   ProfScope prof(stream, PROF_GEMM, epilogue, p.M, p.N, p.K, 2.0 * mn * p.K,
                  2.0 * (static_cast<double>(p.M) + p.N) * p.K +
-                     (epilogue <= EPI_PATCH ? 2.0 * mn : 0.0) * (epilogue == EPI_BIAS_RESID ? 2.0 : 1.0) +
+                     (epilogue <= EPI_PATCH || ln ? 2.0 * mn : 0.0) * (epilogue == EPI_BIAS_RESID ? 2.0 : 1.0) +
                      (epilogue == EPI_F32 ? 4.0 * mn : 0.0));
   CUtensorMap ta, tb, tc, tr;
   int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
@@ -476,6 +568,8 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
     case EPI_PATCH: return launch<EPI_PATCH>(ta, tb, tc, tr, p, stream);
     case EPI_F32: return launch<EPI_F32>(ta, tb, tc, tr, p, stream);
     case EPI_TARGET: return launch<EPI_TARGET>(ta, tb, tc, tr, p, stream);
+    case EPI_LN_BIAS: return launch<EPI_LN_BIAS>(ta, tb, tc, tr, p, stream);
+    case EPI_LN_BIAS_QGELU: return launch<EPI_LN_BIAS_QGELU>(ta, tb, tc, tr, p, stream);
     default: return launch<EPI_COUNT>(ta, tb, tc, tr, p, stream);
   }
 }

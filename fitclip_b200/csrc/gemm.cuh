@@ -12,7 +12,9 @@ enum Epilogue : int {
   EPI_F32 = 4,         // C(fp32) = alpha * acc                       (materialised similarity / scores)
   EPI_TARGET = 5,      // tscore_out[row] = acc[row, target[row] - col_offset]
   EPI_COUNT = 6,       // counts[row] += #{col: acc > ts[row]} + #{col: acc == ts[row] and gcol < target[row]}
-  EPI_NUM = 7,
+  EPI_LN_BIAS = 7,        // C(bf16) = rstd_m * (acc - mean_m * colsum_n) + bias_n   == LayerNorm(A) . W^T + b with the
+  EPI_LN_BIAS_QGELU = 8,  //   LayerNorm affine folded into B / colsum / bias (see fold_ln_weights); 8 adds QuickGELU
+  EPI_NUM = 9,
 };
 
 struct GemmParams {
@@ -23,6 +25,13 @@ struct GemmParams {
   const bf16* resid = nullptr;   // [M, ldr]
   int64_t ldr = 0;
   float alpha = 1.f;
+  // EPI_LN_*: per-row partial (sum, sumsq) of A's rows, [M, ln_parts, 2] fp32; colsum[n] = sum_k B[n,k]
+  const float* ln_stats = nullptr;
+  int ln_parts = 0;
+  const float* colsum = nullptr;
+  float ln_eps = 1e-5f;
+  // EPI_BIAS_RESID: optional per-row partial (sum, sumsq) of the OUTPUT rows, [M, N/64, 2] fp32 (feeds the next EPI_LN_*)
+  float* stats_out = nullptr;
   // EPI_PATCH
   const float* pos = nullptr;    // [patches_per_frame + 1, N]
   int patches_per_frame = 0;

@@ -9,12 +9,15 @@ namespace fc {
 enum DType : int { FC_DTYPE_F32 = 0, FC_DTYPE_BF16 = 1, FC_DTYPE_F16 = 2 };
 
 // elementwise.cu
+// stats_out (optional): per-row (sum, sumsq) of the OUTPUT, layout [rows, D/64, 2]
 int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float* gamma, const float* beta,
-                   int64_t rows, int D, float eps, cudaStream_t s);
+                   int64_t rows, int D, float eps, float* stats_out, cudaStream_t s);
+int fold_ln_weights(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* colsum,
+                    float* bias_f, int N, int K, cudaStream_t s);
 int im2col_patches(const void* frames, int dtype, bf16* patches, int64_t F, int R, int P, cudaStream_t s);
 int cls_rows(bf16* x, const float* cls, const float* pos, int64_t F, int L, int D, cudaStream_t s);
 int text_embed(const int32_t* ids, const float* tok, const float* pos, bf16* x, int64_t C, int L, int D, int vocab,
-               int* err_flag, cudaStream_t s);
+               int* err_flag, float* stats_out, cudaStream_t s);
 int head_project(const bf16* x, const int32_t* ids, const float* gamma, const float* beta, const float* proj,
                  float* out, int64_t seqs, int L, int W, int E, float eps, cudaStream_t s);
 int pool_normalize(const float* x, float* out, bf16* out_bf16, int64_t B, int T, int D, float scale, cudaStream_t s);
