@@ -7,8 +7,11 @@
 //   warps 4-11 epilogue      : two groups of 4 warps (one warp per TMEM lane quarter)
 //
 // Three pipelines: smem full/empty (TMA<->MMA, 4 stages of 48 KiB), TMEM full/empty (MMA<->epilogue, 2 stages), and a
-// static persistent tile scheduler (tile = blockIdx.x + i*gridDim.x, N fastest so the CTAs of one wave share A
-// tiles in L2 while the weight matrix B stays L2-resident).
+// static persistent tile scheduler over CTA PAIRS (thread-block cluster of 2): a pair owns two vertically adjacent
+// 128-row tiles of the same 256-column block, each CTA TMA-loads its own A tile plus HALF of the B tile and multicasts
+// that half into both CTAs' shared memory, so L2->SM traffic per CTA drops from 48 to 32 KiB per K block.  Stage
+// release is a multicast tcgen05.commit onto both CTAs' empty barriers.  N is the fastest tile index, so the pairs of
+// one wave share A tiles in L2 while the weight matrix B stays L2-resident.
 //
 // Epilogues
 //   staged (bias / bias+QuickGELU / bias+residual / folded-LayerNorm variants, bf16 out): each warp group owns the
@@ -73,8 +76,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_m_tiles = (p.M + BM - 1) / BM;
   const int num_n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_k = (p.K + BK - 1) / BK;
+  // CTA pairs (cluster of 2): the pair works on two vertically adjacent 128-row tiles of the SAME 256-column block, so
+  // each CTA fetches only half of the B tile and multicasts it into both CTAs' shared memory.
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_tiles = ((num_m_tiles + 1) / 2) * num_n_tiles;  // pair-tiles; tile -> (m pair, n block), N fastest
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
   if (warp == 0 && lane == 0) {
@@ -86,7 +93,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], 2);  // released by the MMA commits of BOTH CTAs (each reads multicast data)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -97,7 +104,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // the peer's barriers must exist before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -106,15 +113,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = 2 * (tile / num_n_tiles) + cta_rank, n_blk = tile % num_n_tiles;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * STAGE_BYTES;
-          uint8_t* sB = sA + A_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sB = sA + A_BYTES + cta_rank * (B_BYTES / 2);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);  // own A + both halves of B
           tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          tma_load_2d_multicast(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN + cta_rank * (BN / 2), 0x3);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -130,7 +137,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -145,7 +152,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2), umma_desc_k_sw128(b_addr + k * UMMA_K * 2),
                          idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          umma_commit_multicast(&empty_bar[stage], 0x3);  // frees the slot in BOTH CTAs when these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -177,7 +184,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float nxt_bias = 0.f, nxt_cs = 0.f, nxt_s1 = 0.f, nxt_s2 = 0.f;
     auto prefetch_tile = [&](int t) {
       if (!kStaged || t >= num_tiles) return;
-      const int mb = t / num_n_tiles, nb = t % num_n_tiles;
+      const int mb = 2 * (t / num_n_tiles) + cta_rank, nb = t % num_n_tiles;
       const int n = nb * BN + etid;
       nxt_bias = n < p.N ? __ldg(p.bias + n) : 0.f;
       if (kLn) {
@@ -195,10 +202,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     };
-    prefetch_tile(blockIdx.x);
+    prefetch_tile(cluster_id);
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = 2 * (tile / num_n_tiles) + cta_rank, n_blk = tile % num_n_tiles;
       const int row = m_blk * BM + row_in_tile;
       const int n0 = n_blk * BN;
       const bool row_ok = row < p.M;
@@ -218,7 +225,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ln_rstd = rsqrtf(var + p.ln_eps);
           ln_shift = -ln_rstd * mean;
         }
-        prefetch_tile(tile + gridDim.x);
+        prefetch_tile(tile + num_clusters);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         bool released = false;
@@ -329,9 +336,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (EPI == EPI_BIAS_RESID && issuer) {
           // start fetching the residual of the next tile's first sub-tile now: its latency overlaps the tile hand-over
           resid_prefetched = false;
-          const int nt = tile + gridDim.x;
+          const int nt = tile + num_clusters;
           if (nt < num_tiles) {
-            const int nm = nt / num_n_tiles, nn = nt % num_n_tiles;
+            const int nm = 2 * (nt / num_n_tiles) + cta_rank, nn = nt % num_n_tiles;
             const int ncol0 = nn * BN + grp * SUB_N;
             if (ncol0 < p.N) {
               bulk_wait_group_read<0>();
@@ -440,8 +447,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (kStaged && issuer) bulk_wait_group<0>();  // smem must outlive the last TMA store's reads
   }
 
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // neither CTA may exit while its peer can still multicast into it or signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -496,10 +504,23 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     FC_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tn_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, tr, p);
-  FC_CHECK_LAUNCH();
+  const int pair_tiles = (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN);
+  const int max_clusters = num_sms() / 2;
+  const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  note_launch();
+  FC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI>, ta, tb, tc, tr, p));
   return FC_OK;
 }
 
@@ -548,7 +569,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   CUtensorMap ta, tb, tc, tr;
   int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap(&tb, B, p.N, p.K, ldb, BN);
+  rc = make_tmap(&tb, B, p.N, p.K, ldb, BN / 2);  // each CTA of a pair loads (and multicasts) half of the B tile
   if (rc) return rc;
   tc = ta;
   tr = ta;
