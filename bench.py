@@ -113,6 +113,12 @@ def run_ours(args) -> None:
     import oracle
     from fitclip_b200 import B200ClipVideoTextEncoder, _lib, metrics_from_ranks, retrieval_ranks
 
+    # Libraries (NCCL's version banner, ...) may write to fd 1; the contract is ONE JSON line on stdout, so everything
+    # but the final print goes to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,7 +257,9 @@ def run_ours(args) -> None:
             "metrics": {k: float(v) for k, v in metrics.items()},
         }
         line["cpu_baseline"] = cpu_baseline(sample_videos=args.cpu_sample)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

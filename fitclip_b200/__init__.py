@@ -1,9 +1,11 @@
 """fitclip_b200 -- B200-native (sm_100a) implementation of FitCLIP's evaluation hot path behind the reference's
 ``VideoTextEncoder`` plugin interface.  See DESIGN.md / INTEGRATION.md."""
 from .api import VideoEncoder, VideoTextEncoder  # noqa: F401
+from .classification import VideoTextClassificationModule  # noqa: F401
 from .encoder import B200Clip, B200ClipVideoTextEncoder, load_clip_model  # noqa: F401
 from .metrics import Accuracy, MeanRank, MedianRank, Rank, Recall  # noqa: F401
 from .retrieval import TextVideoRetrievalModule, metrics_from_ranks, retrieval_ranks, shard_bounds  # noqa: F401
+from .teacher_student import TeacherStudentScoringModule  # noqa: F401
 from .wise import wise, wise_state_dict  # noqa: F401
 
 __version__ = "0.1.0"
