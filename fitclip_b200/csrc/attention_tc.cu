@@ -78,6 +78,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     return w;
   };
 
+  griddep_launch_dependents();
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   if (threadIdx.x == 128) {
     tma_prefetch_desc(&tmQ);
@@ -96,6 +97,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
 
   if (warp == 4) {
     // ===================== TMA + MMA thread =====================
@@ -343,8 +345,18 @@ int launch_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaSt
   if (grid > items) grid = items;
   if (tiles == 2 && (grid & 1)) grid -= 1;
   const float scale_log2 = 0.125f * 1.4426950408889634f;
-  attention_tc_kernel<KP><<<grid, ATT_THREADS, S::BYTES, s>>>(tq, tkv, to, L, heads, tiles, items, scale_log2);
-  FC_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(ATT_THREADS);
+  cfg.dynamicSmemBytes = S::BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  note_launch();
+  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<KP>, tq, tkv, to, L, heads, tiles, items, scale_log2));
   return FC_OK;
 }
 

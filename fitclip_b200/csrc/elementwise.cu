@@ -248,20 +248,24 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ ids,
+constexpr int HEAD_SEQS = 4;   // sequences per CTA: every projection weight fetched from L2 feeds 4 FMAs
+constexpr int HEAD_COLS = 128;  // output columns per CTA (grid.y tiles the embedding dimension)
+
+__global__ void __launch_bounds__(HEAD_COLS) head_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ ids,
                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                   const float* __restrict__ proj, float* __restrict__ out, int L,
-                                                   int W, int E, float eps) {
-  extern __shared__ float sh[];  // W normalised values + 32 reduction slots
-  float* y = sh;
-  float* red = sh + W;
-  __shared__ int s_pos;
-  const int64_t seq = blockIdx.x;
-  if (threadIdx.x < 32) {
+                                                   const float* __restrict__ proj, float* __restrict__ out,
+                                                   int64_t seqs, int L, int W, int E, float eps) {
+  extern __shared__ float sh[];  // HEAD_SEQS x W normalised values + 32 reduction slots
+  float* red = sh + HEAD_SEQS * W;
+  __shared__ int s_pos[HEAD_SEQS];
+  const int64_t seq0 = static_cast<int64_t>(blockIdx.x) * HEAD_SEQS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < HEAD_SEQS) {  // one warp per sequence finds the pooled position
     int pos = 0;
-    if (ids != nullptr) {  // first index of the maximum id (torch.argmax semantics)
+    const int64_t seq = seq0 + warp;
+    if (ids != nullptr && seq < seqs) {  // first index of the maximum id (torch.argmax semantics)
       int best = INT_MIN, best_i = 0;
-      for (int l = threadIdx.x; l < L; l += 32) {
+      for (int l = lane; l < L; l += 32) {
         const int v = ids[seq * L + l];
         if (v > best) {
           best = v;
@@ -279,30 +283,47 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ x, c
       }
       pos = best_i;
     }
-    if (threadIdx.x == 0) s_pos = pos;
+    if (lane == 0) s_pos[warp] = pos;
   }
   __syncthreads();
-  const bf16* row = x + (seq * L + s_pos) * static_cast<int64_t>(W);
-  float part = 0.f;
-  for (int k = threadIdx.x; k < W; k += blockDim.x) {
-    const float v = __bfloat162float(row[k]);
-    y[k] = v;
-    part += v;
+  for (int sq = 0; sq < HEAD_SEQS; ++sq) {
+    float* y = sh + sq * W;
+    const int64_t seq = seq0 + sq;
+    if (seq >= seqs) {  // block-uniform
+      for (int k = threadIdx.x; k < W; k += blockDim.x) y[k] = 0.f;
+      continue;
+    }
+    const bf16* row = x + (seq * L + s_pos[sq]) * static_cast<int64_t>(W);
+    float part = 0.f;
+    for (int k = threadIdx.x; k < W; k += blockDim.x) {
+      const float v = __bfloat162float(row[k]);
+      y[k] = v;
+      part += v;
+    }
+    const float mean = block_sum(part, red) / static_cast<float>(W);
+    part = 0.f;
+    for (int k = threadIdx.x; k < W; k += blockDim.x) {
+      const float d = y[k] - mean;
+      part += d * d;
+    }
+    const float rstd = rsqrtf(block_sum(part, red) / static_cast<float>(W) + eps);
+    for (int k = threadIdx.x; k < W; k += blockDim.x) y[k] = (y[k] - mean) * rstd * gamma[k] + beta[k];
   }
-  const float mean = block_sum(part, red) / static_cast<float>(W);
-  part = 0.f;
-  for (int k = threadIdx.x; k < W; k += blockDim.x) {
-    const float d = y[k] - mean;
-    part += d * d;
-  }
-  const float rstd = rsqrtf(block_sum(part, red) / static_cast<float>(W) + eps);
-  for (int k = threadIdx.x; k < W; k += blockDim.x) y[k] = (y[k] - mean) * rstd * gamma[k] + beta[k];
   __syncthreads();
-  for (int n = threadIdx.x; n < E; n += blockDim.x) {
-    float acc = 0.f;
+  const int n = blockIdx.y * HEAD_COLS + threadIdx.x;
+  if (n < E) {
+    float acc[HEAD_SEQS];
+#pragma unroll
+    for (int sq = 0; sq < HEAD_SEQS; ++sq) acc[sq] = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < W; ++k) acc = fmaf(y[k], __ldg(proj + static_cast<int64_t>(k) * E + n), acc);
-    out[seq * E + n] = acc;
+    for (int k = 0; k < W; ++k) {  // k-sequential fp32 accumulation; the 8-way unroll keeps 8 weight loads in flight
+      const float wv = __ldg(proj + static_cast<int64_t>(k) * E + n);
+#pragma unroll
+      for (int sq = 0; sq < HEAD_SEQS; ++sq) acc[sq] = fmaf(sh[sq * W + k], wv, acc[sq]);
+    }
+#pragma unroll
+    for (int sq = 0; sq < HEAD_SEQS; ++sq)
+      if (seq0 + sq < seqs) out[(seq0 + sq) * E + n] = acc[sq];
   }
 }
 
@@ -464,8 +485,9 @@ int head_project(const bf16* x, const int32_t* ids, const float* gamma, const fl
                  float* out, int64_t seqs, int L, int W, int E, float eps, cudaStream_t s) {
   if (seqs == 0) return FC_OK;
   ProfScope prof(s, PROF_OTHER, 3, seqs, W, E, 2.0 * seqs * W * E, 4.0 * seqs * W * E);
-  const size_t smem = (W + 32) * sizeof(float);
-  head_kernel<<<static_cast<unsigned>(seqs), 256, smem, s>>>(x, ids, gamma, beta, proj, out, L, W, E, eps);
+  const size_t smem = (HEAD_SEQS * W + 32) * sizeof(float);
+  const dim3 grid(static_cast<unsigned>((seqs + HEAD_SEQS - 1) / HEAD_SEQS), (E + HEAD_COLS - 1) / HEAD_COLS);
+  head_kernel<<<grid, HEAD_COLS, smem, s>>>(x, ids, gamma, beta, proj, out, seqs, L, W, E, eps);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }

@@ -83,6 +83,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_tiles = ((num_m_tiles + 1) / 2) * num_n_tiles;  // pair-tiles; tile -> (m pair, n block), N fastest
 
+  griddep_launch_dependents();  // PDL: the next kernel's prologue may overlap this kernel's tail
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -107,6 +108,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();  // the peer's barriers must exist before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // PDL: everything above overlapped the previous kernel; from here on we touch its outputs
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -512,13 +514,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   note_launch();
   FC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI>, ta, tb, tc, tr, p));
   return FC_OK;

@@ -1,0 +1,264 @@
+"""Lightning/Hydra-free runner for the reference's command line (``aligner/__main__.py:27-93``, ``aligner/cli.py:81-150``):
+
+    python -m aligner command=evaluate encoder=clip_vit_b_16 data=synthetic_msrvtt
+    python -m aligner command=evaluate encoder=wise +encoder@encoder.model1=clip_vit_b_16 \
+        +encoder@encoder.model2=clip_vit_b_16 encoder.model2.model.seed=1 data=synthetic_ucf101
+    python -m aligner command=predict encoder=clip_vit_b_16 data=synthetic_msrvtt output_path=predictions.pt
+
+It implements the subset of Hydra the reference relies on for evaluation: a root config with a
+``defaults`` list, ``group=name`` selection with per-file ``defaults`` chains, ``+group@package=name`` placement,
+dotted ``key=value`` / ``+key=value`` overrides, ``${key}`` interpolation of top-level scalars and recursive
+``_target_`` instantiation.  The loop reproduces the hook order of PL 1.6's evaluation loop: ``on_validation_start``,
+``validation_step`` -> ``validation_step_end`` per batch, ``validation_epoch_end`` once, and prints the logged keys.
+Real datasets / video decoding are out of scope (no network, no decord): ``data=synthetic_*`` feeds tensors of the
+shapes and dtypes the reference's data modules emit."""
+from __future__ import annotations
+
+import copy
+import importlib
+import json
+import os
+import re
+import sys
+from typing import Any, Dict, Iterator, List, Mapping, Optional, Sequence
+
+import torch
+import yaml
+
+CONFIG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config")
+
+
+# ------------------------------------------------------------------------------------------------- config resolution
+def _load_yaml(path: str) -> Dict[str, Any]:
+    with open(path) as f:
+        return yaml.safe_load(f) or {}
+
+
+def _merge(dst: Dict[str, Any], src: Mapping[str, Any]) -> Dict[str, Any]:
+    for k, v in src.items():
+        if isinstance(v, Mapping) and isinstance(dst.get(k), dict):
+            _merge(dst[k], v)
+        else:
+            dst[k] = copy.deepcopy(v)
+    return dst
+
+
+def load_group(group: str, name: str, config_dir: str = CONFIG_DIR) -> Dict[str, Any]:
+    """``config/<group>/<name>.yaml`` with its own ``defaults`` chain resolved (entries of the same group first,
+    ``_self_`` last unless placed explicitly; ``- key: null`` placeholders are skipped)."""
+    cfg = _load_yaml(os.path.join(config_dir, group, f"{name}.yaml"))
+    defaults = cfg.pop("defaults", [])
+    merged: Dict[str, Any] = {}
+    self_done = False
+    for entry in defaults:
+        if entry == "_self_":
+            _merge(merged, cfg)
+            self_done = True
+        elif isinstance(entry, str):
+            _merge(merged, load_group(group, entry, config_dir))
+        # mappings such as {model1: null} are optional slots filled from the command line
+    if not self_done:
+        _merge(merged, cfg)
+    return merged
+
+
+def _set_path(cfg: Dict[str, Any], dotted: str, value: Any) -> None:
+    *parents, leaf = dotted.split(".")
+    node = cfg
+    for p in parents:
+        if not isinstance(node.get(p), dict):
+            node[p] = {}
+        node = node[p]
+    if isinstance(value, Mapping) and isinstance(node.get(leaf), dict):
+        _merge(node[leaf], value)
+    else:
+        node[leaf] = value
+
+
+def _interpolate(node: Any, root: Mapping[str, Any]) -> Any:
+    if isinstance(node, dict):
+        return {k: _interpolate(v, root) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_interpolate(v, root) for v in node]
+    if isinstance(node, str):
+        m = re.fullmatch(r"\$\{(\w+)\}", node)
+        if m:
+            return root[m.group(1)]
+        return re.sub(r"\$\{(\w+)\}", lambda mm: str(root[mm.group(1)]), node)
+    return node
+
+
+def compose(overrides: Sequence[str], config_dir: str = CONFIG_DIR, config_name: str = "trainer") -> Dict[str, Any]:
+    cfg = _load_yaml(os.path.join(config_dir, f"{config_name}.yaml"))
+    groups = [next(iter(d)) for d in cfg.pop("defaults", []) if isinstance(d, Mapping)]
+    values: List[tuple] = []
+    for ov in overrides:
+        key, _, raw = ov.partition("=")
+        key = key.lstrip("+")
+        if "@" in key:  # +group@package.path=name
+            group, package = key.split("@", 1)
+            _set_path(cfg, package, load_group(group, raw, config_dir))
+        elif key in groups and os.path.exists(os.path.join(config_dir, key, f"{raw}.yaml")):
+            cfg[key] = load_group(key, raw, config_dir)
+        else:
+            values.append((key, yaml.safe_load(raw)))
+    for key, value in values:  # plain value overrides win over group contents
+        _set_path(cfg, key, value)
+    cfg = _interpolate(cfg, cfg)
+    missing = [k for k, v in cfg.items() if v == "???"]
+    if missing:
+        raise ValueError(f"Missing mandatory value(s): {', '.join(missing)} (e.g. command=evaluate encoder=clip_vit_b_16 "
+                         f"data=synthetic_msrvtt)")
+    return cfg
+
+
+def instantiate(node: Any, **extra: Any) -> Any:
+    """``hydra.utils.instantiate``: children first, then import ``_target_`` and call it with the remaining keys."""
+    if isinstance(node, Mapping):
+        if "_target_" in node:
+            kwargs = {k: instantiate(v) for k, v in node.items() if not k.startswith("_")}
+            kwargs.update(extra)
+            unresolved = [k for k, v in kwargs.items() if v == "???"]
+            if unresolved:
+                raise ValueError(f"{node['_target_']}: missing mandatory value(s) {unresolved}")
+            module, _, attr = node["_target_"].rpartition(".")
+            return getattr(importlib.import_module(module), attr)(**kwargs)
+        return {k: instantiate(v) for k, v in node.items()}
+    if isinstance(node, list):
+        return [instantiate(v) for v in node]
+    return node
+
+
+# ------------------------------------------------------------------------------------------------- synthetic plug-ins
+def random_init_clip(seed: int = 0, **kwargs: int):
+    """``clip.model.CLIP(**kwargs)`` with its published initialisation (config/encoder/clip_from_scratch_vit_b_16.yaml);
+    returns a :class:`fitclip_b200.B200Clip` holding the parameters."""
+    from . import B200Clip
+    from ._init import init_clip_state_dict
+    return B200Clip(init_clip_state_dict(seed=seed, **kwargs))
+
+
+class SyntheticRetrievalData:
+    """Batches shaped like ``VideoTextDataModule`` output: ``{"video": (B,T,3,R,R) fp32, "text": {"input_ids": (B,77)},
+    "video_id": [...]}`` -- N(0,1) frames generated on the device, ``[SOT] + random ids + [EOT]`` captions."""
+
+    def __init__(self, encoder, num_videos: int = 1000, batch_size: int = 32, caption_length: int = 77,
+                 seed: int = 1234) -> None:
+        self.encoder, self.num_videos, self.batch_size = encoder, num_videos, batch_size
+        self.caption_length, self.seed = caption_length, seed
+
+    def _geometry(self):
+        enc = self.encoder
+        model = enc.model
+        return enc.num_frames, model.visual.input_resolution, model.context_length, model.vocab_size
+
+    def val_batches(self, device: torch.device) -> Iterator[Dict[str, Any]]:
+        frames, res, ctx, vocab = self._geometry()
+        for i, lo in enumerate(range(0, self.num_videos, self.batch_size)):
+            b = min(self.batch_size, self.num_videos - lo)
+            g = torch.Generator(device=device).manual_seed(self.seed + i)
+            video = torch.randn(b, frames, 3, res, res, device=device, generator=g)
+            gc = torch.Generator().manual_seed(self.seed + 7919 * (i + 1))
+            ids = torch.zeros(b, ctx, dtype=torch.int32)
+            n = min(self.caption_length, ctx)
+            ids[:, :n] = torch.randint(1, vocab - 2, (b, n), generator=gc, dtype=torch.int32)
+            ids[:, 0] = vocab - 2
+            ids[:, n - 1] = vocab - 1
+            yield {"video": video, "text": {"input_ids": ids.to(device)},
+                   "video_id": [f"video{lo + j}" for j in range(b)]}
+
+
+class SyntheticClassificationData(SyntheticRetrievalData):
+    """Batches shaped like ``VideoClassificationDataModule`` output (``target = (name, id)``) plus the label prompts."""
+
+    def __init__(self, encoder, num_videos: int = 3783, num_frames: int = 8, num_labels: int = 101,
+                 num_templates: int = 48, batch_size: int = 32, seed: int = 1234) -> None:
+        super().__init__(encoder, num_videos, batch_size, 16, seed)
+        self.num_frames, self.num_labels, self.num_templates = num_frames, num_labels, num_templates
+        self.categories = [f"class{i}" for i in range(num_labels)]
+        self.templates = [f"template{t} of {{}}" for t in range(num_templates)]
+
+    def tokenized_prompts(self) -> Dict[str, torch.Tensor]:
+        _, _, ctx, vocab = self._geometry()
+        g = torch.Generator().manual_seed(self.seed + 1)
+        n = self.num_labels * self.num_templates
+        lengths = torch.randint(6, 20, (n,), generator=g)
+        ids = torch.zeros(n, ctx, dtype=torch.int32)
+        body = torch.randint(1, vocab - 2, (n, ctx), generator=g, dtype=torch.int32)
+        for i in range(n):
+            k = int(lengths[i])
+            ids[i, :k] = body[i, :k]
+            ids[i, 0], ids[i, k - 1] = vocab - 2, vocab - 1
+        return {"input_ids": ids}
+
+    def val_batches(self, device: torch.device) -> Iterator[Dict[str, Any]]:
+        _, res, _, _ = self._geometry()
+        gl = torch.Generator().manual_seed(7)
+        labels = torch.randint(0, self.num_labels, (self.num_videos,), generator=gl)
+        for i, lo in enumerate(range(0, self.num_videos, self.batch_size)):
+            b = min(self.batch_size, self.num_videos - lo)
+            g = torch.Generator(device=device).manual_seed(self.seed + i)
+            video = torch.randn(b, self.num_frames, 3, res, res, device=device, generator=g)
+            y = labels[lo:lo + b].to(device)
+            yield {"video": video, "target": ([self.categories[int(t)] for t in y], y),
+                   "video_id": [f"video{lo + j}" for j in range(b)]}
+
+
+# ------------------------------------------------------------------------------------------------- commands
+def _to_float(v: Any) -> Any:
+    if isinstance(v, torch.Tensor):
+        return v.tolist() if v.numel() > 1 else v.item()
+    return v
+
+
+def evaluate(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> Dict[str, Any]:
+    from . import VideoTextClassificationModule
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(cfg.get("seed", 42))  # init_cli: seed_everything (aligner/cli.py:43-50)
+    encoder = instantiate(cfg["encoder"]).to(device)
+    data = instantiate(cfg["data"], encoder=encoder)
+    if isinstance(data, SyntheticClassificationData):  # aligner/cli.py:110-115 switches the model class the same way
+        model = VideoTextClassificationModule(encoder, data.categories, data.templates,
+                                              tokenized_labels=data.tokenized_prompts())
+    else:
+        model = instantiate(cfg["model"], encoder=encoder).to(device)
+    command = cfg["command"]
+    with torch.inference_mode():
+        if hasattr(model, "on_validation_start"):
+            model.on_validation_start()
+        if command == "predict":
+            outs = [model.predict_step(batch, i) for i, batch in enumerate(data.val_batches(device))]
+            result = {k: (torch.cat([o[k] for o in outs]).cpu() if isinstance(outs[0][k], torch.Tensor)
+                          else [x for o in outs for x in o[k]]) for k in outs[0]}
+            torch.save(result, cfg.get("output_path", "predictions.pt"))  # aligner/__main__.py:70-91
+            return {"saved": cfg.get("output_path", "predictions.pt"), "count": len(result["video_ids"])}
+        outputs = []
+        for i, batch in enumerate(data.val_batches(device)):
+            out = model.validation_step(batch, i)
+            if hasattr(model, "validation_step_end"):
+                out = model.validation_step_end(out)
+            outputs.append(out)
+        result = model.validation_epoch_end(outputs)
+    if hasattr(encoder, "model") and hasattr(encoder.model, "check_inputs"):
+        encoder.model.check_inputs()
+    return {k: _to_float(v) for k, v in result.items()}
+
+
+def main(argv: Sequence[str]) -> int:
+    cfg = compose(list(argv))
+    command = cfg["command"]
+    if command not in ("evaluate", "validate", "test", "predict"):
+        raise ValueError(f"command={command} is outside the evaluation hot path this package implements "
+                         f"(supported: evaluate | validate | test | predict)")
+    result = evaluate(cfg)
+    if not cfg.get("silent"):
+        width = max(len(k) for k in result)
+        for k, v in result.items():
+            if not (isinstance(v, list) and len(v) > 20):
+                print(f"{k:<{width}}  {v}")
+    print(json.dumps({k: v for k, v in result.items() if not isinstance(v, list)}))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))

@@ -1,0 +1,93 @@
+"""`python -m aligner ...` shim: config composition (CPU) and an end-to-end evaluate / predict run (GPU)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from fitclip_b200 import runner
+from fitclip_b200._init import init_clip_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TINY = ["encoder.model.vision_layers=1", "encoder.model.transformer_layers=1"]
+
+
+def test_compose_encoder_chain_and_overrides():
+    cfg = runner.compose(["command=evaluate", "encoder=clip_vit_b_16", "data=synthetic_msrvtt", "data.num_videos=64",
+                          "+encoder.num_frames=2"])
+    assert cfg["encoder"]["_target_"] == "fitclip_b200.B200ClipVideoTextEncoder"  # from clip.yaml through the chain
+    assert cfg["encoder"]["model"]["vision_width"] == 768 and cfg["encoder"]["model"]["transformer_heads"] == 8
+    assert cfg["encoder"]["num_frames"] == 2 and cfg["data"]["num_videos"] == 64
+    assert cfg["model"]["init_temperature"] == 0.015 and cfg["model"]["fit_temperature"] is False
+
+
+def test_compose_wise_with_package_placement():
+    cfg = runner.compose(["command=evaluate", "encoder=wise", "+encoder@encoder.model1=clip_vit_b_16",
+                          "+encoder@encoder.model2=clip_vit_b_16", "encoder.model2.model.seed=1",
+                          "encoder.weight_for_2=0.5", "data=synthetic_msrvtt"])
+    enc = cfg["encoder"]
+    assert enc["_target_"] == "fitclip_b200.wise.wise" and enc["weight_for_2"] == 0.5
+    assert enc["model1"]["model"]["seed"] == 0 and enc["model2"]["model"]["seed"] == 1
+
+
+def test_missing_mandatory_values_are_reported():
+    with pytest.raises(ValueError, match="Missing mandatory"):
+        runner.compose(["command=evaluate"])
+    with pytest.raises(ValueError):
+        runner.main(["command=train", "encoder=clip_vit_b_16", "data=synthetic_msrvtt"])
+
+
+def test_instantiate_is_recursive_and_rejects_unfilled_slots():
+    obj = runner.instantiate({"_target_": "collections.OrderedDict", "a": {"_target_": "datetime.timedelta", "days": 7}})
+    assert obj["a"].days == 7
+    with pytest.raises(ValueError):
+        runner.instantiate({"_target_": "builtins.dict", "model1": "???"})
+
+
+def test_random_init_statistics_match_the_published_init():
+    sd = init_clip_state_dict(seed=0, vision_layers=1, transformer_layers=2)
+    assert len(sd) == 1 + 5 + 12 * 2 + 8 + 12 * 1 and sd["visual.positional_embedding"].shape == (197, 768)
+    w = sd["transformer.resblocks.0.attn.in_proj_weight"]
+    assert abs(w.std().item() - 512 ** -0.5) < 2e-3
+    assert abs(sd["transformer.resblocks.1.mlp.c_proj.weight"].std().item() - (512 ** -0.5) * (4 ** -0.5)) < 1e-3
+    assert abs(sd["token_embedding.weight"].std().item() - 0.02) < 1e-3
+    v = sd["visual.transformer.resblocks.0.attn.in_proj_weight"]
+    assert v.abs().max().item() <= (6.0 / (4 * 768)) ** 0.5 + 1e-6  # xavier-uniform bound
+    assert torch.count_nonzero(sd["visual.transformer.resblocks.0.attn.in_proj_bias"]) == 0
+    # deterministic per seed, different across seeds
+    assert torch.equal(sd["text_projection"], init_clip_state_dict(seed=0, vision_layers=1, transformer_layers=2)["text_projection"])
+    assert not torch.equal(sd["text_projection"], init_clip_state_dict(seed=1, vision_layers=1, transformer_layers=2)["text_projection"])
+
+
+@pytest.mark.gpu
+def test_evaluate_and_predict_commands(tmp_path):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-m", "aligner", "command=evaluate", "encoder=clip_vit_b_16",
+                          "data=synthetic_msrvtt", "data.num_videos=80", *TINY], cwd=ROOT, env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    result = json.loads(out.stdout.strip().splitlines()[-1])
+    assert set(result) == {"r1", "r5", "r10", "mr", "loss/val"}
+    assert 0.0 <= result["r10"] <= 1.0 and 1 <= result["mr"] <= 80
+    pred = tmp_path / "predictions.pt"
+    out = subprocess.run([sys.executable, "-m", "aligner", "command=predict", "encoder=clip_vit_b_16",
+                          "data=synthetic_msrvtt", "data.num_videos=40", f"output_path={pred}", *TINY], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    saved = torch.load(pred)
+    assert saved["encoded_videos"].shape == (40, 512) and saved["encoded_texts"].shape == (40, 512)
+    assert len(saved["video_ids"]) == 40  # the reference's predictions.pt keys (aligner/video_text_module.py:85-91)
+
+
+@pytest.mark.gpu
+def test_evaluate_wise_classification():
+    cfg = runner.compose(["command=evaluate", "encoder=wise", "+encoder@encoder.model1=clip_vit_b_16",
+                          "+encoder@encoder.model2=clip_vit_b_16", "encoder.model2.model.seed=1",
+                          "encoder.weight_for_2=0.5", "data=synthetic_ucf101", "data.num_videos=24", "data.num_frames=2",
+                          "data.num_labels=7", "data.num_templates=3",
+                          "encoder.model1.model.vision_layers=1", "encoder.model1.model.transformer_layers=1",
+                          "encoder.model2.model.vision_layers=1", "encoder.model2.model.transformer_layers=1"])
+    result = runner.evaluate(cfg)  # the models are built on the CPU like the reference's; the lerp itself runs on the GPU
+    assert set(result) == {"a1", "a5", "mr"} and 1 <= int(result["mr"]) <= 7
