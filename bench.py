@@ -250,6 +250,11 @@ def run_ours(args) -> None:
         shapes = sorted(gemm, key=lambda r: -r["ms"])
         step_flops = VIDEOS_PER_GPU * FRAMES * FLOP_PER_FRAME + CAPTIONS_PER_GPU * FLOP_PER_CAPTION \
             + 2.0 * n_total * VIDEOS_PER_GPU * 512
+        traffic = None
+        traffic_path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+        if os.path.exists(traffic_path):  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from ncu --set full
+            with open(traffic_path) as f:
+                traffic = json.load(f)
         line = {
             "metric": "videos/sec (ViT-B/16 encode+sim+rank)", "value": n_total / (ms_per_step * 1e-3),
             "unit": "videos/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -266,7 +271,10 @@ def run_ours(args) -> None:
             "gpu_launches": int(launches), "profiled_ms_per_step": profiled_ms_per_step,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": src,
+                         "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_kernel": traffic["kernel"] if traffic else None,
+                         "traffic_algorithmic_bytes": traffic["algorithmic_bytes_per_launch"] if traffic else None,
+                         "peak_source": src,
                          "frac_of_sustained": achieved / sustained, "kernel": "gemm_bf16_tn_kernel (all shapes)",
                          "kernel_share_of_step": g_ms / total_ms if total_ms else None,
                          "ms_by_kernel_class": by_kind,
