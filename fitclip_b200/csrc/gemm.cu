@@ -1,17 +1,21 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * B[N,K]^T), bf16 in, fp32 acc.
 //
-//   warp 0    TMA producer   : cp.async.bulk.tensor (128B-swizzled 128x64 A tile + 256x64 B tile per stage)
-//   warp 1    MMA issuer     : one elected thread issues tcgen05.mma 128x256x16, accumulators in TMEM
+//   warp 0    TMA producer   : cp.async.bulk.tensor (128B-swizzled 128x64 A tile + 128x64 half B tile per stage)
+//   warp 1    MMA issuer     : (leader CTA) one thread issues tcgen05.mma.cta_group::2 256x256x16, accumulators in TMEM
 //   warp 2    TMEM allocator : 512 columns = 2 accumulator stages of 256 fp32 columns
 //   warp 3    idle
 //   warps 4-11 epilogue      : two groups of 4 warps (one warp per TMEM lane quarter)
 //
-// Three pipelines: smem full/empty (TMA<->MMA, 4 stages of 48 KiB), TMEM full/empty (MMA<->epilogue, 2 stages), and a
-// static persistent tile scheduler over CTA PAIRS (thread-block cluster of 2): a pair owns two vertically adjacent
-// 128-row tiles of the same 256-column block, each CTA TMA-loads its own A tile plus HALF of the B tile and multicasts
-// that half into both CTAs' shared memory, so L2->SM traffic per CTA drops from 48 to 32 KiB per K block.  Stage
-// release is a multicast tcgen05.commit onto both CTAs' empty barriers.  N is the fastest tile index, so the pairs of
-// one wave share A tiles in L2 while the weight matrix B stays L2-resident.
+// CTA PAIRS (thread-block cluster of 2, tcgen05 cta_group::2): a pair owns a 256x256 output tile.  Each CTA TMA-loads
+// its own 128 rows of A and HALF of the B tile (128 of 256 rows) into its own shared memory -- 32 KiB per K block
+// instead of 48 -- and the pair's LEADER issues one tcgen05.mma.cta_group::2 (M = 256) per K step that reads both
+// CTAs' operands and accumulates each CTA's 128 rows into that CTA's TMEM.  Halving the B bytes per SM matters twice:
+// L2->SM traffic, and shared-memory bandwidth -- a cta_group::1 128x256 tile moves 96 KiB through a 128 B/clk shared
+// memory per 512-cycle K block (48 KiB TMA writes + 48 KiB operand reads) and is capped near 67 % tensor utilisation.
+// Three pipelines: smem full/empty (TMA<->MMA, 6 stages of 32 KiB; both CTAs' loads complete on the leader's full
+// barrier, the leader's multicast tcgen05.commit releases the stage in both CTAs), TMEM full/empty (MMA<->epilogue,
+// 2 accumulator stages; both epilogues release onto the leader's barrier), and a static persistent tile scheduler
+// over pairs with N fastest, so the pairs of one wave share A tiles in L2 while B stays L2-resident.
 //
 // Epilogues
 //   staged (bias / bias+QuickGELU / bias+residual / folded-LayerNorm variants, bf16 out): each warp group owns the
@@ -33,9 +37,9 @@ namespace fc {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 6, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;        // this CTA's 128 rows of the pair's 256-row A tile
+constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half (128 of 256 rows) of the B tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_THREADS = 256;               // 8 epilogue warps = 2 groups of 128
 constexpr int SUB_N = 64;                      // staged sub-tile width (64 bf16 = one 128-byte swizzle row)
@@ -43,7 +47,8 @@ constexpr int STAGING_BYTES = BM * SUB_N * 2;  // 16 KiB per warp group
 constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
 constexpr int OFF_BIAS = OFF_STAGING + 2 * STAGING_BYTES;
 constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4;  // bias[256] + colsum[256]
-constexpr int SMEM_BYTES = OFF_BARS + 128;
+constexpr int SMEM_BYTES = OFF_BARS + 256;  // 2*STAGES + 6 mbarriers + the TMEM slot
+static_assert((2 * STAGES + 6) * 8 + 4 <= 256, "barrier block overflows its reservation");
 constexpr int NUM_THREADS = 128 + EPI_THREADS;
 constexpr uint32_t TMEM_COLS = 512;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
@@ -93,17 +98,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 2);  // released by the MMA commits of BOTH CTAs (each reads multicast data)
+      mbar_init(&full_bar[i], 1);   // (leader's is the one in use) armed with the bytes of BOTH CTAs' loads
+      mbar_init(&empty_bar[i], 1);  // released by the leader's multicast tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], EPI_THREADS);
+      mbar_init(&tmem_empty[i], 2 * EPI_THREADS);  // (leader's) both CTAs' epilogue threads arrive
       mbar_init(&resid_bar[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);  // same warp in both CTAs, same address in both
   tc_fence_before();
   cluster_sync_all();  // the peer's barriers must exist before anything is multicast into this CTA
   tc_fence_after();
@@ -120,10 +125,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * STAGE_BYTES;
-          uint8_t* sB = sA + A_BYTES + cta_rank * (B_BYTES / 2);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);  // own A + both halves of B
-          tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d_multicast(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN + cta_rank * (BN / 2), 0x3);
+          uint8_t* sB = sA + A_BYTES;
+          // both CTAs' bytes are credited to the LEADER's full barrier, which alone gates the pair's MMAs
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_2cta(sA, &tmA, leader_full, kb * BK, m_blk * BM);
+          tma_load_2d_2cta(sB, &tmB, leader_full, kb * BK, n_blk * BN + cta_rank * (BN / 2));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -133,8 +140,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);  // M = 256 across the CTA pair
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -151,16 +158,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance along K inside the 128-byte swizzle atom: +32 bytes per UMMA_K
-            umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2), umma_desc_k_sw128(b_addr + k * UMMA_K * 2),
-                         idesc, (kb | k) != 0);
+            umma_bf16_ss_2cta(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2),
+                              umma_desc_k_sw128(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
           }
-          umma_commit_multicast(&empty_bar[stage], 0x3);  // frees the slot in BOTH CTAs when these MMAs retire
+          umma_commit_2cta_multicast(&empty_bar[stage], 0x3);  // frees the slot in BOTH CTAs when these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        umma_commit_2cta_multicast(&tmem_full[acc], 0x3);  // accumulators ready for both CTAs' epilogues
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -176,6 +183,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     uint32_t resid_phase = 0;
     const bool issuer = (etid & 127) == 0;  // one thread per warp group drives its TMA traffic
+    // accumulator release goes to the LEADER's tmem_empty barriers (the leader's MMA thread waits for both epilogues)
+    const uint32_t leader_tmem_empty[2] = {mapa_shared(smem_u32(&tmem_empty[0]), 0),
+                                           mapa_shared(smem_u32(&tmem_empty[1]), 0)};
     bool resid_prefetched = false;          // (issuer only) the residual of the coming sub-tile is already in flight
     uint8_t* stg_ptr = smem + OFF_STAGING + grp * STAGING_BYTES;
     const uint32_t stg_row = smem_u32(stg_ptr) + row_in_tile * 128;
@@ -184,6 +194,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Values the next tile's epilogue needs from global memory (bias / column sums of its 256 columns, the LayerNorm
     // partial sums of this thread's row) are fetched one tile ahead, so their latency hides behind the current tile.
     float nxt_bias = 0.f, nxt_cs = 0.f, nxt_s1 = 0.f, nxt_s2 = 0.f;
+    float4 nxt_st[8];  // raw partial sums of the next tile's row: summed only when that tile starts, so the loads
+                       // stay in flight behind the current tile's work instead of stalling here
+    const bool st_vec = kLn && (p.ln_parts & 1) == 0 && p.ln_parts <= 16;
     auto prefetch_tile = [&](int t) {
       if (!kStaged || t >= num_tiles) return;
       const int mb = 2 * (t / num_n_tiles) + cta_rank, nb = t % num_n_tiles;
@@ -194,7 +207,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         nxt_s1 = 0.f;
         nxt_s2 = 0.f;
         const int r = mb * BM + row_in_tile;
-        if (r < p.M) {
+        if (st_vec) {
+          const float4* ps = reinterpret_cast<const float4*>(p.ln_stats + static_cast<int64_t>(r < p.M ? r : 0) * p.ln_parts * 2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            nxt_st[i] = (r < p.M && 2 * i < p.ln_parts) ? __ldg(ps + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (r < p.M) {
           const float2* ps = reinterpret_cast<const float2*>(p.ln_stats) + static_cast<int64_t>(r) * p.ln_parts;
           for (int i = 0; i < p.ln_parts; ++i) {
             const float2 v = __ldg(ps + i);
@@ -221,6 +239,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // folded LayerNorm: this row's mean / rstd from the producer's partial sums
         float ln_rstd = 1.f, ln_shift = 0.f;  // out = rstd * acc + shift * colsum + bias,  shift = -rstd * mean
         if (kLn) {
+          if (st_vec) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              nxt_s1 += nxt_st[i].x + nxt_st[i].z;
+              nxt_s2 += nxt_st[i].y + nxt_st[i].w;
+            }
+          }
           const float inv_k = 1.f / static_cast<float>(p.K);
           const float mean = nxt_s1 * inv_k;
           const float var = fmaxf(nxt_s2 * inv_k - mean * mean, 0.f);
@@ -254,7 +279,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_wait_fence(r1);
           if (si == 1 || col0 + 2 * SUB_N >= p.N) {  // last TMEM read of this tile by this thread
             tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            mbar_arrive_cluster(leader_tmem_empty[acc]);
             released = true;
           }
           if (EPI == EPI_BIAS_RESID) {
@@ -333,7 +358,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (!released) {  // group had no sub-tile inside N (ragged N): it still owes the accumulator release
           tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
+          mbar_arrive_cluster(leader_tmem_empty[acc]);
         }
         if (EPI == EPI_BIAS_RESID && issuer) {
           // start fetching the residual of the next tile's first sub-tile now: its latency overlaps the tile hand-over
@@ -441,7 +466,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (EPI == EPI_COUNT && row_ok && cnt) atomicAdd(p.counts + row, cnt);
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive_cluster(leader_tmem_empty[acc]);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -454,7 +479,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();  // neither CTA may exit while its peer can still multicast into it or signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -542,7 +567,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   if (ln) {
     FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.bias,
                "gemm: folded-LayerNorm epilogue needs bf16 C (N %% 32 == 0, ldc %% 8 == 0) and a bias");
-    FC_REQUIRE(p.ln_stats && p.colsum && p.ln_parts > 0 && (reinterpret_cast<uintptr_t>(p.ln_stats) & 7) == 0,
+    FC_REQUIRE(p.ln_stats && p.colsum && p.ln_parts > 0 && (reinterpret_cast<uintptr_t>(p.ln_stats) & 15) == 0,
                "gemm: folded-LayerNorm epilogue needs row statistics and column sums");
   } else if (epilogue <= EPI_PATCH) {
     FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0, "gemm: bf16 epilogues need N %% 32 == 0 and ldc %% 8 == 0");
