@@ -53,6 +53,17 @@ constexpr int NUM_THREADS = 128 + EPI_THREADS;
 constexpr uint32_t TMEM_COLS = 512;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
+#ifdef FC_GEMM_TIMING
+// Diagnostics build only (make TIMING=1): cycle counters summed over all CTAs.
+//   [0] MMA thread: whole loop  [1] MMA: waiting for a drained accumulator  [2] MMA: waiting for TMA bytes
+//   [3] producer: waiting for a free stage  [4] epilogue thread 0: whole loop  [5] epilogue: waiting for accumulators
+//   [6] tiles  [7] MMA threads
+__device__ unsigned long long g_gemm_timing[8];
+#define FC_T(...) __VA_ARGS__
+#else
+#define FC_T(...)
+#endif
+
 __device__ __forceinline__ float quick_gelu(float v) {
   // x * sigmoid(1.702 x)  (reference twin: aligner/encoder/slip.py:359-361), written with one MUFU op:
   // sigmoid(y) = 0.5 + 0.5 tanh(y/2); tanh.approx is ~2^-11 accurate, far inside the bf16 output rounding (2^-9).
@@ -120,10 +131,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      FC_T(long long w_stage = 0;)
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = 2 * (tile / num_n_tiles) + cta_rank, n_blk = tile % num_n_tiles;
         for (int kb = 0; kb < num_k; ++kb) {
+          FC_T(const long long tw = clock64();)
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          FC_T(w_stage += clock64() - tw;)
           uint8_t* sA = smem + stage * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
           // both CTAs' bytes are credited to the LEADER's full barrier, which alone gates the pair's MMAs
@@ -137,6 +151,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      FC_T(atomicAdd(&g_gemm_timing[3], static_cast<unsigned long long>(w_stage));)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -146,12 +161,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      FC_T(const long long t_begin = clock64(); long long w_acc = 0, w_tma = 0; long long n_tiles = 0;)
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        FC_T(long long tw = clock64();)
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
+        FC_T(w_acc += clock64() - tw; ++n_tiles;)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k; ++kb) {
+          FC_T(tw = clock64();)
           mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
+          FC_T(w_tma += clock64() - tw;)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
@@ -171,6 +191,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      FC_T(atomicAdd(&g_gemm_timing[0], static_cast<unsigned long long>(clock64() - t_begin));
+           atomicAdd(&g_gemm_timing[1], static_cast<unsigned long long>(w_acc));
+           atomicAdd(&g_gemm_timing[2], static_cast<unsigned long long>(w_tma));
+           atomicAdd(&g_gemm_timing[6], static_cast<unsigned long long>(n_tiles));
+           atomicAdd(&g_gemm_timing[7], 1ull);)
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
@@ -223,6 +248,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     };
     prefetch_tile(cluster_id);
+    FC_T(const long long e_begin = clock64(); long long w_full = 0;)
 
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = 2 * (tile / num_n_tiles) + cta_rank, n_blk = tile % num_n_tiles;
@@ -253,7 +279,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ln_shift = -ln_rstd * mean;
         }
         prefetch_tile(tile + num_clusters);
+        FC_T(const long long tw = clock64();)
         mbar_wait(&tmem_full[acc], acc_phase);
+        FC_T(w_full += clock64() - tw;)
         tc_fence_after();
         bool released = false;
 #pragma unroll 1
@@ -472,6 +500,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (acc == 0) acc_phase ^= 1;
     }
     if (kStaged && issuer) bulk_wait_group<0>();  // smem must outlive the last TMA store's reads
+    FC_T(if (etid == 0 && cta_rank == 0) {
+      atomicAdd(&g_gemm_timing[4], static_cast<unsigned long long>(clock64() - e_begin));
+      atomicAdd(&g_gemm_timing[5], static_cast<unsigned long long>(w_full));
+    })
   }
 
   __syncwarp();
@@ -554,6 +586,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 }
 
 }  // namespace
+
+#ifdef FC_GEMM_TIMING
+extern "C" __attribute__((visibility("default"))) int fc_debug_gemm_timing(unsigned long long* out, int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (out && cudaMemcpyFromSymbol(out, g_gemm_timing, sizeof(g_gemm_timing)) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[8] = {};
+    if (cudaMemcpyToSymbol(g_gemm_timing, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif
 
 int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, const GemmParams& p,
                  cudaStream_t stream) {
