@@ -37,18 +37,18 @@ namespace fc {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 6, UMMA_K = 16;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 5, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;        // this CTA's 128 rows of the pair's 256-row A tile
 constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half (128 of 256 rows) of the B tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_THREADS = 256;               // 8 epilogue warps = 2 groups of 128
 constexpr int SUB_N = 64;                      // staged sub-tile width (64 bf16 = one 128-byte swizzle row)
-constexpr int STAGING_BYTES = BM * SUB_N * 2;  // 16 KiB per warp group
+constexpr int STAGING_BYTES = BM * SUB_N * 2;  // 16 KiB; every warp group owns TWO (one per sub-tile of a tile)
 constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-constexpr int OFF_BIAS = OFF_STAGING + 2 * STAGING_BYTES;
+constexpr int OFF_BIAS = OFF_STAGING + 4 * STAGING_BYTES;
 constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4;  // bias[256] + colsum[256]
-constexpr int SMEM_BYTES = OFF_BARS + 256;  // 2*STAGES + 6 mbarriers + the TMEM slot
-static_assert((2 * STAGES + 6) * 8 + 4 <= 256, "barrier block overflows its reservation");
+constexpr int SMEM_BYTES = OFF_BARS + 256;  // 2*STAGES + 8 mbarriers + the TMEM slot
+static_assert((2 * STAGES + 8) * 8 + 4 <= 256, "barrier block overflows its reservation");
 constexpr int NUM_THREADS = 128 + EPI_THREADS;
 constexpr uint32_t TMEM_COLS = 512;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
@@ -84,8 +84,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* resid_bar = tmem_empty + 2;  // [2], one per epilogue warp group
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 2);
+  uint64_t* resid_bar = tmem_empty + 2;  // [2][2]: per epilogue warp group, per staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 4);
   float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5;
@@ -115,7 +115,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * EPI_THREADS);  // (leader's) both CTAs' epilogue threads arrive
-      mbar_init(&resid_bar[i], 1);
+      mbar_init(&resid_bar[2 * i], 1);
+      mbar_init(&resid_bar[2 * i + 1], 1);
     }
     fence_barrier_init();
   }
@@ -206,15 +207,32 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int etid = threadIdx.x - 128;  // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t resid_phase = 0;
+    uint32_t resid_phase = 0;  // bit si: parity of staging tile si's residual barrier
+    bool prev_two = true;  // the previous tile issued a store from BOTH staging tiles of this group (false: ragged N)
     const bool issuer = (etid & 127) == 0;  // one thread per warp group drives its TMA traffic
     // accumulator release goes to the LEADER's tmem_empty barriers (the leader's MMA thread waits for both epilogues)
     const uint32_t leader_tmem_empty[2] = {mapa_shared(smem_u32(&tmem_empty[0]), 0),
                                            mapa_shared(smem_u32(&tmem_empty[1]), 0)};
-    bool resid_prefetched = false;          // (issuer only) the residual of the coming sub-tile is already in flight
-    uint8_t* stg_ptr = smem + OFF_STAGING + grp * STAGING_BYTES;
-    const uint32_t stg_row = smem_u32(stg_ptr) + row_in_tile * 128;
+    // Two staging tiles per warp group (sub-tile si of a tile -> tile si): the TMA store of one drains while the
+    // other is being filled, and BOTH residual sub-tiles of the next tile are fetched while this one is finished.
+    uint8_t* const stg_base = smem + OFF_STAGING + grp * 2 * STAGING_BYTES;
     const int sw = row_in_tile & 7;
+    // (issuer) TMA-load the residual sub-tiles of pair-tile t into this group's staging tiles.  `drained`: the caller
+    // has made sure no earlier TMA store still reads them.
+    auto prefetch_resid = [&](int t, bool two_pending) {
+      if (EPI != EPI_BIAS_RESID || t >= num_tiles) return;
+      const int mb = 2 * (t / num_n_tiles) + cta_rank, nb = t % num_n_tiles;
+#pragma unroll
+      for (int si = 0; si < 2; ++si) {
+        const int c0 = nb * BN + (grp + 2 * si) * SUB_N;
+        if (c0 >= p.N) break;
+        // stores were committed in the order tile 0, tile 1: tile 0 is free once at most one group is pending
+        if (si == 0 && two_pending) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+        mbar_expect_tx(&resid_bar[2 * grp + si], STAGING_BYTES);
+        tma_load_2d(stg_base + si * STAGING_BYTES, &tmR, &resid_bar[2 * grp + si], c0, mb * BM);
+      }
+    };
+    if (issuer) prefetch_resid(cluster_id, false);
 
     // Values the next tile's epilogue needs from global memory (bias / column sums of its 256 columns, the LayerNorm
     // partial sums of this thread's row) are fetched one tile ahead, so their latency hides behind the current tile.
@@ -289,15 +307,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int sub = grp + 2 * si;  // 64-column sub-tile of this warp group
           const int col0 = n0 + sub * SUB_N;
           if (col0 >= p.N) break;  // uniform across the group
-          // (a) the staging tile is free once the group's previous TMA store has finished reading it
-          if (issuer && !(si == 0 && resid_prefetched)) {
-            bulk_wait_group_read<0>();
-            if (EPI == EPI_BIAS_RESID) {
-              mbar_expect_tx(&resid_bar[grp], STAGING_BYTES);
-              tma_load_2d(stg_ptr, &tmR, &resid_bar[grp], col0, m_blk * BM);
+          uint8_t* const stg_ptr = stg_base + si * STAGING_BYTES;
+          const uint32_t stg_row = smem_u32(stg_ptr) + row_in_tile * 128;
+          // (a) staging tile si is free once the store issued from it one tile ago has finished reading it (the
+          //     residual path learns that -- and that the residual has landed -- from resid_bar below)
+          if (EPI != EPI_BIAS_RESID) {
+            if (issuer) {
+              if (prev_two) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
             }
+            named_bar_sync(2 + grp, 128);
           }
-          named_bar_sync(2 + grp, 128);
           // (b) accumulators: 64 fp32 columns of this thread's row
           uint32_t r0[32], r1[32];
           const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + sub * SUB_N;
@@ -311,8 +330,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             released = true;
           }
           if (EPI == EPI_BIAS_RESID) {
-            mbar_wait(&resid_bar[grp], resid_phase);
-            resid_phase ^= 1;
+            mbar_wait(&resid_bar[2 * grp + si], (resid_phase >> si) & 1u);
+            resid_phase ^= 1u << si;
           }
           const float* bias_s = sbias + sub * SUB_N;
           float st1 = 0.f, st2 = 0.f;
@@ -388,21 +407,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_before();
           mbar_arrive_cluster(leader_tmem_empty[acc]);
         }
-        if (EPI == EPI_BIAS_RESID && issuer) {
-          // start fetching the residual of the next tile's first sub-tile now: its latency overlaps the tile hand-over
-          resid_prefetched = false;
-          const int nt = tile + num_clusters;
-          if (nt < num_tiles) {
-            const int nm = 2 * (nt / num_n_tiles) + cta_rank, nn = nt % num_n_tiles;
-            const int ncol0 = nn * BN + grp * SUB_N;
-            if (ncol0 < p.N) {
-              bulk_wait_group_read<0>();
-              mbar_expect_tx(&resid_bar[grp], STAGING_BYTES);
-              tma_load_2d(stg_ptr, &tmR, &resid_bar[grp], ncol0, nm * BM);
-              resid_prefetched = true;
-            }
-          }
-        }
+        // fetch both residual sub-tiles of the next tile now: their latency hides behind the accumulator hand-over
+        prev_two = n0 + (grp + 2) * SUB_N < p.N;
+        if (issuer) prefetch_resid(tile + num_clusters, prev_two);
       } else {
         // ---------------- direct epilogues ----------------
         mbar_wait(&tmem_full[acc], acc_phase);
