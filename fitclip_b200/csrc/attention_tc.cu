@@ -6,13 +6,18 @@
 //   TMA      Q tile [128 x 64], K [KP x 64], V [KP x 64] through 3-D tensor maps (dims: column, token-in-sequence,
 //            sequence) so tokens beyond the sequence are ZERO-FILLED on load and CLIPPED on store -- a tile never
 //            touches its neighbour sequence.
-//   MMA      S = Q K^T      tcgen05.mma M=128 N=KP K=16 x4, both operands K-major (128B swizzle), S -> TMEM cols [0,KP)
+//   MMA      S = Q K^T      tcgen05.mma M=128 K=16 x4, both operands K-major (128B swizzle), in TWO column groups:
+//            "main" keys [0, KP-16) -> TMEM cols [0, KP-16) and "tail" keys [KP-16, KP) -> cols [KP-16, KP)
 //   softmax  4 warps, one query row per thread: two passes over the row in TMEM (max; exp2 + sum), P rounded to bf16
 //            and written BACK INTO TMEM over the dead S columns (tcgen05.st) -- P never touches shared memory
 //   MMA      O = P V        tcgen05.mma M=128 N=64 K=16 x KP/16, A = P from TMEM, B = V MN-major from smem -> TMEM
-//   epilogue O / rowsum -> bf16 -> per-warp 32x64 staging tile -> 3-D TMA store
-// The TMA/MMA thread prefetches the next item's Q,K as soon as S is done and V as soon as O is done, so loads overlap the
-// softmax; the second co-resident CTA overlaps its MMAs with this CTA's MUFU-bound softmax.
+//            cols [KP-16, KP+48): over the (dead) tail columns and the rest of the 256-column allocation
+//   epilogue O / rowsum -> bf16 -> global, one full 128-byte row segment per thread (no staging, no fences)
+// Pipelining inside a CTA: the main part of S(i+1) is issued right behind P(i).V (tensor-pipe order guarantees P(i) has
+// been consumed before it is overwritten) and does not touch the O(i) columns, so it runs while the softmax warps read
+// O(i) and store it; only the 16-column tail of S(i+1) has to wait for O(i) to be drained.  The TMA/MMA thread
+// prefetches the next item's Q,K as soon as S is done and V as soon as O is done; the second co-resident CTA overlaps
+// what is left of the MMA latency with this CTA's MUFU-bound softmax.
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,9 +31,15 @@ namespace {
 constexpr int HD = 64;
 constexpr int QT = 128;                    // query rows per tile
 constexpr int Q_BYTES = QT * 128;          // 16 KiB
-constexpr int STG_BYTES = 4 * 32 * 128;    // 4 warps x (32 rows x 128 B)
-constexpr int O_COL = 128;                 // O accumulator columns [128, 192): inside the (dead) S region
 constexpr uint32_t TMEM_COLS_ATT = 256;
+constexpr int STG_BYTES = 4 * 32 * 128;    // 4 warps x (32 rows x 128 B) output staging (TMA-store epilogue)
+// tuning switches (kept as macros so variants can be built side by side: make VARIANT=x EXTRA=-DATT_...=v)
+#ifndef ATT_DIRECT_STORE
+#define ATT_DIRECT_STORE 0  // 1: epilogue writes O rows straight to global memory instead of staging + TMA store
+#endif
+#ifndef ATT_PHALF
+#define ATT_PHALF 1  // 1: hand the first 96 keys of P to the tensor core before the softmax has finished the row
+#endif
 constexpr int ATT_THREADS = 160;           // warps 0-3 softmax/epilogue, warp 4 TMA + MMA + TMEM alloc
 
 template <int KP>
@@ -38,21 +49,56 @@ struct AttSmem {
   static constexpr int OFF_K = Q_BYTES;
   static constexpr int OFF_V = OFF_K + ((KV_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_STG = OFF_V + ((KV_BYTES + 1023) / 1024) * 1024;
-  static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
-  static constexpr int BYTES = OFF_BAR + 64;
+  static constexpr int OFF_BAR = OFF_STG + (ATT_DIRECT_STORE ? 0 : STG_BYTES);
+  static constexpr int BYTES = OFF_BAR + 128;
 };
 
-struct AttItem {
-  int seq, head, tile;
+#ifdef FC_GEMM_TIMING
+// Diagnostics build only (make TIMING=1): cycles of softmax warp 0, summed over CTAs and items.
+//   [0] whole loop  [1] wait S main  [2] pass 1  [3] wait S tail  [4] pass 2  [5] wait O  [6] epilogue  [7] items
+__device__ unsigned long long g_att_timing[8];
+#define FC_T(...) __VA_ARGS__
+#else
+#define FC_T(...)
+#endif
+
+// Work-item cursor: item -> (sequence, head, query tile) without a division per item (the grid stride is decomposed once).
+struct ItemCursor {
+  int t, head, seq;
+  int dt, dhead, dseq, tiles, heads;
+  __device__ __forceinline__ void init(int item, int step, int tiles_, int heads_) {
+    tiles = tiles_;
+    heads = heads_;
+    t = item % tiles;
+    const int sh = item / tiles;
+    head = sh % heads;
+    seq = sh / heads;
+    dt = step % tiles;
+    const int dsh = step / tiles;
+    dhead = dsh % heads;
+    dseq = dsh / heads;
+  }
+  __device__ __forceinline__ void advance() {
+    t += dt;
+    int c = t >= tiles ? 1 : 0;
+    t -= c * tiles;
+    head += dhead + c;
+    c = head >= heads ? 1 : 0;
+    head -= c * heads;
+    seq += dseq + c;
+  }
 };
 
 template <int KP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                    const __grid_constant__ CUtensorMap tmO, int L, int heads, int tiles, int num_items,
-                    float scale_log2) {
+                    const __grid_constant__ CUtensorMap tmO, bf16* __restrict__ out, int L, int heads, int tiles,
+                    int num_items, float scale_log2) {
   using S = AttSmem<KP>;
-  static_assert(KP % 16 == 0 && KP >= 16 && KP <= 256, "padded key count");
+  static_assert(KP % 32 == 16 && KP >= 112 && KP <= 208, "padded key count: whole x32 chunks plus one 16-key tail");
+  constexpr int KMAIN = KP - 16;  // keys / S columns of the main group
+  constexpr int O_COL = KMAIN;    // O accumulator columns [KP-16, KP+48): the tail of S and the columns behind it
+  constexpr int KHALF = 96;       // keys whose P is handed to the tensor core early (3 x32 chunks = 6 MMA k-steps)
   static_assert(KP / 2 <= O_COL && O_COL + HD <= 256, "P / O column ranges must not overlap");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* kq_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -61,35 +107,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_full = kq_full + 3;
   uint64_t* o_full = kq_full + 4;
   uint64_t* o_empty = kq_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 6);
+  uint64_t* t_full = kq_full + 6;  // tail columns of S
+  uint64_t* p_half = kq_full + 7;  // P of the first KHALF keys is in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * HD;
   const bool flip_ok = (gridDim.x & 1) == 0 && tiles == 2;  // alternate heavy/light tiles between iterations
-
-  auto decode = [&](int item, int it) {
-    AttItem w;
-    int t = item % tiles;
-    const int sh = item / tiles;
-    if (flip_ok) t ^= (it & 1);
-    w.tile = t;
-    w.head = sh % heads;
-    w.seq = sh / heads;
-    return w;
-  };
 
   griddep_launch_dependents();
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   if (threadIdx.x == 128) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    tma_prefetch_desc(&tmO);
+    if (!ATT_DIRECT_STORE) tma_prefetch_desc(&tmO);
     mbar_init(kq_full, 1);
     mbar_init(v_full, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 128);
+    mbar_init(t_full, 1);
+    mbar_init(p_half, 128);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
@@ -102,144 +141,213 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 4) {
     // ===================== TMA + MMA thread =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(QT, KP);
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(QT, KMAIN);
+      constexpr uint32_t idesc_t = umma_idesc_bf16_f32(QT, 16);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32_bmn(QT, HD);
       const uint32_t q_addr = smem_u32(smem + S::OFF_Q);
       const uint32_t k_addr = smem_u32(smem + S::OFF_K);
       const uint32_t v_addr = smem_u32(smem + S::OFF_V);
-      auto load_qk = [&](const AttItem& w) {
+      // `n`: ordinal of the item within this CTA (decides the heavy/light flip)
+      auto load_qk = [&](const ItemCursor& c, int n) {
+        const int tile = flip_ok ? (c.t ^ (n & 1)) : c.t;
         mbar_expect_tx(kq_full, Q_BYTES + S::KV_BYTES);
-        tma_load_3d(smem + S::OFF_Q, &tmQ, kq_full, w.head * HD, w.tile * QT, w.seq);
-        tma_load_3d(smem + S::OFF_K, &tmKV, kq_full, D + w.head * HD, 0, w.seq);
+        tma_load_3d(smem + S::OFF_Q, &tmQ, kq_full, c.head * HD, tile * QT, c.seq);
+        tma_load_3d(smem + S::OFF_K, &tmKV, kq_full, D + c.head * HD, 0, c.seq);
       };
-      auto load_v = [&](const AttItem& w) {
+      auto load_v = [&](const ItemCursor& c) {
         mbar_expect_tx(v_full, S::KV_BYTES);
-        tma_load_3d(smem + S::OFF_V, &tmKV, v_full, 2 * D + w.head * HD, 0, w.seq);
+        tma_load_3d(smem + S::OFF_V, &tmKV, v_full, 2 * D + c.head * HD, 0, c.seq);
       };
-      int it = 0;
-      if (static_cast<int>(blockIdx.x) < num_items) {
-        const AttItem w0 = decode(blockIdx.x, 0);
-        load_qk(w0);
-        load_v(w0);
-      }
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const uint32_t ph = it & 1;
-        const int next = item + gridDim.x;
-        // S(it) overwrites TMEM columns the epilogue of item it-1 may still be reading
-        if (it > 0) mbar_wait(o_empty, (it - 1) & 1);
-        mbar_wait(kq_full, ph);
-        tc_fence_after();
+      auto issue_s_main = [&]() {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s,
                        k != 0);
         umma_commit(s_full);
-        mbar_wait(s_full, ph);  // Q and K tiles are free again
-        if (next < num_items) load_qk(decode(next, it + 1));
+      };
+      auto issue_s_tail = [&]() {  // keys [KMAIN, KP): K rows from byte offset KMAIN * 128 (a whole number of 8-row atoms)
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base + KMAIN, umma_desc_k_sw128(q_addr + k * 32),
+                       umma_desc_k_sw128(k_addr + KMAIN * 128 + k * 32), idesc_t, k != 0);
+        umma_commit(t_full);
+      };
+      ItemCursor cv, cqk;  // the items whose V / whose Q,K are loaded next
+      cv.init(blockIdx.x, gridDim.x, tiles, heads);
+      cqk = cv;
+      if (static_cast<int>(blockIdx.x) < num_items) {
+        load_qk(cqk, 0);
+        load_v(cv);
+        cqk.advance();
+        cv.advance();
+        mbar_wait(kq_full, 0);
+        tc_fence_after();
+        issue_s_main();
+        issue_s_tail();
+        mbar_wait(t_full, 0);  // Q and K tiles are free again
+        if (static_cast<int>(blockIdx.x + gridDim.x) < num_items) load_qk(cqk, 1);
+        cqk.advance();
+      }
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int next = item + gridDim.x, next2 = next + gridDim.x;
+        const bool has_next = next < num_items;
         mbar_wait(v_full, ph);
-        mbar_wait(p_full, ph);  // all 128 rows of P are in TMEM
+        if (ATT_PHALF) {
+          mbar_wait(p_half, ph);  // P of keys [0, KHALF) is in TMEM: start O = P.V while the softmax finishes the rest
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < KHALF / 16; ++k)
+            umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
+        }
+        mbar_wait(p_full, ph);  // all of P is in TMEM
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < KP / 16; ++k)
+        for (int k = ATT_PHALF ? KHALF / 16 : 0; k < KP / 16; ++k)
           umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
         umma_commit(o_full);
+        if (has_next) {
+          // main part of S(it+1): queued right behind P.V (which consumes P before these MMAs overwrite it); it leaves
+          // the O columns alone, so it overlaps the softmax warps' read-out of O(it)
+          mbar_wait(kq_full, ph ^ 1);
+          tc_fence_after();
+          issue_s_main();
+        }
         mbar_wait(o_full, ph);  // V tile is free again
-        if (next < num_items) load_v(decode(next, it + 1));
+        if (has_next) {
+          load_v(cv);
+          cv.advance();
+          mbar_wait(o_empty, ph);  // O(it) has been read out: the tail columns may be overwritten
+          tc_fence_after();
+          issue_s_tail();
+          mbar_wait(t_full, ph ^ 1);  // Q and K tiles are free again
+          if (next2 < num_items) load_qk(cqk, it + 2);
+          cqk.advance();
+        }
       }
     }
   } else {
     // ===================== softmax + epilogue warps (one query row per thread) =====================
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    uint8_t* stg_ptr = smem + S::OFF_STG + warp * (32 * 128);
-    const uint32_t stg_row = smem_u32(stg_ptr) + lane * 128;
-    const int sw = lane & 7;
-    constexpr int NFULL = KP / 32;      // x32 chunks
-    constexpr bool REM = (KP % 32) != 0;  // one trailing x16 chunk
+    constexpr int NFULL = KP / 32;  // x32 chunks (main columns); the 16-column tail follows
+    static_assert(KHALF % 32 == 0 && KHALF / 32 < NFULL, "early hand-over must end on a chunk boundary");
+    ItemCursor cur;
+    cur.init(blockIdx.x, gridDim.x, tiles, heads);
     int it = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+    FC_T(long long tq[7] = {0, 0, 0, 0, 0, 0, 0}; long long n_it = 0; const long long t_begin = clock64();)
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it, cur.advance()) {
       const uint32_t ph = it & 1;
-      const AttItem w = decode(item, it);
-      const int row0 = w.tile * QT + warp * 32;
+      const int tile = flip_ok ? (cur.t ^ (it & 1)) : cur.t;
+      const int row0 = tile * QT + warp * 32;
       const bool active = row0 < L;  // warp-uniform: warps whose 32 rows all lie beyond the sequence only sync
+      FC_T(long long t0 = clock64(); long long t1;)
       mbar_wait(s_full, ph);
+      FC_T(t1 = clock64(); tq[1] += t1 - t0; t0 = t1; ++n_it;)
       tc_fence_after();
       float l = 0.f;
+      float m = -INFINITY;
       if (active) {
-        // ---- pass 1: row maximum
-        float m = -INFINITY;
-        {
-          uint32_t r[2][32];
-          uint32_t r16[16];
-          tmem_ld_32x32b_x32(trow, r[0]);
+        // ---- pass 1 (main columns): row maximum; four independent FMNMX3 chains, two columns per instruction
+        float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(trow, r[0]);
 #pragma unroll
-          for (int j = 0; j < NFULL; ++j) {
-            tmem_ld_wait_fence(r[j & 1]);
-            if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
-            else if (REM) tmem_ld_32x32b_x16(trow + NFULL * 32, r16);
-            if ((j + 1) * 32 <= L) {
+        for (int j = 0; j < NFULL; ++j) {
+          tmem_ld_wait_fence(r[j & 1]);
+          if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
+          const uint32_t(&rc)[32] = r[j & 1];
+          if ((j + 1) * 32 <= L) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(r[j & 1][c]));
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (j * 32 + c < L) m = fmaxf(m, __uint_as_float(r[j & 1][c]));
+            for (int c = 0; c < 32; c += 8) {
+              m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
+              m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
+              m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
+              m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
             }
-          }
-          if (REM) {
-            tmem_ld_wait_fence16(r16);
+          } else {
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
-              if (NFULL * 32 + c < L) m = fmaxf(m, __uint_as_float(r16[c]));
+            for (int c = 0; c < 32; ++c)
+              if (j * 32 + c < L) m = fmaxf(m, __uint_as_float(rc[c]));
           }
         }
-        // ---- pass 2: P = exp2((s - m) * scale * log2e), row sum in fp32, P -> bf16 -> TMEM (over the S columns)
+        m = fmaxf(max3(m, m1, m2), m3);
+      }
+      FC_T(t1 = clock64(); tq[2] += t1 - t0; t0 = t1;)
+      mbar_wait(t_full, ph);  // the 16 tail columns arrive a little later (they share TMEM columns with the previous O)
+      FC_T(t1 = clock64(); tq[3] += t1 - t0; t0 = t1;)
+      tc_fence_after();
+      if (active) {
+        // ---- pass 2: P = exp2((s - m) * scale * log2e), row sum in fp32, P -> bf16 -> TMEM (over the S columns).
+        // The tail goes FIRST and its P waits in registers: the early P.V below writes O over the tail's S columns.
+        uint32_t r16[16];
+        tmem_ld_32x32b_x16(trow + NFULL * 32, r16);
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(trow, r[0]);
+        tmem_ld_wait_fence16(r16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (NFULL * 32 + c < L) m = fmaxf(m, __uint_as_float(r16[c]));
         const float mc = m * scale_log2;
-        {
-          uint32_t r[2][32];
-          uint32_t r16[16];
-          tmem_ld_32x32b_x32(trow, r[0]);
+        const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nmc2 = pack_f32x2(-mc, -mc);
+        uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;  // packed partial row sums (FADD2), two chains
+        uint32_t pk_tail[8];
 #pragma unroll
-          for (int j = 0; j < NFULL; ++j) {
-            tmem_ld_wait_fence(r[j & 1]);
-            if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
-            else if (REM) tmem_ld_32x32b_x16(trow + NFULL * 32, r16);
-            uint32_t pk[16];
-            const bool full = (j + 1) * 32 <= L;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(r[j & 1][2 * c]), scale_log2, -mc));
-              float p1 = ex2_approx(fmaf(__uint_as_float(r[j & 1][2 * c + 1]), scale_log2, -mc));
-              if (!full) {
-                if (j * 32 + 2 * c >= L) p0 = 0.f;
-                if (j * 32 + 2 * c + 1 >= L) p1 = 0.f;
-              }
-              l += p0 + p1;
-              pk[c] = pack_bf16x2(p0, p1);
-            }
-            tmem_st_32x32b_x16(trow + j * 16, pk);
-          }
-          if (REM) {
-            tmem_ld_wait_fence16(r16);
-            uint32_t pk[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(r16[2 * c]), scale_log2, -mc));
-              float p1 = ex2_approx(fmaf(__uint_as_float(r16[2 * c + 1]), scale_log2, -mc));
-              if (NFULL * 32 + 2 * c >= L) p0 = 0.f;
-              if (NFULL * 32 + 2 * c + 1 >= L) p1 = 0.f;
-              l += p0 + p1;
-              pk[c] = pack_bf16x2(p0, p1);
-            }
-            tmem_st_32x32b_x8(trow + NFULL * 16, pk);
-          }
-          tmem_st_wait();
+        for (int c = 0; c < 8; ++c) {
+          float x0, x1;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r16[2 * c]), __uint_as_float(r16[2 * c + 1])), sc2, nmc2), x0,
+                       x1);
+          float p0 = ex2_approx(x0);
+          float p1 = ex2_approx(x1);
+          if (NFULL * 32 + 2 * c >= L) p0 = 0.f;
+          if (NFULL * 32 + 2 * c + 1 >= L) p1 = 0.f;
+          l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+          pk_tail[c] = pack_bf16x2(p0, p1);
         }
+#pragma unroll
+        for (int j = 0; j < NFULL; ++j) {
+          tmem_ld_wait_fence(r[j & 1]);
+          if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
+          uint32_t pk[16];
+          const bool full = (j + 1) * 32 <= L;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float x0, x1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
+                                   sc2, nmc2),
+                         x0, x1);
+            float p0 = ex2_approx(x0);
+            float p1 = ex2_approx(x1);
+            if (!full) {
+              if (j * 32 + 2 * c >= L) p0 = 0.f;
+              if (j * 32 + 2 * c + 1 >= L) p1 = 0.f;
+            }
+            if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+            else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
+            pk[c] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x32b_x16(trow + j * 16, pk);
+          if (ATT_PHALF && j == KHALF / 32 - 1) {  // first KHALF keys done: let the tensor core start on them
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_half);
+          }
+        }
+        tmem_st_32x32b_x8(trow + NFULL * 16, pk_tail);
+        tmem_st_wait();
+        float la, lb;
+        unpack_f32x2(add_f32x2(l2a, l2b), la, lb);
+        l = la + lb;
+      } else if (ATT_PHALF) {
+        mbar_arrive(p_half);
       }
       tc_fence_before();
       mbar_arrive(p_full);
+      FC_T(t1 = clock64(); tq[4] += t1 - t0; t0 = t1;)
 
-      // ---- epilogue: O / l -> bf16 -> staging -> TMA store
+      // ---- epilogue: O / l -> bf16 -> global (every thread owns one 128-byte row segment: full lines, no staging)
       mbar_wait(o_full, ph);
+      FC_T(t1 = clock64(); tq[5] += t1 - t0; t0 = t1;)
       tc_fence_after();
       uint32_t o0[32], o1[32];
       if (active) {
@@ -250,30 +358,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(o_empty);
-      if (active) {
+      const int row = row0 + lane;
+      if (ATT_DIRECT_STORE ? (active && row < L) : active) {
         const float inv = 1.f / l;
-        if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous store has finished reading its staging tile
-        __syncwarp();
+        const uint64_t inv2 = pack_f32x2(inv, inv);
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(cur.seq) * L + row) * D + cur.head * HD);
+        uint8_t* stg_ptr = smem + S::OFF_STG + warp * (32 * 128);
+        const uint32_t stg_row = smem_u32(stg_ptr) + lane * 128;
+        const int sw = lane & 7;
+        if (!ATT_DIRECT_STORE) {
+          if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous store has finished reading its staging tile
+          __syncwarp();
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint32_t(&rr)[32] = c < 4 ? o0 : o1;
           const int o = (c & 3) * 8;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(rr[o + 2 * e]), __uint_as_float(rr[o + 2 * e + 1])), inv2),
+                         v[2 * e], v[2 * e + 1]);
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(rr[o + 0]) * inv, __uint_as_float(rr[o + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(rr[o + 2]) * inv, __uint_as_float(rr[o + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(rr[o + 4]) * inv, __uint_as_float(rr[o + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(rr[o + 6]) * inv, __uint_as_float(rr[o + 7]) * inv);
-          st_shared_v4(stg_row + ((c ^ sw) << 4), u);
+          u.x = pack_bf16x2(v[0], v[1]);
+          u.y = pack_bf16x2(v[2], v[3]);
+          u.z = pack_bf16x2(v[4], v[5]);
+          u.w = pack_bf16x2(v[6], v[7]);
+          if (ATT_DIRECT_STORE) dst[c] = u;
+          else st_shared_v4(stg_row + ((c ^ sw) << 4), u);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&tmO, stg_ptr, w.head * HD, row0, w.seq);  // rows >= L are clipped by the tensor map
-          bulk_commit_group();
+        if (!ATT_DIRECT_STORE) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO, stg_ptr, cur.head * HD, row0, cur.seq);  // rows >= L are clipped by the tensor map
+            bulk_commit_group();
+          }
         }
       }
+      FC_T(t1 = clock64(); tq[6] += t1 - t0;)
     }
-    if (lane == 0) bulk_wait_group<0>();
+    FC_T(if (threadIdx.x == 0) {
+      atomicAdd(&g_att_timing[0], static_cast<unsigned long long>(clock64() - t_begin));
+      for (int i = 1; i < 7; ++i) atomicAdd(&g_att_timing[i], static_cast<unsigned long long>(tq[i]));
+      atomicAdd(&g_att_timing[7], static_cast<unsigned long long>(n_it));
+    })
+    if (!ATT_DIRECT_STORE && lane == 0) bulk_wait_group<0>();
   }
 
   tc_fence_before();
@@ -356,11 +486,23 @@ int launch_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaSt
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   note_launch();
-  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<KP>, tq, tkv, to, L, heads, tiles, items, scale_log2));
+  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<KP>, tq, tkv, to, out, L, heads, tiles, items, scale_log2));
   return FC_OK;
 }
 
 }  // namespace
+
+#ifdef FC_GEMM_TIMING
+extern "C" __attribute__((visibility("default"))) int fc_debug_att_timing(unsigned long long* out, int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (out && cudaMemcpyFromSymbol(out, g_att_timing, sizeof(g_att_timing)) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[8] = {};
+    if (cudaMemcpyToSymbol(g_att_timing, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif
 
 // tcgen05 path: un-masked sequences of 193..208 tokens (the ViT-B/16 image sequence, 197). Returns 1 if it handled the call.
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
