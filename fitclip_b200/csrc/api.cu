@@ -394,8 +394,8 @@ int fc_model_create(const fc_config* cfg, fc_model** out) {
     set_error("fc_model_create: sequence length above 208 tokens is not supported yet");
     return FC_ERR_INVALID;
   }
-  m->maxF = c.max_frames_per_pass > 0 ? c.max_frames_per_pass : 256;
-  m->maxC = c.max_texts_per_pass > 0 ? c.max_texts_per_pass : 984;
+  m->maxF = c.max_frames_per_pass > 0 ? c.max_frames_per_pass : 512;
+  m->maxC = c.max_texts_per_pass > 0 ? c.max_texts_per_pass : 1024;
   ArenaPlan sizing;
   plan_model(m, sizing, false);
   m->arena_bytes = sizing.off;
@@ -468,7 +468,10 @@ int fc_encode_video(fc_model* m, const void* frames, int dtype, int64_t videos, 
   const fc_config& c = m->cfg;
   const int64_t frame_elems = int64_t(3) * c.image_resolution * c.image_resolution;
   const int64_t esz = dtype == FC_F32 ? 4 : 2;
-  const int64_t vids_per_pass = m->maxF / T;
+  // equal-sized passes (a short last pass would pay the same launch latencies and wave tails as a full one)
+  const int64_t max_vids = m->maxF / T;
+  const int64_t n_passes = (videos + max_vids - 1) / max_vids;
+  const int64_t vids_per_pass = n_passes ? (videos + n_passes - 1) / n_passes : 1;
   for (int64_t v0 = 0; v0 < videos; v0 += vids_per_pass) {
     const int64_t nv = std::min(vids_per_pass, videos - v0);
     const uint8_t* src = static_cast<const uint8_t*>(frames) + v0 * T * frame_elems * esz;
@@ -490,8 +493,10 @@ int fc_encode_text(fc_model* m, const int32_t* ids, int64_t texts, float* out_te
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (int frc = finalize(m, s)) return frc;
   const fc_config& c = m->cfg;
-  for (int64_t c0 = 0; c0 < texts; c0 += m->maxC) {
-    const int64_t n = std::min<int64_t>(m->maxC, texts - c0);
+  const int64_t n_passes = (texts + m->maxC - 1) / m->maxC;
+  const int64_t per_pass = n_passes ? (texts + n_passes - 1) / n_passes : 1;
+  for (int64_t c0 = 0; c0 < texts; c0 += per_pass) {
+    const int64_t n = std::min<int64_t>(per_pass, texts - c0);
     int rc = text_pass(m, ids + c0 * c.context_length, n, m->feat, s);
     if (rc) return rc;
     rc = pool_normalize(m->feat, out_text + c0 * c.embed_dim, nullptr, n, 1, c.embed_dim, 1.f, s);

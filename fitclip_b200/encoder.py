@@ -84,8 +84,8 @@ class B200Clip(nn.Module):
     ``state_dict()`` uses the OpenAI names (e.g. ``clip.model.CLIP``); ``logit_scale`` is kept if present so that
     checkpoints load strictly, exactly like the reference's model object."""
 
-    def __init__(self, source: Union[Mapping[str, torch.Tensor], nn.Module], max_frames_per_pass: int = 256,
-                 max_texts_per_pass: int = 984) -> None:
+    def __init__(self, source: Union[Mapping[str, torch.Tensor], nn.Module], max_frames_per_pass: int = 512,
+                 max_texts_per_pass: int = 1024) -> None:
         super().__init__()
         state_dict = source.state_dict() if isinstance(source, nn.Module) else source
         state_dict = {k: v for k, v in state_dict.items()

@@ -57,8 +57,8 @@ typedef struct fc_config {
   int32_t transformer_width;
   int32_t transformer_heads;
   int32_t transformer_layers;
-  int32_t max_frames_per_pass; /* frames encoded per internal pass (workspace is sized for it); 0 = 256 */
-  int32_t max_texts_per_pass;  /* captions encoded per internal pass; 0 = 984 */
+  int32_t max_frames_per_pass; /* max frames per internal pass (workspace is sized for it; passes are equal-sized); 0 = 512 */
+  int32_t max_texts_per_pass;  /* max captions per internal pass; 0 = 1024 */
 } fc_config;
 
 typedef struct fc_model fc_model;
