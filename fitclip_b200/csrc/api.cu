@@ -518,6 +518,13 @@ int fc_model_check(fc_model* m, void* stream) {
   return FC_OK;
 }
 
+int fc_preprocess_frames(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size, const float* mean,
+                         const float* std, void* out, int out_dtype, void* stream) {
+  int rc = check_arch();
+  if (rc) return rc;
+  return preprocess_frames(frames, n, H, W, size, mean, std, out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
 int fc_pool_normalize(const float* x, float* out, void* out_bf16, int64_t rows_out, int32_t T, int32_t D, float scale,
                       void* stream) {
   return pool_normalize(x, out, static_cast<bf16*>(out_bf16), rows_out, T, D, scale,

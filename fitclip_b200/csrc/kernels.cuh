@@ -25,6 +25,10 @@ int wise_lerp(const float* p1, const float* p2, float* out, bf16* out_bf16, int6
 int f32_to_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s);
 int split_bf16(const float* in, bf16* out, int64_t rows, int D, int mode, int terms, cudaStream_t s);
 
+// preprocess.cu : uint8 (F,H,W,3) -> [x/255 -> bicubic resize (shorter side = size) -> centre crop -> normalise] -> (F,3,size,size)
+int preprocess_frames(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
+                      void* out, int out_dtype, cudaStream_t s);
+
 // attention.cu : out[s*L + l, h*64 + d] = softmax(q k^T / 8 [+ causal mask]) v, qkv rows are [q | k | v] of width 3*D
 int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s);
 // attention_tc.cu : tcgen05 path for the un-masked 193..208-token case; *handled = 1 when it took the call

@@ -1,0 +1,127 @@
+// Evaluation pre-processing on the GPU: what the reference does per frame on CPU DataLoader
+// workers -- aligner/encoder/clip_video_text_encoder.py:124-133:
+//   ConvertBHWCtoBCHW -> ConvertImageDtype(float) [x / 255] -> Resize(size, BICUBIC) [shorter side -> size, no
+//   antialias for tensors in the pinned torchvision 0.12] -> CenterCrop(size) -> Normalize(mean, std)
+// fused into one pass: uint8 (F, H, W, 3) -> fp32 / bf16 (F, 3, size, size), only the cropped window is computed.
+// The arithmetic restates ATen's upsample_bicubic2d (align_corners = false, A = -0.75, border-replicated taps).
+#include <math.h>
+
+#include "kernels.cuh"
+
+namespace fc {
+
+namespace {
+
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+  const float A = -0.75f;
+  c[0] = cubic2(t + 1.f, A);
+  c[1] = cubic1(t, A);
+  const float u = 1.f - t;
+  c[2] = cubic1(u, A);
+  c[3] = cubic2(u + 1.f, A);
+}
+
+struct PreParams {
+  int H, W;        // source frame
+  int RH, RW;      // resized frame (shorter side == size)
+  int top, left;   // crop offset inside the resized frame
+  int size;        // output side
+  float scale_h, scale_w;
+  float mean[3], stdv[3];
+};
+
+template <typename TOut>
+__device__ __forceinline__ void store_px(TOut* p, float v);
+template <>
+__device__ __forceinline__ void store_px<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_px<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// One thread = one output pixel (all three channels); consecutive threads walk an output row, so the three channel
+// planes are written with fully coalesced stores and the byte taps of neighbouring threads share cache lines.
+template <typename TOut>
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out,
+                                                         int64_t frames, const PreParams p) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  const int64_t f = blockIdx.z;
+  if (ox >= p.size) return;
+  // source coordinates of this output pixel in the resized (un-cropped) frame
+  const float ry = p.scale_h * (static_cast<float>(oy + p.top) + 0.5f) - 0.5f;
+  const float rx = p.scale_w * (static_cast<float>(ox + p.left) + 0.5f) - 0.5f;
+  const float fy = floorf(ry), fx = floorf(rx);
+  const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+  float cy[4], cx[4];
+  cubic_coeffs(ry - fy, cy);
+  cubic_coeffs(rx - fx, cx);
+  int xs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) xs[j] = min(max(ix - 1 + j, 0), p.W - 1) * 3;
+  const uint8_t* src = in + f * static_cast<int64_t>(p.H) * p.W * 3;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int y = min(max(iy - 1 + i, 0), p.H - 1);
+    const uint8_t* row = src + static_cast<int64_t>(y) * p.W * 3;
+    float r[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) r[c] += (static_cast<float>(__ldg(row + xs[j] + c)) / 255.f) * cx[j];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += r[c] * cy[i];
+  }
+  const int64_t plane = static_cast<int64_t>(p.size) * p.size;
+  TOut* dst = out + f * 3 * plane + static_cast<int64_t>(oy) * p.size + ox;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) store_px<TOut>(dst + c * plane, (acc[c] - p.mean[c]) / p.stdv[c]);
+}
+
+}  // namespace
+
+int preprocess_frames(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
+                      void* out, int out_dtype, cudaStream_t s) {
+  FC_REQUIRE(frames && out && mean && stdv, "preprocess: null pointer");
+  FC_REQUIRE(F >= 0 && H > 0 && W > 0 && size > 0, "preprocess: bad shape F=%lld H=%d W=%d size=%d",
+             static_cast<long long>(F), H, W, size);
+  FC_REQUIRE(F <= 65535, "preprocess: at most 65535 frames per call (got %lld)", static_cast<long long>(F));
+  if (F == 0) return FC_OK;
+  PreParams p;
+  p.H = H;
+  p.W = W;
+  p.size = size;
+  // torchvision _compute_resized_output_size: the shorter side becomes `size`, the longer int(size * long / short)
+  if (W <= H) {
+    p.RW = size;
+    p.RH = static_cast<int>(static_cast<double>(size) * H / W);
+  } else {
+    p.RH = size;
+    p.RW = static_cast<int>(static_cast<double>(size) * W / H);
+  }
+  // torchvision center_crop: int(round((h - crop) / 2.0)) with Python's round-half-to-even
+  p.top = static_cast<int>(nearbyint((p.RH - size) / 2.0));
+  p.left = static_cast<int>(nearbyint((p.RW - size) / 2.0));
+  p.scale_h = static_cast<float>(H) / static_cast<float>(p.RH);
+  p.scale_w = static_cast<float>(W) / static_cast<float>(p.RW);
+  for (int c = 0; c < 3; ++c) {
+    p.mean[c] = mean[c];
+    p.stdv[c] = stdv[c];
+    FC_REQUIRE(stdv[c] != 0.f, "preprocess: std[%d] is zero", c);
+  }
+  ProfScope prof(s, PROF_OTHER, 1, F, H, W, 0.0,
+                 static_cast<double>(F) * (3.0 * H * W + 3.0 * size * size * (out_dtype == FC_DTYPE_F32 ? 4 : 2)));
+  dim3 grid((size + 255) / 256, size, static_cast<unsigned>(F));
+  if (out_dtype == FC_DTYPE_F32)
+    preprocess_kernel<float><<<grid, 256, 0, s>>>(frames, static_cast<float*>(out), F, p);
+  else if (out_dtype == FC_DTYPE_BF16)
+    preprocess_kernel<bf16><<<grid, 256, 0, s>>>(frames, static_cast<bf16*>(out), F, p);
+  else
+    FC_REQUIRE(false, "preprocess: output dtype must be fp32 (0) or bf16 (1), got %d", out_dtype);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+}  // namespace fc

@@ -230,6 +230,15 @@ class B200ClipVideoTextEncoder(VideoTextEncoder):
         # clip_video_text_encoder.py:80-89 -- fused natively: encode_image, x/||x|| per frame, mean over frames
         return self.model.encode_video_pooled(video)
 
+    def encode_video_uint8(self, video: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+        """Raw decoded frames ``(B, T, H, W, 3)`` uint8 on the GPU -> ``(B, E)``: the eval transform
+        (``get_eval_transform``, clip_video_text_encoder.py:124-133) runs as one CUDA kernel in front of the encoder
+        instead of on DataLoader workers.  ``dtype`` is the precision of the normalised frames handed to the patch
+        embedding (the tensor cores consume bf16 either way)."""
+        from . import ops
+        frames = ops.preprocess_frames(video, self.model.visual.input_resolution, CLIP_MEAN, CLIP_STD, dtype)
+        return self.model.encode_video_pooled(frames)
+
     def encode_text(self, text: TYPE_TEXT_INPUT) -> torch.Tensor:
         # clip_video_text_encoder.py:92-94
         return self.model.encode_text_normalized(text["input_ids"])

@@ -54,6 +54,29 @@ def attention_bf16(qkv: torch.Tensor, seqs: int, L: int, heads: int, causal: boo
     return out
 
 
+def preprocess_frames(frames: torch.Tensor, size: int, mean, std, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """uint8 ``(..., H, W, 3)`` frames -> ``(..., 3, size, size)`` of ``dtype`` (fp32 / bf16): the reference's eval
+    transform (``aligner/encoder/clip_video_text_encoder.py:124-133``: /255, bicubic resize of the shorter side to
+    ``size``, centre crop, normalise) as one kernel on the GPU."""
+    import ctypes as C
+    dev = _dev(frames)
+    if frames.dtype != torch.uint8 or frames.dim() < 3 or frames.shape[-1] != 3:
+        raise ValueError(f"expected uint8 frames of shape (..., H, W, 3), got {frames.dtype} {tuple(frames.shape)}")
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("preprocess_frames emits fp32 or bf16")
+    lead, (H, W) = frames.shape[:-3], frames.shape[-3:-1]
+    flat = frames.reshape(-1, H, W, 3).contiguous()
+    out = torch.empty(flat.shape[0], 3, size, size, device=dev, dtype=dtype)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    with torch.cuda.device(dev):
+        for lo in range(0, flat.shape[0], 65535):  # the kernel takes at most 65535 frames per launch
+            chunk = flat[lo:lo + 65535]
+            check(_lib.load().fc_preprocess_frames(ptr(chunk), chunk.shape[0], H, W, size, m3, s3, ptr(out[lo:]),
+                                                   _lib.DTYPE_CODE[dtype], stream_ptr(dev)))
+    return out.reshape(*lead, 3, size, size)
+
+
 def pool_normalize(x: torch.Tensor, frames_per_row: int, scale: float = 1.0) -> torch.Tensor:
     """``x (B*T, D)`` fp32 -> ``(B, D)``: L2-normalise every row, mean over each group of T rows
     (``aligner/encoder/clip_video_text_encoder.py:85-89``)."""

@@ -1,6 +1,10 @@
 """Pre-processing hooks returned by the encoder (``aligner/encoder/clip_video_text_encoder.py:113-133``,
 ``aligner/transforms.py:13-17,56-61``).  They run on CPU inside DataLoader workers, so they are plain picklable
-torchvision pipelines; nothing here touches CUDA."""
+torchvision pipelines; nothing here touches CUDA.  (The GPU twin of the eval pipeline is
+``fitclip_b200.ops.preprocess_frames`` / ``B200ClipVideoTextEncoder.encode_video_uint8``.)
+
+``antialias=False`` is spelled out: the reference pins torchvision 0.12, which never antialiases tensor inputs, while
+current torchvision defaults to antialiasing -- the explicit flag keeps the reference's pixels on any version."""
 from __future__ import annotations
 
 import random
@@ -25,14 +29,14 @@ class RandomResizedCropWithRandomInterpolation(RandomResizedCrop):
     def forward(self, img: torch.Tensor) -> torch.Tensor:
         i, j, h, w = self.get_params(img, self.scale, self.ratio)
         interpolation = random.choice([InterpolationMode.BILINEAR, InterpolationMode.BICUBIC])
-        return F.resized_crop(img, i, j, h, w, self.size, interpolation)
+        return F.resized_crop(img, i, j, h, w, self.size, interpolation, antialias=False)
 
 
 def eval_transform(size: int, dtype: torch.dtype, mean: Sequence[float], std: Sequence[float]) -> T.Compose:
     return T.Compose([
         ConvertBHWCtoBCHW(),
         T.ConvertImageDtype(dtype),
-        T.Resize(size, interpolation=InterpolationMode.BICUBIC),
+        T.Resize(size, interpolation=InterpolationMode.BICUBIC, antialias=False),
         T.CenterCrop(size),
         T.Normalize(mean=mean, std=std),
     ])

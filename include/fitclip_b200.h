@@ -112,6 +112,14 @@ FC_API int fc_encode_text(fc_model* m, const int32_t* ids, int64_t texts, float*
 /* Synchronises `stream` and reports deferred device-side input errors (bad token ids). */
 FC_API int fc_model_check(fc_model* m, void* stream);
 
+/* ---- evaluation pre-processing (the step before the path; the reference runs it on CPU DataLoader workers) ------
+ * ClipVideoTextEncoder.get_eval_transform (clip_video_text_encoder.py:124-133): uint8 frames (n, H, W, 3) ->
+ * x/255 -> bicubic resize, shorter side = `size` (align_corners = false, no antialias, A = -0.75) -> centre crop
+ * `size` x `size` -> (x - mean[c]) / std[c] -> (n, 3, size, size) of out_dtype (FC_F32 or FC_BF16), which is what
+ * fc_encode_video takes.  mean / std: 3 HOST floats each.  n <= 65535 per call. */
+FC_API int fc_preprocess_frames(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size,
+                                const float* mean, const float* std, void* out, int out_dtype, void* stream);
+
 /* ---- pooling / WiSE ---------------------------------------------------------------------------------------------
  * out[b] = scale * mean_t( x[b*T+t] / ||x[b*T+t]||_2 ), fp32 (clip_video_text_encoder.py:85-89; T = 1 is the text
  * normalisation of :94).  out_bf16 may be NULL. */

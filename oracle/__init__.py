@@ -16,4 +16,5 @@ from .encoder_ref import RefClipVideoTextEncoder  # noqa: F401
 from .metrics_ref import (ref_accuracy_at_k, ref_median_rank, ref_rank, ref_recall_at_k,  # noqa: F401
                           ref_retrieval_metrics, ref_stable_rank)
 from .wise_ref import ref_wise, ref_wise_state_dict  # noqa: F401
+from .preprocess_ref import ref_eval_transform, ref_resized_size  # noqa: F401
 from .loss_ref import ref_nce_loss, ref_teacher_student_nce_loss  # noqa: F401

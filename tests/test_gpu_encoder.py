@@ -128,3 +128,49 @@ def test_bad_inputs_fail_loudly(models, dev):
     enc.encode_text({"input_ids": bad})
     with pytest.raises(_lib.FitclipError):
         enc.model.check_inputs()
+
+
+GEOMETRIES = {
+    # config/encoder/clip_vit_b_32.yaml: 224 / 32 -> 49 + 1 = 50 image tokens, 3072-wide patches
+    "vit_b_32": dict(vision_patch_size=32, vision_layers=2, transformer_layers=2),
+    # a narrow model: every width / head count / sequence length differs from ViT-B/16 (101 image tokens, 32 text tokens)
+    "narrow": dict(embed_dim=256, image_resolution=160, vision_width=512, vision_layers=2, context_length=32,
+                   transformer_width=256, transformer_heads=4, transformer_layers=2, vocab_size=1000),
+    # the widest tower the GEMM row-statistics path takes (ViT-L width, 16 heads) on the 197-token sequence
+    "wide": dict(vision_width=1024, vision_layers=1, transformer_layers=1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GEOMETRIES))
+def test_other_clip_geometries(dev, name):
+    """the kernels are shape-generic (widths multiples of 64 up to 1024, head dim 64, sequences up
+    to 208 tokens, patch sizes multiples of 8); the geometry is inferred from the state dict like clip.build_model."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder
+    cfg = GEOMETRIES[name]
+    ref_model = oracle.clip_vit_b_16(seed=3, **cfg)
+    ref = oracle.RefClipVideoTextEncoder(copy.deepcopy(ref_model))
+    enc = B200ClipVideoTextEncoder(ref_model.state_dict(), num_frames=2).to(dev)
+    res = cfg.get("image_resolution", 224)
+    ctx = cfg.get("context_length", 77)
+    vocab = cfg.get("vocab_size", 49408)
+    video = torch.randn(5, 2, 3, res, res, generator=torch.Generator().manual_seed(11))
+    ids = oracle.tokenize_synthetic(9, (3, ctx), seed=12, context_length=ctx, vocab_size=vocab)
+    with torch.inference_mode():
+        ev, et = ref(video, {"input_ids": ids})
+        gv, gt = enc(video.to(dev), {"input_ids": ids.to(dev)})
+    cos_v, max_v, _ = _report(f"{name} video", gv.cpu(), ev)
+    cos_t, max_t, _ = _report(f"{name} text", gt.cpu(), et)
+    assert cos_v >= 0.999 and cos_t >= 0.999
+    assert max_v <= 2e-2 and max_t <= 2e-2
+
+
+def test_unsupported_geometry_is_refused(dev):
+    """ViT-L/14 (257 image tokens, 14-pixel patches) is outside what the kernels take: the error must say so instead of
+    computing something else."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder, _lib
+    model = oracle.clip_vit_b_16(seed=0, vision_patch_size=14, vision_layers=1, transformer_layers=1)
+    enc = B200ClipVideoTextEncoder(model.state_dict()).to(dev)
+    with pytest.raises(_lib.FitclipError, match="patch size|sequence length"):
+        enc.encode_video(torch.zeros(1, 1, 3, 224, 224, device=dev))

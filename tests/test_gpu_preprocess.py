@@ -1,0 +1,66 @@
+"""GPU eval pre-processing kernel (fc_preprocess_frames) against the CPU oracle of the reference transform
+(oracle/preprocess_ref.py <- aligner/encoder/clip_video_text_encoder.py:124-133).
+
+Tolerance: fp32 taps and weights on both sides, different summation order and FMA contraction: max-abs <= 2e-5 on
+normalised pixels (|x| <= ~2.7, 1/std ~ 3.7 amplifies the interpolation rounding); bf16 output: one bf16 rounding
+(2^-9 relative)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MEAN, STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+
+
+@pytest.mark.parametrize("h,w", [(240, 320), (360, 202), (224, 224), (256, 256), (113, 400), (480, 270), (1080, 1920)])
+def test_preprocess_matches_oracle(dev, h, w):
+    import oracle
+    from fitclip_b200 import ops
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    video = torch.randint(0, 256, (2, h, w, 3), dtype=torch.uint8, generator=g)
+    ref = oracle.ref_eval_transform(video, 224, MEAN, STD)
+    got = ops.preprocess_frames(video.to(dev), 224, MEAN, STD)
+    assert got.shape == (2, 3, 224, 224) and got.dtype == torch.float32
+    err = (got.cpu() - ref).abs().max().item()
+    assert err <= 2e-5, err
+    got16 = ops.preprocess_frames(video.to(dev), 224, MEAN, STD, torch.bfloat16)
+    assert got16.dtype == torch.bfloat16
+    assert torch.allclose(got16.float().cpu(), ref, atol=1e-5, rtol=2 ** -8)
+
+
+def test_preprocess_batched_leading_dims_and_flat_colour(dev):
+    from fitclip_b200 import ops
+    # a constant image must stay constant through the cubic kernel (weights sum to one)
+    video = torch.full((2, 3, 300, 260, 3), 128, dtype=torch.uint8, device=dev)
+    out = ops.preprocess_frames(video, 224, MEAN, STD)
+    assert out.shape == (2, 3, 3, 224, 224)
+    for c in range(3):
+        expect = (128 / 255 - MEAN[c]) / STD[c]
+        assert (out[:, :, c] - expect).abs().max().item() <= 1e-5
+
+
+def test_encode_video_uint8_equals_transform_then_encode(dev):
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder, ops
+    sd = oracle.clip_vit_b_16(seed=0, vision_layers=1, transformer_layers=1).state_dict()
+    enc = B200ClipVideoTextEncoder(sd, num_frames=2).to(dev)
+    g = torch.Generator().manual_seed(5)
+    raw = torch.randint(0, 256, (3, 2, 240, 320, 3), dtype=torch.uint8, generator=g).to(dev)
+    a = enc.encode_video_uint8(raw, dtype=torch.float32)
+    b = enc.encode_video(ops.preprocess_frames(raw, 224, MEAN, STD))
+    assert torch.equal(a, b)
+    # and against the CPU path: hook on the CPU -> oracle encoder
+    ref_enc = oracle.RefClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0, vision_layers=1, transformer_layers=1))
+    frames = torch.stack([oracle.ref_eval_transform(v, 224, MEAN, STD) for v in raw.cpu()])
+    with torch.inference_mode():
+        ref = ref_enc.encode_video(frames)
+    cos = torch.nn.functional.cosine_similarity(a.cpu(), ref).min().item()
+    assert cos >= 0.999, cos
+
+
+def test_preprocess_rejects_bad_input(dev):
+    from fitclip_b200 import _lib, ops
+    with pytest.raises(ValueError):
+        ops.preprocess_frames(torch.zeros(1, 8, 8, 3, device=dev), 224, MEAN, STD)  # not uint8
+    with pytest.raises(_lib.FitclipError):
+        ops.preprocess_frames(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), 224, MEAN, STD)  # CPU tensor
