@@ -94,6 +94,7 @@ struct Slot {
   int64_t numel;
   bool as_bf16;
   bool loaded;
+  int cols = 0, ld = 0;  // bf16 copies stored with a padded row pitch (cols of the source, ld of the copy); 0 = dense
 };
 
 }  // namespace fc
@@ -102,7 +103,8 @@ struct fc_model {
   fc_config cfg;
   int device = 0;
   // geometry
-  int L_img = 0, grid = 0, patch_dim = 0;
+  int L_img = 0, grid = 0, patch_dim = 0;  // patch_dim: 3*P*P rounded up to a multiple of 8 (row pitch of the patch matrix)
+  int patch_cols = 0;                      // 3*P*P
   int maxF = 0, maxC = 0;
   // arena
   uint8_t* arena = nullptr;
@@ -205,7 +207,18 @@ static void plan_model(fc_model* m, ArenaPlan& plan, bool assign) {
       m->slots.push_back({name, *dst, numel, bf, false});
     }
   };
-  one("visual.conv1.weight", reinterpret_cast<void**>(&m->conv_w), int64_t(W) * m->patch_dim, true);
+  {  // conv1.weight (W, 3, P, P) -> bf16 (W, patch_dim) with zero padding columns when 3*P*P is not a multiple of 8
+    const int64_t o = plan.take(int64_t(W) * m->patch_dim * 2);
+    if (assign) {
+      m->conv_w = reinterpret_cast<bf16*>(m->arena + o);
+      Slot sl{"visual.conv1.weight", m->conv_w, int64_t(W) * m->patch_cols, true, false};
+      if (m->patch_cols != m->patch_dim) {
+        sl.cols = m->patch_cols;
+        sl.ld = m->patch_dim;
+      }
+      m->slots.push_back(sl);
+    }
+  }
   one("visual.class_embedding", reinterpret_cast<void**>(&m->cls), W, false);
   one("visual.positional_embedding", reinterpret_cast<void**>(&m->vpos), int64_t(m->L_img) * W, false);
   one("visual.ln_pre.weight", reinterpret_cast<void**>(&m->ln_pre_g), W, false);
@@ -381,17 +394,20 @@ int fc_model_create(const fc_config* cfg, fc_model** out) {
              "fc_model_create: widths must be multiples of 64 and <= 1024 (got %d / %d)", c.vision_width,
              c.transformer_width);
   FC_REQUIRE(c.transformer_heads * 64 == c.transformer_width, "fc_model_create: text head dim must be 64");
-  FC_REQUIRE(c.image_resolution % c.vision_patch_size == 0 && c.vision_patch_size % 8 == 0,
-             "fc_model_create: patch size %d unsupported", c.vision_patch_size);
+  FC_REQUIRE(c.image_resolution % c.vision_patch_size == 0,
+             "fc_model_create: image resolution %d is not a multiple of the patch size %d", c.image_resolution,
+             c.vision_patch_size);
   fc_model* m = new fc_model();
   m->cfg = c;
   FC_CUDA(cudaGetDevice(&m->device));
   m->grid = c.image_resolution / c.vision_patch_size;
   m->L_img = m->grid * m->grid + 1;
-  m->patch_dim = 3 * c.vision_patch_size * c.vision_patch_size;
-  if (m->L_img > 208 || c.context_length > 208) {
+  m->patch_cols = 3 * c.vision_patch_size * c.vision_patch_size;
+  m->patch_dim = (m->patch_cols + 7) / 8 * 8;
+  if (m->L_img > 768 || c.context_length > 768) {
     delete m;
-    set_error("fc_model_create: sequence length above 208 tokens is not supported yet");
+    set_error("fc_model_create: sequence length above 768 tokens is not supported (image %d, text %d)", m->L_img,
+              c.context_length);
     return FC_ERR_INVALID;
   }
   m->maxF = c.max_frames_per_pass > 0 ? c.max_frames_per_pass : 512;
@@ -430,7 +446,8 @@ int fc_model_set_param(fc_model* m, const char* name, const float* data, int64_t
       FC_REQUIRE(sl.numel == numel, "fc_model_set_param: %s has %lld elements, expected %lld", name,
                  static_cast<long long>(numel), static_cast<long long>(sl.numel));
       if (sl.as_bf16) {
-        int rc = f32_to_bf16(data, static_cast<bf16*>(sl.dst), numel, s);
+        int rc = sl.ld ? f32_to_bf16_padded(data, static_cast<bf16*>(sl.dst), numel / sl.cols, sl.cols, sl.ld, s)
+                       : f32_to_bf16(data, static_cast<bf16*>(sl.dst), numel, s);
         if (rc) return rc;
       } else {
         FC_CUDA(cudaMemcpyAsync(sl.dst, data, numel * 4, cudaMemcpyDeviceToDevice, s));

@@ -183,6 +183,95 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(const bf16* __re
   }
 }
 
+// Long sequences (209..768 tokens: ViT-L/14 has 257, ViT-L/14@336 577 -- SURVEY.md 8f row f4): the K and V of one
+// (sequence, head) still fit shared memory, the queries do not, so a CTA takes a chunk of QCH = NWARPS * 16 query rows
+// and walks the keys in blocks of 64 with the same online-softmax block routine.
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) attention_long_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                                     int L, int LPK, int D, int causal,
+                                                                     float scale_log2) {
+  constexpr int QCH = NWARPS * 16;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int h = blockIdx.x;
+  const int64_t seq = blockIdx.y;
+  const int q0 = blockIdx.z * QCH;
+  const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const uint32_t sK = sQ + QCH * 128;
+  const uint32_t sV = sK + LPK * 128;
+  // causal: keys beyond the last query row of this chunk are never needed
+  const int kend = causal ? min(LPK, ((q0 + QCH + 63) / 64) * 64) : LPK;
+
+  const bf16* base = qkv + seq * L * static_cast<int64_t>(3 * D) + h * HD;
+  for (int i = threadIdx.x; i < QCH * 8; i += NWARPS * 32) {
+    const int row = i >> 3, chunk = i & 7;
+    const bool valid = q0 + row < L;
+    cp_async16(sQ + sw(row, chunk), base + static_cast<int64_t>(valid ? q0 + row : 0) * (3 * D) + chunk * 8, valid);
+  }
+  for (int i = threadIdx.x; i < 2 * kend * 8; i += NWARPS * 32) {
+    const int part = i / (kend * 8);
+    const int rem = i - part * (kend * 8);
+    const int row = rem >> 3, chunk = rem & 7;
+    const bool valid = row < L;
+    const bf16* src = base + static_cast<int64_t>(valid ? row : 0) * (3 * D) + (part + 1) * D + chunk * 8;
+    cp_async16((part ? sV : sK) + sw(row, chunk), src, valid);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int qrow0 = q0 + warp * 16;  // global query row of this warp's tile
+  if (qrow0 >= L) return;
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldmatrix_x4(qf[ks], sQ + sw(warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), ks * 2 + (lane >> 4)));
+  float o[8][4];
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  for (int key0 = 0; key0 < kend; key0 += 64) {
+    if (causal && key0 > qrow0 + 15) break;  // warp-uniform: the whole block lies above the diagonal
+    key_block<8>(qf, sK, sV, key0, L, causal != 0, qrow0, scale_log2, o, m, l);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  const float inv0 = 1.f / l[0], inv1 = 1.f / l[1];
+  const int r0 = qrow0 + g, r1 = r0 + 8;
+  bf16* o0 = out + (seq * L + r0) * static_cast<int64_t>(D) + h * HD + tq * 2;
+  bf16* o1 = out + (seq * L + r1) * static_cast<int64_t>(D) + h * HD + tq * 2;
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) {
+    if (r0 < L) *reinterpret_cast<uint32_t*>(o0 + dn * 8) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
+    if (r1 < L) *reinterpret_cast<uint32_t*>(o1 + dn * 8) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
+  }
+}
+
+int launch_long(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s) {
+  constexpr int NWARPS = 8, QCH = NWARPS * 16;
+  const int LPK = (L + 63) / 64 * 64;
+  const int smem = QCH * 128 + 2 * LPK * 128;
+  static int configured = 0;
+  if (configured < smem) {
+    FC_CUDA(cudaFuncSetAttribute(attention_long_kernel<NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+  for (int64_t s0 = 0; s0 < seqs; s0 += 65535) {
+    const int64_t n = seqs - s0 < 65535 ? seqs - s0 : 65535;
+    dim3 grid(heads, static_cast<unsigned>(n), (L + QCH - 1) / QCH);
+    attention_long_kernel<NWARPS><<<grid, NWARPS * 32, smem, s>>>(
+        qkv + s0 * L * static_cast<int64_t>(3 * heads * HD), out + s0 * L * static_cast<int64_t>(heads * HD), L, LPK,
+        heads * HD, causal, scale_log2);
+    FC_CHECK_LAUNCH();
+  }
+  return FC_OK;
+}
+
 template <int LP, int NT0, int NT1, int NWARPS>
 int launch(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s) {
   constexpr int smem = 3 * LP * 128;
@@ -209,7 +298,7 @@ int launch(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causa
 
 int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s) {
   FC_REQUIRE(qkv && out, "attention: null pointer");
-  FC_REQUIRE(L >= 1 && L <= 208, "attention: sequence length %d unsupported (1..208)", L);
+  FC_REQUIRE(L >= 1 && L <= 768, "attention: sequence length %d unsupported (1..768)", L);
   if (seqs == 0) return FC_OK;
   // dense count (QK^T + PV = 4 L^2 64 per head), the figure SURVEY.md 8d uses for both towers
   ProfScope prof(s, PROF_ATTENTION, causal, seqs, L, heads, 4.0 * L * L * HD * heads * static_cast<double>(seqs),
@@ -219,6 +308,7 @@ int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, i
     const int rc = attention_bf16_tc(qkv, out, seqs, L, heads, causal, s, &handled);
     if (rc || handled) return rc;
   }
+  if (L > 208) return launch_long(qkv, out, seqs, L, heads, causal, s);  // ViT-L/14: 257, ViT-L/14@336: 577
   if (L <= 16) return launch<16, 2, 0, 1>(qkv, out, seqs, L, heads, causal, s);
   if (L <= 32) return launch<32, 4, 0, 2>(qkv, out, seqs, L, heads, causal, s);
   if (L <= 48) return launch<48, 6, 0, 3>(qkv, out, seqs, L, heads, causal, s);

@@ -153,6 +153,27 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ frame
   *reinterpret_cast<uint4*>(patches + row * (3 * P * P) + col) = o;
 }
 
+// Patch sizes that are not multiples of 8 (ViT-L/14): one thread per patch-matrix element, columns padded with zeros up
+// to `ldp` (a multiple of 8, what the GEMM's TMA loads need).
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_generic_kernel(const T* __restrict__ frames, bf16* __restrict__ patches,
+                                                             int64_t total, int R, int P, int ldp) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int col = static_cast<int>(idx % ldp);
+  const int64_t row = idx / ldp;
+  float v = 0.f;
+  if (col < 3 * P * P) {
+    const int G = R / P;
+    const int px = static_cast<int>(row % G);
+    const int py = static_cast<int>((row / G) % G);
+    const int64_t f = row / (static_cast<int64_t>(G) * G);
+    const int kx = col % P, ky = (col / P) % P, c = col / (P * P);
+    v = static_cast<float>(frames[((f * 3 + c) * R + py * P + ky) * static_cast<int64_t>(R) + px * P + kx]);
+  }
+  patches[idx] = __float2bfloat16(v);
+}
+
 // class-token row: x[f*L + 0, :] = class_embedding + positional_embedding[0]
 __global__ void cls_row_kernel(bf16* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                int64_t frames, int L, int D) {
@@ -388,11 +409,16 @@ __global__ void __launch_bounds__(256) wise_lerp_kernel(const float* __restrict_
 }
 
 // fp32 -> bf16 weight conversion at load time
+// (rows, cols) fp32, contiguous -> (rows, ld) bf16 with zero-filled padding columns (ld == cols: plain conversion)
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
-                                                          int64_t n) {
+                                                          int64_t rows, int cols, int ld) {
+  const int64_t n = rows * ld;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = __float2bfloat16(in[i]);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / ld;
+    const int c = static_cast<int>(i - r * ld);
+    out[i] = c < cols ? __float2bfloat16(in[r * cols + c]) : __float2bfloat16(0.f);
+  }
 }
 
 // split an fp32 matrix (rows, D) into bf16 hi / lo parts laid out for the 3-term similarity GEMM:
@@ -444,9 +470,25 @@ int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float
 
 int im2col_patches(const void* frames, int dtype, bf16* patches, int64_t F, int R, int P, cudaStream_t s) {
   FC_REQUIRE(frames && patches, "im2col: null pointer");
-  FC_REQUIRE(R % P == 0 && P % 8 == 0, "im2col: resolution %d / patch %d unsupported (patch must be a multiple of 8)",
-             R, P);
+  FC_REQUIRE(R % P == 0, "im2col: resolution %d is not a multiple of the patch size %d", R, P);
   if (F == 0) return FC_OK;
+  if (P % 8 != 0) {
+    const int ldp = (3 * P * P + 7) / 8 * 8;
+    const int G = R / P;
+    const int64_t total = F * G * G * ldp;
+    ProfScope prof(s, PROF_OTHER, 0, F, R, P, 0.0, static_cast<double>(F) * 3 * R * R * ((dtype == FC_DTYPE_F32 ? 4 : 2) + 2));
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    if (dtype == FC_DTYPE_F32)
+      im2col_generic_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(frames), patches, total, R, P, ldp);
+    else if (dtype == FC_DTYPE_BF16)
+      im2col_generic_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(frames), patches, total, R, P, ldp);
+    else if (dtype == FC_DTYPE_F16)
+      im2col_generic_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(frames), patches, total, R, P, ldp);
+    else
+      FC_REQUIRE(false, "im2col: unsupported frame dtype %d", dtype);
+    FC_CHECK_LAUNCH();
+    return FC_OK;
+  }
   ProfScope prof(s, PROF_OTHER, 0, F, R, P, 0.0, static_cast<double>(F) * 3 * R * R * ((dtype == FC_DTYPE_F32 ? 4 : 2) + 2));
   const int64_t total = F * 3 * R * (R / 8);
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
@@ -525,7 +567,14 @@ int fold_ln_weights(const float* W, const float* gamma, const float* beta, const
 
 int f32_to_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s) {
   if (n == 0) return FC_OK;
-  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, n);
+  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, out, 1, static_cast<int>(n), static_cast<int>(n));
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+int f32_to_bf16_padded(const float* in, bf16* out, int64_t rows, int cols, int ld, cudaStream_t s) {
+  if (rows == 0) return FC_OK;
+  f32_to_bf16_kernel<<<grid_for(rows * ld, 256), 256, 0, s>>>(in, out, rows, cols, ld);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }

@@ -23,6 +23,8 @@ int head_project(const bf16* x, const int32_t* ids, const float* gamma, const fl
 int pool_normalize(const float* x, float* out, bf16* out_bf16, int64_t B, int T, int D, float scale, cudaStream_t s);
 int wise_lerp(const float* p1, const float* p2, float* out, bf16* out_bf16, int64_t n, double w, cudaStream_t s);
 int f32_to_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s);
+// (rows, cols) fp32 -> (rows, ld >= cols) bf16, padding columns zeroed
+int f32_to_bf16_padded(const float* in, bf16* out, int64_t rows, int cols, int ld, cudaStream_t s);
 int split_bf16(const float* in, bf16* out, int64_t rows, int D, int mode, int terms, cudaStream_t s);
 
 // preprocess.cu : uint8 (F,H,W,3) -> [x/255 -> bicubic resize (shorter side = size) -> centre crop -> normalise] -> (F,3,size,size)

@@ -136,15 +136,21 @@ GEOMETRIES = {
     # a narrow model: every width / head count / sequence length differs from ViT-B/16 (101 image tokens, 32 text tokens)
     "narrow": dict(embed_dim=256, image_resolution=160, vision_width=512, vision_layers=2, context_length=32,
                    transformer_width=256, transformer_heads=4, transformer_layers=2, vocab_size=1000),
-    # the widest tower the GEMM row-statistics path takes (ViT-L width, 16 heads) on the 197-token sequence
-    "wide": dict(vision_width=1024, vision_layers=1, transformer_layers=1),
+    # config/encoder/clip_vit_l_14.yaml: 14-pixel patches (588-wide patch rows, padded to 592), 257 image tokens,
+    # width 1024 / 16 heads, 768-wide text tower, 768-d embeddings
+    "vit_l_14": dict(embed_dim=768, vision_patch_size=14, vision_width=1024, vision_layers=2, transformer_width=768,
+                     transformer_heads=12, transformer_layers=1),
+    # config/encoder/clip_vit_l_14_336px.yaml: 336 / 14 -> 576 + 1 = 577 image tokens
+    "vit_l_14_336": dict(embed_dim=768, image_resolution=336, vision_patch_size=14, vision_width=1024, vision_layers=1,
+                         transformer_width=768, transformer_heads=12, transformer_layers=1),
 }
 
 
 @pytest.mark.parametrize("name", sorted(GEOMETRIES))
 def test_other_clip_geometries(dev, name):
     """the kernels are shape-generic (widths multiples of 64 up to 1024, head dim 64, sequences up
-    to 208 tokens, patch sizes multiples of 8); the geometry is inferred from the state dict like clip.build_model."""
+    to 768 tokens, any patch size dividing the resolution); the geometry is inferred from the state dict like
+    clip.build_model."""
     import oracle
     from fitclip_b200 import B200ClipVideoTextEncoder
     cfg = GEOMETRIES[name]
@@ -166,11 +172,11 @@ def test_other_clip_geometries(dev, name):
 
 
 def test_unsupported_geometry_is_refused(dev):
-    """ViT-L/14 (257 image tokens, 14-pixel patches) is outside what the kernels take: the error must say so instead of
-    computing something else."""
+    """8-pixel patches at 224 px give 785 image tokens, beyond the 768 the attention kernels take: the error must say so
+    instead of computing something else."""
     import oracle
     from fitclip_b200 import B200ClipVideoTextEncoder, _lib
-    model = oracle.clip_vit_b_16(seed=0, vision_patch_size=14, vision_layers=1, transformer_layers=1)
+    model = oracle.clip_vit_b_16(seed=0, vision_patch_size=8, vision_layers=1, transformer_layers=1)
     enc = B200ClipVideoTextEncoder(model.state_dict()).to(dev)
-    with pytest.raises(_lib.FitclipError, match="patch size|sequence length"):
+    with pytest.raises(_lib.FitclipError, match="sequence length"):
         enc.encode_video(torch.zeros(1, 1, 3, 224, 224, device=dev))

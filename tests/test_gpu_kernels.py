@@ -37,7 +37,9 @@ def _ref_attention(qkv, seqs, L, heads, causal):
     (3, 197, 12, False), (5, 77, 8, True), (2, 77, 8, False), (4, 16, 2, True), (3, 50, 4, False),
     (2, 130, 3, True), (1, 208, 1, False), (7, 1, 2, True),
     # many items per persistent CTA: exercises the S(i+1) / O(i) overlap of the tcgen05 kernel
-    (70, 197, 12, False), (33, 193, 12, False), (40, 208, 6, False), (61, 200, 5, False)])
+    (70, 197, 12, False), (33, 193, 12, False), (40, 208, 6, False), (61, 200, 5, False),
+    # long sequences (key blocks of 64 streamed past a 128-row query chunk): ViT-L/14 257, ViT-L/14@336 577
+    (3, 257, 16, False), (2, 577, 4, False), (2, 300, 2, True), (1, 768, 1, True), (2, 209, 3, False)])
 def test_attention(dev, seqs, L, heads, causal):
     from fitclip_b200 import ops
     torch.manual_seed(1)
