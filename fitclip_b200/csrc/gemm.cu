@@ -30,6 +30,8 @@
 // This one kernel serves every dense contraction of the hot path (reference call sites in SURVEY.md 2.2):
 //   K1 patch-embed, K3 QKV, K5 out-proj(+residual), K6 MLP fc1(+QuickGELU)/fc2(+residual), K11/K12 similarity,
 //   K13 rank counting fused into the similarity epilogue (the similarity matrix is never materialised).
+#include <stdlib.h>
+
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -334,50 +336,57 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             resid_phase ^= 1u << si;
           }
           const float* bias_s = sbias + sub * SUB_N;
-          float st1 = 0.f, st2 = 0.f;
+          // Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2): the epilogue's CUDA-core work is a visible share of the
+          // energy of the K = 768 GEMMs, and two columns per instruction halve its issue slots.
+          uint64_t st1_2 = pack_f32x2(0.f, 0.f), st2_2 = st1_2;
+          const uint64_t rstd2 = pack_f32x2(ln_rstd, ln_rstd), shift2 = pack_f32x2(ln_shift, ln_shift);
+          const uint64_t half2 = pack_f32x2(0.5f, 0.5f), k2 = pack_f32x2(0.851f, 0.851f);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 columns = 16 bytes of bf16 each
             const uint32_t(&rr)[32] = c < 4 ? r0 : r1;
             const int o = (c & 3) * 8;
             const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c * 8 + 4);
-            float v[8];
+            const uint64_t bias2[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y),
+                                       pack_f32x2(b1.z, b1.w)};
+            uint64_t v2[4];
             if (kLn) {
               const float4 c0 = *reinterpret_cast<const float4*>(bias_s + BN + c * 8);
               const float4 c1 = *reinterpret_cast<const float4*>(bias_s + BN + c * 8 + 4);
-              v[0] = fmaf(ln_rstd, __uint_as_float(rr[o + 0]), fmaf(ln_shift, c0.x, b0.x));
-              v[1] = fmaf(ln_rstd, __uint_as_float(rr[o + 1]), fmaf(ln_shift, c0.y, b0.y));
-              v[2] = fmaf(ln_rstd, __uint_as_float(rr[o + 2]), fmaf(ln_shift, c0.z, b0.z));
-              v[3] = fmaf(ln_rstd, __uint_as_float(rr[o + 3]), fmaf(ln_shift, c0.w, b0.w));
-              v[4] = fmaf(ln_rstd, __uint_as_float(rr[o + 4]), fmaf(ln_shift, c1.x, b1.x));
-              v[5] = fmaf(ln_rstd, __uint_as_float(rr[o + 5]), fmaf(ln_shift, c1.y, b1.y));
-              v[6] = fmaf(ln_rstd, __uint_as_float(rr[o + 6]), fmaf(ln_shift, c1.z, b1.z));
-              v[7] = fmaf(ln_rstd, __uint_as_float(rr[o + 7]), fmaf(ln_shift, c1.w, b1.w));
+              const uint64_t cs2[4] = {pack_f32x2(c0.x, c0.y), pack_f32x2(c0.z, c0.w), pack_f32x2(c1.x, c1.y),
+                                       pack_f32x2(c1.z, c1.w)};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)  // rstd * acc + (shift * colsum + bias)
+                v2[e] = fma_f32x2(rstd2, pack_f32x2(__uint_as_float(rr[o + 2 * e]), __uint_as_float(rr[o + 2 * e + 1])),
+                                  fma_f32x2(shift2, cs2[e], bias2[e]));
             } else {
-              v[0] = __uint_as_float(rr[o + 0]) + b0.x;
-              v[1] = __uint_as_float(rr[o + 1]) + b0.y;
-              v[2] = __uint_as_float(rr[o + 2]) + b0.z;
-              v[3] = __uint_as_float(rr[o + 3]) + b0.w;
-              v[4] = __uint_as_float(rr[o + 4]) + b1.x;
-              v[5] = __uint_as_float(rr[o + 5]) + b1.y;
-              v[6] = __uint_as_float(rr[o + 6]) + b1.z;
-              v[7] = __uint_as_float(rr[o + 7]) + b1.w;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                v2[e] = add_f32x2(pack_f32x2(__uint_as_float(rr[o + 2 * e]), __uint_as_float(rr[o + 2 * e + 1])), bias2[e]);
             }
             if (kGelu) {
+              // x * sigmoid(1.702 x) = h + h * tanh(0.851 x), h = x / 2  (see quick_gelu)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = quick_gelu(v[j]);
+              for (int e = 0; e < 4; ++e) {
+                const uint64_t h2 = mul_f32x2(v2[e], half2);
+                float a0, a1;
+                unpack_f32x2(mul_f32x2(v2[e], k2), a0, a1);
+                v2[e] = fma_f32x2(h2, pack_f32x2(tanh_approx(a0), tanh_approx(a1)), h2);
+              }
             }
             const uint32_t addr = stg_row + ((c ^ sw) << 4);
             if (EPI == EPI_BIAS_RESID) {
               const uint4 u = ld_shared_v4(addr);
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = unpack_bf16x2(w[t]);
-                v[2 * t] += f.x;
-                v[2 * t + 1] += f.y;
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w[e]);
+                v2[e] = add_f32x2(v2[e], pack_f32x2(f.x, f.y));
               }
             }
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) unpack_f32x2(v2[e], v[2 * e], v[2 * e + 1]);
             uint4 u;
             u.x = pack_bf16x2(v[0], v[1]);
             u.y = pack_bf16x2(v[2], v[3]);
@@ -386,11 +395,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             st_shared_v4(addr, u);
             if (EPI == EPI_BIAS_RESID) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                st1 += v[j];
-                st2 = fmaf(v[j], v[j], st2);
+              for (int e = 0; e < 4; ++e) {
+                st1_2 = add_f32x2(st1_2, v2[e]);
+                st2_2 = fma_f32x2(v2[e], v2[e], st2_2);
               }
             }
+          }
+          float st1 = 0.f, st2 = 0.f;
+          if (EPI == EPI_BIAS_RESID) {
+            float a0, a1, q0, q1;
+            unpack_f32x2(st1_2, a0, a1);
+            unpack_f32x2(st2_2, q0, q1);
+            st1 = a0 + a1;
+            st2 = q0 + q1;
           }
           if (EPI == EPI_BIAS_RESID && p.stats_out != nullptr && row_ok)  // row statistics for the next folded LayerNorm
             *reinterpret_cast<float2*>(p.stats_out + (static_cast<int64_t>(row) * (p.N / SUB_N) + (col0 / SUB_N)) * 2) =
@@ -571,7 +588,14 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     configured = true;
   }
   const int pair_tiles = (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN);
-  const int max_clusters = num_sms() / 2;
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    max_clusters = num_sms() / 2;
+    if (const char* e = getenv("FC_GEMM_MAX_CLUSTERS")) {  // diagnostics: run the persistent grid on fewer SM pairs
+      const int v = atoi(e);
+      if (v > 0 && v < max_clusters) max_clusters = v;
+    }
+  }
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
