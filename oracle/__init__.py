@@ -3,13 +3,19 @@
 TEST INFRASTRUCTURE ONLY. Nothing under ``fitclip_b200/`` imports this package; only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may.
 
-Parity status: **parity unpinned by the reference** -- the reference repository holds no golden vectors,
-known-answer tests or fixtures for this path and its arithmetic lives in
-un-vendored third-party packages (openai/CLIP@b46f5ac, torchmetrics 0.9) that are not importable here.
-The restatement is therefore pinned against (a) an independent implementation that *is* in the image,
-``transformers.CLIPModel`` (tests/test_oracle_clip.py), (b) the in-tree structural twin
-``aligner/encoder/slip.py:350-480`` that it follows line by line, and (c) seeded golden vectors frozen under
-``tests/golden/`` by ``tests/golden/make_golden.py``.
+Parity status: **partly pinned against the reference's own code, partly unpinned**.  The reference repository holds no
+golden vectors, known-answer tests or fixtures for this path, and the arithmetic of its vision
+tower and of ``Recall`` / ``Accuracy`` lives in un-vendored third-party packages (openai/CLIP@b46f5ac, torchmetrics 0.9)
+that are not importable here.  What IS in the reference tree has been executed in the build container (third-party
+imports stubbed, no reference file copied: ``tests/golden/make_reference_golden.py``) and its outputs are frozen in
+``tests/golden/reference_outputs.pt``: the ``ClipVideoTextEncoder`` wrapper (``encode_video`` / ``encode_text``), the
+in-tree twin of the CLIP text tower (``aligner/encoder/slip.py:350-480``), ``wise`` / ``wise_state_dict``, ``nce_loss`` /
+``teacher_student_nce_loss``, ``Rank`` / ``MedianRank`` and the eval frame sampler -- ``tests/test_reference_golden.py``
+checks this oracle (CPU) and the CUDA path (GPU) against them.  The rest is pinned against (a) independent
+implementations in the image -- ``transformers.CLIPModel`` for both towers (tests/test_oracle_clip.py), torchvision for
+the eval transform (tests/test_oracle_preprocess.py) -- and (b) seeded golden vectors frozen under ``tests/golden/`` by
+``tests/golden/make_golden.py``; **the vision tower and the torchmetrics definitions stay "parity unpinned"** in the
+sense of the task statement.
 """
 from .clip_ref import CLIP, build_model, clip_vit_b_16, tokenize_synthetic  # noqa: F401
 from .encoder_ref import RefClipVideoTextEncoder  # noqa: F401
