@@ -10,8 +10,10 @@ that are not importable here.  What IS in the reference tree has been executed i
 imports stubbed, no reference file copied: ``tests/golden/make_reference_golden.py``) and its outputs are frozen in
 ``tests/golden/reference_outputs.pt``: the ``ClipVideoTextEncoder`` wrapper (``encode_video`` / ``encode_text``), the
 in-tree twin of the CLIP text tower (``aligner/encoder/slip.py:350-480``), ``wise`` / ``wise_state_dict``, ``nce_loss`` /
-``teacher_student_nce_loss``, ``Rank`` / ``MedianRank`` and the eval frame sampler -- ``tests/test_reference_golden.py``
-checks this oracle (CPU) and the CUDA path (GPU) against them.  The rest is pinned against (a) independent
+``teacher_student_nce_loss``, ``Rank`` / ``MedianRank``, the eval frame sampler, and the evaluation flows of
+``TextVideoRetrievalLightningModule``, ``VideoTextClassificationLightningModule`` and ``TeacherStudentLightningModule``
+(on a stub ``pl.LightningModule``) -- ``tests/test_reference_golden.py`` checks this oracle (CPU) and the CUDA path (GPU)
+against them.  The rest is pinned against (a) independent
 implementations in the image -- ``transformers.CLIPModel`` for both towers (tests/test_oracle_clip.py), torchvision for
 the eval transform (tests/test_oracle_preprocess.py) -- and (b) seeded golden vectors frozen under ``tests/golden/`` by
 ``tests/golden/make_golden.py``; **the vision tower and the torchmetrics definitions stay "parity unpinned"** in the

@@ -17,6 +17,14 @@ then imports and RUNS the reference's own modules:
                                             ``ResidualAttentionBlock``, ``Transformer``, ``CLIP.encode_text`` with its
                                             causal mask and EOT pooling), loaded with the oracle's text weights
 * ``aligner/data/frame_sampler.py``         ``UniformFrameSampler`` (the eval sampler the encoder returns)
+* ``aligner/video_text_module.py``, ``aligner/text_video_retrieval.py``   ``validation_step`` -> ``validation_step_end``
+                                            (scaled per-batch scores + NCE ``loss/val``) -> ``validation_epoch_end``
+                                            (``scores = T @ V.T``, ``target = arange``, ``MedianRank`` / ``Rank``)
+* ``aligner/video_text_classification.py``  prompt construction, ``_on_start`` (template mean), ``forward``,
+                                            ``validation_step`` (``MedianRank``), ``predict_step``
+* ``aligner/teacher_student.py``            ``_step`` + ``_dataset_step_end`` for the labelled and unlabelled split
+  (these three run on a stub ``pl.LightningModule`` = ``nn.Module`` + ``log`` / ``all_gather`` / ``print``; ``Recall`` and
+  ``Accuracy`` are third-party: the stub restates micro top-k and their values are stored under ``*_restated`` keys)
 
 What stays pinned only against independent implementations (not against reference code, because the code is not in
 the reference tree): CLIP's vision tower (``transformers.CLIPModel``, tests/test_oracle_clip.py), torchmetrics'
@@ -67,25 +75,98 @@ def install_stubs() -> None:
             self.update(*args, **kwargs)
             return self.compute()
 
+        def clone(self):
+            import copy
+            return copy.deepcopy(self)
+
+    class TopK(Metric):  # [3P] torchmetrics Recall / Accuracy (multiclass, micro): restated, NOT reference code
+        def __init__(self, top_k=None, **kwargs) -> None:
+            super().__init__()
+            self.top_k = top_k or 1
+            self.correct, self.total = 0, 0
+
+        def update(self, preds, target) -> None:
+            hits = (preds.topk(self.top_k, dim=1).indices == target.unsqueeze(-1)).any(dim=1)
+            self.correct += int(hits.sum())
+            self.total += int(hits.numel())
+
+        def compute(self):
+            return torch.tensor(self.correct / self.total, dtype=torch.float32)
+
     def unavailable(*_a, **_k):
         raise RuntimeError("third-party class not available in the stub")
 
-    module("torchmetrics", Metric=Metric, Recall=unavailable, Accuracy=unavailable)
+    module("torchmetrics", Metric=Metric, Recall=TopK, Accuracy=TopK)
 
     registry = module("timm.models.registry", register_model=lambda f: f)
     models = module("timm.models", registry=registry, vision_transformer=types.SimpleNamespace())
     module("timm", models=models, create_model=unavailable)
 
     clip_model = module("clip.model", CLIP=oracle.CLIP)
-    clip_clip = module("clip.clip", load=unavailable, tokenize=unavailable, _tokenizer=None, model=clip_model)
+    clip_clip = module("clip.clip", load=unavailable, tokenize=lambda texts, truncate=True: synthetic_tokenize(texts),
+                       _tokenizer=None, model=clip_model)
     pkg = module("clip", clip=clip_clip, model=clip_model)
     pkg.__path__ = []  # a package, so that `from clip import clip` / `from clip.model import CLIP` resolve
 
-    apply_func = module("pytorch_lightning.utilities.apply_func", apply_to_collection=unavailable)
+    def apply_to_collection(data, dtype, function, *args, **kwargs):  # [3P] PL utility, restated
+        if isinstance(data, dtype):
+            return function(data, *args, **kwargs)
+        if isinstance(data, dict) or hasattr(data, "items"):
+            return {k: apply_to_collection(v, dtype, function, *args, **kwargs) for k, v in data.items()}
+        if isinstance(data, (list, tuple)):
+            return type(data)(apply_to_collection(v, dtype, function, *args, **kwargs) for v in data)
+        return data
+
+    class LightningModule(nn.Module):  # [3P] the members the reference modules touch during evaluation
+        def __init__(self) -> None:
+            super().__init__()
+            self.logged = []
+            self.global_step = 0
+            self._current_dataloader_idx = None
+
+        def log(self, name, value, **kwargs) -> None:
+            value = value.compute() if hasattr(value, "compute") else value
+            self.logged.append((name, value.detach().clone() if isinstance(value, torch.Tensor) else value,
+                                kwargs.get("batch_size")))
+
+        def all_gather(self, data, group=None, sync_grads=False):  # one device: identity
+            return data
+
+        def print(self, *args, **kwargs) -> None:
+            pass
+
+    class RichProgressBar:
+        class _Progress:
+            def add_task(self, **kwargs):
+                return 0
+
+            def update(self, *args, **kwargs) -> None:
+                pass
+
+        def __init__(self) -> None:
+            self.progress = self._Progress()
+
+    apply_func = module("pytorch_lightning.utilities.apply_func", apply_to_collection=apply_to_collection)
     utilities = module("pytorch_lightning.utilities", apply_func=apply_func)
-    callbacks = module("pytorch_lightning.callbacks", RichProgressBar=object)
-    pl = module("pytorch_lightning", LightningModule=nn.Module, utilities=utilities, callbacks=callbacks)
+    callbacks = module("pytorch_lightning.callbacks", RichProgressBar=RichProgressBar)
+    pl = module("pytorch_lightning", LightningModule=LightningModule, utilities=utilities, callbacks=callbacks)
     pl.__path__ = []
+
+
+def synthetic_tokenize(texts, context_length: int = 16, vocab_size: int = 512, truncate: bool = True) -> torch.Tensor:
+    """Stand-in for ``clip.tokenize`` (third-party, vocabulary file not on disk): a deterministic word hash with CLIP's
+    framing -- SOT = vocab-2, EOT = vocab-1 (the row maximum, which is what the EOT pooling looks for), zero padding,
+    truncation keeps EOT last."""
+    import zlib
+    rows = []
+    for text in texts:
+        ids = [vocab_size - 2] + [1 + zlib.crc32(w.encode()) % (vocab_size - 3) for w in text.lower().split()] + \
+              [vocab_size - 1]
+        if len(ids) > context_length:
+            ids = ids[:context_length]
+            ids[-1] = vocab_size - 1
+        rows.append(ids + [0] * (context_length - len(ids)))
+    return torch.tensor(rows, dtype=torch.int32)
 
 
 def main() -> None:
@@ -110,8 +191,8 @@ def main() -> None:
     m2 = oracle.clip_vit_b_16(seed=1, **TINY)
     out["state_dict_1"] = {k: v.clone() for k, v in m1.state_dict().items()}
     out["state_dict_2"] = {k: v.clone() for k, v in m2.state_dict().items()}
-    video = torch.randn(6, 3, 3, 32, 32, generator=g)
-    ids = oracle.tokenize_synthetic(6, (3, 16), seed=77, context_length=16, vocab_size=512)
+    video = torch.randn(12, 3, 3, 32, 32, generator=g)
+    ids = oracle.tokenize_synthetic(12, (3, 16), seed=77, context_length=16, vocab_size=512)
     enc1 = ClipVideoTextEncoder(m1, num_frames=3)
     enc2 = ClipVideoTextEncoder(m2, num_frames=3)
     assert not hasattr(enc1.model, "logit_scale")  # :75-77
@@ -173,6 +254,61 @@ def main() -> None:
         idx = [int(i) for i in UniformFrameSampler(max_frames)(a, b, 30.0)]
         sampler_cases.append({"max_frames": max_frames, "start": a, "end": b, "indices": idx})
     out["uniform_sampler_cases"] = sampler_cases
+
+    # ---- retrieval evaluation flow (video_text_module.py:38-44, text_video_retrieval.py:40-98) in batches of 6
+    from aligner.teacher_student import TeacherStudentLightningModule  # noqa: E402
+    from aligner.text_video_retrieval import TextVideoRetrievalLightningModule  # noqa: E402
+    from aligner.video_text_classification import VideoTextClassificationLightningModule  # noqa: E402
+    module = TextVideoRetrievalLightningModule(encoder=enc1, init_temperature=0.015, fit_temperature=False,
+                                               compute_rank=True)
+    outputs = []
+    with torch.inference_mode():
+        for lo in (0, 6):
+            batch = {"video": video[lo:lo + 6], "text": {"input_ids": ids[lo:lo + 6]},
+                     "video_id": [f"v{i}" for i in range(lo, lo + 6)]}
+            outputs.append(module.validation_step_end(module.validation_step(batch)))
+        module.validation_epoch_end(outputs)
+    logged = module.logged
+    out["retrieval"] = {
+        "init_temperature": 0.015, "batch_losses": [v for n, v, _ in logged if n == "loss/val"],
+        "batch_sizes": [b for n, _, b in logged if n == "loss/val"],
+        "mr": next(v for n, v, _ in logged if n == "mr"), "rank": next(v for n, v, _ in logged if n == "rank"),
+        "r1_restated": next(v for n, v, _ in logged if n == "r1"), "r5_restated": next(v for n, v, _ in logged if n == "r5"),
+        "encoded_videos": torch.cat([o[0] for o in outputs]).clone(), "encoded_texts": torch.cat([o[1] for o in outputs]).clone()}
+
+    # ---- zero-shot classification flow (video_text_classification.py:30-140)
+    labels = ["archery", "baby crawling", "cutting in kitchen", "drumming", "fencing", "golf swing", "knitting"]
+    templates = ["a video of a person {}.", "{} in action", "someone is {} here"]
+    cls = VideoTextClassificationLightningModule(enc1, labels=labels, templates=templates, init_temperature=0.015,
+                                                 fit_temperature=False)
+    cls.trainer = types.SimpleNamespace(callbacks=[sys.modules["pytorch_lightning.callbacks"].RichProgressBar()],
+                                        is_global_zero=True)
+    label_ids = torch.tensor([3, 0, 6, 6, 2, 5, 1, 4, 0, 3, 5, 2])
+    with torch.inference_mode():
+        cls.on_validation_start()
+        cls_scores = cls(video)
+        cls.validation_step({"video": video, "target": (["x"] * 12, label_ids)})
+        pred = cls.predict_step({"video": video, "target": (["x"] * 12, label_ids), "video_id": list(range(12))})
+    out["classification"] = {
+        "labels": labels, "templates": templates, "tokenized_prompts": cls.tokenized_labels["input_ids"].detach().clone(),
+        "encoded_labels": cls.encoded_labels.detach().clone(), "scores": cls_scores.clone(), "label_ids": label_ids,
+        "mr": next(v for n, v, _ in cls.logged if n == "mr"), "a1_restated": next(v for n, v, _ in cls.logged if n == "a1"),
+        "a5_restated": next(v for n, v, _ in cls.logged if n == "a5"), "predictions": pred["predictions"].clone()}
+
+    # ---- teacher-student scoring (teacher_student.py:93-96,142-173): labelled -> NCE, unlabelled -> KL * scale^2
+    ts = TeacherStudentLightningModule(encoder=enc1, teacher=enc2, init_temperature=0.015, fit_temperature=False)
+    with torch.inference_mode():
+        step = ts._step({"video_student": video, "text_student": {"input_ids": ids}, "video_teacher": video,
+                         "text_teacher": {"input_ids": ids}})
+        ts._dataset_step_end(step, split="val", dataset_name="labeled")
+        ts._dataset_step_end(step, split="val", dataset_name="unlabeled")
+    out["teacher_student"] = {"init_temperature": 0.015,
+                              "loss_labeled": next(v for n, v, _ in ts.logged if n == "loss/val_labeled"),
+                              "loss_unlabeled": next(v for n, v, _ in ts.logged if n == "loss/val_unlabeled"),
+                              "teacher_video_emb": step[1][0].clone(), "teacher_text_emb": step[1][1].clone()}
+    out["reference_files"] += ["aligner/video_text_module.py", "aligner/text_video_retrieval.py",
+                               "aligner/video_text_classification.py", "aligner/teacher_student.py",
+                               "util/tensor_utils.py"]
 
     path = os.path.join(ROOT, "tests", "golden", "reference_outputs.pt")
     torch.save(out, path)

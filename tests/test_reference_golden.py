@@ -145,3 +145,130 @@ def test_cuda_ranks_match_reference(ref, dev):
             med_m.update(scores[lo:hi], target[lo:hi])
         assert torch.equal(rank_m.compute().cpu(), case["ranks"])
         assert int(med_m.compute()) == int(case["median_rank"])
+
+
+# ------------------------------------------------------------------------- module flows run by the reference's own classes
+def test_oracle_retrieval_flow_matches_reference_module(ref):
+    """TextVideoRetrievalLightningModule (validation_step -> validation_step_end -> validation_epoch_end) as executed by
+    the reference: per-batch scaled NCE loss, then ranks of `T @ V.T` against `arange`."""
+    from oracle.encoder_ref import ref_batch_scores, ref_retrieval_scores
+    r = ref["retrieval"]
+    enc = _oracle_encoder(ref)
+    scale = 1.0 / r["init_temperature"]
+    vs, ts = [], []
+    with torch.inference_mode():
+        for i, lo in enumerate((0, 6)):
+            v, t = enc(ref["video"][lo:lo + 6], {"input_ids": ref["input_ids"][lo:lo + 6]})
+            loss = oracle.ref_nce_loss(ref_batch_scores(v, t, scale))
+            assert abs(loss.item() - r["batch_losses"][i].item()) <= 1e-4 * abs(r["batch_losses"][i].item())
+            vs.append(v)
+            ts.append(t)
+    scores = ref_retrieval_scores(torch.cat(ts), torch.cat(vs))
+    ranks = oracle.ref_rank(scores, torch.arange(12))
+    assert torch.equal(ranks, r["rank"])
+    assert int(oracle.ref_median_rank(ranks)) == int(r["mr"])
+    m = oracle.ref_retrieval_metrics(scores)
+    assert abs(float(m["r1"]) - float(r["r1_restated"])) < 1e-7 and abs(float(m["r5"]) - float(r["r5_restated"])) < 1e-7
+
+
+def test_oracle_classification_flow_matches_reference_module(ref):
+    from oracle.encoder_ref import ref_class_embeddings
+    c = ref["classification"]
+    enc = _oracle_encoder(ref)
+    with torch.inference_mode():
+        emb = ref_class_embeddings(enc, c["tokenized_prompts"], len(c["templates"]))
+        scores = enc.encode_video(ref["video"]) @ emb.T
+    assert torch.allclose(emb, c["encoded_labels"], atol=1e-6, rtol=0)
+    assert torch.allclose(scores, c["scores"], atol=1e-6, rtol=0)
+    ranks = oracle.ref_rank(c["scores"], c["label_ids"])
+    assert int(oracle.ref_median_rank(ranks)) == int(c["mr"])
+    assert torch.equal(c["scores"].argmax(dim=-1), c["predictions"])
+    assert abs(float(oracle.ref_accuracy_at_k(c["scores"], c["label_ids"], 1)) - float(c["a1_restated"])) < 1e-7
+
+
+def test_oracle_teacher_student_scoring_matches_reference_module(ref):
+    from oracle.encoder_ref import ref_batch_scores
+    t = ref["teacher_student"]
+    scale = 1.0 / t["init_temperature"]
+    student, teacher = _oracle_encoder(ref, "state_dict_1"), _oracle_encoder(ref, "state_dict_2")
+    with torch.inference_mode():
+        sv, st = student(ref["video"], {"input_ids": ref["input_ids"]})
+        tv, tt = teacher(ref["video"], {"input_ids": ref["input_ids"]})
+    assert torch.allclose(tv, t["teacher_video_emb"], atol=1e-6) and torch.allclose(tt, t["teacher_text_emb"], atol=1e-6)
+    scores, teacher_scores = ref_batch_scores(sv, st, scale), ref_batch_scores(tv, tt, scale)
+    labeled = oracle.ref_nce_loss(scores)
+    unlabeled = oracle.ref_teacher_student_nce_loss(scores, teacher_scores, reduction="batchmean") * scale ** 2
+    assert abs(labeled.item() - t["loss_labeled"].item()) <= 1e-4 * abs(t["loss_labeled"].item())
+    assert abs(unlabeled.item() - t["loss_unlabeled"].item()) <= 1e-3 * abs(t["loss_unlabeled"].item())
+
+
+@pytest.mark.gpu
+def test_cuda_retrieval_module_matches_reference_module(ref, dev):
+    from fitclip_b200 import B200ClipVideoTextEncoder, TextVideoRetrievalModule
+    r = ref["retrieval"]
+    enc = B200ClipVideoTextEncoder(ref["state_dict_1"], num_frames=3).to(dev)
+    module = TextVideoRetrievalModule(enc, init_temperature=r["init_temperature"], fit_temperature=False,
+                                      compute_rank=True).to(dev)
+    outputs = []
+    with torch.inference_mode():
+        for lo in (0, 6):
+            batch = {"video": ref["video"][lo:lo + 6].to(dev), "text": {"input_ids": ref["input_ids"][lo:lo + 6].to(dev)},
+                     "video_id": [f"v{i}" for i in range(lo, lo + 6)]}
+            outputs.append(module.validation_step_end(module.validation_step(batch)))
+        result = module.validation_epoch_end(outputs)
+    # loss/val: PL's batch-size weighted mean of the per-batch losses; bf16 encoder vs fp32 reference at scale 66.7
+    expect = sum(float(l) * b for l, b in zip(r["batch_losses"], r["batch_sizes"])) / sum(r["batch_sizes"])
+    assert abs(float(result["loss/val"]) - expect) <= 3e-2 * abs(expect)
+    # the epoch-end logic on the REFERENCE'S embeddings: exact ranks / MdR
+    injected = [(r["encoded_videos"][lo:lo + 6].to(dev), r["encoded_texts"][lo:lo + 6].to(dev)) for lo in (0, 6)]
+    exact = module._validate_dataset(injected)
+    assert torch.equal(exact["rank"].cpu(), r["rank"])
+    assert int(exact["mr"]) == int(r["mr"])
+    assert abs(float(exact["r1"]) - float(r["r1_restated"])) < 1e-7 and abs(float(exact["r5"]) - float(r["r5_restated"])) < 1e-7
+
+
+@pytest.mark.gpu
+def test_cuda_classification_module_matches_reference_module(ref, dev):
+    from fitclip_b200 import B200ClipVideoTextEncoder, ops
+    from fitclip_b200.classification import VideoTextClassificationModule
+    c = ref["classification"]
+    enc = B200ClipVideoTextEncoder(ref["state_dict_1"], num_frames=3).to(dev)
+    module = VideoTextClassificationModule(enc, labels=c["labels"], templates=c["templates"],
+                                           tokenized_labels={"input_ids": c["tokenized_prompts"]})
+    with torch.inference_mode():
+        module.on_validation_start()
+        scores = module(ref["video"].to(dev))
+    assert F.cosine_similarity(module.encoded_labels.cpu(), c["encoded_labels"]).min().item() >= 0.999
+    assert (scores.cpu() - c["scores"]).abs().max().item() <= 2e-2
+    # metric / prediction logic on the REFERENCE'S scores: exact
+    ref_scores = c["scores"].to(dev)
+    ranks = ops.rank_from_scores(ref_scores, c["label_ids"].to(dev))
+    assert int(ranks.cpu().median()) + 1 == int(c["mr"])
+    _, idx = ops.topk_rows(ref_scores, 1)
+    assert torch.equal(idx[:, 0].long().cpu(), c["predictions"])
+
+
+@pytest.mark.gpu
+def test_cuda_teacher_student_module_matches_reference_module(ref, dev):
+    from fitclip_b200 import B200ClipVideoTextEncoder
+    from fitclip_b200.teacher_student import TeacherStudentScoringModule
+    t, r = ref["teacher_student"], ref["retrieval"]
+    student = B200ClipVideoTextEncoder(ref["state_dict_1"], num_frames=3).to(dev)
+    teacher = B200ClipVideoTextEncoder(ref["state_dict_2"], num_frames=3).to(dev)
+    module = TeacherStudentScoringModule(student, teacher, init_temperature=t["init_temperature"]).to(dev)
+    # the scoring arithmetic on the REFERENCE'S embeddings
+    injected = ((r["encoded_videos"].to(dev), r["encoded_texts"].to(dev)),
+                (t["teacher_video_emb"].to(dev), t["teacher_text_emb"].to(dev)))
+    labeled = float(module._dataset_step_end(injected, dataset_name="labeled"))
+    unlabeled = float(module._dataset_step_end(injected, dataset_name="unlabeled"))
+    assert abs(labeled - float(t["loss_labeled"])) <= 1e-3 * abs(float(t["loss_labeled"]))
+    assert abs(unlabeled - float(t["loss_unlabeled"])) <= 1e-3 * abs(float(t["loss_unlabeled"]))
+    # and end to end through both native encoders (bf16 embeddings, scores scaled by 66.7, KL scaled by 66.7^2)
+    batch = {"video_student": ref["video"].to(dev), "text_student": {"input_ids": ref["input_ids"].to(dev)},
+             "video_teacher": ref["video"].to(dev), "text_teacher": {"input_ids": ref["input_ids"].to(dev)}}
+    with torch.inference_mode():
+        step = module._step(batch)
+        labeled = float(module._dataset_step_end(step, dataset_name="labeled"))
+        unlabeled = float(module._dataset_step_end(step, dataset_name="unlabeled"))
+    assert abs(labeled - float(t["loss_labeled"])) <= 5e-2 * abs(float(t["loss_labeled"]))
+    assert abs(unlabeled - float(t["loss_unlabeled"])) <= 1e-1 * abs(float(t["loss_unlabeled"]))
