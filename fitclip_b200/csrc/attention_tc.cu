@@ -38,7 +38,12 @@ constexpr int STG_BYTES = 4 * 32 * 128;    // 4 warps x (32 rows x 128 B) output
 #define ATT_DIRECT_STORE 0  // 1: epilogue writes O rows straight to global memory instead of staging + TMA store
 #endif
 #ifndef ATT_PHALF
-#define ATT_PHALF 1  // 1: hand the first 96 keys of P to the tensor core before the softmax has finished the row
+#define ATT_PHALF 2  // early hand-overs of P to the tensor core while the softmax still works on the row: 0 = none,
+                     // 1 = after 96 keys, 2 = after 64 and after 128 keys
+#endif
+#ifndef ATT_KNOCKOUT
+#define ATT_KNOCKOUT 0  // timing experiments only (results are WRONG): 1 = no exp2, 2 = no row-max pass, 4 = no P store,
+                       // 8 = no pass 2 at all, 16 = no epilogue
 #endif
 constexpr int ATT_THREADS = 160;           // warps 0-3 softmax/epilogue, warp 4 TMA + MMA + TMEM alloc
 
@@ -98,7 +103,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   static_assert(KP % 32 == 16 && KP >= 112 && KP <= 208, "padded key count: whole x32 chunks plus one 16-key tail");
   constexpr int KMAIN = KP - 16;  // keys / S columns of the main group
   constexpr int O_COL = KMAIN;    // O accumulator columns [KP-16, KP+48): the tail of S and the columns behind it
-  constexpr int KHALF = 96;       // keys whose P is handed to the tensor core early (3 x32 chunks = 6 MMA k-steps)
+  constexpr int KHALF = ATT_PHALF == 2 ? 64 : 96;  // keys per early hand-over (a whole number of x32 chunks)
   static_assert(KP / 2 <= O_COL && O_COL + HD <= 256, "P / O column ranges must not overlap");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* kq_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -108,8 +113,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_full = kq_full + 4;
   uint64_t* o_empty = kq_full + 5;
   uint64_t* t_full = kq_full + 6;  // tail columns of S
-  uint64_t* p_half = kq_full + 7;  // P of the first KHALF keys is in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 8);
+  uint64_t* p_half = kq_full + 7;  // [2] P of the first KHALF / 2 * KHALF keys is in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * HD;
@@ -129,6 +134,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(o_empty, 128);
     mbar_init(t_full, 1);
     mbar_init(p_half, 128);
+    mbar_init(p_half + 1, 128);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
@@ -194,17 +200,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int next = item + gridDim.x, next2 = next + gridDim.x;
         const bool has_next = next < num_items;
         mbar_wait(v_full, ph);
-        if (ATT_PHALF) {
-          mbar_wait(p_half, ph);  // P of keys [0, KHALF) is in TMEM: start O = P.V while the softmax finishes the rest
+#pragma unroll
+        for (int part = 0; part < ATT_PHALF; ++part) {
+          mbar_wait(p_half + part, ph);  // P of the next KHALF keys is in TMEM: O += P.V while the softmax goes on
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < KHALF / 16; ++k)
+          for (int k = part * (KHALF / 16); k < (part + 1) * (KHALF / 16); ++k)
             umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
         }
         mbar_wait(p_full, ph);  // all of P is in TMEM
         tc_fence_after();
 #pragma unroll
-        for (int k = ATT_PHALF ? KHALF / 16 : 0; k < KP / 16; ++k)
+        for (int k = ATT_PHALF * (KHALF / 16); k < KP / 16; ++k)
           umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
         umma_commit(o_full);
         if (has_next) {
@@ -231,7 +238,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ===================== softmax + epilogue warps (one query row per thread) =====================
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     constexpr int NFULL = KP / 32;  // x32 chunks (main columns); the 16-column tail follows
-    static_assert(KHALF % 32 == 0 && KHALF / 32 < NFULL, "early hand-over must end on a chunk boundary");
+    static_assert(KHALF % 32 == 0 && ATT_PHALF * (KHALF / 32) < NFULL, "early hand-overs must end on chunk boundaries");
     ItemCursor cur;
     cur.init(blockIdx.x, gridDim.x, tiles, heads);
     int it = 0;
@@ -247,16 +254,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_after();
       float l = 0.f;
       float m = -INFINITY;
-      if (active) {
-        // ---- pass 1 (main columns): row maximum; four independent FMNMX3 chains, two columns per instruction
+      if (active && !(ATT_KNOCKOUT & 2)) {
+        // ---- pass 1 (main columns): row maximum; four independent FMNMX3 chains, two columns per instruction.  The
+        // loop is TMEM-load latency bound, so two x32 chunks are kept in flight (a third costs spills under the 168-register cap).
         float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        uint32_t r[2][32];
-        tmem_ld_32x32b_x32(trow, r[0]);
+        constexpr int DEPTH = 2;
+        uint32_t r[DEPTH][32];
+#pragma unroll
+        for (int j = 0; j < DEPTH && j < NFULL; ++j) tmem_ld_32x32b_x32(trow + j * 32, r[j]);
 #pragma unroll
         for (int j = 0; j < NFULL; ++j) {
-          tmem_ld_wait_fence(r[j & 1]);
-          if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
-          const uint32_t(&rc)[32] = r[j & 1];
+          // loads complete in issue order; waiting for all outstanding ones is exact for the oldest
+          tmem_ld_wait_fence(r[j % DEPTH]);
+          const uint32_t(&rc)[32] = r[j % DEPTH];
           if ((j + 1) * 32 <= L) {
 #pragma unroll
             for (int c = 0; c < 32; c += 8) {
@@ -270,6 +280,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int c = 0; c < 32; ++c)
               if (j * 32 + c < L) m = fmaxf(m, __uint_as_float(rc[c]));
           }
+          if (j + DEPTH < NFULL) tmem_ld_32x32b_x32(trow + (j + DEPTH) * 32, r[j % DEPTH]);
         }
         m = fmaxf(max3(m, m1, m2), m3);
       }
@@ -277,7 +288,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(t_full, ph);  // the 16 tail columns arrive a little later (they share TMEM columns with the previous O)
       FC_T(t1 = clock64(); tq[3] += t1 - t0; t0 = t1;)
       tc_fence_after();
-      if (active) {
+      if (active && !(ATT_KNOCKOUT & 8)) {
         // ---- pass 2: P = exp2((s - m) * scale * log2e), row sum in fp32, P -> bf16 -> TMEM (over the S columns).
         // The tail goes FIRST and its P waits in registers: the early P.V below writes O over the tail's S columns.
         uint32_t r16[16];
@@ -297,8 +308,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           float x0, x1;
           unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r16[2 * c]), __uint_as_float(r16[2 * c + 1])), sc2, nmc2), x0,
                        x1);
-          float p0 = ex2_approx(x0);
-          float p1 = ex2_approx(x1);
+          float p0 = (ATT_KNOCKOUT & 1) ? x0 : ex2_approx(x0);
+          float p1 = (ATT_KNOCKOUT & 1) ? x1 : ex2_approx(x1);
           if (NFULL * 32 + 2 * c >= L) p0 = 0.f;
           if (NFULL * 32 + 2 * c + 1 >= L) p1 = 0.f;
           l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
@@ -316,8 +327,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
                                    sc2, nmc2),
                          x0, x1);
-            float p0 = ex2_approx(x0);
-            float p1 = ex2_approx(x1);
+            float p0 = (ATT_KNOCKOUT & 1) ? x0 : ex2_approx(x0);
+            float p1 = (ATT_KNOCKOUT & 1) ? x1 : ex2_approx(x1);
             if (!full) {
               if (j * 32 + 2 * c >= L) p0 = 0.f;
               if (j * 32 + 2 * c + 1 >= L) p1 = 0.f;
@@ -326,11 +337,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
             pk[c] = pack_bf16x2(p0, p1);
           }
-          tmem_st_32x32b_x16(trow + j * 16, pk);
-          if (ATT_PHALF && j == KHALF / 32 - 1) {  // first KHALF keys done: let the tensor core start on them
-            tmem_st_wait();
+          if (!(ATT_KNOCKOUT & 4)) tmem_st_32x32b_x16(trow + j * 16, pk);
+          else asm volatile("" ::"r"(pk[0]), "r"(pk[5]), "r"(pk[11]), "r"(pk[15]));
+          if (ATT_PHALF && (j + 1) % (KHALF / 32) == 0 && (j + 1) / (KHALF / 32) <= ATT_PHALF) {
+            tmem_st_wait();  // KHALF more keys of P are complete: let the tensor core start on them
             tc_fence_before();
-            mbar_arrive(p_half);
+            mbar_arrive(p_half + (j + 1) / (KHALF / 32) - 1);
           }
         }
         tmem_st_32x32b_x8(trow + NFULL * 16, pk_tail);
@@ -338,8 +350,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float la, lb;
         unpack_f32x2(add_f32x2(l2a, l2b), la, lb);
         l = la + lb;
-      } else if (ATT_PHALF) {
-        mbar_arrive(p_half);
+      } else {
+        l = 1.f;
+#pragma unroll
+        for (int part = 0; part < ATT_PHALF; ++part) mbar_arrive(p_half + part);
       }
       tc_fence_before();
       mbar_arrive(p_full);
@@ -350,7 +364,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       FC_T(t1 = clock64(); tq[5] += t1 - t0; t0 = t1;)
       tc_fence_after();
       uint32_t o0[32], o1[32];
-      if (active) {
+      if (active && !(ATT_KNOCKOUT & 16)) {
         tmem_ld_32x32b_x32(trow + O_COL, o0);
         tmem_ld_32x32b_x32(trow + O_COL + 32, o1);
         tmem_ld_wait_fence(o0);
@@ -359,7 +373,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(o_empty);
       const int row = row0 + lane;
-      if (ATT_DIRECT_STORE ? (active && row < L) : active) {
+      if ((ATT_DIRECT_STORE ? (active && row < L) : active) && !(ATT_KNOCKOUT & 16)) {
         const float inv = 1.f / l;
         const uint64_t inv2 = pack_f32x2(inv, inv);
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(cur.seq) * L + row) * D + cur.head * HD);
