@@ -372,6 +372,64 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const float* __rest
   }
 }
 
+// Fast path for D = NV * 128 <= 1024 (CLIP: 512, 768): one WARP per output row, the frame lives in registers, every
+// input element is read from HBM exactly once with 128-bit streaming loads; the next frame is already in flight while
+// the current one is reduced.  Same arithmetic as above (x / ||x|| per element, frames summed in order).
+template <int NV>
+__global__ void __launch_bounds__(256) pool_normalize_warp_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                  bf16* __restrict__ out_bf16, int64_t B, int T,
+                                                                  float scale) {
+  constexpr int D = NV * 128;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* r = reinterpret_cast<const uint4*>(x + b * T * static_cast<int64_t>(D)) + lane;
+  float acc[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  uint4 cur[NV], nxt[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) cur[i] = ld_nc_v4(r + 32 * i);
+  for (int t = 0; t < T; ++t) {
+    if (t + 1 < T) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nxt[i] = ld_nc_v4(r + static_cast<int64_t>(t + 1) * (D / 4) + 32 * i);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float v0 = __uint_as_float(cur[i].x), v1 = __uint_as_float(cur[i].y), v2 = __uint_as_float(cur[i].z),
+                  v3 = __uint_as_float(cur[i].w);
+      ss += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
+    }
+    const float nrm = sqrtf(warp_sum(ss));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      acc[i][0] += __uint_as_float(cur[i].x) / nrm;
+      acc[i][1] += __uint_as_float(cur[i].y) / nrm;
+      acc[i][2] += __uint_as_float(cur[i].z) / nrm;
+      acc[i][3] += __uint_as_float(cur[i].w) / nrm;
+      cur[i] = nxt[i];
+    }
+  }
+  const float tf = static_cast<float>(T);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float4 o;
+    o.x = (T == 1 ? acc[i][0] : acc[i][0] / tf) * scale;
+    o.y = (T == 1 ? acc[i][1] : acc[i][1] / tf) * scale;
+    o.z = (T == 1 ? acc[i][2] : acc[i][2] / tf) * scale;
+    o.w = (T == 1 ? acc[i][3] : acc[i][3] / tf) * scale;
+    reinterpret_cast<float4*>(out + b * D)[lane + 32 * i] = o;
+    if (out_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(out_bf16 + b * D)[lane + 32 * i] = pk;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- WiSE lerp (K14)
 // out = c1 * p1 + c2 * p2 with two rounded products and a rounded add -- exactly what torch evaluates for
 // `(1 - w) * p1 + w * p2` (aligner/wise.py:16); __fmul_rn/__fadd_rn forbid FMA contraction.
@@ -539,7 +597,23 @@ int pool_normalize(const float* x, float* out, bf16* out_bf16, int64_t B, int T,
   FC_REQUIRE(T >= 1 && T <= 4096 && D >= 1, "pool_normalize: bad T=%d D=%d", T, D);
   if (B == 0) return FC_OK;
   ProfScope prof(s, PROF_OTHER, 4, B, T, D, 0.0, 4.0 * B * D * (2.0 * T + 1));
-  pool_normalize_kernel<<<static_cast<unsigned>(B), 256, T * sizeof(float), s>>>(x, out, out_bf16, T, D, scale);
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                       (out_bf16 == nullptr || (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0);
+  const unsigned wgrid = static_cast<unsigned>((B + 7) / 8);
+  if (aligned && D % 128 == 0 && D <= 1024) {
+    switch (D / 128) {
+      case 1: pool_normalize_warp_kernel<1><<<wgrid, 256, 0, s>>>(x, out, out_bf16, B, T, scale); break;
+      case 2: pool_normalize_warp_kernel<2><<<wgrid, 256, 0, s>>>(x, out, out_bf16, B, T, scale); break;
+      case 3: pool_normalize_warp_kernel<3><<<wgrid, 256, 0, s>>>(x, out, out_bf16, B, T, scale); break;
+      case 4: pool_normalize_warp_kernel<4><<<wgrid, 256, 0, s>>>(x, out, out_bf16, B, T, scale); break;
+      case 5: pool_normalize_warp_kernel<5><<<wgrid, 256, 0, s>>>(x, out, out_bf16, B, T, scale); break;
+      case 6: pool_normalize_warp_kernel<6><<<wgrid, 256, 0, s>>>(x, out, out_bf16, B, T, scale); break;
+      case 7: pool_normalize_warp_kernel<7><<<wgrid, 256, 0, s>>>(x, out, out_bf16, B, T, scale); break;
+      default: pool_normalize_warp_kernel<8><<<wgrid, 256, 0, s>>>(x, out, out_bf16, B, T, scale); break;
+    }
+  } else {
+    pool_normalize_kernel<<<static_cast<unsigned>(B), 256, T * sizeof(float), s>>>(x, out, out_bf16, T, D, scale);
+  }
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
