@@ -256,95 +256,104 @@ __global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------- heads (K7 / K10)
-// One CTA per sequence: pick the pooled token row (class token, or the EOT position = first argmax of the ids),
-// LayerNorm it in fp32, multiply by the fp32 projection (W, E) and write the un-normalised embedding.
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  v = warp_sum(v);
-  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[w] = v;
-  __syncthreads();
-  float t = 0.f;
-  for (int i = 0; i < nw; ++i) t += red[i];
-  return t;
-}
-
-constexpr int HEAD_SEQS = 4;   // sequences per CTA: every projection weight fetched from L2 feeds 4 FMAs
+// A CTA takes HEAD_SEQS sequences x HEAD_COLS output columns.  Phase 1: one WARP per sequence picks the pooled token
+// row (class token, or the EOT position = first argmax of the ids) and LayerNorms it in fp32 into shared memory.
+// Phase 2: the K dimension of the fp32 projection (W, E) is split over HEAD_KG thread groups so that 16 warps per CTA
+// hide the L2 latency of the weight loads (the kernel is latency-, not bandwidth-bound); every weight feeds HEAD_SEQS
+// FMAs.  Phase 3: the HEAD_KG partial sums are added in a fixed order and the un-normalised embedding is written.
+constexpr int HEAD_SEQS = 8;
 constexpr int HEAD_COLS = 128;  // output columns per CTA (grid.y tiles the embedding dimension)
+constexpr int HEAD_KG = 4;      // K groups
+constexpr int HEAD_THREADS = HEAD_COLS * HEAD_KG;
+static_assert(HEAD_SEQS <= HEAD_THREADS / 32, "one warp per sequence in phase 1");
 
-__global__ void __launch_bounds__(HEAD_COLS) head_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ ids,
-                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                   const float* __restrict__ proj, float* __restrict__ out,
-                                                   int64_t seqs, int L, int W, int E, float eps) {
-  extern __shared__ float sh[];  // HEAD_SEQS x W normalised values + 32 reduction slots
-  float* red = sh + HEAD_SEQS * W;
-  __shared__ int s_pos[HEAD_SEQS];
+__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ ids,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ proj, float* __restrict__ out,
+                                                            int64_t seqs, int L, int W, int E, float eps) {
+  extern __shared__ float sh[];  // HEAD_SEQS x W normalised values, then HEAD_KG x HEAD_SEQS x HEAD_COLS partial sums
+  float* part = sh + HEAD_SEQS * W;
   const int64_t seq0 = static_cast<int64_t>(blockIdx.x) * HEAD_SEQS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < HEAD_SEQS) {  // one warp per sequence finds the pooled position
-    int pos = 0;
+  if (warp < HEAD_SEQS) {
+    float* y = sh + warp * W;
     const int64_t seq = seq0 + warp;
-    if (ids != nullptr && seq < seqs) {  // first index of the maximum id (torch.argmax semantics)
-      int best = INT_MIN, best_i = 0;
-      for (int l = lane; l < L; l += 32) {
-        const int v = ids[seq * L + l];
-        if (v > best) {
-          best = v;
-          best_i = l;
+    if (seq >= seqs) {  // warp-uniform
+      for (int k = lane; k < W; k += 32) y[k] = 0.f;
+    } else {
+      int pos = 0;
+      if (ids != nullptr) {  // first index of the maximum id (torch.argmax semantics)
+        int best = INT_MIN, best_i = 0;
+        for (int l = lane; l < L; l += 32) {
+          const int v = ids[seq * L + l];
+          if (v > best) {
+            best = v;
+            best_i = l;
+          }
         }
-      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ob > best || (ob == best && oi < best_i)) {
-          best = ob;
-          best_i = oi;
+        for (int o = 16; o > 0; o >>= 1) {
+          const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          if (ob > best || (ob == best && oi < best_i)) {
+            best = ob;
+            best_i = oi;
+          }
         }
+        pos = best_i;
       }
-      pos = best_i;
+      const bf16* row = x + (seq * L + pos) * static_cast<int64_t>(W);
+      float sum = 0.f;
+      for (int k = lane; k < W; k += 32) {
+        const float v = __bfloat162float(row[k]);
+        y[k] = v;
+        sum += v;
+      }
+      const float mean = warp_sum(sum) / static_cast<float>(W);
+      float sq = 0.f;
+      for (int k = lane; k < W; k += 32) {
+        const float d = y[k] - mean;
+        sq += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(W) + eps);
+      for (int k = lane; k < W; k += 32) y[k] = (y[k] - mean) * rstd * gamma[k] + beta[k];
     }
-    if (lane == 0) s_pos[warp] = pos;
   }
   __syncthreads();
-  for (int sq = 0; sq < HEAD_SEQS; ++sq) {
-    float* y = sh + sq * W;
-    const int64_t seq = seq0 + sq;
-    if (seq >= seqs) {  // block-uniform
-      for (int k = threadIdx.x; k < W; k += blockDim.x) y[k] = 0.f;
-      continue;
-    }
-    const bf16* row = x + (seq * L + s_pos[sq]) * static_cast<int64_t>(W);
-    float part = 0.f;
-    for (int k = threadIdx.x; k < W; k += blockDim.x) {
-      const float v = __bfloat162float(row[k]);
-      y[k] = v;
-      part += v;
-    }
-    const float mean = block_sum(part, red) / static_cast<float>(W);
-    part = 0.f;
-    for (int k = threadIdx.x; k < W; k += blockDim.x) {
-      const float d = y[k] - mean;
-      part += d * d;
-    }
-    const float rstd = rsqrtf(block_sum(part, red) / static_cast<float>(W) + eps);
-    for (int k = threadIdx.x; k < W; k += blockDim.x) y[k] = (y[k] - mean) * rstd * gamma[k] + beta[k];
-  }
-  __syncthreads();
-  const int n = blockIdx.y * HEAD_COLS + threadIdx.x;
+  const int col = threadIdx.x % HEAD_COLS, kg = threadIdx.x / HEAD_COLS;
+  const int n = blockIdx.y * HEAD_COLS + col;
+  float acc[HEAD_SEQS];
+#pragma unroll
+  for (int sq = 0; sq < HEAD_SEQS; ++sq) acc[sq] = 0.f;
   if (n < E) {
-    float acc[HEAD_SEQS];
+    const int kq = W / HEAD_KG;  // W is a multiple of 64: a whole number of 4-wide steps per group
+    const int k0 = kg * kq;
+    // four k per step: 16 weight loads in flight (4-way unroll), one 128-bit shared-memory read per sequence
+#pragma unroll 4
+    for (int k = k0; k < k0 + kq; k += 4) {
+      const float w0 = __ldg(proj + static_cast<int64_t>(k) * E + n);
+      const float w1 = __ldg(proj + static_cast<int64_t>(k + 1) * E + n);
+      const float w2 = __ldg(proj + static_cast<int64_t>(k + 2) * E + n);
+      const float w3 = __ldg(proj + static_cast<int64_t>(k + 3) * E + n);
 #pragma unroll
-    for (int sq = 0; sq < HEAD_SEQS; ++sq) acc[sq] = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < W; ++k) {  // k-sequential fp32 accumulation; the 8-way unroll keeps 8 weight loads in flight
-      const float wv = __ldg(proj + static_cast<int64_t>(k) * E + n);
-#pragma unroll
-      for (int sq = 0; sq < HEAD_SEQS; ++sq) acc[sq] = fmaf(sh[sq * W + k], wv, acc[sq]);
+      for (int sq = 0; sq < HEAD_SEQS; ++sq) {
+        const float4 yv = *reinterpret_cast<const float4*>(sh + sq * W + k);
+        acc[sq] = fmaf(yv.w, w3, fmaf(yv.z, w2, fmaf(yv.y, w1, fmaf(yv.x, w0, acc[sq]))));
+      }
     }
+  }
 #pragma unroll
-    for (int sq = 0; sq < HEAD_SEQS; ++sq)
-      if (seq0 + sq < seqs) out[(seq0 + sq) * E + n] = acc[sq];
+  for (int sq = 0; sq < HEAD_SEQS; ++sq) part[(kg * HEAD_SEQS + sq) * HEAD_COLS + col] = acc[sq];
+  __syncthreads();
+  for (int i = threadIdx.x; i < HEAD_SEQS * HEAD_COLS; i += HEAD_THREADS) {
+    const int sq = i / HEAD_COLS, c = i % HEAD_COLS;
+    const int nn = blockIdx.y * HEAD_COLS + c;
+    if (seq0 + sq < seqs && nn < E) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < HEAD_KG; ++g) t += part[(g * HEAD_SEQS + sq) * HEAD_COLS + c];
+      out[(seq0 + sq) * E + nn] = t;
+    }
   }
 }
 
@@ -585,9 +594,9 @@ int head_project(const bf16* x, const int32_t* ids, const float* gamma, const fl
                  float* out, int64_t seqs, int L, int W, int E, float eps, cudaStream_t s) {
   if (seqs == 0) return FC_OK;
   ProfScope prof(s, PROF_OTHER, 3, seqs, W, E, 2.0 * seqs * W * E, 4.0 * seqs * W * E);
-  const size_t smem = (HEAD_SEQS * W + 32) * sizeof(float);
+  const size_t smem = (HEAD_SEQS * W + HEAD_KG * HEAD_SEQS * HEAD_COLS) * sizeof(float);
   const dim3 grid(static_cast<unsigned>((seqs + HEAD_SEQS - 1) / HEAD_SEQS), (E + HEAD_COLS - 1) / HEAD_COLS);
-  head_kernel<<<grid, HEAD_COLS, smem, s>>>(x, ids, gamma, beta, proj, out, seqs, L, W, E, eps);
+  head_kernel<<<grid, HEAD_THREADS, smem, s>>>(x, ids, gamma, beta, proj, out, seqs, L, W, E, eps);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
