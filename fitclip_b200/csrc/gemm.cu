@@ -427,6 +427,81 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // fetch both residual sub-tiles of the next tile now: their latency hides behind the accumulator hand-over
         prev_two = n0 + (grp + 2) * SUB_N < p.N;
         if (issuer) prefetch_resid(tile + num_clusters, prev_two);
+      } else if (EPI == EPI_PATCH && (p.N % SUB_N) == 0) {
+        // ---------------- patch-embed epilogue: + positional embedding, rows shifted by one class-token row per frame.
+        // The shift rules out a TMA store (a 128-row tile straddles frames), so the bf16 sub-tile is staged in shared
+        // memory and copied out by the warp group with full 128-byte lines per row (8 threads x 16 bytes).
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const float* pos_row = nullptr;
+        if (row_ok) {
+          const int f = row / p.patches_per_frame, pp = row - f * p.patches_per_frame;
+          pos_row = p.pos + static_cast<int64_t>(pp + 1) * p.N;
+        }
+        const int gt = etid & 127;  // thread within the warp group
+        bool released = false;
+#pragma unroll 1
+        for (int si = 0; si < 2; ++si) {
+          const int sub = grp + 2 * si;
+          const int col0 = n0 + sub * SUB_N;
+          if (col0 >= p.N) break;  // uniform across the group
+          uint8_t* const stg_ptr = stg_base + si * STAGING_BYTES;
+          const uint32_t stg_row = smem_u32(stg_ptr) + row_in_tile * 128;
+          uint32_t r0[32], r1[32];
+          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + sub * SUB_N;
+          tmem_ld_32x32b_x32(t_addr, r0);
+          tmem_ld_32x32b_x32(t_addr + 32, r1);
+          tmem_ld_wait_fence(r0);
+          tmem_ld_wait_fence(r1);
+          if (si == 1 || col0 + 2 * SUB_N >= p.N) {
+            tc_fence_before();
+            mbar_arrive_cluster(leader_tmem_empty[acc]);
+            released = true;
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t(&rr)[32] = c < 4 ? r0 : r1;
+              const int o = (c & 3) * 8;
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(pos_row + col0 + c * 8));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(pos_row + col0 + c * 8 + 4));
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(rr[o + 0]) + a0.x, __uint_as_float(rr[o + 1]) + a0.y);
+              u.y = pack_bf16x2(__uint_as_float(rr[o + 2]) + a0.z, __uint_as_float(rr[o + 3]) + a0.w);
+              u.z = pack_bf16x2(__uint_as_float(rr[o + 4]) + a1.x, __uint_as_float(rr[o + 5]) + a1.y);
+              u.w = pack_bf16x2(__uint_as_float(rr[o + 6]) + a1.z, __uint_as_float(rr[o + 7]) + a1.w);
+              st_shared_v4(stg_row + ((c ^ sw) << 4), u);
+            }
+          }
+          named_bar_sync(2 + grp, 128);  // the sub-tile is complete in shared memory
+          {
+            const int chunk = gt & 7;
+            int r = gt >> 3;                 // rows r, r + 16, ... of the tile
+            int grow = m_blk * BM + r;       // global patch row
+            int f = grow / p.patches_per_frame;
+            int rem = grow - f * p.patches_per_frame;
+            bf16* const cbase = static_cast<bf16*>(p.C) + col0 + chunk * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (grow < p.M) {
+                const uint4 u = ld_shared_v4(smem_u32(stg_ptr) + r * 128 + ((chunk ^ (r & 7)) << 4));
+                *reinterpret_cast<uint4*>(cbase + (static_cast<int64_t>(grow) + f + 1) * p.ldc) = u;
+              }
+              r += 16;
+              grow += 16;
+              rem += 16;
+              while (rem >= p.patches_per_frame) {
+                rem -= p.patches_per_frame;
+                ++f;
+              }
+            }
+          }
+          named_bar_sync(2 + grp, 128);  // the staging tile may be overwritten
+        }
+        if (!released) {
+          tc_fence_before();
+          mbar_arrive_cluster(leader_tmem_empty[acc]);
+        }
       } else {
         // ---------------- direct epilogues ----------------
         mbar_wait(&tmem_full[acc], acc_phase);
