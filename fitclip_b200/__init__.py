@@ -4,7 +4,8 @@ from .api import VideoEncoder, VideoTextEncoder  # noqa: F401
 from .classification import VideoTextClassificationModule  # noqa: F401
 from .encoder import B200Clip, B200ClipVideoTextEncoder, load_clip_model  # noqa: F401
 from .metrics import Accuracy, MeanRank, MedianRank, Rank, Recall  # noqa: F401
-from .retrieval import TextVideoRetrievalModule, metrics_from_ranks, retrieval_ranks, shard_bounds  # noqa: F401
+from .retrieval import (TextVideoRetrievalModule, metrics_from_ranks, retrieval_ranks, retrieval_topk,  # noqa: F401
+                        shard_bounds)
 from .teacher_student import TeacherStudentScoringModule  # noqa: F401
 from .wise import wise, wise_state_dict  # noqa: F401
 

@@ -94,6 +94,54 @@ def retrieval_ranks(text_local: torch.Tensor, video_local: torch.Tensor, group=N
     return counts.to(torch.int64)
 
 
+def retrieval_topk(text_local: torch.Tensor, video_local: torch.Tensor, k: int = 10, group=None, terms: int = 3,
+                   row_chunk: int = 8192, similarity_factory: Callable[..., Any] = ops.Similarity,
+                   topk_fn: Callable[..., Tuple[torch.Tensor, torch.Tensor]] = ops.topk_rows
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The ``k`` best videos of every query over ALL videos: ``(values (Nt_total, k) fp32, indices (Nt_total, k) int64
+    global video index)``, identical on every rank -- what ``torch.topk(texts @ videos.T, k)`` returns on one device
+    (``Recall(top_k)`` looks at exactly this set, ``aligner/text_video_retrieval.py:21``), with ties broken towards the
+    lower video index.
+
+    Sharding as in :func:`retrieval_ranks`: text embeddings are all-gathered, every rank scores its own video-column
+    slab in chunks of ``row_chunk`` queries (so the ``Nt x Nv`` matrix never exists), keeps a local top-k per query, and
+    the ``world x k`` candidates per query are all-gathered and merged with the same top-k kernel.  ``k`` may exceed a
+    shard's (or the gallery's) size: missing slots are ``-inf`` / ``-1``."""
+    world, rank = _world(group)
+    text_all, _ = all_gather_rows(text_local.contiguous(), group)
+    dev = text_all.device
+    nt, nv_local = text_all.shape[0], video_local.shape[0]
+    if world > 1:
+        nv = torch.tensor([nv_local], device=dev, dtype=torch.int64)
+        sizes = [torch.zeros_like(nv) for _ in range(world)]
+        dist.all_gather(sizes, nv, group=group)
+        col_offset = int(sum(int(s.item()) for s in sizes[:rank]))
+    else:
+        col_offset = 0
+    values = torch.full((nt, k), float("-inf"), device=dev, dtype=torch.float32)
+    indices = torch.full((nt, k), -1, device=dev, dtype=torch.int64)
+    kl = min(k, nv_local)
+    if kl > 0:
+        video_local = video_local.contiguous()
+        for lo in range(0, nt, row_chunk):
+            hi = min(nt, lo + row_chunk)
+            scores = similarity_factory(text_all[lo:hi].contiguous(), video_local, terms).scores()
+            v, i = topk_fn(scores, kl)
+            values[lo:hi, :kl] = v
+            indices[lo:hi, :kl] = i.to(torch.int64) + col_offset
+    if world == 1:
+        return values, indices
+    # merge: candidates ordered by rank = by ascending column offset, so "first among equals" is the lowest video index
+    all_v = [torch.empty_like(values) for _ in range(world)]
+    all_i = [torch.empty_like(indices) for _ in range(world)]
+    dist.all_gather(all_v, values, group=group)
+    dist.all_gather(all_i, indices, group=group)
+    cand_v = torch.cat(all_v, dim=1).contiguous()
+    cand_i = torch.cat(all_i, dim=1)
+    best_v, pos = topk_fn(cand_v, k)
+    return best_v, torch.gather(cand_i, 1, pos.to(torch.int64))
+
+
 def metrics_from_ranks(ranks: torch.Tensor, num_candidates: int) -> Dict[str, torch.Tensor]:
     """r1/r5/r10 (fp32 fractions) and mr (int64, lower median + 1) -- the keys of ``text_video_retrieval.py:21``."""
     recall, median, _ = ops.metrics_from_ranks(ranks.contiguous(), num_candidates)

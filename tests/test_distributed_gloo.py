@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 import oracle
 from fitclip_b200 import shard_bounds
-from fitclip_b200.retrieval import all_gather_rows, retrieval_ranks
+from fitclip_b200.retrieval import all_gather_rows, retrieval_ranks, retrieval_topk
 
 
 class CpuSimilarity:
@@ -28,6 +28,9 @@ class CpuSimilarity:
         out = torch.zeros(self.s.shape[0])
         out[ok] = self.s[ok, local[ok]]
         return out
+
+    def scores(self, alpha=1.0):
+        return alpha * self.s
 
     def counts(self, target, tscore, col_offset=0):
         gcol = torch.arange(self.nv).unsqueeze(0) + col_offset
@@ -56,6 +59,20 @@ def _worker(rank, world, port, n, ties, out_dir):
         assert torch.equal(gathered, t) and sum(sizes) == n
         expect = oracle.ref_stable_rank(t @ v.T, torch.arange(n))
         assert torch.equal(ranks, expect), (rank, ranks.tolist(), expect.tolist())
+        # distributed top-k: local top-k per column slab, all-gather of the candidates, merge.  (Not on the tied case:
+        # the CPU stand-in's per-slab matmuls differ from the full matmul in the last bit, which reorders exact ties; the
+        # GPU kernel computes a score identically wherever its tile lies -- tests/test_gpu_multi.py covers ties.)
+        if not ties:
+            def cpu_topk(scores, k):
+                order = torch.argsort(scores, dim=1, descending=True, stable=True)[:, :k]
+                return scores.gather(1, order), order.to(torch.int32)
+            k = min(5, n)
+            values, indices = retrieval_topk(t[lo:hi], v[lo:hi], k=k, row_chunk=7, similarity_factory=CpuSimilarity,
+                                             topk_fn=cpu_topk)
+            full = t @ v.T
+            order = torch.argsort(full, dim=1, descending=True, stable=True)[:, :k]
+            assert torch.equal(indices, order), (rank, indices[:3].tolist(), order[:3].tolist())
+            assert torch.allclose(values, full.gather(1, order), atol=1e-6)
         torch.save(ranks, os.path.join(out_dir, f"ranks_{rank}.pt"))
     finally:
         dist.destroy_process_group()

@@ -26,7 +26,7 @@ def _worker(rank, world, port, n, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         import oracle
-        from fitclip_b200 import metrics_from_ranks, ops, retrieval_ranks, shard_bounds
+        from fitclip_b200 import metrics_from_ranks, ops, retrieval_ranks, retrieval_topk, shard_bounds
         g = torch.Generator().manual_seed(0)
         v = torch.nn.functional.normalize(torch.randn(n, 512, generator=g), dim=-1)
         t = torch.nn.functional.normalize(v + 1.2 * torch.randn(n, 512, generator=g), dim=-1)
@@ -41,6 +41,11 @@ def _worker(rank, world, port, n, out_dir):
         assert torch.equal(ranks, single), (rank, (ranks != single).nonzero().flatten().tolist()[:10])
         expect = oracle.ref_stable_rank(full.scores().cpu(), torch.arange(n))
         assert torch.equal(ranks.cpu(), expect)
+        # distributed top-k (local top-k per slab -> all-gather -> merge) == top-k of the full score matrix, incl. the tie
+        values, indices = retrieval_topk(t[lo:hi].to(dev), v[lo:hi].to(dev), k=10, row_chunk=300)
+        full_scores = full.scores()
+        order = torch.argsort(full_scores, dim=1, descending=True, stable=True)[:, :10]
+        assert torch.equal(indices, order) and torch.equal(values, full_scores.gather(1, order))
         m = metrics_from_ranks(ranks, n)
         assert int(m["mr"]) == int(expect.median()) + 1
         torch.save(ranks.cpu(), os.path.join(out_dir, f"ranks_{rank}.pt"))

@@ -170,3 +170,27 @@ def test_fused_rank_at_webvid_scale(dev):
     assert int(m["mr"]) == int(r.median()) + 1
     for k, name in ((1, "r1"), (5, "r5"), (10, "r10")):
         assert abs(float(m[name]) - float((r < k).float().mean())) < 1e-7
+
+
+@pytest.mark.parametrize("nt,nv,k,row_chunk", [(1000, 1000, 10, 8192), (777, 2050, 5, 256), (50, 7, 10, 16)])
+def test_retrieval_topk_single_gpu(dev, nt, nv, k, row_chunk):
+    """retrieval_topk == torch.topk of the scores the same kernel materialises (tie-free random embeddings); queries are
+    processed in chunks so the full matrix never exists; k beyond the gallery size pads with -inf / -1."""
+    from fitclip_b200 import ops, retrieval_topk
+    torch.manual_seed(11)
+    t = torch.nn.functional.normalize(torch.randn(nt, 512), dim=-1).to(dev)
+    v = torch.nn.functional.normalize(torch.randn(nv, 512), dim=-1).to(dev)
+    values, indices = retrieval_topk(t, v, k=k, row_chunk=row_chunk)
+    assert values.shape == (nt, k) and indices.shape == (nt, k) and indices.dtype == torch.int64
+    scores = ops.Similarity(t, v, 3).scores()
+    kk = min(k, nv)
+    ev, ei = torch.topk(scores, kk, dim=1)
+    assert torch.equal(values[:, :kk], ev) and torch.equal(indices[:, :kk], ei)
+    if k > nv:
+        assert torch.isinf(values[:, nv:]).all() and (indices[:, nv:] == -1).all()
+    # Recall@k as torchmetrics defines it (target in the top-k set) from the top-k lists == from the ranks
+    if nt == nv:
+        from fitclip_b200 import metrics_from_ranks, retrieval_ranks
+        hits = (indices == torch.arange(nt, device=dev).unsqueeze(1)).any(dim=1).float().mean()
+        m = metrics_from_ranks(retrieval_ranks(t, v), nv)
+        assert abs(float(hits) - float(m["r10"])) < 1e-7
