@@ -43,6 +43,15 @@ def infer_config(state_dict: Mapping[str, torch.Tensor]) -> Dict[str, int]:
         transformer_layers=len({k.split(".")[2] for k in state_dict if k.startswith("transformer.resblocks")}))
 
 
+def _version_of(t: torch.Tensor) -> int:
+    """In-place edit counter; tensors created under ``torch.inference_mode()`` have none (they cannot be edited in place
+    outside inference mode either), so their storage pointer alone identifies them."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 class _Node(nn.Module):
     """Anonymous container used to reproduce the dotted OpenAI parameter names."""
 
@@ -121,7 +130,7 @@ class B200Clip(nn.Module):
             if p.device != device or p.dtype != torch.float32:
                 raise _lib.FitclipError(-101, f"B200Clip parameters must be fp32 on {device} (found {p.dtype} on "
                                               f"{p.device}); call .to(device).float() first")
-        signature = tuple((p.data_ptr(), p._version) for _, p in params)
+        signature = tuple((p.data_ptr(), _version_of(p)) for _, p in params)
         eng, lib = self._engine, _lib.load()
         with torch.cuda.device(device):
             if eng.handle is None or eng.device != device:

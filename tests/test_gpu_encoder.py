@@ -180,3 +180,19 @@ def test_unsupported_geometry_is_refused(dev):
     enc = B200ClipVideoTextEncoder(model.state_dict()).to(dev)
     with pytest.raises(_lib.FitclipError, match="sequence length"):
         enc.encode_video(torch.zeros(1, 1, 3, 224, 224, device=dev))
+
+
+def test_parameters_created_under_inference_mode(dev):
+    """wise() / load_state_dict may run inside torch.inference_mode() (the reference wraps evaluation in it,
+    aligner/__main__.py:64-66): such parameters have no version counter and must still be picked up."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder, wise
+    cfg = dict(vision_layers=1, transformer_layers=1)
+    with torch.inference_mode():
+        a = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0, **cfg).state_dict()).to(dev)
+        b = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=1, **cfg).state_dict()).to(dev)
+        merged = wise(a, b, weight_for_2=0.5)
+        video = torch.randn(2, 2, 3, 224, 224, device=dev)
+        out = merged.encode_video(video)
+        assert out.shape == (2, 512) and torch.isfinite(out).all()
+        assert not torch.equal(out, a.encode_video(video))
