@@ -292,7 +292,7 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
-def cpu_baseline(sample_videos: int = 16, steps: int = 1) -> dict:
+def cpu_baseline(sample_videos: int = 128, steps: int = 1) -> dict:
     """The oracle (the reference's path restated: fp32 torch on the host cores) on a bounded sample of the workload:
     `sample_videos` videos x 4 frames + as many captions in batches of 32 (aligner/data/video_data_module.py:32),
     plus the full 1000 x 1000 similarity + argsort rank + metrics; encode time is extrapolated linearly to 1000."""
@@ -353,7 +353,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=16, help="videos in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=128,
+                    help="videos in the bounded CPU-baseline sample (128 videos x 4 frames + 128 captions: 10-30 s of CPU work)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
