@@ -39,7 +39,10 @@ namespace fc {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 5, UMMA_K = 16;
+#ifndef GEMM_STAGES
+#define GEMM_STAGES 5  // 5 x 32 KiB operand stages + 4 x 16 KiB staging tiles fill the 227 KiB of shared memory
+#endif
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = GEMM_STAGES, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;        // this CTA's 128 rows of the pair's 256-row A tile
 constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half (128 of 256 rows) of the B tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
