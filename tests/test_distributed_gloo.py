@@ -93,3 +93,38 @@ def test_single_process_path_needs_no_process_group():
     target = torch.randint(0, 20, (20,))
     ranks = retrieval_ranks(t, v, target_local=target, similarity_factory=CpuSimilarity)
     assert torch.equal(ranks, oracle.ref_stable_rank(t @ v.T, target))
+
+
+def _metric_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fitclip_b200.metrics import Rank
+        # "cat" state reduction (aligner/metrics.py:13) with uneven per-rank contributions, fed in two updates
+        mine = torch.arange(10 * rank, 10 * rank + 3 + 2 * rank, dtype=torch.int64)
+        m = Rank()
+        m.update_from_ranks(mine[:2], 100)
+        m.update_from_ranks(mine[2:], 100)
+        allr = m.compute()  # Rank.compute is the plain concatenation: no kernel involved
+        expect = torch.cat([torch.arange(10 * r, 10 * r + 3 + 2 * r, dtype=torch.int64) for r in range(world)])
+        assert torch.equal(allr, expect), (rank, allr.tolist())
+        # classification-style sharding: every rank holds ALL class columns and a slice of the query rows with explicit
+        # targets; retrieval_ranks with target_local gathers queries and targets, columns are sharded
+        g = torch.Generator().manual_seed(3)
+        q = torch.randn(23, 16, generator=g)
+        c = torch.randn(11, 16, generator=g)
+        tgt = torch.randint(0, 11, (23,), generator=g)
+        from fitclip_b200 import shard_bounds
+        qlo, qhi = shard_bounds(23, world, rank)
+        clo, chi = shard_bounds(11, world, rank)
+        ranks = retrieval_ranks(q[qlo:qhi], c[clo:chi], target_local=tgt[qlo:qhi], similarity_factory=CpuSimilarity)
+        assert torch.equal(ranks, oracle.ref_stable_rank(q @ c.T, tgt)), rank
+        torch.save(allr, os.path.join(out_dir, f"m_{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_metric_state_cat_and_explicit_targets(tmp_path):
+    mp.spawn(_metric_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    outs = [torch.load(tmp_path / f"m_{r}.pt") for r in range(3)]
+    assert all(torch.equal(o, outs[0]) for o in outs)
