@@ -1,5 +1,6 @@
-"""Timing of the pooled-token head (LayerNorm + projection) through a 1-layer encoder is not separable, so this times
-fc_encode paths indirectly: it calls the profiler around a full vision pass and prints the per-kernel-class times."""
+"""Per-kernel times of one 500-frame vision pass (the library's CUDA-event profiler, fc_profile_start/stop), sorted by
+time: the place to look at the small kernels (patch-embed GEMM = kind 0 tag 3, head = kind 3 tag 3, im2col = kind 3 tag 0,
+ln_pre = kind 2, pool = kind 3 tag 4).  FITCLIP_VARIANT=name runs a `make VARIANT=name` build for A/B comparisons."""
 import os
 import sys
 
