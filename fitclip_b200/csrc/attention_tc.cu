@@ -31,7 +31,6 @@ namespace {
 constexpr int HD = 64;
 constexpr int QT = 128;                    // query rows per tile
 constexpr int Q_BYTES = QT * 128;          // 16 KiB
-constexpr uint32_t TMEM_COLS_ATT = 256;
 constexpr int STG_BYTES = 4 * 32 * 128;    // 4 warps x (32 rows x 128 B) output staging (TMA-store epilogue)
 // tuning switches (kept as macros so variants can be built side by side: make VARIANT=x EXTRA=-DATT_...=v)
 #ifndef ATT_DIRECT_STORE
@@ -94,16 +93,20 @@ struct ItemCursor {
   }
 };
 
-template <int KP>
+// KP: keys padded to whole x32 chunks + one 16-key tail (208 for the 197-token image sequence, 80 for the 77-token
+// text sequence).  CAUSAL: query row i attends to keys 0..i (aligner/encoder/slip.py:454-460).  NPH: early hand-overs
+// of P (see ATT_PHALF).
+template <int KP, bool CAUSAL, int NPH>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     const __grid_constant__ CUtensorMap tmO, bf16* __restrict__ out, int L, int heads, int tiles,
                     int num_items, float scale_log2) {
   using S = AttSmem<KP>;
-  static_assert(KP % 32 == 16 && KP >= 112 && KP <= 208, "padded key count: whole x32 chunks plus one 16-key tail");
+  static_assert(KP % 32 == 16 && KP >= 48 && KP <= 208, "padded key count: whole x32 chunks plus one 16-key tail");
   constexpr int KMAIN = KP - 16;  // keys / S columns of the main group
   constexpr int O_COL = KMAIN;    // O accumulator columns [KP-16, KP+48): the tail of S and the columns behind it
-  constexpr int KHALF = ATT_PHALF == 2 ? 64 : 96;  // keys per early hand-over (a whole number of x32 chunks)
+  constexpr int KHALF = NPH == 2 ? 64 : 96;  // keys per early hand-over (a whole number of x32 chunks)
+  constexpr uint32_t TMEM_COLS = O_COL + HD <= 128 ? 128 : 256;
   static_assert(KP / 2 <= O_COL && O_COL + HD <= 256, "P / O column ranges must not overlap");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* kq_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -137,7 +140,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(p_half + 1, 128);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
+  if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -201,7 +204,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool has_next = next < num_items;
         mbar_wait(v_full, ph);
 #pragma unroll
-        for (int part = 0; part < ATT_PHALF; ++part) {
+        for (int part = 0; part < NPH; ++part) {
           mbar_wait(p_half + part, ph);  // P of the next KHALF keys is in TMEM: O += P.V while the softmax goes on
           tc_fence_after();
 #pragma unroll
@@ -211,7 +214,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(p_full, ph);  // all of P is in TMEM
         tc_fence_after();
 #pragma unroll
-        for (int k = ATT_PHALF * (KHALF / 16); k < KP / 16; ++k)
+        for (int k = NPH * (KHALF / 16); k < KP / 16; ++k)
           umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
         umma_commit(o_full);
         if (has_next) {
@@ -238,7 +241,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ===================== softmax + epilogue warps (one query row per thread) =====================
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     constexpr int NFULL = KP / 32;  // x32 chunks (main columns); the 16-column tail follows
-    static_assert(KHALF % 32 == 0 && ATT_PHALF * (KHALF / 32) < NFULL, "early hand-overs must end on chunk boundaries");
+    static_assert(NPH == 0 || (KHALF % 32 == 0 && NPH * (KHALF / 32) < NFULL), "early hand-overs must end on chunk boundaries");
     ItemCursor cur;
     cur.init(blockIdx.x, gridDim.x, tiles, heads);
     int it = 0;
@@ -248,6 +251,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int tile = flip_ok ? (cur.t ^ (it & 1)) : cur.t;
       const int row0 = tile * QT + warp * 32;
       const bool active = row0 < L;  // warp-uniform: warps whose 32 rows all lie beyond the sequence only sync
+      // keys this thread's query row may attend to: [0, lim).  Without a mask lim = L for every row (warp-uniform, the
+      // branches below stay uniform); causal rows see keys 0..row.
+      const int lim = CAUSAL ? min(L, row0 + lane + 1) : L;
       FC_T(long long t0 = clock64(); long long t1;)
       mbar_wait(s_full, ph);
       FC_T(t1 = clock64(); tq[1] += t1 - t0; t0 = t1; ++n_it;)
@@ -267,7 +273,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // loads complete in issue order; waiting for all outstanding ones is exact for the oldest
           tmem_ld_wait_fence(r[j % DEPTH]);
           const uint32_t(&rc)[32] = r[j % DEPTH];
-          if ((j + 1) * 32 <= L) {
+          if ((j + 1) * 32 <= lim) {
 #pragma unroll
             for (int c = 0; c < 32; c += 8) {
               m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
@@ -278,7 +284,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-              if (j * 32 + c < L) m = fmaxf(m, __uint_as_float(rc[c]));
+              if (j * 32 + c < lim) m = fmaxf(m, __uint_as_float(rc[c]));
           }
           if (j + DEPTH < NFULL) tmem_ld_32x32b_x32(trow + (j + DEPTH) * 32, r[j % DEPTH]);
         }
@@ -298,7 +304,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_ld_wait_fence16(r16);
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-          if (NFULL * 32 + c < L) m = fmaxf(m, __uint_as_float(r16[c]));
+          if (NFULL * 32 + c < lim) m = fmaxf(m, __uint_as_float(r16[c]));
         const float mc = m * scale_log2;
         const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nmc2 = pack_f32x2(-mc, -mc);
         uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;  // packed partial row sums (FADD2), two chains
@@ -310,8 +316,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                        x1);
           float p0 = (ATT_KNOCKOUT & 1) ? x0 : ex2_approx(x0);
           float p1 = (ATT_KNOCKOUT & 1) ? x1 : ex2_approx(x1);
-          if (NFULL * 32 + 2 * c >= L) p0 = 0.f;
-          if (NFULL * 32 + 2 * c + 1 >= L) p1 = 0.f;
+          if (NFULL * 32 + 2 * c >= lim) p0 = 0.f;
+          if (NFULL * 32 + 2 * c + 1 >= lim) p1 = 0.f;
           l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
           pk_tail[c] = pack_bf16x2(p0, p1);
         }
@@ -320,7 +326,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_ld_wait_fence(r[j & 1]);
           if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
           uint32_t pk[16];
-          const bool full = (j + 1) * 32 <= L;
+          const bool full = (j + 1) * 32 <= lim;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             float x0, x1;
@@ -330,8 +336,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float p0 = (ATT_KNOCKOUT & 1) ? x0 : ex2_approx(x0);
             float p1 = (ATT_KNOCKOUT & 1) ? x1 : ex2_approx(x1);
             if (!full) {
-              if (j * 32 + 2 * c >= L) p0 = 0.f;
-              if (j * 32 + 2 * c + 1 >= L) p1 = 0.f;
+              if (j * 32 + 2 * c >= lim) p0 = 0.f;
+              if (j * 32 + 2 * c + 1 >= lim) p1 = 0.f;
             }
             if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
             else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
@@ -339,7 +345,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           if (!(ATT_KNOCKOUT & 4)) tmem_st_32x32b_x16(trow + j * 16, pk);
           else asm volatile("" ::"r"(pk[0]), "r"(pk[5]), "r"(pk[11]), "r"(pk[15]));
-          if (ATT_PHALF && (j + 1) % (KHALF / 32) == 0 && (j + 1) / (KHALF / 32) <= ATT_PHALF) {
+          if (NPH > 0 && (j + 1) % (KHALF / 32) == 0 && (j + 1) / (KHALF / 32) <= NPH) {
             tmem_st_wait();  // KHALF more keys of P are complete: let the tensor core start on them
             tc_fence_before();
             mbar_arrive(p_half + (j + 1) / (KHALF / 32) - 1);
@@ -353,7 +359,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       } else {
         l = 1.f;
 #pragma unroll
-        for (int part = 0; part < ATT_PHALF; ++part) mbar_arrive(p_half + part);
+        for (int part = 0; part < NPH; ++part) mbar_arrive(p_half + part);
       }
       tc_fence_before();
       mbar_arrive(p_full);
@@ -424,7 +430,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS_ATT>(tmem_base);
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -467,12 +473,12 @@ int make_tmap_3d(CUtensorMap* tm, const bf16* base, int64_t cols, int64_t L, int
   return FC_OK;
 }
 
-template <int KP>
+template <int KP, bool CAUSAL, int NPH>
 int launch_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaStream_t s) {
   using S = AttSmem<KP>;
   static bool configured = false;
   if (!configured) {
-    FC_CUDA(cudaFuncSetAttribute(attention_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    FC_CUDA(cudaFuncSetAttribute(attention_tc_kernel<KP, CAUSAL, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
     configured = true;
   }
   const int D = heads * HD;
@@ -500,7 +506,7 @@ int launch_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaSt
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   note_launch();
-  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<KP>, tq, tkv, to, out, L, heads, tiles, items, scale_log2));
+  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<KP, CAUSAL, NPH>, tq, tkv, to, out, L, heads, tiles, items, scale_log2));
   return FC_OK;
 }
 
@@ -518,20 +524,25 @@ extern "C" __attribute__((visibility("default"))) int fc_debug_att_timing(unsign
 }
 #endif
 
-// tcgen05 path: un-masked sequences of 193..208 tokens (the ViT-B/16 image sequence, 197). Returns 1 if it handled the call.
+// tcgen05 path: un-masked sequences of 193..208 tokens (the ViT-B/16 image sequence, 197) and causal sequences of
+// 65..80 tokens (the CLIP text sequence, 77). *handled = 1 when it took the call.
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                       int* handled) {
   *handled = 0;
   static int disabled = -1;
   if (disabled < 0) {
-    const char* e = getenv("FC_ATTENTION");
+    const char* e = getenv("FC_ATTENTION");  // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels
     disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
   }
-  if (disabled || causal || L <= 192 || L > 208) return FC_OK;
+  if (disabled) return FC_OK;
+  const bool image = !causal && L > 192 && L <= 208;
+  const bool text = causal && L > 64 && L <= 80;
+  if (!image && !text) return FC_OK;
   FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "attention: buffers must be 16-byte aligned");
   *handled = 1;
-  return launch_tc<208>(qkv, out, seqs, L, heads, s);
+  if (image) return launch_tc<208, false, ATT_PHALF>(qkv, out, seqs, L, heads, s);
+  return launch_tc<80, true, 0>(qkv, out, seqs, L, heads, s);
 }
 
 }  // namespace fc

@@ -39,7 +39,9 @@ def _ref_attention(qkv, seqs, L, heads, causal):
     # many items per persistent CTA: exercises the S(i+1) / O(i) overlap of the tcgen05 kernel
     (70, 197, 12, False), (33, 193, 12, False), (40, 208, 6, False), (61, 200, 5, False),
     # long sequences (key blocks of 64 streamed past a 128-row query chunk): ViT-L/14 257, ViT-L/14@336 577
-    (3, 257, 16, False), (2, 577, 4, False), (2, 300, 2, True), (1, 768, 1, True), (2, 209, 3, False)])
+    (3, 257, 16, False), (2, 577, 4, False), (2, 300, 2, True), (1, 768, 1, True), (2, 209, 3, False),
+    # the causal text sequence on the tcgen05 kernel (65..80 tokens), many items per persistent CTA
+    (300, 77, 8, True), (9, 65, 2, True), (11, 80, 3, True), (64, 64, 2, True)])
 def test_attention(dev, seqs, L, heads, causal):
     from fitclip_b200 import ops
     torch.manual_seed(1)
