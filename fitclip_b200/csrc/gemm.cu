@@ -9,23 +9,25 @@
 // CTA PAIRS (thread-block cluster of 2, tcgen05 cta_group::2): a pair owns a 256x256 output tile.  Each CTA TMA-loads
 // its own 128 rows of A and HALF of the B tile (128 of 256 rows) into its own shared memory -- 32 KiB per K block
 // instead of 48 -- and the pair's LEADER issues one tcgen05.mma.cta_group::2 (M = 256) per K step that reads both
-// CTAs' operands and accumulates each CTA's 128 rows into that CTA's TMEM.  Halving the B bytes per SM matters twice:
-// L2->SM traffic, and shared-memory bandwidth -- a cta_group::1 128x256 tile moves 96 KiB through a 128 B/clk shared
-// memory per 512-cycle K block (48 KiB TMA writes + 48 KiB operand reads) and is capped near 67 % tensor utilisation.
-// Three pipelines: smem full/empty (TMA<->MMA, 6 stages of 32 KiB; both CTAs' loads complete on the leader's full
+// CTAs' operands and accumulates each CTA's 128 rows into that CTA's TMEM.  The main loop is bound by the operand bytes
+// delivered into an SM (measured: DESIGN.md 3.1), so the bytes per unit of MMA work are what counts.
+// Three pipelines: smem full/empty (TMA<->MMA, 5 stages of 32 KiB; both CTAs' loads complete on the leader's full
 // barrier, the leader's multicast tcgen05.commit releases the stage in both CTAs), TMEM full/empty (MMA<->epilogue,
-// 2 accumulator stages; both epilogues release onto the leader's barrier), and a static persistent tile scheduler
-// over pairs with N fastest, so the pairs of one wave share A tiles in L2 while B stays L2-resident.
+// 2 accumulator stages; both epilogues release onto the leader's barrier with a relaxed cluster-scope arrive), and a
+// static persistent tile scheduler over pairs with N fastest, so the pairs of one wave share A tiles in L2 while B
+// stays L2-resident.
 //
 // Epilogues
 //   staged (bias / bias+QuickGELU / bias+residual / folded-LayerNorm variants, bf16 out): each warp group owns the
-//     64-column sub-tiles
-//     {g, g+2} of the 128x256 tile.  tcgen05.ld -> registers -> bias (smem) / activation / residual -> bf16 ->
-//     128B-swizzled 128x64 staging tile in smem -> ONE TMA store per sub-tile (full 128-byte lines, rows beyond M
-//     clipped by the hardware).  The residual sub-tile is TMA-LOADED into the same staging tile first and updated in
-//     place, so the epilogue issues no per-thread global loads or stores at all.
-//   direct (patch-embed scatter, fp32 scores, target-score extraction, rank counting): registers -> global, with the
-//     TMEM load of the next 32-column chunk in flight while the current one is consumed.
+//     64-column sub-tiles {g, g+2} of the 128x256 tile and two 16 KiB staging tiles.  tcgen05.ld -> registers ->
+//     packed fp32x2 arithmetic (folded LayerNorm, bias, QuickGELU, residual) -> bf16 -> 128B-swizzled 128x64 staging
+//     tile -> ONE TMA store per sub-tile (full 128-byte lines, rows beyond M clipped by the hardware).  The residual
+//     sub-tiles of the NEXT tile are TMA-loaded into the staging tiles while the current tile finishes and are updated
+//     in place, so the epilogue issues no per-thread global loads or stores at all.
+//   patch-embed (+ positional embedding, rows shifted by one class-token row per frame): staged the same way, copied
+//     out by the warp group with full 128-byte lines per row (the row shift rules out a TMA store).
+//   direct (fp32 scores, target-score extraction, rank counting): registers -> global, with the TMEM load of the next
+//     32-column chunk in flight while the current one is consumed.
 //
 // This one kernel serves every dense contraction of the hot path (reference call sites in SURVEY.md 2.2):
 //   K1 patch-embed, K3 QKV, K5 out-proj(+residual), K6 MLP fc1(+QuickGELU)/fc2(+residual), K11/K12 similarity,
