@@ -310,18 +310,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float mc = m * scale_log2;
         const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nmc2 = pack_f32x2(-mc, -mc);
         uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;  // packed partial row sums (FADD2), two chains
+        // Causal kernel only: lanes whose row lies beyond the sequence or whose keys in a chunk are all masked skip the
+        // arithmetic of that chunk (the MUFU works through a warp's ACTIVE lanes): 65.5 -> 63.9 us on the text
+        // sequence.  The same branches cost the un-masked 197-token kernel 16 % (73.1 -> 84.8 us: the chunk bodies no
+        // longer interleave with the TMEM loads), so there the conditions are compile-time true.
+        const bool row_valid = !CAUSAL || row0 + lane < L;
         uint32_t pk_tail[8];
+        if (row_valid && (!CAUSAL || NFULL * 32 < lim)) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float x0, x1;
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r16[2 * c]), __uint_as_float(r16[2 * c + 1])), sc2, nmc2), x0,
-                       x1);
-          float p0 = (ATT_KNOCKOUT & 1) ? x0 : ex2_approx(x0);
-          float p1 = (ATT_KNOCKOUT & 1) ? x1 : ex2_approx(x1);
-          if (NFULL * 32 + 2 * c >= lim) p0 = 0.f;
-          if (NFULL * 32 + 2 * c + 1 >= lim) p1 = 0.f;
-          l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
-          pk_tail[c] = pack_bf16x2(p0, p1);
+          for (int c = 0; c < 8; ++c) {
+            float x0, x1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r16[2 * c]), __uint_as_float(r16[2 * c + 1])), sc2, nmc2),
+                         x0, x1);
+            float p0 = (ATT_KNOCKOUT & 1) ? x0 : ex2_approx(x0);
+            float p1 = (ATT_KNOCKOUT & 1) ? x1 : ex2_approx(x1);
+            if (NFULL * 32 + 2 * c >= lim) p0 = 0.f;
+            if (NFULL * 32 + 2 * c + 1 >= lim) p1 = 0.f;
+            l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+            pk_tail[c] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) pk_tail[c] = 0u;
         }
 #pragma unroll
         for (int j = 0; j < NFULL; ++j) {
@@ -329,21 +339,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
           uint32_t pk[16];
           const bool full = (j + 1) * 32 <= lim;
+          if (row_valid && (!CAUSAL || j * 32 < lim)) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float x0, x1;
-            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
-                                   sc2, nmc2),
-                         x0, x1);
-            float p0 = (ATT_KNOCKOUT & 1) ? x0 : ex2_approx(x0);
-            float p1 = (ATT_KNOCKOUT & 1) ? x1 : ex2_approx(x1);
-            if (!full) {
-              if (j * 32 + 2 * c >= lim) p0 = 0.f;
-              if (j * 32 + 2 * c + 1 >= lim) p1 = 0.f;
+            for (int c = 0; c < 16; ++c) {
+              float x0, x1;
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
+                                     sc2, nmc2),
+                           x0, x1);
+              float p0 = (ATT_KNOCKOUT & 1) ? x0 : ex2_approx(x0);
+              float p1 = (ATT_KNOCKOUT & 1) ? x1 : ex2_approx(x1);
+              if (!full) {
+                if (j * 32 + 2 * c >= lim) p0 = 0.f;
+                if (j * 32 + 2 * c + 1 >= lim) p1 = 0.f;
+              }
+              if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+              else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
+              pk[c] = pack_bf16x2(p0, p1);
             }
-            if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
-            else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
-            pk[c] = pack_bf16x2(p0, p1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pk[c] = 0u;
           }
           if (!(ATT_KNOCKOUT & 4)) tmem_st_32x32b_x16(trow + j * 16, pk);
           else asm volatile("" ::"r"(pk[0]), "r"(pk[5]), "r"(pk[11]), "r"(pk[15]));
