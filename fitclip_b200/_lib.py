@@ -67,6 +67,23 @@ SIGNATURES = {
     "fc_gemm_bf16": (C.c_int, [C.c_int, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _f32, _i32, _i32, _i32, _p]),
     "fc_layernorm_bf16": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _f32, _p]),
     "fc_attention_bf16": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p]),
+    # training step (row f3)
+    "fc_gemm_bf16_splitk": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _f32, _i32, _i32, _i32, _i32, _p]),
+    "fc_transpose_bf16": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p, _p]),
+    "fc_layernorm_bwd_bf16": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _f32, _p]),
+    "fc_quickgelu_bf16": (C.c_int, [_p, _p, _i64, _p]),
+    "fc_quickgelu_bwd_bf16": (C.c_int, [_p, _p, _p, _i64, _p]),
+    "fc_attention_bwd_bf16": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "fc_loss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i32, _p, _f32, _p, _p, _i64, _p]),
+    "fc_sgemm_f32": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _f32, _p, _i64, _p, _i64, _p, _i64, _p]),
+    "fc_pool_normalize_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _f32, _p]),
+    "fc_seq_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "fc_seq_sum": (C.c_int, [_p, _p, _i64, _i32, _i32, _p]),
+    "fc_token_scatter_add": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p]),
+    "fc_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _p]),
+    "fc_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
+    "fc_patch_embed": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "fc_text_embed": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
 }
 
 EPI_BIAS, EPI_BIAS_QGELU, EPI_BIAS_RESID, EPI_F32 = 0, 1, 2, 4

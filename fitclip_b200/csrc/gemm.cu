@@ -104,7 +104,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // each CTA fetches only half of the B tile and multicasts it into both CTAs' shared memory.
   const uint32_t cta_rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int num_tiles = ((num_m_tiles + 1) / 2) * num_n_tiles;  // pair-tiles; tile -> (m pair, n block), N fastest
+  // pair-tiles; tile -> (m pair, n block), N fastest.  EPI_F32_SPLITK: `k_splits` work items per pair-tile (item ->
+  // (k split, m pair, n block)), each accumulating its K range into a zero-initialised fp32 C with red.global.add.
+  constexpr bool kSplit = (EPI == EPI_F32_SPLITK);
+  const int num_m_pairs = (num_m_tiles + 1) / 2;
+  const int num_tiles = num_m_pairs * num_n_tiles * (kSplit ? p.k_splits : 1);
+  auto m_pair_of = [&](int t) { return kSplit ? (t / num_n_tiles) % num_m_pairs : t / num_n_tiles; };
+  auto k_begin = [&](int t) {
+    return kSplit ? static_cast<int>(static_cast<int64_t>(t / (num_n_tiles * num_m_pairs)) * num_k / p.k_splits) : 0;
+  };
+  auto k_end = [&](int t) {
+    return kSplit ? static_cast<int>(static_cast<int64_t>(t / (num_n_tiles * num_m_pairs) + 1) * num_k / p.k_splits)
+                  : num_k;
+  };
 
   griddep_launch_dependents();  // PDL: the next kernel's prologue may overlap this kernel's tail
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
@@ -141,8 +153,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       FC_T(long long w_stage = 0;)
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = 2 * (tile / num_n_tiles) + cta_rank, n_blk = tile % num_n_tiles;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int m_blk = 2 * m_pair_of(tile) + cta_rank, n_blk = tile % num_n_tiles;
+        const int kb1 = k_end(tile);
+        for (int kb = k_begin(tile); kb < kb1; ++kb) {
           FC_T(const long long tw = clock64();)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           FC_T(w_stage += clock64() - tw;)
@@ -176,7 +189,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         FC_T(w_acc += clock64() - tw; ++n_tiles;)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int kb0 = k_begin(tile), kb1 = k_end(tile);
+        for (int kb = kb0; kb < kb1; ++kb) {
           FC_T(tw = clock64();)
           mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
           FC_T(w_tma += clock64() - tw;)
@@ -187,7 +201,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance along K inside the 128-byte swizzle atom: +32 bytes per UMMA_K
             umma_bf16_ss_2cta(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2),
-                              umma_desc_k_sw128(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0);
+                              umma_desc_k_sw128(b_addr + k * UMMA_K * 2), idesc, ((kb - kb0) | k) != 0);
           }
           umma_commit_2cta_multicast(&empty_bar[stage], 0x3);  // frees the slot in BOTH CTAs when these MMAs retire
           if (++stage == STAGES) {
@@ -276,7 +290,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     FC_T(const long long e_begin = clock64(); long long w_full = 0;)
 
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = 2 * (tile / num_n_tiles) + cta_rank, n_blk = tile % num_n_tiles;
+      const int m_blk = 2 * m_pair_of(tile) + cta_rank, n_blk = tile % num_n_tiles;
       const int row = m_blk * BM + row_in_tile;
       const int n0 = n_blk * BN;
       const bool row_ok = row < p.M;
@@ -561,6 +575,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
               out4[j] = u;
             }
+          } else if (EPI == EPI_F32_SPLITK) {
+            float* out = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(out + j, p.alpha * __uint_as_float(rc[j]));
           } else if (EPI == EPI_F32) {
             float* out = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
             if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
@@ -667,7 +686,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     FC_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  const int pair_tiles = (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN);
+  const int pair_tiles = (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN) * (EPI == EPI_F32_SPLITK ? p.k_splits : 1);
   static int max_clusters = 0;
   if (!max_clusters) {
     max_clusters = num_sms() / 2;
@@ -738,6 +757,10 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
     }
   } else if (epilogue == EPI_F32) {
     FC_REQUIRE(p.C, "gemm: null C");
+  } else if (epilogue == EPI_F32_SPLITK) {
+    FC_REQUIRE(p.C, "gemm: null C");
+    FC_REQUIRE(p.k_splits >= 1 && p.k_splits <= (p.K + BK - 1) / BK, "gemm: k_splits=%d outside 1..%d", p.k_splits,
+               (p.K + BK - 1) / BK);
   } else if (epilogue == EPI_TARGET) {
     FC_REQUIRE(p.target && p.tscore_out, "gemm: target epilogue needs target and tscore_out");
   } else if (epilogue == EPI_COUNT) {
@@ -749,7 +772,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   ProfScope prof(stream, PROF_GEMM, epilogue, p.M, p.N, p.K, 2.0 * mn * p.K,
                  2.0 * (static_cast<double>(p.M) + p.N) * p.K +
                      (epilogue <= EPI_PATCH || ln ? 2.0 * mn : 0.0) * (epilogue == EPI_BIAS_RESID ? 2.0 : 1.0) +
-                     (epilogue == EPI_F32 ? 4.0 * mn : 0.0));
+                     (epilogue == EPI_F32 || epilogue == EPI_F32_SPLITK ? 4.0 * mn : 0.0));
   CUtensorMap ta, tb, tc, tr;
   int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
   if (rc) return rc;
@@ -772,6 +795,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
     case EPI_BIAS_RESID: return launch<EPI_BIAS_RESID>(ta, tb, tc, tr, p, stream);
     case EPI_PATCH: return launch<EPI_PATCH>(ta, tb, tc, tr, p, stream);
     case EPI_F32: return launch<EPI_F32>(ta, tb, tc, tr, p, stream);
+    case EPI_F32_SPLITK: return launch<EPI_F32_SPLITK>(ta, tb, tc, tr, p, stream);
     case EPI_TARGET: return launch<EPI_TARGET>(ta, tb, tc, tr, p, stream);
     case EPI_LN_BIAS: return launch<EPI_LN_BIAS>(ta, tb, tc, tr, p, stream);
     case EPI_LN_BIAS_QGELU: return launch<EPI_LN_BIAS_QGELU>(ta, tb, tc, tr, p, stream);

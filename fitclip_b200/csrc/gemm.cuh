@@ -14,7 +14,9 @@ enum Epilogue : int {
   EPI_COUNT = 6,       // counts[row] += #{col: acc > ts[row]} + #{col: acc == ts[row] and gcol < target[row]}
   EPI_LN_BIAS = 7,        // C(bf16) = rstd_m * (acc - mean_m * colsum_n) + bias_n   == LayerNorm(A) . W^T + b with the
   EPI_LN_BIAS_QGELU = 8,  //   LayerNorm affine folded into B / colsum / bias (see fold_ln_weights); 8 adds QuickGELU
-  EPI_NUM = 9,
+  EPI_F32_SPLITK = 9,     // C(fp32) += alpha * acc over `k_splits` K ranges (atomic adds; the caller zeroes C): weight
+                          //   gradients, whose few output tiles would otherwise leave most SM pairs idle
+  EPI_NUM = 10,
 };
 
 struct GemmParams {
@@ -25,6 +27,7 @@ struct GemmParams {
   const bf16* resid = nullptr;   // [M, ldr]
   int64_t ldr = 0;
   float alpha = 1.f;
+  int k_splits = 1;              // EPI_F32_SPLITK
   // EPI_LN_*: per-row partial (sum, sumsq) of A's rows, [M, ln_parts, 2] fp32; colsum[n] = sum_k B[n,k]
   const float* ln_stats = nullptr;
   int ln_parts = 0;

@@ -167,6 +167,60 @@ FC_API int fc_nce_loss(const float* scores, int64_t ld, int32_t B, float* worksp
 FC_API int fc_ts_nce_loss(const float* scores, const float* teacher_scores, int64_t ld, int32_t B, float* workspace,
                           float* out, void* stream);
 
+/* ---- training step: TeacherStudentLightningModule.training_step / _dataset_step_end
+ * (aligner/teacher_student.py:99-183) + torch.optim.AdamW (config/trainer.yaml:22-24).  The reference differentiates
+ * with torch.autograd; these are the explicit gradient kernels the Python trainer (fitclip_b200/training.py) chains.
+ * All activations are bf16 row-major (tokens, width); gradients of parameters are fp32 and ACCUMULATE (+=). -------- */
+/* C(fp32, M x N, zeroed or holding a running sum) += alpha * A[M,K] . B[N,K]^T, the K range cut into `k_splits` work
+ * items per output tile (0 = enough to fill the SMs): the weight-gradient GEMM dW = dY^T . X, whose K is the token count. */
+FC_API int fc_gemm_bf16_splitk(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                               float alpha, int32_t M, int32_t N, int32_t K, int32_t k_splits, void* stream);
+/* out (cols, ld_out) = transpose of the kept rows of in (rows, ld_in): rows come in groups of `group_len` whose first
+ * `group_skip` are dropped (0, 0 = keep all); columns [kept_rows, ld_out) are zero-filled.  colsum (optional, fp32
+ * (cols)) += column sums of the kept rows -- the bias gradient of a Linear whose output gradient is `in`. */
+FC_API int fc_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t kept_rows, int32_t cols,
+                             int32_t group_len, int32_t group_skip, float* colsum, void* stream);
+/* LayerNorm backward (slip.py:350-356): dx = [add +] dLN(x, dy); dgamma += , dbeta += .  dx may alias add. */
+FC_API int fc_layernorm_bwd_bf16(const void* x, const void* dy, const float* gamma, const void* add, void* dx,
+                                 float* dgamma, float* dbeta, int64_t rows, int32_t D, float eps, void* stream);
+/* QuickGELU (slip.py:359-361) forward g = u sigmoid(1.702 u) and backward du = dg * dg/du; du may alias dg. */
+FC_API int fc_quickgelu_bf16(const void* u, void* g, int64_t n, void* stream);
+FC_API int fc_quickgelu_bwd_bf16(const void* u, const void* dg, void* du, int64_t n, void* stream);
+/* Backward of fc_attention_bf16: qkv / dqkv (seqs*L, 3*heads*64), out / dout (seqs*L, heads*64); L <= 432. */
+FC_API int fc_attention_bwd_bf16(const void* qkv, const void* out, const void* dout, void* dqkv, int64_t seqs,
+                                 int32_t L, int32_t heads, int32_t causal, void* stream);
+/* nce_loss (teacher == NULL; aligner/loss.py:13-26) or TeacherStudentNCELoss("batchmean") (loss.py:29-39,
+ * teacher_student.py:73) of (B, ld) fp32 scores: value (optional) and gscale * d loss / d scores (optional).
+ * lse: 4*B floats of workspace. */
+FC_API int fc_loss_fwd_bwd(const float* scores, const float* teacher, int64_t ld, int32_t B, float* lse, float gscale,
+                           float* loss_out, float* dscores, int64_t ldd, void* stream);
+/* C = alpha * op(A) . op(B) in fp32 (score-matrix gradients dV = dS . T, dT = dS^T . V); trans_x: operand stored transposed. */
+FC_API int fc_sgemm_f32(int32_t trans_a, int32_t trans_b, int32_t M, int32_t N, int32_t K, float alpha, const float* A,
+                        int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, void* stream);
+/* Backward of fc_pool_normalize: x fp32 (rows_out*T, D), dout fp32 (rows_out, D) -> dx bf16 (rows_out*T, D). */
+FC_API int fc_pool_normalize_bwd(const float* x, const float* dout, void* dx_bf16, int64_t rows_out, int32_t T,
+                                 int32_t D, float scale, void* stream);
+/* Row of each sequence that feeds the head: EOT = first argmax of ids (slip.py:478), or row 0 (class token) when ids is
+ * NULL.  scatter = 0: rows[s] = x[s, eot];  1: x[s, eot] = rows[s] (x zeroed by the caller). */
+FC_API int fc_seq_rows(void* x, const int32_t* ids, void* rows, int64_t seqs, int32_t L, int32_t W, int32_t scatter,
+                       void* stream);
+/* out (L, W) fp32 += sum over sequences of dx (seqs, L, W): positional-embedding (and class-embedding) gradient. */
+FC_API int fc_seq_sum(const void* dx, float* out, int64_t seqs, int32_t L, int32_t W, void* stream);
+/* dtok[ids[t]] += dx[t]: token_embedding gradient. */
+FC_API int fc_token_scatter_add(const int32_t* ids, const void* dx, float* dtok, int64_t tokens, int32_t W,
+                                int32_t vocab, void* stream);
+/* One AdamW step over a flat fp32 buffer (decoupled weight decay, bias-corrected; step counts from 1); p_bf16
+ * (optional) receives the rounded parameters. */
+FC_API int fc_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int32_t step, void* stream);
+FC_API int fc_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+/* Training-forward front ends: conv1 patch embedding + class token + positional embedding (patches: bf16 scratch
+ * (F*G*G, 3*P*P), kept for the weight gradient), and token + positional embedding. */
+FC_API int fc_patch_embed(const void* frames, int dtype, const void* conv_w_bf16, const float* cls, const float* pos,
+                          void* patches, void* x, int64_t F, int32_t R, int32_t P, int32_t W, void* stream);
+FC_API int fc_text_embed(const int32_t* ids, const float* tok, const float* pos, void* x, int64_t C, int32_t L,
+                         int32_t W, int32_t vocab, int32_t* err_flag, void* stream);
+
 /* ---- kernel-level entry points (parity tests, microbenchmarks) -------------------------------------------------- */
 /* C[M,N] = epilogue(A[M,K] . B[N,K]^T): bf16 operands, K contiguous, fp32 accumulation in TMEM (tcgen05.mma). */
 FC_API int fc_gemm_bf16(int epilogue, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
