@@ -1,0 +1,365 @@
+"""Teacher-student training step on B200.
+
+Reference: ``TeacherStudentLightningModule`` (``aligner/teacher_student.py:43-183``): student and frozen teacher encode
+the same batch (``_step``, ``:93-96``); per dataset the scaled ``B x B`` score matrix feeds ``nce_loss`` (labelled) or
+``TeacherStudentNCELoss("batchmean") * exp(ts_scale)^2`` (unlabelled) (``_dataset_step_end``, ``:142-173``); the
+dataset losses are mixed with ``dataset_loss_share`` (``training_step_end``, ``:176-183``); Lightning then runs
+``loss.backward()`` and ``torch.optim.AdamW(lr=3e-6).step()`` (``config/trainer.yaml:22-24``, ``aligner/cli.py:126-134``).
+
+The reference gets the backward pass from torch.autograd.  Here it is an explicit chain of the kernels in
+``csrc/train.cu`` plus the tcgen05 GEMM (``fitclip_b200.train_ops``):
+
+* all parameters of the student live in ONE flat fp32 buffer (the ``nn.Parameter``s of the :class:`B200Clip` become
+  views into it), with flat fp32 gradient / Adam-moment buffers and a flat bf16 mirror next to it: the optimizer is one
+  launch, the gradient all-reduce across GPUs one NCCL call, and ``zero_grad`` one memset;
+* the forward keeps the activations the backward needs (per block: block input, QKV, attention output, post-attention
+  residual, MLP pre-activation = 10 x tokens x width bf16; 74 GB for 2048 frames of ViT-B/16, which is what the 180 GB
+  of HBM are for) -- nothing is recomputed except LayerNorm outputs and QuickGELU values (memory-bound, cheap);
+* dgrad GEMMs read transposed bf16 weight copies (refreshed after every optimizer step), wgrad GEMMs read transposed
+  activations and split K (= the token count) across the SMs.
+
+The kernel set is injected (``kernels=``) so that the orchestration can be checked on CPU against torch.autograd with
+torch stand-ins for every kernel (``tests/torch_kernels.py``, test infrastructure); the default and only product path
+is :class:`NativeKernels` -- there is no fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops, train_ops as T
+from .encoder import B200Clip
+
+GEMM_2D = ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight")
+
+
+class NativeKernels:
+    """The product kernel set: every call lands in ``libfitclip_b200.so``."""
+    act_dtype = torch.bfloat16
+
+    def __init__(self, device: torch.device) -> None:
+        self.device = device
+        self._zeros: Dict[int, torch.Tensor] = {}
+        self.err_flag = torch.zeros(64, device=device, dtype=torch.int32)
+
+    def zero_bias(self, n: int) -> torch.Tensor:
+        if n not in self._zeros:
+            self._zeros[n] = torch.zeros(n, device=self.device, dtype=torch.float32)
+        return self._zeros[n]
+
+    cast = staticmethod(T.f32_to_bf16)
+
+    def linear(self, a, w, bias=None, resid=None):
+        bias = self.zero_bias(w.shape[0]) if bias is None else bias
+        return ops.gemm_bf16(a, w, bias, resid, _lib.EPI_BIAS if resid is None else _lib.EPI_BIAS_RESID)
+
+    @staticmethod
+    def matmul_f32(a, b):
+        return ops.gemm_bf16(a, b, epilogue=_lib.EPI_F32)
+
+    layernorm = staticmethod(ops.layernorm_bf16)
+    layernorm_bwd = staticmethod(T.layernorm_bwd)
+    attention = staticmethod(ops.attention_bf16)
+    attention_bwd = staticmethod(T.attention_bwd)
+    quickgelu = staticmethod(T.quickgelu)
+    quickgelu_bwd = staticmethod(T.quickgelu_bwd)
+    transpose = staticmethod(T.transpose)
+    wgrad = staticmethod(T.gemm_splitk)
+    patch_embed = staticmethod(T.patch_embed)
+    gather_seq_rows = staticmethod(T.gather_seq_rows)
+    scatter_seq_rows = staticmethod(T.scatter_seq_rows)
+    seq_sum = staticmethod(T.seq_sum)
+    token_scatter_add = staticmethod(T.token_scatter_add)
+    pool_normalize = staticmethod(ops.pool_normalize)
+    pool_normalize_bwd = staticmethod(T.pool_normalize_bwd)
+    sgemm = staticmethod(T.sgemm)
+    loss_fwd_bwd = staticmethod(T.loss_fwd_bwd)
+    adamw_step = staticmethod(T.adamw_step)
+
+    def text_embed(self, ids, tok, pos):
+        return T.text_embed(ids, tok, pos, self.err_flag)
+
+
+class ClipTrainer:
+    """Forward-with-saved-activations, backward and AdamW for one :class:`B200Clip` (the student)."""
+
+    def __init__(self, model: B200Clip, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, kernels: Any = None) -> None:
+        self.model = model
+        self.cfg = dict(model.config)
+        if (3 * self.cfg["vision_patch_size"] ** 2) % 8:
+            raise ValueError("training needs 3 * patch_size^2 to be a multiple of 8 (ViT-B/16, ViT-B/32)")
+        named = [(n, p) for n, p in model.named_parameters() if n != "logit_scale"]
+        device = named[0][1].device
+        self.K = NativeKernels(device) if kernels is None else kernels
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+        # ---- one flat fp32 master buffer; the module's parameters become views into it
+        total = sum((p.numel() + 63) // 64 * 64 for _, p in named)  # 256-byte aligned slots (TMA / 16-byte loads)
+        self.flat = torch.zeros(total, device=device, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.flat_act = torch.zeros(total, device=device, dtype=self.K.act_dtype)
+        self.w: Dict[str, torch.Tensor] = {}   # fp32 parameter views
+        self.g: Dict[str, torch.Tensor] = {}   # fp32 gradient views
+        self.wb: Dict[str, torch.Tensor] = {}  # act-dtype (bf16) views of the mirror, GEMM weights as (N, K)
+        self.wt: Dict[str, torch.Tensor] = {}  # transposed act-dtype copies (K, N) for the dgrad GEMMs / projections
+        off = 0
+        for name, p in named:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + n].view(p.shape)
+            p.requires_grad_(False)
+            self.w[name] = p.data
+            self.g[name] = self.grad[off:off + n].view(p.shape)
+            self.wb[name] = self.flat_act[off:off + n].view(p.shape)
+            off += (n + 63) // 64 * 64
+        self._transposed = [n for n in self.w if n.endswith(GEMM_2D)] + ["visual.proj", "text_projection"]
+        self.refresh_weight_copies(full=True)
+
+    # ------------------------------------------------------------------------------------------------ weights
+    def refresh_weight_copies(self, full: bool = False) -> None:
+        """bf16 mirror (``full``: after an external edit of the fp32 parameters; AdamW refreshes it itself) and the
+        transposed copies the dgrad GEMMs read."""
+        if full:
+            self.K.cast(self.flat, out=self.flat_act)
+        for name in self._transposed:
+            w2 = self.wb[name]
+            self.wt[name] = self.K.transpose(w2.reshape(w2.shape[0], -1), out=self.wt.get(name))
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+    def optimizer_step(self, group=None) -> None:
+        """All-reduce(SUM) of the flat gradient across ``group`` (each rank holds the gradient of the GLOBAL-batch loss
+        through its own samples), then one fused AdamW launch and the weight-copy refresh."""
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                 and torch.distributed.get_world_size() > 1):
+            torch.distributed.all_reduce(self.grad, group=group)
+        self.step_count += 1
+        self.K.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
+                          self.eps, self.weight_decay, p_bf16=self.flat_act)
+        self.refresh_weight_copies()
+        # the evaluation engine of the module re-uploads its folded copies when it next runs
+        self.model._engine.signature = None
+
+    # ------------------------------------------------------------------------------------------------ blocks
+    def _blocks_forward(self, x, prefix: str, layers: int, seqs: int, L: int, heads: int, causal: bool, saved: List):
+        K, w, wb = self.K, self.w, self.wb
+        for i in range(layers):
+            p = f"{prefix}resblocks.{i}."
+            ln1 = K.layernorm(x, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
+            qkv = K.linear(ln1, wb[p + "attn.in_proj_weight"], w[p + "attn.in_proj_bias"])
+            att = K.attention(qkv, seqs, L, heads, causal)
+            x_mid = K.linear(att, wb[p + "attn.out_proj.weight"], w[p + "attn.out_proj.bias"], resid=x)
+            ln2 = K.layernorm(x_mid, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
+            u = K.linear(ln2, wb[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"])
+            act = K.quickgelu(u)
+            x_out = K.linear(act, wb[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"], resid=x_mid)
+            saved.append((x, qkv, att, x_mid, u))
+            x = x_out
+        return x
+
+    def _linear_backward(self, dy, x_in, name_w: str, name_b: str, want_dx: bool = True):
+        """Gradients of ``y = x_in @ W.T + b``: db += colsum(dy) (fused into the transpose of dy), dW += dy^T x_in,
+        returns dx = dy @ W."""
+        K = self.K
+        dy_t = K.transpose(dy, colsum=self.g[name_b] if name_b else None)
+        x_t = K.transpose(x_in)
+        gw = self.g[name_w]
+        K.wgrad(dy_t, x_t, gw.view(gw.shape[0], -1))
+        return K.linear(dy, self.wt[name_w]) if want_dx else None
+
+    def _blocks_backward(self, dx, prefix: str, layers: int, seqs: int, L: int, heads: int, causal: bool, saved: List):
+        K, w, g = self.K, self.w, self.g
+        for i in reversed(range(layers)):
+            p = f"{prefix}resblocks.{i}."
+            x_in, qkv, att, x_mid, u = saved.pop()
+            # x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
+            act = K.quickgelu(u)
+            dact = self._linear_backward(dx, act, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias")
+            del act
+            du = K.quickgelu_bwd(u, dact, out=dact)
+            ln2 = K.layernorm(x_mid, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
+            dln2 = self._linear_backward(du, ln2, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias")
+            del du, dact, ln2
+            dx_mid = K.layernorm_bwd(x_mid, dln2, w[p + "ln_2.weight"], g[p + "ln_2.weight"], g[p + "ln_2.bias"],
+                                     add=dx, out=dx)
+            # x_mid = x_in + out_proj(attention(in_proj(ln_1(x_in))))
+            datt = self._linear_backward(dx_mid, att, p + "attn.out_proj.weight", p + "attn.out_proj.bias")
+            dqkv = K.attention_bwd(qkv, att, datt, seqs, L, heads, causal)
+            ln1 = K.layernorm(x_in, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
+            dln1 = self._linear_backward(dqkv, ln1, p + "attn.in_proj_weight", p + "attn.in_proj_bias")
+            del dqkv, datt, ln1
+            dx = K.layernorm_bwd(x_in, dln1, w[p + "ln_1.weight"], g[p + "ln_1.weight"], g[p + "ln_1.bias"],
+                                 add=dx_mid, out=dx_mid)
+        return dx
+
+    # ------------------------------------------------------------------------------------------------ heads
+    def _head_forward(self, x, ids, seqs: int, L: int, ln: str, proj: str, pool: int, ctx: Dict) -> torch.Tensor:
+        K, w = self.K, self.w
+        rows = K.gather_seq_rows(x, ids, seqs, L)
+        normed = K.layernorm(rows, w[ln + ".weight"], w[ln + ".bias"])
+        feat = K.matmul_f32(normed, self.wt[proj])  # (seqs, E) fp32 = ln(x[eot]) @ proj
+        ctx.update(rows=rows, normed=normed, feat=feat, ids=ids, seqs=seqs, L=L, pool=pool)
+        return K.pool_normalize(feat, pool)
+
+    def _head_backward(self, dpooled, ln: str, proj: str, ctx: Dict):
+        K, w, g = self.K, self.w, self.g
+        dfeat = K.pool_normalize_bwd(ctx["feat"], dpooled.contiguous(), ctx["pool"])
+        # feat = normed @ proj with proj (W, E):  dproj += normed^T dfeat,  dnormed = dfeat @ proj^T
+        K.wgrad(K.transpose(ctx["normed"]), K.transpose(dfeat), g[proj])
+        dnormed = K.linear(dfeat, self.wb[proj])
+        drows = K.layernorm_bwd(ctx["rows"], dnormed, w[ln + ".weight"], g[ln + ".weight"], g[ln + ".bias"])
+        return K.scatter_seq_rows(drows, ctx["ids"], ctx["L"])
+
+    # ------------------------------------------------------------------------------------------------ towers
+    def encode_video(self, video: torch.Tensor) -> torch.Tensor:
+        """``ClipVideoTextEncoder.encode_video`` (clip_video_text_encoder.py:80-89) keeping what backward needs."""
+        K, w, c = self.K, self.w, self.cfg
+        B, Tn = video.shape[:2]
+        F = B * Tn
+        G = c["image_resolution"] // c["vision_patch_size"]
+        L, W = G * G + 1, c["vision_width"]
+        frames = video.reshape(F, *video.shape[2:]).contiguous()
+        conv = self.wb["visual.conv1.weight"].view(W, -1)
+        x0, patches = K.patch_embed(frames, conv, w["visual.class_embedding"], w["visual.positional_embedding"],
+                                    c["vision_patch_size"])
+        x = K.layernorm(x0, w["visual.ln_pre.weight"], w["visual.ln_pre.bias"])
+        saved: List = []
+        x = self._blocks_forward(x, "visual.transformer.", c["vision_layers"], F, L, W // 64, False, saved)
+        head: Dict = {}
+        out = self._head_forward(x, None, F, L, "visual.ln_post", "visual.proj", Tn, head)
+        self._vis = dict(x0=x0, patches=patches, saved=saved, head=head, F=F, L=L, W=W)
+        return out
+
+    def backward_video(self, dvideo: torch.Tensor) -> None:
+        K, w, g, c, v = self.K, self.w, self.g, self.cfg, self._vis
+        F, L, W = v["F"], v["L"], v["W"]
+        dx = self._head_backward(dvideo, "visual.ln_post", "visual.proj", v["head"])
+        dx = self._blocks_backward(dx, "visual.transformer.", c["vision_layers"], F, L, W // 64, False, v["saved"])
+        dx0 = K.layernorm_bwd(v["x0"], dx, w["visual.ln_pre.weight"], g["visual.ln_pre.weight"],
+                              g["visual.ln_pre.bias"], out=dx)
+        # x0[f, 0] = class_embedding + pos[0];  x0[f, 1 + p] = conv1(patch p) + pos[1 + p]
+        K.seq_sum(dx0, g["visual.positional_embedding"], F, L)
+        K.seq_sum(K.gather_seq_rows(dx0, None, F, L), g["visual.class_embedding"], F, 1)
+        gconv = g["visual.conv1.weight"]
+        K.wgrad(K.transpose(dx0, group_len=L, group_skip=1), K.transpose(v["patches"]), gconv.view(W, -1))
+        self._vis = None
+
+    def encode_text(self, ids: torch.Tensor) -> torch.Tensor:
+        """``ClipVideoTextEncoder.encode_text`` (clip_video_text_encoder.py:92-94) keeping what backward needs."""
+        K, w, c = self.K, self.w, self.cfg
+        ids = ids.to(torch.int32).contiguous()
+        C, L = ids.shape
+        W = c["transformer_width"]
+        x = K.text_embed(ids, w["token_embedding.weight"], w["positional_embedding"])
+        saved: List = []
+        x = self._blocks_forward(x, "transformer.", c["transformer_layers"], C, L, c["transformer_heads"], True, saved)
+        head: Dict = {}
+        out = self._head_forward(x, ids, C, L, "ln_final", "text_projection", 1, head)
+        self._txt = dict(ids=ids, saved=saved, head=head, C=C, L=L)
+        return out
+
+    def backward_text(self, dtext: torch.Tensor) -> None:
+        K, g, c, t = self.K, self.g, self.cfg, self._txt
+        C, L = t["C"], t["L"]
+        dx = self._head_backward(dtext, "ln_final", "text_projection", t["head"])
+        dx = self._blocks_backward(dx, "transformer.", c["transformer_layers"], C, L, c["transformer_heads"], True,
+                                   t["saved"])
+        K.seq_sum(dx, g["positional_embedding"], C, L)
+        K.token_scatter_add(t["ids"].view(-1), dx, g["token_embedding.weight"])
+        self._txt = None
+
+
+def _all_gather_rows(t: torch.Tensor, group) -> Tuple[torch.Tensor, int]:
+    """(world * B, D) concatenation of every rank's (B, D) rows + this rank's row offset (``all_gather`` of
+    ``util/tensor_utils.py:48-66``; equal local batch sizes, as the reference's DistributedSampler gives)."""
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t, 0
+    out = torch.empty(dist.get_world_size(group) * t.shape[0], *t.shape[1:], device=t.device, dtype=t.dtype)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out, dist.get_rank(group) * t.shape[0]
+
+
+class TeacherStudentTrainingModule:
+    """``TeacherStudentLightningModule`` training path without Lightning: :meth:`training_step` is
+    ``training_step`` + ``training_step_end`` + ``backward`` + ``optimizer_step`` of the reference loop.
+
+    ``batch``: ``video_student`` / ``video_teacher`` ``(B,T,3,R,R)``, ``text_student`` / ``text_teacher``
+    ``{"input_ids": (B, 77)}``, and ``dataset``: a sequence of dataset names, one per sample, grouped
+    (``teacher_student.py:101-103``); default: all samples belong to the unlabelled dataset."""
+
+    def __init__(self, encoder, teacher, init_temperature: float = 0.05, labeled_dataset_name: str = "labeled",
+                 labeled_dataset_loss_share: Optional[float] = None,
+                 dataset_names: Sequence[str] = ("labeled", "unlabeled"), lr: float = 3e-6,
+                 weight_decay: float = 1e-2, group=None, kernels: Any = None) -> None:
+        self.encoder, self.teacher = encoder, teacher
+        self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels)
+        self.K = self.trainer.K
+        self.group = group
+        self.logit_scale = -math.log(init_temperature)                # video_text_module.py:32
+        self.teacher_student_logit_scale = self.logit_scale          # teacher_student.py:70-71
+        self.labeled_dataset_name = labeled_dataset_name
+        names = list(dataset_names)
+        if labeled_dataset_loss_share is None:                        # teacher_student.py:60-66
+            self.dataset_loss_share = {n: 1 / len(names) for n in names}
+        else:
+            self.dataset_loss_share = {n: (1 - labeled_dataset_loss_share) / (len(names) - 1) for n in names}
+            self.dataset_loss_share[labeled_dataset_name] = labeled_dataset_loss_share
+        self.unlabeled_dataset_name = next(n for n in names if n != labeled_dataset_name)
+
+    def _sections(self, batch: Mapping[str, Any], n: int) -> List[Tuple[str, int, int]]:
+        names = batch.get("dataset")
+        if names is None:
+            return [(self.unlabeled_dataset_name, 0, n)]
+        out, start = [], 0
+        for i in range(1, n + 1):
+            if i == n or names[i] != names[start]:
+                out.append((names[start], start, i))
+                start = i
+        return out
+
+    def training_step(self, batch: Mapping[str, Any], _batch_idx: int = 0, optimize: bool = True) -> torch.Tensor:
+        K, tr = self.K, self.trainer
+        tr.zero_grad()
+        # _step (teacher_student.py:93-96): student with saved activations, teacher on the evaluation path
+        v_local = tr.encode_video(batch["video_student"])
+        t_local = tr.encode_text(batch["text_student"]["input_ids"])
+        with torch.no_grad():
+            tv_local = self.teacher.encode_video(batch["video_teacher"])
+            tt_local = self.teacher.encode_text(batch["text_teacher"])
+        n_local = v_local.shape[0]
+        # _dataset_step_end (:142-173): gather across ranks (sections are per-rank contiguous, so gather per section)
+        scale, ts_scale = math.exp(self.logit_scale), math.exp(self.teacher_student_logit_scale)
+        dv = torch.zeros_like(v_local)
+        dt = torch.zeros_like(t_local)
+        total = None
+        for name, lo, hi in self._sections(batch, n_local):
+            v, off = _all_gather_rows(v_local[lo:hi].contiguous(), self.group)
+            t, _ = _all_gather_rows(t_local[lo:hi].contiguous(), self.group)
+            share = self.dataset_loss_share[name]
+            scores = K.sgemm(v, t, trans_b=True, alpha=scale)
+            if name == self.labeled_dataset_name:
+                loss, dscores = K.loss_fwd_bwd(scores, None, gscale=share)
+                loss = loss * share
+            else:
+                tv, _ = _all_gather_rows(tv_local[lo:hi].contiguous(), self.group)
+                tt, _ = _all_gather_rows(tt_local[lo:hi].contiguous(), self.group)
+                teacher_scores = K.sgemm(tv, tt, trans_b=True, alpha=ts_scale)
+                loss, dscores = K.loss_fwd_bwd(scores, teacher_scores, gscale=share * ts_scale ** 2)
+                loss = loss * (share * ts_scale ** 2)
+            total = loss if total is None else total + loss
+            # scores = scale * V T^T:  dV = scale * dS T,  dT = scale * dS^T V; keep this rank's rows
+            n = hi - lo
+            dv[lo:hi] = K.sgemm(dscores[off:off + n], t, alpha=scale)
+            dt[lo:hi] = K.sgemm(dscores[:, off:off + n], v, trans_a=True, alpha=scale)
+        tr.backward_text(dt)
+        tr.backward_video(dv)
+        if optimize:
+            tr.optimizer_step(self.group)
+        return total

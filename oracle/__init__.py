@@ -26,3 +26,4 @@ from .metrics_ref import (ref_accuracy_at_k, ref_median_rank, ref_rank, ref_reca
 from .wise_ref import ref_wise, ref_wise_state_dict  # noqa: F401
 from .preprocess_ref import ref_eval_transform, ref_resized_size  # noqa: F401
 from .loss_ref import ref_nce_loss, ref_teacher_student_nce_loss  # noqa: F401
+from .train_ref import ref_training_loss, ref_training_step  # noqa: F401

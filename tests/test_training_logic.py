@@ -1,0 +1,153 @@
+"""Orchestration of the explicit training step (fitclip_b200/training.py) on CPU: with torch
+stand-ins for every kernel (tests/torch_kernels.py) the trainer's loss, every parameter gradient and the AdamW update
+must equal torch.autograd + torch.optim.AdamW on the oracle's restatement of the reference step
+(oracle/train_ref.py <- aligner/teacher_student.py:93-183).  The kernels themselves are checked on the GPU
+(tests/test_gpu_train_kernels.py); the two together with tests/test_gpu_training.py cover the CUDA path."""
+import copy
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from fitclip_b200 import B200ClipVideoTextEncoder
+from fitclip_b200.training import ClipTrainer, TeacherStudentTrainingModule
+from torch_kernels import TorchKernels
+
+TINY = dict(embed_dim=32, image_resolution=32, vision_layers=2, vision_width=128, vision_patch_size=8,
+            context_length=12, vocab_size=64, transformer_width=64, transformer_heads=1, transformer_layers=2)
+
+
+def make_models():
+    student = oracle.clip_vit_b_16(seed=0, **TINY)
+    teacher = oracle.clip_vit_b_16(seed=1, **TINY)
+    # non-trivial LayerNorm affines and biases, so that every gradient path carries signal
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for n, p in student.named_parameters():
+            if n.endswith("bias") or "ln_" in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    return student.train(), teacher.eval()
+
+
+def make_batch(n, seed=0, names=None):
+    g = torch.Generator().manual_seed(seed)
+    video = torch.randn(n, 2, 3, 32, 32, generator=g)
+    ids = oracle.tokenize_synthetic(n, (4, 12), seed=seed + 1, context_length=12, vocab_size=64)
+    batch = {"video_student": video, "video_teacher": video, "text_student": {"input_ids": ids},
+             "text_teacher": {"input_ids": ids}}
+    if names is not None:
+        batch["dataset"] = names
+    return batch
+
+
+def sections_of(names, n):
+    if names is None:
+        return [("unlabeled", 0, n)]
+    out, start = [], 0
+    for i in range(1, n + 1):
+        if i == n or names[i] != names[start]:
+            out.append((names[start], start, i))
+            start = i
+    return out
+
+
+@pytest.mark.parametrize("names", [None, ["labeled"] * 3 + ["unlabeled"] * 5])
+def test_gradients_and_adamw_match_autograd(names):
+    student, teacher = make_models()
+    ref_student = oracle.RefClipVideoTextEncoder(copy.deepcopy(student))
+    ref_teacher = oracle.RefClipVideoTextEncoder(teacher)
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    module = TeacherStudentTrainingModule(enc, ref_teacher, lr=1e-3, kernels=TorchKernels())
+    opt = torch.optim.AdamW(ref_student.model.parameters(), lr=1e-3)
+    for step in range(2):
+        batch = make_batch(8, seed=10 * step, names=names)
+        shares = {"labeled": 0.5, "unlabeled": 0.5}
+        ref_loss, ref_grads = oracle.ref_training_step(ref_student, ref_teacher, batch, sections_of(names, 8), opt,
+                                                       shares=shares)
+        loss = module.training_step(batch, step, optimize=False)
+        assert torch.allclose(loss, ref_loss, rtol=1e-4, atol=1e-5), (float(loss), float(ref_loss))
+        tr = module.trainer
+        assert set(ref_grads) <= set(tr.g)
+        for name, ref in ref_grads.items():
+            got = tr.g[name]
+            scale = ref.abs().max().item()
+            err = (got - ref).abs().max().item()
+            assert err <= 2e-4 * scale + 1e-6, f"{name}: {err:.3e} vs {scale:.3e}"
+        # Adam divides by sqrt(v): entries whose true gradient is zero (the key bias of every attention: softmax is
+        # shift-invariant) are pure rounding noise and get a +-lr update of arbitrary sign in BOTH implementations.  The
+        # optimizer is therefore compared on identical gradient inputs (their parity is asserted above).
+        for name, ref in ref_grads.items():
+            tr.g[name].copy_(ref)
+        tr.optimizer_step()
+        for name, p in ref_student.model.named_parameters():
+            assert torch.allclose(tr.w[name], p.detach(), rtol=1e-5, atol=1e-6), name
+        # the module's own parameters ARE the trained ones (views into the flat buffer)
+        assert enc.model.visual.proj.data_ptr() == tr.w["visual.proj"].data_ptr()
+
+
+def test_flat_buffers_and_weight_copies():
+    student, _ = make_models()
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    tr = ClipTrainer(enc.model, kernels=TorchKernels())
+    sd = student.state_dict()
+    for name, p in enc.model.named_parameters():
+        assert torch.equal(p, sd[name]) and p.data_ptr() >= tr.flat.data_ptr()
+        assert (p.data_ptr() - tr.flat.data_ptr()) % 256 == 0
+    w = tr.wb["visual.transformer.resblocks.0.mlp.c_fc.weight"]
+    assert torch.equal(tr.wt["visual.transformer.resblocks.0.mlp.c_fc.weight"], w.T)
+    assert torch.equal(tr.wt["visual.proj"], tr.w["visual.proj"].T)
+    tr.grad.fill_(1.0)
+    tr.zero_grad()
+    assert float(tr.grad.abs().sum()) == 0.0
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        student, teacher = make_models()
+        enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+        module = TeacherStudentTrainingModule(enc, oracle.RefClipVideoTextEncoder(teacher), lr=1e-3,
+                                              kernels=TorchKernels())
+        full = make_batch(8, seed=3)
+        per = 8 // world
+        sl = slice(rank * per, (rank + 1) * per)
+        local = {"video_student": full["video_student"][sl], "video_teacher": full["video_teacher"][sl],
+                 "text_student": {"input_ids": full["text_student"]["input_ids"][sl]},
+                 "text_teacher": {"input_ids": full["text_teacher"]["input_ids"][sl]}}
+        loss = module.training_step(local, 0, optimize=True)
+        torch.save({"loss": loss, "flat": module.trainer.flat.clone(), "grad": module.trainer.grad.clone()},
+                   os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_match_one(tmp_path):
+    """Data-parallel step on 2 gloo ranks (embeddings all-gathered, flat gradient all-reduced) == the same step on the
+    whole batch in one process."""
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    student, teacher = make_models()
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    module = TeacherStudentTrainingModule(enc, oracle.RefClipVideoTextEncoder(teacher), lr=1e-3, kernels=TorchKernels())
+    loss = module.training_step(make_batch(8, seed=3), 0, optimize=True)
+    for rank in range(2):
+        got = torch.load(os.path.join(str(tmp_path), f"rank{rank}.pt"))
+        assert torch.allclose(got["loss"], loss, rtol=1e-5, atol=1e-6)
+        scale = module.trainer.grad.abs().max().item()
+        assert (got["grad"] - module.trainer.grad).abs().max().item() <= 1e-4 * scale
+        # parameters: compared where the gradient is above rounding noise (Adam turns noise into +-lr steps)
+        sig = module.trainer.grad.abs() > 1e-4 * scale
+        assert torch.allclose(got["flat"][sig], module.trainer.flat[sig], rtol=1e-4, atol=2e-5)
+    a, b = (torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(2))
+    assert torch.equal(a["grad"], b["grad"]) and torch.equal(a["flat"], b["flat"])  # replicas stay bit-identical
