@@ -69,10 +69,13 @@ SIGNATURES = {
     "fc_attention_bf16": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p]),
     # training step (row f3)
     "fc_gemm_bf16_splitk": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _f32, _i32, _i32, _i32, _i32, _p]),
+    "fc_gemm_bf16_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _f32, _i32,
+                                      _i32, _i32, _i32, _p]),
+    "fc_colsum_bf16": (C.c_int, [_p, _i64, _i64, _i32, _p, _p]),
     "fc_transpose_bf16": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p, _p]),
     "fc_layernorm_bwd_bf16": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _f32, _p]),
     "fc_quickgelu_bf16": (C.c_int, [_p, _p, _i64, _p]),
-    "fc_quickgelu_bwd_bf16": (C.c_int, [_p, _p, _p, _i64, _p]),
+    "fc_quickgelu_bwd_bf16": (C.c_int, [_p, _p, _p, _p, _i64, _p]),
     "fc_attention_bwd_bf16": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "fc_loss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i32, _p, _f32, _p, _p, _i64, _p]),
     "fc_sgemm_f32": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _f32, _p, _i64, _p, _i64, _p, _i64, _p]),
@@ -86,7 +89,7 @@ SIGNATURES = {
     "fc_text_embed": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
 }
 
-EPI_BIAS, EPI_BIAS_QGELU, EPI_BIAS_RESID, EPI_F32 = 0, 1, 2, 4
+EPI_BIAS, EPI_BIAS_QGELU, EPI_BIAS_RESID, EPI_F32, EPI_F32_SPLITK = 0, 1, 2, 4, 9
 DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 _lib: Optional[C.CDLL] = None

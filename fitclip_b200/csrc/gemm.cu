@@ -78,7 +78,11 @@ __device__ __forceinline__ float quick_gelu(float v) {
   return fmaf(h, tanh_approx(0.851f * v), h);
 }
 
-template <int EPI>
+// MAJ: bit 0 = A is MN-major (stored [K rows][M contiguous]), bit 1 = B is MN-major (stored [K rows][N contiguous]).
+// An MN-major 128 x 64 operand tile is fetched as two 64 (MN) x 64 (K) boxes of 8 KiB: K rows of 128 bytes, 128-byte
+// swizzle, LBO = 8 KiB between the two MN halves, SBO = 1 KiB between groups of 8 K rows, +2 KiB per UMMA_K step.  The
+// backward GEMMs use it to read dY / X / W exactly as the forward pass stored them (no transposed copies).
+template <int EPI, int MAJ = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -86,6 +90,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr bool kLn = (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_QGELU);
   constexpr bool kGelu = (EPI == EPI_BIAS_QGELU || EPI == EPI_LN_BIAS_QGELU);
   constexpr bool kStaged = (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || EPI == EPI_BIAS_RESID || kLn);
+  constexpr bool kAmn = (MAJ & 1) != 0, kBmn = (MAJ & 2) != 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -164,8 +169,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // both CTAs' bytes are credited to the LEADER's full barrier, which alone gates the pair's MMAs
           if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
           const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_2cta(sA, &tmA, leader_full, kb * BK, m_blk * BM);
-          tma_load_2d_2cta(sB, &tmB, leader_full, kb * BK, n_blk * BN + cta_rank * (BN / 2));
+          if (kAmn) {
+            tma_load_2d_2cta(sA, &tmA, leader_full, m_blk * BM, kb * BK);
+            tma_load_2d_2cta(sA + A_BYTES / 2, &tmA, leader_full, m_blk * BM + 64, kb * BK);
+          } else {
+            tma_load_2d_2cta(sA, &tmA, leader_full, kb * BK, m_blk * BM);
+          }
+          if (kBmn) {
+            tma_load_2d_2cta(sB, &tmB, leader_full, n_blk * BN + cta_rank * (BN / 2), kb * BK);
+            tma_load_2d_2cta(sB + B_BYTES / 2, &tmB, leader_full, n_blk * BN + cta_rank * (BN / 2) + 64, kb * BK);
+          } else {
+            tma_load_2d_2cta(sB, &tmB, leader_full, kb * BK, n_blk * BN + cta_rank * (BN / 2));
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -177,7 +192,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);  // M = 256 across the CTA pair
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN) | (kAmn ? (1u << 15) : 0u) | (kBmn ? (1u << 16) : 0u);  // M = 256 across the CTA pair
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -200,8 +215,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance along K inside the 128-byte swizzle atom: +32 bytes per UMMA_K
-            umma_bf16_ss_2cta(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2),
-                              umma_desc_k_sw128(b_addr + k * UMMA_K * 2), idesc, ((kb - kb0) | k) != 0);
+            const uint64_t a_desc = kAmn ? umma_desc_mn_sw128_lbo(a_addr + k * UMMA_K * 128, A_BYTES / 2)
+                                         : umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t b_desc = kBmn ? umma_desc_mn_sw128_lbo(b_addr + k * UMMA_K * 128, B_BYTES / 2)
+                                         : umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
+            umma_bf16_ss_2cta(d_tmem, a_desc, b_desc, idesc, ((kb - kb0) | k) != 0);
           }
           umma_commit_2cta_multicast(&empty_bar[stage], 0x3);  // frees the slot in BOTH CTAs when these MMAs retire
           if (++stage == STAGES) {
@@ -678,12 +696,34 @@ int make_tmap(CUtensorMap* tm, const bf16* base, int64_t rows, int64_t cols, int
   return FC_OK;
 }
 
-template <int EPI>
+// MN-major operand: stored [k_rows][mn_cols] with mn contiguous; box = 64 (MN) x 64 (K rows), 128B swizzle.
+int make_tmap_mn(CUtensorMap* tm, const bf16* base, int64_t k_rows, int64_t mn_cols, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return FC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(mn_cols), static_cast<cuuint64_t>(k_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(bf16)};
+  cuuint32_t box[2] = {64, BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (MN-major) failed (CUresult %d) k=%lld mn=%lld ld=%lld", static_cast<int>(r),
+              static_cast<long long>(k_rows), static_cast<long long>(mn_cols), static_cast<long long>(ld));
+    return FC_ERR_CUDA;
+  }
+  return FC_OK;
+}
+
+template <int EPI, int MAJ = 0>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
            const GemmParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    FC_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FC_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI, MAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   const int pair_tiles = (((p.M + BM - 1) / BM + 1) / 2) * ((p.N + BN - 1) / BN) * (EPI == EPI_F32_SPLITK ? p.k_splits : 1);
@@ -711,7 +751,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   note_launch();
-  FC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI>, ta, tb, tc, tr, p));
+  FC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI, MAJ>, ta, tb, tc, tr, p));
   return FC_OK;
 }
 
@@ -733,7 +773,8 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
                  cudaStream_t stream) {
   FC_REQUIRE(A && B, "gemm: null operand");
   FC_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  FC_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm: K/lda/ldb must be multiples of 8 (K=%d)", p.K);
+  FC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ((p.a_mn && p.b_mn) || p.K % 8 == 0),
+             "gemm: lda/ldb (and K of a K-major operand) must be multiples of 8 (K=%d)", p.K);
   FC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
              "gemm: operands must be 16-byte aligned");
   const bool ln = epilogue == EPI_LN_BIAS || epilogue == EPI_LN_BIAS_QGELU;
@@ -774,9 +815,14 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
                      (epilogue <= EPI_PATCH || ln ? 2.0 * mn : 0.0) * (epilogue == EPI_BIAS_RESID ? 2.0 : 1.0) +
                      (epilogue == EPI_F32 || epilogue == EPI_F32_SPLITK ? 4.0 * mn : 0.0));
   CUtensorMap ta, tb, tc, tr;
-  int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
+  const int maj = (p.a_mn ? 1 : 0) | (p.b_mn ? 2 : 0);
+  FC_REQUIRE(maj == 0 || (maj == 2 && (epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESID || epilogue == EPI_F32)) ||
+                 (maj == 3 && epilogue == EPI_F32_SPLITK),
+             "gemm: operand layout a_mn=%d b_mn=%d is not built for epilogue %d", p.a_mn, p.b_mn, epilogue);
+  int rc = p.a_mn ? make_tmap_mn(&ta, A, p.K, p.M, lda) : make_tmap(&ta, A, p.M, p.K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap(&tb, B, p.N, p.K, ldb, BN / 2);  // each CTA of a pair loads (and multicasts) half of the B tile
+  // each CTA of a pair loads half of the B tile
+  rc = p.b_mn ? make_tmap_mn(&tb, B, p.K, p.N, ldb) : make_tmap(&tb, B, p.N, p.K, ldb, BN / 2);
   if (rc) return rc;
   tc = ta;
   tr = ta;
@@ -789,6 +835,12 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
       if (rc) return rc;
     }
   }
+  if (maj == 2) {
+    if (epilogue == EPI_BIAS) return launch<EPI_BIAS, 2>(ta, tb, tc, tr, p, stream);
+    if (epilogue == EPI_BIAS_RESID) return launch<EPI_BIAS_RESID, 2>(ta, tb, tc, tr, p, stream);
+    return launch<EPI_F32, 2>(ta, tb, tc, tr, p, stream);
+  }
+  if (maj == 3) return launch<EPI_F32_SPLITK, 3>(ta, tb, tc, tr, p, stream);
   switch (epilogue) {
     case EPI_BIAS: return launch<EPI_BIAS>(ta, tb, tc, tr, p, stream);
     case EPI_BIAS_QGELU: return launch<EPI_BIAS_QGELU>(ta, tb, tc, tr, p, stream);

@@ -28,6 +28,9 @@ struct GemmParams {
   int64_t ldr = 0;
   float alpha = 1.f;
   int k_splits = 1;              // EPI_F32_SPLITK
+  // operand storage: false = K-major ([rows][K contiguous], the default), true = MN-major ([K rows][M or N contiguous],
+  // i.e. the operand is the transpose of a row-major matrix and is read in place).  lda / ldb stay the row strides.
+  bool a_mn = false, b_mn = false;
   // EPI_LN_*: per-row partial (sum, sumsq) of A's rows, [M, ln_parts, 2] fp32; colsum[n] = sum_k B[n,k]
   const float* ln_stats = nullptr;
   int ln_parts = 0;

@@ -12,6 +12,7 @@
 //   memory-bound        LayerNorm backward (+ residual add), QuickGELU forward/backward, pool+normalise backward,
 //                       embedding scatter/sums, loss gradients, fused AdamW over ONE flat parameter buffer.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/fitclip_b200.h"
 #include "gemm.cuh"
@@ -83,6 +84,39 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
       for (int i = 0; i < 8; ++i) a += cs[i][threadIdx.x];
       atomicAdd(colsum + c0 + threadIdx.x, a);
     }
+  }
+}
+
+// colsum[c] += sum_r x[r, c]: the bias gradient of a Linear from its output gradient (one read of dY, fp32 atomics).
+// A CTA owns 64 columns x `rows_per_block` rows; a warp reads one 128-byte row segment per step.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ld, int64_t rows, int cols,
+                                                          int64_t rows_per_block, float* __restrict__ colsum) {
+  __shared__ float cs[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * tx;
+  const int64_t r0 = blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+  if (c < cols) {
+    int64_t r = r0 + ty;
+    for (; r + 8 < r1; r += 16) {  // two independent loads in flight per thread
+      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+      const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + (r + 8) * ld + c));
+      s0 += a.x; s1 += a.y; t0 += b.x; t1 += b.y;
+    }
+    if (r < r1) {
+      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+      s0 += a.x; s1 += a.y;
+    }
+  }
+  cs[ty][2 * tx] = s0 + t0;
+  cs[ty][2 * tx + 1] = s1 + t1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += cs[i][threadIdx.x];
+    atomicAdd(colsum + blockIdx.x * 64 + threadIdx.x, a);
   }
 }
 
@@ -230,24 +264,24 @@ __global__ void __launch_bounds__(256) quickgelu_kernel(const bf16* __restrict__
   }
 }
 
-__device__ __forceinline__ float quickgelu_grad(float u, float dg) {
-  const float s = 1.f / (1.f + __expf(-1.702f * u));
-  return dg * s * (1.f + 1.702f * u * (1.f - s));
-}
-
+// g_out (optional): also writes g = quickgelu(u), which the weight gradient of the following Linear reads -- one pass
+// over u instead of a separate recomputation.
 __global__ void __launch_bounds__(256) quickgelu_bwd_kernel(const bf16* __restrict__ u, const bf16* dg, bf16* du,
-                                                            int64_t n8) {
+                                                            bf16* __restrict__ g_out, int64_t n8) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
     const uint4 a = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i);
     const uint4 b = *(reinterpret_cast<const uint4*>(dg) + i);
     const uint32_t w[4] = {a.x, a.y, a.z, a.w}, v[4] = {b.x, b.y, b.z, b.w};
-    uint32_t o[4];
+    uint32_t o[4], go[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const float2 f = unpack_bf16x2(w[t]), d = unpack_bf16x2(v[t]);
-      o[t] = pack_bf16x2(quickgelu_grad(f.x, d.x), quickgelu_grad(f.y, d.y));
+      const float s0 = 1.f / (1.f + __expf(-1.702f * f.x)), s1 = 1.f / (1.f + __expf(-1.702f * f.y));
+      o[t] = pack_bf16x2(d.x * s0 * (1.f + 1.702f * f.x * (1.f - s0)), d.y * s1 * (1.f + 1.702f * f.y * (1.f - s1)));
+      go[t] = pack_bf16x2(f.x * s0, f.y * s1);
     }
     *(reinterpret_cast<uint4*>(du) + i) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (g_out) st_na_v4(reinterpret_cast<uint4*>(g_out) + i, make_uint4(go[0], go[1], go[2], go[3]));
   }
 }
 
@@ -283,6 +317,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ uint32_t sw(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+__device__ __forceinline__ float ex2(float x) {  // one MUFU op; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // 16 x 64 A-operand fragments of rows row0.. of a swizzled tile
 __device__ __forceinline__ void load_a_frags(uint32_t (&f)[4][4], uint32_t tile, int row0, int lane) {
@@ -351,13 +390,13 @@ __device__ __forceinline__ void bwd_lse_block(const uint32_t (&qf)[4][4], uint32
     mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
     mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
     const float mnew = fmaxf(m[r], mx[r]);
-    l[r] *= exp2f((m[r] - mnew) * scale_log2);
+    l[r] *= ex2((m[r] - mnew) * scale_log2);
     m[r] = mnew;
   }
 #pragma unroll
   for (int j = 0; j < NT; ++j)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) l[e >> 1] += exp2f((s[j][e] - m[e >> 1]) * scale_log2);
+    for (int e = 0; e < 4; ++e) l[e >> 1] += ex2((s[j][e] - m[e >> 1]) * scale_log2);
 }
 
 // Phase A, pass 2: dQ += (P o (dP - delta)) K over one block of keys.
@@ -376,7 +415,7 @@ __device__ __forceinline__ void bwd_dq_block(const uint32_t (&qf)[4][4], const u
     for (int e = 0; e < 4; ++e) {
       const int col = key0 + j * 8 + tq * 2 + (e & 1), row = qrow0 + g + ((e >> 1) << 3);
       const bool dead = col >= L || row >= L || (causal && col > row);
-      const float pv = dead ? 0.f : exp2f(fmaf(s[j][e], scale_log2, -lse2[e >> 1]));
+      const float pv = dead ? 0.f : ex2(fmaf(s[j][e], scale_log2, -lse2[e >> 1]));
       s[j][e] = pv * (dp[j][e] - delta[e >> 1]);
     }
   mm_rows_as_k<NT>(dq, s, sK, key0, lane);
@@ -398,7 +437,7 @@ __device__ __forceinline__ void bwd_dkv_block(const uint32_t (&kf)[4][4], const 
     for (int e = 0; e < 4; ++e) {
       const int qcol = q0 + j * 8 + tq * 2 + (e & 1), key = krow0 + g + ((e >> 1) << 3);
       const bool dead = qcol >= L || key >= L || (causal && key > qcol);
-      const float pv = dead ? 0.f : exp2f(fmaf(st[j][e], scale_log2, -sLse[qcol]));
+      const float pv = dead ? 0.f : ex2(fmaf(st[j][e], scale_log2, -sLse[qcol]));
       st[j][e] = pv;
       dpt[j][e] = pv * (dpt[j][e] - (dead ? 0.f : sDelta[qcol]));
     }
@@ -406,8 +445,8 @@ __device__ __forceinline__ void bwd_dkv_block(const uint32_t (&kf)[4][4], const 
   mm_rows_as_k<NT>(dk, dpt, sQ, q0, lane);
 }
 
-template <int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32) attention_bwd_kernel(const bf16* __restrict__ qkv,
+template <int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) attention_bwd_kernel(const bf16* __restrict__ qkv,
                                                                     const bf16* __restrict__ O,
                                                                     const bf16* __restrict__ dO,
                                                                     bf16* __restrict__ dqkv, int L, int LP, int D,
@@ -524,14 +563,14 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_bwd_kernel(const bf16* 
   }
 }
 
-template <int NWARPS>
+template <int NWARPS, int MINB>
 int launch_attention_bwd(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, int64_t seqs, int L, int heads,
                          int causal, cudaStream_t s) {
   const int LP = (L + 15) / 16 * 16;
   const int smem = 4 * LP * 128 + 2 * LP * 4;
   static int configured = 0;
   if (configured < smem) {
-    FC_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FC_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<NWARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   const float scale = 0.125f, scale_log2 = 0.125f * 1.4426950408889634f;
@@ -539,7 +578,7 @@ int launch_attention_bwd(const bf16* qkv, const bf16* O, const bf16* dO, bf16* d
   for (int64_t s0 = 0; s0 < seqs; s0 += 65535) {
     const int64_t n = seqs - s0 < 65535 ? seqs - s0 : 65535;
     dim3 grid(heads, static_cast<unsigned>(n));
-    attention_bwd_kernel<NWARPS><<<grid, NWARPS * 32, smem, s>>>(qkv + s0 * L * static_cast<int64_t>(3 * D),
+    attention_bwd_kernel<NWARPS, MINB><<<grid, NWARPS * 32, smem, s>>>(qkv + s0 * L * static_cast<int64_t>(3 * D),
                                                                   O + s0 * L * static_cast<int64_t>(D),
                                                                   dO + s0 * L * static_cast<int64_t>(D),
                                                                   dqkv + s0 * L * static_cast<int64_t>(3 * D), L, LP, D,
@@ -825,6 +864,46 @@ int fc_gemm_bf16_splitk(const void* A, int64_t lda, const void* B, int64_t ldb, 
                       static_cast<cudaStream_t>(stream));
 }
 
+int fc_gemm_bf16_layout(int epilogue, int a_mn, int b_mn, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                        int64_t ldc, const float* bias, const void* resid, int64_t ldr, float alpha, int32_t M,
+                        int32_t N, int32_t K, int32_t k_splits, void* stream) {
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
+  p.resid = static_cast<const bf16*>(resid); p.ldr = ldr; p.alpha = alpha;
+  p.a_mn = a_mn != 0; p.b_mn = b_mn != 0;
+  if (epilogue == EPI_F32_SPLITK) {
+    const int num_k = (K + 63) / 64;
+    if (k_splits <= 0) {
+      const int64_t tiles = static_cast<int64_t>((((M + 127) / 128) + 1) / 2) * ((N + 255) / 256);
+      const int64_t want = (2 * static_cast<int64_t>(num_sms() / 2) + tiles - 1) / tiles;
+      k_splits = static_cast<int>(want < 1 ? 1 : want);
+    }
+    p.k_splits = k_splits > num_k ? num_k : k_splits;
+  } else {
+    FC_REQUIRE(epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESID || epilogue == EPI_F32,
+               "fc_gemm_bf16_layout: epilogue %d is not exposed", epilogue);
+  }
+  return gemm_bf16_tn(epilogue, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb, p,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int fc_colsum_bf16(const void* x, int64_t ld, int64_t rows, int32_t cols, float* colsum, void* stream) {
+  FC_REQUIRE(x && colsum && cols > 0 && cols % 2 == 0 && ld % 2 == 0, "fc_colsum_bf16: bad arguments");
+  if (rows == 0) return FC_OK;
+  const int col_blocks = (cols + 63) / 64;
+  int64_t slabs = (4 * static_cast<int64_t>(num_sms()) + col_blocks - 1) / col_blocks;  // ~4 CTAs per SM
+  const int64_t max_slabs = (rows + 63) / 64;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs > 65535) slabs = 65535;
+  const int64_t per = (rows + slabs - 1) / slabs;
+  dim3 grid(col_blocks, static_cast<unsigned>((rows + per - 1) / per));
+  ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 11, rows, cols, 0, 0.0, 2.0 * rows * cols);
+  colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x), ld, rows, cols,
+                                                                          per, colsum);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
 int fc_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t kept_rows, int32_t cols,
                       int32_t group_len, int32_t group_skip, float* colsum, void* stream) {
   FC_REQUIRE(in && out, "fc_transpose_bf16: null pointer");
@@ -838,6 +917,7 @@ int fc_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, 
   const int64_t row_blocks = (ld_out + 64 * TR_TILES - 1) / (64 * TR_TILES);
   FC_REQUIRE(row_blocks <= 65535, "fc_transpose_bf16: too many rows");
   dim3 grid((cols + 63) / 64, static_cast<unsigned>(row_blocks));
+  ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 10, kept_rows, cols, 0, 0.0, 4.0 * kept_rows * cols);
   transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(in), ld_in, static_cast<bf16*>(out), ld_out, kept_rows, cols, group_len, group_skip,
       colsum);
@@ -852,6 +932,7 @@ int fc_layernorm_bwd_bf16(const void* x, const void* dy, const float* gamma, con
   if (rows == 0) return FC_OK;
   const int64_t want = (rows + 7) / 8;
   const int blocks = static_cast<int>(want < 2 * num_sms() ? want : 2 * num_sms());
+  ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 12, rows, D, 0, 0.0, (add ? 8.0 : 6.0) * rows * D);
   ln_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x), static_cast<const bf16*>(dy), gamma, static_cast<const bf16*>(add),
       static_cast<bf16*>(dx), dgamma, dbeta, rows, D, eps);
@@ -862,17 +943,19 @@ int fc_layernorm_bwd_bf16(const void* x, const void* dy, const float* gamma, con
 int fc_quickgelu_bf16(const void* u, void* g, int64_t n, void* stream) {
   FC_REQUIRE(u && g && n % 8 == 0, "fc_quickgelu_bf16: null pointer or n %% 8 != 0");
   if (n == 0) return FC_OK;
+  ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 13, n, 1, 0, 0.0, 4.0 * n);
   quickgelu_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(u), static_cast<bf16*>(g), n / 8);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
 
-int fc_quickgelu_bwd_bf16(const void* u, const void* dg, void* du, int64_t n, void* stream) {
+int fc_quickgelu_bwd_bf16(const void* u, const void* dg, void* du, void* g_out, int64_t n, void* stream) {
   FC_REQUIRE(u && dg && du && n % 8 == 0, "fc_quickgelu_bwd_bf16: null pointer or n %% 8 != 0");
   if (n == 0) return FC_OK;
+  ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 14, n, 1, 0, 0.0, (g_out ? 8.0 : 6.0) * n);
   quickgelu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(u), static_cast<const bf16*>(dg), static_cast<bf16*>(du), n / 8);
+      static_cast<const bf16*>(u), static_cast<const bf16*>(dg), static_cast<bf16*>(du), static_cast<bf16*>(g_out), n / 8);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
@@ -890,12 +973,31 @@ int fc_attention_bwd_bf16(const void* qkv, const void* out, const void* dout, vo
   const int tiles = (L + 15) / 16;
   ProfScope prof(s, PROF_ATTENTION, 2 + causal, seqs, L, heads, 10.0 * L * L * HD * heads * static_cast<double>(seqs),
                  static_cast<double>(seqs) * L * heads * HD * 2.0 * 8.0);
-  if (tiles <= 4) return launch_attention_bwd<4>(q, o, d, dq, seqs, L, heads, causal, s);
-  if (tiles == 5 || tiles == 9 || tiles == 10) return launch_attention_bwd<5>(q, o, d, dq, seqs, L, heads, causal, s);
-  if (tiles == 6 || tiles == 11 || tiles == 12 || tiles > 14)
-    return launch_attention_bwd<6>(q, o, d, dq, seqs, L, heads, causal, s);
-  if (tiles == 8) return launch_attention_bwd<8>(q, o, d, dq, seqs, L, heads, causal, s);
-  return launch_attention_bwd<7>(q, o, d, dq, seqs, L, heads, causal, s);  // 7, 13 (197 image tokens), 14
+  // warps per CTA x CTAs per SM (register cap): FC_ATTN_BWD_CFG = 10 * warps + min_blocks overrides (diagnostics)
+  static int cfg_override = -1;
+  if (cfg_override < 0) {
+    const char* e = getenv("FC_ATTN_BWD_CFG");
+    cfg_override = e ? atoi(e) : 0;
+  }
+  int cfg = cfg_override;
+  if (!cfg) {
+    // measured on B200 (tools/attention_bwd_bench.py, 2048 x 197 x 12 heads): 6 warps x 2 CTAs/SM 6.14 ms, 5 x 2 6.41,
+    // 4 x 2 7.05, 7 x 2 (128 registers, spills) 7.29, 7 x 1 8.20, 5 x 1 10.7; the 77-token causal case agrees
+    if (tiles <= 4) cfg = 42;
+    else if (tiles == 5) cfg = 52;
+    else cfg = 62;
+  }
+  switch (cfg) {
+    case 41: return launch_attention_bwd<4, 1>(q, o, d, dq, seqs, L, heads, causal, s);
+    case 42: return launch_attention_bwd<4, 2>(q, o, d, dq, seqs, L, heads, causal, s);
+    case 51: return launch_attention_bwd<5, 1>(q, o, d, dq, seqs, L, heads, causal, s);
+    case 52: return launch_attention_bwd<5, 2>(q, o, d, dq, seqs, L, heads, causal, s);
+    case 61: return launch_attention_bwd<6, 1>(q, o, d, dq, seqs, L, heads, causal, s);
+    case 62: return launch_attention_bwd<6, 2>(q, o, d, dq, seqs, L, heads, causal, s);
+    case 72: return launch_attention_bwd<7, 2>(q, o, d, dq, seqs, L, heads, causal, s);
+    case 81: return launch_attention_bwd<8, 1>(q, o, d, dq, seqs, L, heads, causal, s);
+    default: return launch_attention_bwd<7, 1>(q, o, d, dq, seqs, L, heads, causal, s);
+  }
 }
 
 // lse: 4 B floats of workspace.  teacher == NULL: nce_loss;  else TeacherStudentNCELoss("batchmean").
@@ -977,6 +1079,7 @@ int fc_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, in
   if (n == 0) return FC_OK;
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
   const float bc2s = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+  ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 15, n, 1, 0, 0.0, (p_bf16 ? 30.0 : 28.0) * n);
   adamw_kernel<<<grid_for(n, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, static_cast<bf16*>(p_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
   FC_CHECK_LAUNCH();

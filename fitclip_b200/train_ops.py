@@ -35,6 +35,44 @@ def gemm_splitk(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, alpha: floa
     return out
 
 
+def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, resid: Optional[torch.Tensor] = None,
+            f32: bool = False) -> torch.Tensor:
+    """``a (M,K) @ w (K,N)`` with ``w`` read in place as an MN-major B operand: the dgrad ``dX = dY @ W`` with ``W`` stored
+    ``(N_w, K_w)`` as the forward pass has it (``K`` here = ``N_w``).  bf16 out (+ bias [+ resid]) or fp32 out."""
+    dev = _dev(a)
+    assert a.dtype == BF16 and w.dtype == BF16 and a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[0]
+    M, K = a.shape
+    N = w.shape[1]
+    out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else BF16)
+    epi = _lib.EPI_F32 if f32 else (_lib.EPI_BIAS if resid is None else _lib.EPI_BIAS_RESID)
+    _call(dev, "fc_gemm_bf16_layout", epi, 0, 1, ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0),
+          ptr(bias), ptr(resid), 0 if resid is None else resid.stride(0), 1.0, M, N, K, 1)
+    return out
+
+
+def wgrad_tn(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, alpha: float = 1.0, k_splits: int = 0,
+             rows: Optional[int] = None) -> torch.Tensor:
+    """``out (N,K) fp32 += alpha * dy[:rows].T @ x[:rows]`` with ``dy (rows,N)`` and ``x (rows,K)`` read in place (both
+    operands MN-major), the token dimension split across the SMs."""
+    dev = _dev(dy)
+    assert dy.dtype == BF16 and x.dtype == BF16 and out.dtype == torch.float32
+    assert dy.stride(1) == 1 and x.stride(1) == 1 and out.stride(1) == 1
+    rows = dy.shape[0] if rows is None else rows
+    assert x.shape[0] >= rows and out.shape == (dy.shape[1], x.shape[1])
+    _call(dev, "fc_gemm_bf16_layout", _lib.EPI_F32_SPLITK, 1, 1, ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(out),
+          out.stride(0), None, None, 0, alpha, dy.shape[1], x.shape[1], rows, k_splits)
+    return out
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """``out (cols) fp32 += x.sum(0)`` for bf16 ``x (rows, cols)``."""
+    dev = _dev(x)
+    assert x.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1 and out.dtype == torch.float32
+    assert out.numel() == x.shape[1]
+    _call(dev, "fc_colsum_bf16", ptr(x), x.stride(0), x.shape[0], x.shape[1], ptr(out))
+    return out
+
+
 def transpose(x: torch.Tensor, group_len: int = 0, group_skip: int = 0, colsum: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """bf16 ``(rows, cols)`` -> ``(cols, pad8(kept rows))`` with zero-filled padding columns; ``colsum += x.sum(0)``."""
@@ -72,11 +110,14 @@ def quickgelu(u: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
-def quickgelu_bwd(u: torch.Tensor, dg: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def quickgelu_bwd(u: torch.Tensor, dg: torch.Tensor, out: Optional[torch.Tensor] = None,
+                  g_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``du = dg * quickgelu'(u)``; ``g_out`` (optional) also receives ``quickgelu(u)`` from the same pass."""
     dev = _dev(u)
     assert u.dtype == BF16 and dg.dtype == BF16 and u.is_contiguous() and dg.is_contiguous() and u.shape == dg.shape
+    assert g_out is None or (g_out.dtype == BF16 and g_out.is_contiguous() and g_out.shape == u.shape)
     out = torch.empty_like(u) if out is None else out
-    _call(dev, "fc_quickgelu_bwd_bf16", ptr(u), ptr(dg), ptr(out), u.numel())
+    _call(dev, "fc_quickgelu_bwd_bf16", ptr(u), ptr(dg), ptr(out), ptr(g_out), u.numel())
     return out
 
 

@@ -15,8 +15,10 @@ The reference gets the backward pass from torch.autograd.  Here it is an explici
 * the forward keeps the activations the backward needs (per block: block input, QKV, attention output, post-attention
   residual, MLP pre-activation = 10 x tokens x width bf16; 74 GB for 2048 frames of ViT-B/16, which is what the 180 GB
   of HBM are for) -- nothing is recomputed except LayerNorm outputs and QuickGELU values (memory-bound, cheap);
-* dgrad GEMMs read transposed bf16 weight copies (refreshed after every optimizer step), wgrad GEMMs read transposed
-  activations and split K (= the token count) across the SMs.
+* the backward GEMMs read their operands IN PLACE through MN-major tcgen05 descriptors: dgrad ``dX = dY W`` takes ``W``
+  as the forward pass stores it, wgrad ``dW = dY^T X`` takes ``dY`` and ``X`` as they are and splits K (= the token
+  count) across the SMs -- no transposed copies of weights or activations exist (only the patch-embedding weight
+  gradient, once per step, goes through a transpose because its rows skip the class token).
 
 The kernel set is injected (``kernels=``) so that the orchestration can be checked on CPU against torch.autograd with
 torch stand-ins for every kernel (``tests/torch_kernels.py``, test infrastructure); the default and only product path
@@ -31,8 +33,6 @@ import torch
 
 from . import _lib, ops, train_ops as T
 from .encoder import B200Clip
-
-GEMM_2D = ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight")
 
 
 class NativeKernels:
@@ -50,14 +50,21 @@ class NativeKernels:
         return self._zeros[n]
 
     cast = staticmethod(T.f32_to_bf16)
+    empty_like = staticmethod(torch.empty_like)
 
     def linear(self, a, w, bias=None, resid=None):
         bias = self.zero_bias(w.shape[0]) if bias is None else bias
         return ops.gemm_bf16(a, w, bias, resid, _lib.EPI_BIAS if resid is None else _lib.EPI_BIAS_RESID)
 
-    @staticmethod
-    def matmul_f32(a, b):
-        return ops.gemm_bf16(a, b, epilogue=_lib.EPI_F32)
+    def linear_nt(self, a, w, resid=None):
+        """``a @ w`` (+ resid) with ``w (K, N)`` read in place (MN-major B operand)."""
+        return T.gemm_nt(a, w, self.zero_bias(w.shape[1]), resid)
+
+    def matmul_nt_f32(self, a, w):
+        return T.gemm_nt(a, w, None, f32=True)
+
+    wgrad_tn = staticmethod(T.wgrad_tn)
+    colsum = staticmethod(T.colsum)
 
     layernorm = staticmethod(ops.layernorm_bf16)
     layernorm_bwd = staticmethod(T.layernorm_bwd)
@@ -106,7 +113,6 @@ class ClipTrainer:
         self.w: Dict[str, torch.Tensor] = {}   # fp32 parameter views
         self.g: Dict[str, torch.Tensor] = {}   # fp32 gradient views
         self.wb: Dict[str, torch.Tensor] = {}  # act-dtype (bf16) views of the mirror, GEMM weights as (N, K)
-        self.wt: Dict[str, torch.Tensor] = {}  # transposed act-dtype copies (K, N) for the dgrad GEMMs / projections
         off = 0
         for name, p in named:
             n = p.numel()
@@ -117,18 +123,13 @@ class ClipTrainer:
             self.g[name] = self.grad[off:off + n].view(p.shape)
             self.wb[name] = self.flat_act[off:off + n].view(p.shape)
             off += (n + 63) // 64 * 64
-        self._transposed = [n for n in self.w if n.endswith(GEMM_2D)] + ["visual.proj", "text_projection"]
-        self.refresh_weight_copies(full=True)
+        self.refresh_weight_copies()
 
     # ------------------------------------------------------------------------------------------------ weights
-    def refresh_weight_copies(self, full: bool = False) -> None:
-        """bf16 mirror (``full``: after an external edit of the fp32 parameters; AdamW refreshes it itself) and the
-        transposed copies the dgrad GEMMs read."""
-        if full:
-            self.K.cast(self.flat, out=self.flat_act)
-        for name in self._transposed:
-            w2 = self.wb[name]
-            self.wt[name] = self.K.transpose(w2.reshape(w2.shape[0], -1), out=self.wt.get(name))
+    def refresh_weight_copies(self) -> None:
+        """bf16 mirror of the flat fp32 parameters (needed after an external edit of the parameters; AdamW refreshes
+        it itself)."""
+        self.K.cast(self.flat, out=self.flat_act)
 
     def zero_grad(self) -> None:
         self.grad.zero_()
@@ -142,7 +143,6 @@ class ClipTrainer:
         self.step_count += 1
         self.K.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
                           self.eps, self.weight_decay, p_bf16=self.flat_act)
-        self.refresh_weight_copies()
         # the evaluation engine of the module re-uploads its folded copies when it next runs
         self.model._engine.signature = None
 
@@ -164,14 +164,11 @@ class ClipTrainer:
         return x
 
     def _linear_backward(self, dy, x_in, name_w: str, name_b: str, want_dx: bool = True):
-        """Gradients of ``y = x_in @ W.T + b``: db += colsum(dy) (fused into the transpose of dy), dW += dy^T x_in,
-        returns dx = dy @ W."""
+        """Gradients of ``y = x_in @ W.T + b``: db += colsum(dy), dW += dy^T x_in, returns dx = dy @ W."""
         K = self.K
-        dy_t = K.transpose(dy, colsum=self.g[name_b] if name_b else None)
-        x_t = K.transpose(x_in)
-        gw = self.g[name_w]
-        K.wgrad(dy_t, x_t, gw.view(gw.shape[0], -1))
-        return K.linear(dy, self.wt[name_w]) if want_dx else None
+        K.colsum(dy, self.g[name_b])
+        K.wgrad_tn(dy, x_in, self.g[name_w])
+        return K.linear_nt(dy, self.wb[name_w]) if want_dx else None
 
     def _blocks_backward(self, dx, prefix: str, layers: int, seqs: int, L: int, heads: int, causal: bool, saved: List):
         K, w, g = self.K, self.w, self.g
@@ -179,10 +176,14 @@ class ClipTrainer:
             p = f"{prefix}resblocks.{i}."
             x_in, qkv, att, x_mid, u = saved.pop()
             # x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
-            act = K.quickgelu(u)
-            dact = self._linear_backward(dx, act, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias")
+            # dact first (it does not need quickgelu(u)); then ONE pass over u gives both du and quickgelu(u), which the
+            # c_proj weight gradient reads
+            dact = K.linear_nt(dx, self.wb[p + "mlp.c_proj.weight"])
+            act = K.empty_like(u)
+            du = K.quickgelu_bwd(u, dact, out=dact, g_out=act)
+            K.colsum(dx, g[p + "mlp.c_proj.bias"])
+            K.wgrad_tn(dx, act, g[p + "mlp.c_proj.weight"])
             del act
-            du = K.quickgelu_bwd(u, dact, out=dact)
             ln2 = K.layernorm(x_mid, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
             dln2 = self._linear_backward(du, ln2, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias")
             del du, dact, ln2
@@ -203,7 +204,7 @@ class ClipTrainer:
         K, w = self.K, self.w
         rows = K.gather_seq_rows(x, ids, seqs, L)
         normed = K.layernorm(rows, w[ln + ".weight"], w[ln + ".bias"])
-        feat = K.matmul_f32(normed, self.wt[proj])  # (seqs, E) fp32 = ln(x[eot]) @ proj
+        feat = K.matmul_nt_f32(normed, self.wb[proj])  # (seqs, E) fp32 = ln(x[eot]) @ proj
         ctx.update(rows=rows, normed=normed, feat=feat, ids=ids, seqs=seqs, L=L, pool=pool)
         return K.pool_normalize(feat, pool)
 
@@ -211,7 +212,7 @@ class ClipTrainer:
         K, w, g = self.K, self.w, self.g
         dfeat = K.pool_normalize_bwd(ctx["feat"], dpooled.contiguous(), ctx["pool"])
         # feat = normed @ proj with proj (W, E):  dproj += normed^T dfeat,  dnormed = dfeat @ proj^T
-        K.wgrad(K.transpose(ctx["normed"]), K.transpose(dfeat), g[proj])
+        K.wgrad_tn(ctx["normed"], dfeat, g[proj])
         dnormed = K.linear(dfeat, self.wb[proj])
         drows = K.layernorm_bwd(ctx["rows"], dnormed, w[ln + ".weight"], g[ln + ".weight"], g[ln + ".bias"])
         return K.scatter_seq_rows(drows, ctx["ids"], ctx["L"])

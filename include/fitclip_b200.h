@@ -175,6 +175,16 @@ FC_API int fc_ts_nce_loss(const float* scores, const float* teacher_scores, int6
  * items per output tile (0 = enough to fill the SMs): the weight-gradient GEMM dW = dY^T . X, whose K is the token count. */
 FC_API int fc_gemm_bf16_splitk(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                                float alpha, int32_t M, int32_t N, int32_t K, int32_t k_splits, void* stream);
+/* The tcgen05 GEMM with operands read in place as the TRANSPOSE of a row-major matrix ("MN-major"): a_mn: A is stored
+ * (K, M) with row stride lda; b_mn: B is stored (K, N) with row stride ldb.  Built combinations:
+ *   FC_EPI_BIAS / FC_EPI_BIAS_RESID / FC_EPI_F32 with b_mn   dgrad  dX = dY . W     (B = W as stored, (N_w, K_w))
+ *   epilogue 9 (split-K, C fp32 +=) with a_mn and b_mn       wgrad  dW = dY^T . X   (A = dY, B = X as stored)
+ * so the backward pass needs no transposed copies of weights or activations. */
+FC_API int fc_gemm_bf16_layout(int epilogue, int a_mn, int b_mn, const void* A, int64_t lda, const void* B,
+                               int64_t ldb, void* C, int64_t ldc, const float* bias, const void* resid, int64_t ldr,
+                               float alpha, int32_t M, int32_t N, int32_t K, int32_t k_splits, void* stream);
+/* colsum (cols) fp32 += column sums of the bf16 matrix x (rows, ld): the bias gradient of a Linear. */
+FC_API int fc_colsum_bf16(const void* x, int64_t ld, int64_t rows, int32_t cols, float* colsum, void* stream);
 /* out (cols, ld_out) = transpose of the kept rows of in (rows, ld_in): rows come in groups of `group_len` whose first
  * `group_skip` are dropped (0, 0 = keep all); columns [kept_rows, ld_out) are zero-filled.  colsum (optional, fp32
  * (cols)) += column sums of the kept rows -- the bias gradient of a Linear whose output gradient is `in`. */
@@ -183,9 +193,10 @@ FC_API int fc_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t l
 /* LayerNorm backward (slip.py:350-356): dx = [add +] dLN(x, dy); dgamma += , dbeta += .  dx may alias add. */
 FC_API int fc_layernorm_bwd_bf16(const void* x, const void* dy, const float* gamma, const void* add, void* dx,
                                  float* dgamma, float* dbeta, int64_t rows, int32_t D, float eps, void* stream);
-/* QuickGELU (slip.py:359-361) forward g = u sigmoid(1.702 u) and backward du = dg * dg/du; du may alias dg. */
+/* QuickGELU (slip.py:359-361) forward g = u sigmoid(1.702 u) and backward du = dg * dg/du; du may alias dg.  g_out
+ * (optional) also receives quickgelu(u) in the same pass (the c_proj weight gradient reads it). */
 FC_API int fc_quickgelu_bf16(const void* u, void* g, int64_t n, void* stream);
-FC_API int fc_quickgelu_bwd_bf16(const void* u, const void* dg, void* du, int64_t n, void* stream);
+FC_API int fc_quickgelu_bwd_bf16(const void* u, const void* dg, void* du, void* g_out, int64_t n, void* stream);
 /* Backward of fc_attention_bf16: qkv / dqkv (seqs*L, 3*heads*64), out / dout (seqs*L, heads*64); L <= 432. */
 FC_API int fc_attention_bwd_bf16(const void* qkv, const void* out, const void* dout, void* dqkv, int64_t seqs,
                                  int32_t L, int32_t heads, int32_t causal, void* stream);

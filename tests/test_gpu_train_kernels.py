@@ -84,8 +84,10 @@ def test_quickgelu(dev):
     _close(T.quickgelu(u), ref.detach(), 5e-3, "quickgelu")
     du = T.quickgelu_bwd(u, dg)
     _close(du, uf.grad, 5e-3, "quickgelu backward")
-    T.quickgelu_bwd(u, dg, out=dg)
+    g = torch.empty_like(u)
+    T.quickgelu_bwd(u, dg, out=dg, g_out=g)
     assert torch.equal(dg, du)
+    _close(g, ref.detach(), 5e-3, "quickgelu from the backward pass")
 
 
 def _ref_attention(qkv, seqs, L, heads, causal):
@@ -220,3 +222,44 @@ def test_patch_and_text_embed(dev):
     xt = T.text_embed(ids, tok, tpos, err)
     _close(xt.view(C, L, W), tok[ids.long()] + tpos, 8e-3, "text embed")
     assert int(err[0]) == 0
+
+
+@pytest.mark.parametrize("M,K,N,resid", [(197 * 3, 768, 3072, False), (544, 3072, 768, True), (100, 64, 64, False),
+                                         (1000, 2304, 768, True), (33, 512, 768, False)])
+def test_gemm_nt_reads_b_in_place(dev, M, K, N, resid):
+    """dgrad dX = dY @ W with W (K, N) row-major read through an MN-major tcgen05 descriptor."""
+    from fitclip_b200 import train_ops as T
+    torch.manual_seed(11)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(K, N, device=dev) / K ** 0.5).bfloat16()
+    r = torch.randn(M, N, device=dev).bfloat16() if resid else None
+    bias = torch.randn(N, device=dev)
+    ref = a.float() @ w.float() + bias + (r.float() if resid else 0)
+    _close(T.gemm_nt(a, w, bias, r), ref, 8e-3, "gemm_nt bf16")
+    _close(T.gemm_nt(a, w, None, f32=True), a.float() @ w.float(), 1e-5, "gemm_nt fp32")
+
+
+@pytest.mark.parametrize("rows,N,K", [(197 * 9 + 3, 2304, 768), (77, 64, 64), (1000, 768, 3072), (544, 768, 768),
+                                      (4096 + 8, 512, 2048), (31, 512, 768)])
+def test_wgrad_tn_reads_both_in_place(dev, rows, N, K):
+    """wgrad dW = dY^T @ X with dY (rows, N) and X (rows, K) row-major, both MN-major operands, split-K."""
+    from fitclip_b200 import train_ops as T
+    torch.manual_seed(12)
+    dy = torch.randn(rows, N, device=dev).bfloat16()
+    x = torch.randn(rows, K, device=dev).bfloat16()
+    out = torch.zeros(N, K, device=dev)
+    T.wgrad_tn(dy, x, out, alpha=0.5)
+    ref = 0.5 * (dy.float().T @ x.float())
+    _close(out, ref, 2e-5, "wgrad_tn")
+    T.wgrad_tn(dy, x, out, alpha=0.5, k_splits=3)
+    _close(out, 2 * ref, 2e-5, "wgrad_tn accumulate")
+
+
+@pytest.mark.parametrize("rows,cols", [(197 * 9 + 3, 2304), (1, 64), (100000, 768), (77, 130)])
+def test_colsum(dev, rows, cols):
+    from fitclip_b200 import train_ops as T
+    torch.manual_seed(13)
+    x = torch.randn(rows, cols, device=dev).bfloat16()
+    out = torch.ones(cols, device=dev)
+    T.colsum(x, out)
+    _close(out, 1 + x.float().sum(0), 2e-5, "colsum", floor=1e-3)

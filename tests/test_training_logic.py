@@ -97,9 +97,7 @@ def test_flat_buffers_and_weight_copies():
     for name, p in enc.model.named_parameters():
         assert torch.equal(p, sd[name]) and p.data_ptr() >= tr.flat.data_ptr()
         assert (p.data_ptr() - tr.flat.data_ptr()) % 256 == 0
-    w = tr.wb["visual.transformer.resblocks.0.mlp.c_fc.weight"]
-    assert torch.equal(tr.wt["visual.transformer.resblocks.0.mlp.c_fc.weight"], w.T)
-    assert torch.equal(tr.wt["visual.proj"], tr.w["visual.proj"].T)
+    assert torch.equal(tr.wb["visual.proj"], tr.w["visual.proj"])  # mirror in the activation dtype
     tr.grad.fill_(1.0)
     tr.zero_grad()
     assert float(tr.grad.abs().sum()) == 0.0

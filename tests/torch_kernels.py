@@ -33,8 +33,23 @@ class TorchKernels:
         return y if resid is None else y + resid
 
     @staticmethod
-    def matmul_f32(a, b):
-        return a @ b.T
+    def linear_nt(a, w, resid=None):
+        return a @ w if resid is None else a @ w + resid
+
+    @staticmethod
+    def matmul_nt_f32(a, w):
+        return a @ w
+
+    @staticmethod
+    def wgrad_tn(dy, x, out, alpha=1.0, k_splits=0, rows=None):
+        rows = dy.shape[0] if rows is None else rows
+        out += alpha * (dy[:rows].T @ x[:rows])
+        return out
+
+    @staticmethod
+    def colsum(x, out):
+        out += x.sum(0)
+        return out
 
     @staticmethod
     def layernorm(x, g, b, eps=1e-5, out=None):
@@ -92,10 +107,14 @@ class TorchKernels:
     def quickgelu(u, out=None):
         return u * torch.sigmoid(1.702 * u)
 
+    empty_like = staticmethod(torch.empty_like)
+
     @staticmethod
-    def quickgelu_bwd(u, dg, out=None):
+    def quickgelu_bwd(u, dg, out=None, g_out=None):
         s = torch.sigmoid(1.702 * u)
         du = dg * s * (1 + 1.702 * u * (1 - s))
+        if g_out is not None:
+            g_out.copy_(u * s)
         if out is not None:
             out.copy_(du)
             return out

@@ -84,6 +84,7 @@ def main() -> None:
     module.training_step(batch, 0)
     recs = _lib.profile_stop()
     kinds = {0: "gemm_tcgen05", 1: "attention", 2: "layernorm", 3: "other"}
+    train_tags = {10: "transpose", 11: "colsum", 12: "layernorm_bwd", 13: "quickgelu", 14: "quickgelu_bwd", 15: "adamw"}
     by_kind = {}
     for r in recs:
         key = kinds.get(r["kind"], "other")
@@ -91,12 +92,16 @@ def main() -> None:
             key = "gemm_wgrad_splitk"
         if r["kind"] == 1 and r["tag"] >= 2:
             key = "attention_bwd"
-        d = by_kind.setdefault(key, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        if r["kind"] == 3 and r["tag"] in train_tags:
+            key = train_tags[r["tag"]]
+        d = by_kind.setdefault(key, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         d["ms"] += r["ms"]
         d["flops"] += r["flops"]
+        d["bytes"] += r["bytes"]
         d["launches"] += r["launches"]
     for d in by_kind.values():
         d["tflops"] = d["flops"] / d["ms"] / 1e9 if d["ms"] else 0.0
+        d["gbs"] = d["bytes"] / d["ms"] / 1e6 if d["ms"] else 0.0
     fwd = n * args.frames * FWD_FLOP_PER_FRAME + n * FWD_FLOP_PER_CAPTION
     scale = args.layers / 12
     algorithmic = 4 * fwd * scale  # student forward + backward (2x) + teacher forward
