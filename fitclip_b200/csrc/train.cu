@@ -88,35 +88,44 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
 }
 
 // colsum[c] += sum_r x[r, c]: the bias gradient of a Linear from its output gradient (one read of dY, fp32 atomics).
-// A CTA owns 64 columns x `rows_per_block` rows; a warp reads one 128-byte row segment per step.
+// A CTA owns 256 columns x a slab of rows: a warp reads 512 contiguous bytes of one row per step (16 bytes per lane) and
+// keeps four rows in flight; one shared-memory reduction over the 8 warps, then 256 atomics per CTA.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ld, int64_t rows, int cols,
                                                           int64_t rows_per_block, float* __restrict__ colsum) {
-  __shared__ float cs[8][64];
+  __shared__ float cs[8][256];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 64 + 2 * tx;
+  const int c = blockIdx.x * 256 + 8 * tx;
   const int64_t r0 = blockIdx.y * rows_per_block;
   const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-  if (c < cols) {
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto add = [&](const uint4& u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_bf16x2(w[t]);
+      acc[2 * t] += f.x;
+      acc[2 * t + 1] += f.y;
+    }
+  };
+  if (c < cols) {  // cols % 8 == 0: a lane's 8 columns are all inside or all outside
+    const bf16* base = x + c;
     int64_t r = r0 + ty;
-    for (; r + 8 < r1; r += 16) {  // two independent loads in flight per thread
-      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
-      const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + (r + 8) * ld + c));
-      s0 += a.x; s1 += a.y; t0 += b.x; t1 += b.y;
+    for (; r + 24 < r1; r += 32) {
+      const uint4 a = ld_nc_v4(base + r * ld), b = ld_nc_v4(base + (r + 8) * ld), d = ld_nc_v4(base + (r + 16) * ld),
+                  e = ld_nc_v4(base + (r + 24) * ld);
+      add(a); add(b); add(d); add(e);
     }
-    if (r < r1) {
-      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
-      s0 += a.x; s1 += a.y;
-    }
+    for (; r < r1; r += 8) add(ld_nc_v4(base + r * ld));
   }
-  cs[ty][2 * tx] = s0 + t0;
-  cs[ty][2 * tx + 1] = s1 + t1;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) cs[ty][8 * tx + t] = acc[t];
   __syncthreads();
-  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < cols) {
     float a = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) a += cs[i][threadIdx.x];
-    atomicAdd(colsum + blockIdx.x * 64 + threadIdx.x, a);
+    atomicAdd(colsum + cc, a);
   }
 }
 
@@ -126,13 +135,14 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 //   dgamma += sum_rows dy * xhat,  dbeta += sum_rows dy
 // One warp per row (same register layout as layernorm_bf16_kernel: lane owns 16-byte chunks lane + 32 i), warps walk
 // rows with a grid stride and keep their dgamma/dbeta partials in registers; one block reduction + atomics at the end.
-constexpr int LNB_CHUNKS = 4;
+constexpr int LNB_WARPS = 4;
 
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+template <int LNB_CHUNKS>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                      const float* __restrict__ gamma, const bf16* add, bf16* dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      int64_t rows, int D, float eps) {
-  __shared__ float red[8][1024];
+  __shared__ float red[LNB_WARPS][LNB_CHUNKS * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunks = D >> 3;
   const float inv_d = 1.f / static_cast<float>(D);
@@ -147,8 +157,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
       ab[i][t] = 0.f;
     }
   }
-  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < rows; row += nwarps) {
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * LNB_WARPS;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * LNB_WARPS + warp; row < rows; row += nwarps) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
     const uint4* dr = reinterpret_cast<const uint4*>(dy + row * D);
     float xv[LNB_CHUNKS][8], dv[LNB_CHUNKS][8];
@@ -238,10 +248,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
     }
     __syncthreads();
     float* dst = pass ? dbeta : dgamma;
-    for (int k = threadIdx.x; k < D; k += 256) {
+    for (int k = threadIdx.x; k < D; k += LNB_WARPS * 32) {
       float a = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) a += red[w][k];
+      for (int w = 0; w < LNB_WARPS; ++w) a += red[w][k];
       atomicAdd(dst + k, a);
     }
     __syncthreads();
@@ -251,8 +261,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
 // ------------------------------------------------------------------------------------------- QuickGELU
 // g = u * sigmoid(1.702 u) (aligner/encoder/slip.py:359-361);  du = dg * s * (1 + 1.702 u (1 - s)),  s = sigmoid(1.702 u)
 __global__ void __launch_bounds__(256) quickgelu_kernel(const bf16* __restrict__ u, bf16* __restrict__ g, int64_t n8) {
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
-    const uint4 a = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+  auto apply = [](const uint4& a) {
     const uint32_t w[4] = {a.x, a.y, a.z, a.w};
     uint32_t o[4];
 #pragma unroll
@@ -260,8 +270,20 @@ __global__ void __launch_bounds__(256) quickgelu_kernel(const bf16* __restrict__
       const float2 f = unpack_bf16x2(w[t]);
       o[t] = pack_bf16x2(f.x / (1.f + __expf(-1.702f * f.x)), f.y / (1.f + __expf(-1.702f * f.y)));
     }
-    st_na_v4(reinterpret_cast<uint4*>(g) + i, make_uint4(o[0], o[1], o[2], o[3]));
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  for (; i + 3 * stride < n8; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+    const uint4 a = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i);
+    const uint4 b = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i + stride);
+    const uint4 c = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i + 2 * stride);
+    const uint4 d = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i + 3 * stride);
+    st_na_v4(reinterpret_cast<uint4*>(g) + i, apply(a));
+    st_na_v4(reinterpret_cast<uint4*>(g) + i + stride, apply(b));
+    st_na_v4(reinterpret_cast<uint4*>(g) + i + 2 * stride, apply(c));
+    st_na_v4(reinterpret_cast<uint4*>(g) + i + 3 * stride, apply(d));
   }
+  for (; i < n8; i += stride) st_na_v4(reinterpret_cast<uint4*>(g) + i, apply(ld_nc_v4(reinterpret_cast<const uint4*>(u) + i)));
 }
 
 // g_out (optional): also writes g = quickgelu(u), which the weight gradient of the following Linear reads -- one pass
@@ -290,7 +312,8 @@ __global__ void __launch_bounds__(256) quickgelu_bwd_kernel(const bf16* __restri
 // ResidualAttentionBlock, aligner/encoder/slip.py:368,378-380).  With P = softmax(S), delta_i = sum_d dO_id O_id:
 //   dV = P^T dO,  dP = dO V^T,  dS = P o (dP - delta),  dQ = dS K / 8,  dK = dS^T Q / 8.
 // One CTA per (sequence, head); Q, K, V, dO (LP x 64 bf16 each, 128-byte rows, XOR-8 chunk swizzle) stay in shared
-// memory.  Phase A: a warp owns 16 query rows: row max/sum (log-sum-exp) over all keys, then dQ.  Phase B: a warp owns
+// memory.  Phase A: a warp owns 16 query rows: dQ and the row log-sum-exp in ONE sweep over the keys (online softmax
+// rescaling of the un-normalised dQ).  Phase B: a warp owns
 // 16 keys and walks the queries with the transposed products, producing dK and dV in registers.  P and dS are rounded
 // to bf16 for the second MMA of each product, fp32 accumulation throughout.
 constexpr int HD = 64;
@@ -369,12 +392,17 @@ __device__ __forceinline__ void mm_rows_as_k(float (&o)[8][4], const float (&p)[
   }
 }
 
-// Phase A, pass 1: running row max / sum over one block of keys.
+// Phase A, one block of keys for the 16 query rows of a warp: S = Q K^T, running row max m and sum l with the usual
+// online-softmax rescaling, and dQ~ += (P~ o (dP - delta)) K with P~ = exp2(S c - m c) un-normalised: dQ~ is linear in
+// P~, so it is rescaled with l whenever m moves and divided by the final l once, like O in the forward kernel.
 template <int NT>
-__device__ __forceinline__ void bwd_lse_block(const uint32_t (&qf)[4][4], uint32_t sK, int key0, int L, bool causal,
-                                              int qrow0, float scale_log2, float (&m)[2], float (&l)[2], int lane) {
-  float s[NT][4];
+__device__ __forceinline__ void bwd_q_block(const uint32_t (&qf)[4][4], const uint32_t (&dof)[4][4], uint32_t sK,
+                                            uint32_t sV, int key0, int L, bool causal, int qrow0, float scale_log2,
+                                            const float (&delta)[2], float (&m)[2], float (&l)[2], float (&dq)[8][4],
+                                            int lane) {
+  float s[NT][4], dp[NT][4];
   mm_rows_as_cols<NT>(s, qf, sK, key0, lane);
+  mm_rows_as_cols<NT>(dp, dof, sV, key0, lane);
   const int g = lane >> 2, tq = lane & 3;
   float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
@@ -385,37 +413,30 @@ __device__ __forceinline__ void bwd_lse_block(const uint32_t (&qf)[4][4], uint32
       if (col >= L || (causal && col > row)) s[j][e] = -INFINITY;
       mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
     }
+  float corr[2], mref[2];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
     mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
     const float mnew = fmaxf(m[r], mx[r]);
-    l[r] *= ex2((m[r] - mnew) * scale_log2);
+    corr[r] = ex2((m[r] - mnew) * scale_log2);  // m = -inf on the first block -> 0
     m[r] = mnew;
+    mref[r] = mnew * scale_log2;
+    l[r] *= corr[r];
+  }
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) {
+    dq[dn][0] *= corr[0];
+    dq[dn][1] *= corr[0];
+    dq[dn][2] *= corr[1];
+    dq[dn][3] *= corr[1];
   }
 #pragma unroll
   for (int j = 0; j < NT; ++j)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) l[e >> 1] += ex2((s[j][e] - m[e >> 1]) * scale_log2);
-}
-
-// Phase A, pass 2: dQ += (P o (dP - delta)) K over one block of keys.
-template <int NT>
-__device__ __forceinline__ void bwd_dq_block(const uint32_t (&qf)[4][4], const uint32_t (&dof)[4][4], uint32_t sK,
-                                             uint32_t sV, int key0, int L, bool causal, int qrow0, float scale_log2,
-                                             const float (&lse2)[2], const float (&delta)[2], float (&dq)[8][4],
-                                             int lane) {
-  float s[NT][4], dp[NT][4];
-  mm_rows_as_cols<NT>(s, qf, sK, key0, lane);
-  mm_rows_as_cols<NT>(dp, dof, sV, key0, lane);
-  const int g = lane >> 2, tq = lane & 3;
-#pragma unroll
-  for (int j = 0; j < NT; ++j)
-#pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int col = key0 + j * 8 + tq * 2 + (e & 1), row = qrow0 + g + ((e >> 1) << 3);
-      const bool dead = col >= L || row >= L || (causal && col > row);
-      const float pv = dead ? 0.f : ex2(fmaf(s[j][e], scale_log2, -lse2[e >> 1]));
+      const float pv = ex2(fmaf(s[j][e], scale_log2, -mref[e >> 1]));  // masked entries: ex2(-inf) = 0
+      l[e >> 1] += pv;
       s[j][e] = pv * (dp[j][e] - delta[e >> 1]);
     }
   mm_rows_as_k<NT>(dq, s, sK, key0, lane);
@@ -494,37 +515,32 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) attention_bwd_kernel(const 
     const int qrow0 = tile * 16;
     uint32_t qf[4][4], dof[4][4];
     load_a_frags(qf, sQ, qrow0, lane);
-    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-    for (int key0 = 0; key0 < LP; key0 += 32) {
-      if (cz && key0 > qrow0 + 15) break;
-      if (key0 + 32 <= LP) bwd_lse_block<4>(qf, sK, key0, L, cz, qrow0, scale_log2, m, l, lane);
-      else bwd_lse_block<2>(qf, sK, key0, L, cz, qrow0, scale_log2, m, l, lane);
-    }
-    float lse2[2], delta[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
-      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
-      lse2[r] = m[r] * scale_log2 + log2f(l[r]);
-      delta[r] = sDelta[qrow0 + g + 8 * r];
-      if (tq == 0) sLse[qrow0 + g + 8 * r] = lse2[r];
-    }
     load_a_frags(dof, sdO, qrow0, lane);
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    const float delta[2] = {sDelta[qrow0 + g], sDelta[qrow0 + g + 8]};
     float dq[8][4];
 #pragma unroll
     for (int dn = 0; dn < 8; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
     for (int key0 = 0; key0 < LP; key0 += 32) {
       if (cz && key0 > qrow0 + 15) break;
-      if (key0 + 32 <= LP) bwd_dq_block<4>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, lse2, delta, dq, lane);
-      else bwd_dq_block<2>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, lse2, delta, dq, lane);
+      if (key0 + 32 <= LP) bwd_q_block<4>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, delta, m, l, dq, lane);
+      else bwd_q_block<2>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, delta, m, l, dq, lane);
+    }
+    float inv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+      inv[r] = scale / l[r];
+      if (tq == 0) sLse[qrow0 + g + 8 * r] = m[r] * scale_log2 + log2f(l[r]);
     }
     const int r0 = qrow0 + g, r1 = r0 + 8;
     bf16* o0 = dqkv + (seq * L + r0) * static_cast<int64_t>(3 * D) + h * HD + tq * 2;
     bf16* o1 = dqkv + (seq * L + r1) * static_cast<int64_t>(3 * D) + h * HD + tq * 2;
 #pragma unroll
     for (int dn = 0; dn < 8; ++dn) {
-      if (r0 < L) *reinterpret_cast<uint32_t*>(o0 + dn * 8) = pack_bf16x2(dq[dn][0] * scale, dq[dn][1] * scale);
-      if (r1 < L) *reinterpret_cast<uint32_t*>(o1 + dn * 8) = pack_bf16x2(dq[dn][2] * scale, dq[dn][3] * scale);
+      if (r0 < L) *reinterpret_cast<uint32_t*>(o0 + dn * 8) = pack_bf16x2(dq[dn][0] * inv[0], dq[dn][1] * inv[0]);
+      if (r1 < L) *reinterpret_cast<uint32_t*>(o1 + dn * 8) = pack_bf16x2(dq[dn][2] * inv[1], dq[dn][3] * inv[1]);
     }
   }
   __syncthreads();  // every row's log-sum-exp is in shared memory
@@ -888,9 +904,10 @@ int fc_gemm_bf16_layout(int epilogue, int a_mn, int b_mn, const void* A, int64_t
 }
 
 int fc_colsum_bf16(const void* x, int64_t ld, int64_t rows, int32_t cols, float* colsum, void* stream) {
-  FC_REQUIRE(x && colsum && cols > 0 && cols % 2 == 0 && ld % 2 == 0, "fc_colsum_bf16: bad arguments");
+  FC_REQUIRE(x && colsum && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+             "fc_colsum_bf16: cols and ld must be multiples of 8, x 16-byte aligned");
   if (rows == 0) return FC_OK;
-  const int col_blocks = (cols + 63) / 64;
+  const int col_blocks = (cols + 255) / 256;
   int64_t slabs = (4 * static_cast<int64_t>(num_sms()) + col_blocks - 1) / col_blocks;  // ~4 CTAs per SM
   const int64_t max_slabs = (rows + 63) / 64;
   if (slabs > max_slabs) slabs = max_slabs;
@@ -930,12 +947,16 @@ int fc_layernorm_bwd_bf16(const void* x, const void* dy, const float* gamma, con
   FC_REQUIRE(x && dy && gamma && dx && dgamma && dbeta, "fc_layernorm_bwd_bf16: null pointer");
   FC_REQUIRE(D % 8 == 0 && D >= 8 && D <= 1024, "fc_layernorm_bwd_bf16: D=%d must be a multiple of 8, <= 1024", D);
   if (rows == 0) return FC_OK;
-  const int64_t want = (rows + 7) / 8;
-  const int blocks = static_cast<int>(want < 2 * num_sms() ? want : 2 * num_sms());
-  ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 12, rows, D, 0, 0.0, (add ? 8.0 : 6.0) * rows * D);
-  ln_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<const bf16*>(dy), gamma, static_cast<const bf16*>(add),
-      static_cast<bf16*>(dx), dgamma, dbeta, rows, D, eps);
+  const int64_t want = (rows + LNB_WARPS - 1) / LNB_WARPS;
+  const int blocks = static_cast<int>(want < 6 * num_sms() ? want : 6 * num_sms());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProfScope prof(s, PROF_OTHER, 12, rows, D, 0, 0.0, (add ? 8.0 : 6.0) * rows * D);
+  const bf16 *xb = static_cast<const bf16*>(x), *dyb = static_cast<const bf16*>(dy), *ab = static_cast<const bf16*>(add);
+  bf16* dxb = static_cast<bf16*>(dx);
+  if (D <= 256) ln_bwd_kernel<1><<<blocks, LNB_WARPS * 32, 0, s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
+  else if (D <= 512) ln_bwd_kernel<2><<<blocks, LNB_WARPS * 32, 0, s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
+  else if (D <= 768) ln_bwd_kernel<3><<<blocks, LNB_WARPS * 32, 0, s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
+  else ln_bwd_kernel<4><<<blocks, LNB_WARPS * 32, 0, s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
