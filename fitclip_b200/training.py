@@ -137,9 +137,9 @@ class ClipTrainer:
     def optimizer_step(self, group=None) -> None:
         """All-reduce(SUM) of the flat gradient across ``group`` (each rank holds the gradient of the GLOBAL-batch loss
         through its own samples), then one fused AdamW launch and the weight-copy refresh."""
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                 and torch.distributed.get_world_size() > 1):
-            torch.distributed.all_reduce(self.grad, group=group)
+        dist = torch.distributed
+        if group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, group=group)
         self.step_count += 1
         self.K.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
                           self.eps, self.weight_decay, p_bf16=self.flat_act)
@@ -280,7 +280,7 @@ def _all_gather_rows(t: torch.Tensor, group) -> Tuple[torch.Tensor, int]:
     """(world * B, D) concatenation of every rank's (B, D) rows + this rank's row offset (``all_gather`` of
     ``util/tensor_utils.py:48-66``; equal local batch sizes, as the reference's DistributedSampler gives)."""
     dist = torch.distributed
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    if group is False or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return t, 0
     out = torch.empty(dist.get_world_size(group) * t.shape[0], *t.shape[1:], device=t.device, dtype=t.dtype)
     dist.all_gather_into_tensor(out, t.contiguous(), group=group)
@@ -293,7 +293,9 @@ class TeacherStudentTrainingModule:
 
     ``batch``: ``video_student`` / ``video_teacher`` ``(B,T,3,R,R)``, ``text_student`` / ``text_teacher``
     ``{"input_ids": (B, 77)}``, and ``dataset``: a sequence of dataset names, one per sample, grouped
-    (``teacher_student.py:101-103``); default: all samples belong to the unlabelled dataset."""
+    (``teacher_student.py:101-103``); default: all samples belong to the unlabelled dataset.  ``group``: the process
+    group to gather embeddings / reduce gradients over (None = the default group when one is initialised, False = never
+    communicate)."""
 
     def __init__(self, encoder, teacher, init_temperature: float = 0.05, labeled_dataset_name: str = "labeled",
                  labeled_dataset_loss_share: Optional[float] = None,

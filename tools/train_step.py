@@ -30,13 +30,18 @@ def main() -> None:
     from fitclip_b200 import B200ClipVideoTextEncoder, _lib
     from fitclip_b200._init import init_clip_state_dict
     from fitclip_b200.training import TeacherStudentTrainingModule
-    dev = torch.device("cuda:0")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:  # torchrun: data parallel, `--videos` per GPU (weak scaling)
+        torch.distributed.init_process_group("nccl", device_id=dev)
     kw = dict(vision_layers=args.layers, transformer_layers=args.layers)
     enc = B200ClipVideoTextEncoder(init_clip_state_dict(seed=0, **kw), num_frames=args.frames).to(dev)
     teach = B200ClipVideoTextEncoder(init_clip_state_dict(seed=1, **kw), num_frames=args.frames).to(dev)
     module = TeacherStudentTrainingModule(enc, teach)
     n = args.videos
-    g = torch.Generator(device=dev).manual_seed(1234)
+    g = torch.Generator(device=dev).manual_seed(1234 + local)
     video = torch.randn(n, args.frames, 3, 224, 224, device=dev, generator=g)
     ids = torch.randint(1, 49405, (n, 77), device=dev, generator=g, dtype=torch.int32)
     ids[:, 0], ids[:, -1] = 49406, 49407
@@ -46,6 +51,8 @@ def main() -> None:
     for i in range(args.warmup):
         losses.append(float(module.training_step(batch, i)))
     torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -55,6 +62,17 @@ def main() -> None:
     torch.cuda.synchronize()
     losses.append(float(loss))
     ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:  # the slowest rank sets the step
+        t_ms = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t_ms)
+        n_total = n * world
+        if torch.distributed.get_rank() == 0:
+            print(json.dumps({"metric": "teacher-student training step, data parallel", "n_gpus": world,
+                              "videos_per_step": n_total, "ms_per_step": ms, "videos_per_sec": n_total / ms * 1e3,
+                              "scaling": "weak", "losses": losses}))
+        torch.distributed.destroy_process_group()
+        return
     launches = (_lib.launch_count() - launches0) // args.steps
 
     # phase split of one more step (CUDA events on the same stream)
