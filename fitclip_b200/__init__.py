@@ -7,6 +7,7 @@ from .metrics import Accuracy, MeanRank, MedianRank, Rank, Recall  # noqa: F401
 from .retrieval import (TextVideoRetrievalModule, metrics_from_ranks, retrieval_ranks, retrieval_topk,  # noqa: F401
                         shard_bounds)
 from .teacher_student import TeacherStudentScoringModule  # noqa: F401
+from .training import ClipTrainer, TeacherStudentTrainingModule  # noqa: F401
 from .wise import wise, wise_state_dict  # noqa: F401
 
 __version__ = "0.1.0"

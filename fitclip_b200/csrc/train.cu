@@ -138,37 +138,49 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 constexpr int LNB_WARPS = 4;
 
 template <int LNB_CHUNKS>
-__global__ void __launch_bounds__(LNB_WARPS * 32, 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+__global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                      const float* __restrict__ gamma, const bf16* add, bf16* dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      int64_t rows, int D, float eps) {
   __shared__ float red[LNB_WARPS][LNB_CHUNKS * 256];
+  __shared__ float sgamma[LNB_CHUNKS * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunks = D >> 3;
   const float inv_d = 1.f / static_cast<float>(D);
-  float gm[LNB_CHUNKS][8], ag[LNB_CHUNKS][8], ab[LNB_CHUNKS][8];
+  for (int k = threadIdx.x; k < LNB_CHUNKS * 256; k += LNB_WARPS * 32) sgamma[k] = k < D ? gamma[k] : 0.f;
+  __syncthreads();
+  float ag[LNB_CHUNKS][8], ab[LNB_CHUNKS][8];
 #pragma unroll
-  for (int i = 0; i < LNB_CHUNKS; ++i) {
-    const int c = lane + 32 * i;
+  for (int i = 0; i < LNB_CHUNKS; ++i)
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      gm[i][t] = c < chunks ? gamma[c * 8 + t] : 0.f;
-      ag[i][t] = 0.f;
-      ab[i][t] = 0.f;
+    for (int t = 0; t < 8; ++t) ag[i][t] = ab[i][t] = 0.f;
+  // The next row's x / dy are requested before this row's reductions start, so a warp always has loads in flight
+  // (without the prefetch its loads and its shuffle reductions serialise: 0.36 of the copy peak).
+  uint4 nx[LNB_CHUNKS], nd[LNB_CHUNKS];
+  auto fetch = [&](int64_t r) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + r * D);
+    const uint4* dr = reinterpret_cast<const uint4*>(dy + r * D);
+#pragma unroll
+    for (int i = 0; i < LNB_CHUNKS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < chunks) {
+        nx[i] = ld_nc_v4(xr + c);
+        nd[i] = ld_nc_v4(dr + c);
+      }
     }
-  }
+  };
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * LNB_WARPS;
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * LNB_WARPS + warp; row < rows; row += nwarps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
-    const uint4* dr = reinterpret_cast<const uint4*>(dy + row * D);
+  int64_t row = static_cast<int64_t>(blockIdx.x) * LNB_WARPS + warp;
+  if (row < rows) fetch(row);
+  for (; row < rows; row += nwarps) {
     float xv[LNB_CHUNKS][8], dv[LNB_CHUNKS][8];
+    uint4 av[LNB_CHUNKS];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < LNB_CHUNKS; ++i) {
       const int c = lane + 32 * i;
       if (c < chunks) {
-        const uint4 u = ld_nc_v4(xr + c), d = ld_nc_v4(dr + c);
-        const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, dw[4] = {d.x, d.y, d.z, d.w};
+        const uint32_t uw[4] = {nx[i].x, nx[i].y, nx[i].z, nx[i].w}, dw[4] = {nd[i].x, nd[i].y, nd[i].z, nd[i].w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 a = unpack_bf16x2(uw[t]), b = unpack_bf16x2(dw[t]);
@@ -178,8 +190,10 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 3) ln_bwd_kernel(const bf16* _
           dv[i][2 * t + 1] = b.y;
           sum += a.x + a.y;
         }
+        if (add) av[i] = *(reinterpret_cast<const uint4*>(add + row * D) + c);  // consumed after the reductions
       }
     }
+    if (row + nwarps < rows) fetch(row + nwarps);
     const float mean = warp_sum(sum) * inv_d;
     float sq = 0.f;
 #pragma unroll
@@ -194,19 +208,25 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 3) ln_bwd_kernel(const bf16* _
     const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LNB_CHUNKS; ++i)
-      if (lane + 32 * i < chunks) {
+    for (int i = 0; i < LNB_CHUNKS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < chunks) {
+        const float4 g0 = *reinterpret_cast<const float4*>(sgamma + c * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(sgamma + c * 8 + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const float xh = (xv[i][t] - mean) * rstd;
-          const float g = dv[i][t] * gm[i][t];
-          xv[i][t] = xh;
-          c1 += g;
-          c2 += g * xh;
           ag[i][t] += dv[i][t] * xh;
           ab[i][t] += dv[i][t];
+          const float g = dv[i][t] * gm[t];
+          xv[i][t] = xh;
+          dv[i][t] = g;  // from here on dv holds dy * gamma
+          c1 += g;
+          c2 += g * xh;
         }
       }
+    }
     c1 = warp_sum(c1) * inv_d;
     c2 = warp_sum(c2) * inv_d;
 #pragma unroll
@@ -215,10 +235,9 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 3) ln_bwd_kernel(const bf16* _
       if (c < chunks) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = rstd * (dv[i][t] * gm[i][t] - c1 - xv[i][t] * c2);
+        for (int t = 0; t < 8; ++t) o[t] = rstd * (dv[i][t] - c1 - xv[i][t] * c2);
         if (add) {
-          const uint4 a = *(reinterpret_cast<const uint4*>(add + row * D) + c);
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+          const uint32_t aw[4] = {av[i].x, av[i].y, av[i].z, av[i].w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 f = unpack_bf16x2(aw[t]);
@@ -395,7 +414,7 @@ __device__ __forceinline__ void mm_rows_as_k(float (&o)[8][4], const float (&p)[
 // Phase A, one block of keys for the 16 query rows of a warp: S = Q K^T, running row max m and sum l with the usual
 // online-softmax rescaling, and dQ~ += (P~ o (dP - delta)) K with P~ = exp2(S c - m c) un-normalised: dQ~ is linear in
 // P~, so it is rescaled with l whenever m moves and divided by the final l once, like O in the forward kernel.
-template <int NT>
+template <int NT, bool MASK>
 __device__ __forceinline__ void bwd_q_block(const uint32_t (&qf)[4][4], const uint32_t (&dof)[4][4], uint32_t sK,
                                             uint32_t sV, int key0, int L, bool causal, int qrow0, float scale_log2,
                                             const float (&delta)[2], float (&m)[2], float (&l)[2], float (&dq)[8][4],
@@ -409,8 +428,10 @@ __device__ __forceinline__ void bwd_q_block(const uint32_t (&qf)[4][4], const ui
   for (int j = 0; j < NT; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int col = key0 + j * 8 + tq * 2 + (e & 1), row = qrow0 + g + ((e >> 1) << 3);
-      if (col >= L || (causal && col > row)) s[j][e] = -INFINITY;
+      if (MASK) {  // interior blocks (all keys valid and visible to all 16 rows) skip the index arithmetic
+        const int col = key0 + j * 8 + tq * 2 + (e & 1), row = qrow0 + g + ((e >> 1) << 3);
+        if (col >= L || (causal && col > row)) s[j][e] = -INFINITY;
+      }
       mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
     }
   float corr[2], mref[2];
@@ -443,7 +464,7 @@ __device__ __forceinline__ void bwd_q_block(const uint32_t (&qf)[4][4], const ui
 }
 
 // Phase B: for the 16 keys of this warp, one block of queries: dV += P^T dO, dK += dS^T Q.
-template <int NT>
+template <int NT, bool MASK>
 __device__ __forceinline__ void bwd_dkv_block(const uint32_t (&kf)[4][4], const uint32_t (&vf)[4][4], uint32_t sQ,
                                               uint32_t sdO, const float* sLse, const float* sDelta, int q0, int L,
                                               bool causal, int krow0, float scale_log2, float (&dk)[8][4],
@@ -453,15 +474,22 @@ __device__ __forceinline__ void bwd_dkv_block(const uint32_t (&kf)[4][4], const 
   mm_rows_as_cols<NT>(dpt, vf, sdO, q0, lane);  // dP^T[key, query]
   const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
-  for (int j = 0; j < NT; ++j)
+  for (int j = 0; j < NT; ++j) {
+    // this thread's two query columns of the n-tile: log-sum-exp and delta as one 8-byte load each
+    const int qc0 = q0 + j * 8 + tq * 2;
+    const float2 lse = *reinterpret_cast<const float2*>(sLse + qc0);
+    const float2 dlt = *reinterpret_cast<const float2*>(sDelta + qc0);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int qcol = q0 + j * 8 + tq * 2 + (e & 1), key = krow0 + g + ((e >> 1) << 3);
-      const bool dead = qcol >= L || key >= L || (causal && key > qcol);
-      const float pv = dead ? 0.f : ex2(fmaf(st[j][e], scale_log2, -sLse[qcol]));
+      float pv = ex2(fmaf(st[j][e], scale_log2, -((e & 1) ? lse.y : lse.x)));
+      if (MASK) {  // interior blocks (all queries valid and allowed to see all 16 keys) skip the index arithmetic
+        const int qcol = qc0 + (e & 1), key = krow0 + g + ((e >> 1) << 3);
+        if (qcol >= L || key >= L || (causal && key > qcol)) pv = 0.f;
+      }
       st[j][e] = pv;
-      dpt[j][e] = pv * (dpt[j][e] - (dead ? 0.f : sDelta[qcol]));
+      dpt[j][e] = pv * (dpt[j][e] - ((e & 1) ? dlt.y : dlt.x));
     }
+  }
   mm_rows_as_k<NT>(dv, st, sdO, q0, lane);
   mm_rows_as_k<NT>(dk, dpt, sQ, q0, lane);
 }
@@ -523,8 +551,12 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) attention_bwd_kernel(const 
     for (int dn = 0; dn < 8; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
     for (int key0 = 0; key0 < LP; key0 += 32) {
       if (cz && key0 > qrow0 + 15) break;
-      if (key0 + 32 <= LP) bwd_q_block<4>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, delta, m, l, dq, lane);
-      else bwd_q_block<2>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, delta, m, l, dq, lane);
+      if (key0 + 32 <= L && (!cz || key0 + 31 <= qrow0))
+        bwd_q_block<4, false>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, delta, m, l, dq, lane);
+      else if (key0 + 32 <= LP)
+        bwd_q_block<4, true>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, delta, m, l, dq, lane);
+      else
+        bwd_q_block<2, true>(qf, dof, sK, sV, key0, L, cz, qrow0, scale_log2, delta, m, l, dq, lane);
     }
     float inv[2];
 #pragma unroll
@@ -559,8 +591,12 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) attention_bwd_kernel(const 
     }
     for (int q0 = 0; q0 < LP; q0 += 32) {
       if (cz && q0 + 31 < krow0) continue;  // every query of the block precedes every key of the tile
-      if (q0 + 32 <= LP) bwd_dkv_block<4>(kf, vf, sQ, sdO, sLse, sDelta, q0, L, cz, krow0, scale_log2, dk, dv, lane);
-      else bwd_dkv_block<2>(kf, vf, sQ, sdO, sLse, sDelta, q0, L, cz, krow0, scale_log2, dk, dv, lane);
+      if (q0 + 32 <= L && krow0 + 16 <= L && (!cz || krow0 + 15 <= q0))
+        bwd_dkv_block<4, false>(kf, vf, sQ, sdO, sLse, sDelta, q0, L, cz, krow0, scale_log2, dk, dv, lane);
+      else if (q0 + 32 <= LP)
+        bwd_dkv_block<4, true>(kf, vf, sQ, sdO, sLse, sDelta, q0, L, cz, krow0, scale_log2, dk, dv, lane);
+      else
+        bwd_dkv_block<2, true>(kf, vf, sQ, sdO, sLse, sDelta, q0, L, cz, krow0, scale_log2, dk, dv, lane);
     }
     const int r0 = krow0 + g, r1 = r0 + 8;
     bf16* k0p = dqkv + (seq * L + r0) * static_cast<int64_t>(3 * D) + D + h * HD + tq * 2;

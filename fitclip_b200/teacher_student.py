@@ -1,7 +1,8 @@
 """Scoring forward of the teacher-student step (``aligner/teacher_student.py:93-96,142-173``): student and frozen-teacher
 encoders on the same batch, two scaled ``B x B`` score matrices, NCE on the labelled split and
-``KL(softmax(teacher) || softmax(student)) * exp(ts_scale)^2`` on the unlabelled one.  Forward only -- backward,
-optimizer and prompt splicing belong to training, which is outside the evaluation hot path."""
+``KL(softmax(teacher) || softmax(student)) * exp(ts_scale)^2`` on the unlabelled one.  Forward only (SURVEY.md section
+8a, a16): the validation side of the module.  The training step -- the same scoring plus backward and AdamW -- is
+:class:`fitclip_b200.training.TeacherStudentTrainingModule` (row f3)."""
 from __future__ import annotations
 
 import math
