@@ -4,6 +4,8 @@
     python -m aligner command=evaluate encoder=wise +encoder@encoder.model1=clip_vit_b_16 \
         +encoder@encoder.model2=clip_vit_b_16 encoder.model2.model.seed=1 data=synthetic_ucf101
     python -m aligner command=predict encoder=clip_vit_b_16 data=synthetic_msrvtt output_path=predictions.pt
+    python -m aligner --config-name teacher_student_trainer command=train +encoder@encoder.student=clip_vit_b_16 \
+        +encoder@encoder.teacher=clip_vit_b_16 encoder.teacher.model.seed=1 data=synthetic_teacher_student
 
 It implements the subset of Hydra the reference relies on for evaluation: a root config with a
 ``defaults`` list, ``group=name`` selection with per-file ``defaults`` chains, ``+group@package=name`` placement,
@@ -90,7 +92,14 @@ def _interpolate(node: Any, root: Mapping[str, Any]) -> Any:
 
 def compose(overrides: Sequence[str], config_dir: str = CONFIG_DIR, config_name: str = "trainer") -> Dict[str, Any]:
     cfg = _load_yaml(os.path.join(config_dir, f"{config_name}.yaml"))
-    groups = [next(iter(d)) for d in cfg.pop("defaults", []) if isinstance(d, Mapping)]
+    defaults = cfg.pop("defaults", [])
+    groups = [next(iter(d)) for d in defaults if isinstance(d, Mapping)]
+    # a root config may build on another root config (`defaults: [trainer, _self_]`, config/teacher_student_trainer.yaml)
+    for entry in defaults:
+        if isinstance(entry, str) and entry != "_self_":
+            base = _load_yaml(os.path.join(config_dir, f"{entry}.yaml"))
+            groups += [next(iter(d)) for d in base.pop("defaults", []) if isinstance(d, Mapping)]
+            cfg = _merge(base, cfg)
     values: List[tuple] = []
     for ov in overrides:
         key, _, raw = ov.partition("=")
@@ -105,7 +114,14 @@ def compose(overrides: Sequence[str], config_dir: str = CONFIG_DIR, config_name:
     for key, value in values:  # plain value overrides win over group contents
         _set_path(cfg, key, value)
     cfg = _interpolate(cfg, cfg)
-    missing = [k for k, v in cfg.items() if v == "???"]
+    def _unset(node: Any, path: str) -> List[str]:
+        if node == "???":
+            return [path]
+        if isinstance(node, Mapping) and path == "encoder":  # encoder maps: encoder.student / encoder.teacher
+            return [p for k, v in node.items() if v == "???" for p in [f"{path}.{k}"]]
+        return []
+
+    missing = [p for k, v in cfg.items() for p in _unset(v, k)]
     if missing:
         raise ValueError(f"Missing mandatory value(s): {', '.join(missing)} (e.g. command=evaluate encoder=clip_vit_b_16 "
                          f"data=synthetic_msrvtt)")
@@ -204,6 +220,34 @@ class SyntheticClassificationData(SyntheticRetrievalData):
                    "video_id": [f"video{lo + j}" for j in range(b)]}
 
 
+class SyntheticTeacherStudentData:
+    """Training batches with the keys the reference's data modules emit for an encoder map
+    (``aligner/data/video_dataset.py:40-56``, ``tokenizer_collate.py:84-87``): ``video_student`` / ``video_teacher``,
+    ``text_student`` / ``text_teacher`` and ``dataset`` (one name per sample, grouped: labelled first)."""
+
+    def __init__(self, encoder: Mapping[str, Any], batch_size: int = 512, labeled_fraction: float = 0.5,
+                 caption_length: int = 77, seed: int = 1234) -> None:
+        self.encoder, self.batch_size, self.labeled_fraction = encoder, batch_size, labeled_fraction
+        self.caption_length, self.seed = caption_length, seed
+
+    def train_batches(self, device: torch.device, steps: int) -> Iterator[Dict[str, Any]]:
+        enc = self.encoder["student"]
+        frames, res = enc.num_frames, enc.model.visual.input_resolution
+        ctx, vocab = enc.model.context_length, enc.model.vocab_size
+        n_lab = int(round(self.batch_size * self.labeled_fraction))
+        names = ["labeled"] * n_lab + ["unlabeled"] * (self.batch_size - n_lab)
+        for i in range(steps):
+            g = torch.Generator(device=device).manual_seed(self.seed + i)
+            video = torch.randn(self.batch_size, frames, 3, res, res, device=device, generator=g)
+            n = min(self.caption_length, ctx)
+            ids = torch.zeros(self.batch_size, ctx, dtype=torch.int32, device=device)
+            ids[:, :n] = torch.randint(1, vocab - 2, (self.batch_size, n), device=device, generator=g, dtype=torch.int32)
+            ids[:, 0] = vocab - 2
+            ids[:, n - 1] = vocab - 1
+            yield {"video_student": video, "video_teacher": video, "text_student": {"input_ids": ids},
+                   "text_teacher": {"input_ids": ids}, "dataset": names}
+
+
 # ------------------------------------------------------------------------------------------------- commands
 def _to_float(v: Any) -> Any:
     if isinstance(v, torch.Tensor):
@@ -244,13 +288,47 @@ def evaluate(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> D
     return {k: _to_float(v) for k, v in result.items()}
 
 
+def train(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> Dict[str, Any]:
+    """``command=train`` with an encoder map (``aligner/__main__.py:49-62``: ``trainer.fit``): the teacher-student
+    training loop, ``trainer.max_steps`` steps, logging ``loss/train`` per step like ``training_step_end``
+    (``aligner/teacher_student.py:176-183``)."""
+    if not isinstance(cfg["encoder"], Mapping) or set(cfg["encoder"]) != {"student", "teacher"}:
+        raise ValueError("command=train needs an encoder map: --config-name teacher_student_trainer with "
+                         "+encoder@encoder.student=... +encoder@encoder.teacher=... (single-encoder fine-tuning is "
+                         "not implemented)")
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(cfg.get("seed", 42))
+    encoders = {k: v.to(device) for k, v in instantiate(cfg["encoder"]).items()}
+    data = instantiate(cfg["data"], encoder=encoders)
+    opt = cfg.get("optimizer", {})
+    model = instantiate(cfg["model"], encoder=encoders["student"], teacher=encoders["teacher"],
+                        lr=float(opt.get("lr", 3e-6)), weight_decay=float(opt.get("weight_decay", 1e-2)))
+    steps = int(cfg.get("trainer", {}).get("max_steps", 10))
+    losses = []
+    for i, batch in enumerate(data.train_batches(device, steps)):
+        losses.append(model.training_step(batch, i))
+    losses = [float(x) for x in losses]  # one device read-back at the end
+    encoders["student"].model.check_inputs()
+    return {"loss/train": losses[-1], "step": len(losses), "losses": losses}
+
+
 def main(argv: Sequence[str]) -> int:
-    cfg = compose(list(argv))
+    argv = list(argv)
+    config_name = "trainer"
+    for i, a in enumerate(argv):  # hydra's --config-name / -cn
+        if a in ("--config-name", "-cn"):
+            config_name = argv[i + 1]
+            del argv[i:i + 2]
+            break
+        if a.startswith("--config-name="):
+            config_name = a.split("=", 1)[1]
+            del argv[i]
+            break
+    cfg = compose(argv, config_name=config_name)
     command = cfg["command"]
-    if command not in ("evaluate", "validate", "test", "predict"):
-        raise ValueError(f"command={command} is outside the evaluation hot path this package implements "
-                         f"(supported: evaluate | validate | test | predict)")
-    result = evaluate(cfg)
+    if command not in ("evaluate", "validate", "test", "predict", "train"):
+        raise ValueError(f"command={command} is not implemented (supported: evaluate | validate | test | predict | train)")
+    result = train(cfg) if command == "train" else evaluate(cfg)
     if not cfg.get("silent"):
         width = max(len(k) for k in result)
         for k, v in result.items():

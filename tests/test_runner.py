@@ -91,3 +91,29 @@ def test_evaluate_wise_classification():
                           "encoder.model2.model.vision_layers=1", "encoder.model2.model.transformer_layers=1"])
     result = runner.evaluate(cfg)  # the models are built on the CPU like the reference's; the lerp itself runs on the GPU
     assert set(result) == {"a1", "a5", "mr"} and 1 <= int(result["mr"]) <= 7
+
+
+def test_compose_teacher_student_root_config():
+    cfg = runner.compose(["command=train", "+encoder@encoder.student=clip_vit_b_16", "+encoder@encoder.teacher=clip_vit_b_16",
+                          "encoder.teacher.model.seed=1", "data=synthetic_teacher_student", "data.batch_size=8",
+                          "trainer.max_steps=3"], config_name="teacher_student_trainer")
+    assert cfg["model"]["_target_"].endswith("TeacherStudentTrainingModule") and cfg["trainer"]["max_steps"] == 3
+    assert cfg["encoder"]["teacher"]["model"]["seed"] == 1 and cfg["encoder"]["student"]["model"]["seed"] == 0
+    assert cfg["optimizer"]["lr"] == 3.0e-6 and cfg["seed"] == 42  # optimizer of config/trainer.yaml:22-24; base config merged
+    with pytest.raises(ValueError, match="encoder.teacher"):
+        runner.compose(["command=train", "+encoder@encoder.student=clip_vit_b_16", "data=synthetic_teacher_student"],
+                       config_name="teacher_student_trainer")
+
+
+@pytest.mark.gpu
+def test_train_command():
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    tiny = [f"encoder.{who}.model.{k}=1" for who in ("student", "teacher") for k in ("vision_layers", "transformer_layers")]
+    out = subprocess.run([sys.executable, "-m", "aligner", "--config-name", "teacher_student_trainer", "command=train",
+                          "+encoder@encoder.student=clip_vit_b_16", "+encoder@encoder.teacher=clip_vit_b_16",
+                          "encoder.teacher.model.seed=1", "data=synthetic_teacher_student", "data.batch_size=16",
+                          "trainer.max_steps=4", "optimizer.lr=1e-4", *tiny], cwd=ROOT, env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    result = json.loads(out.stdout.strip().splitlines()[-1])
+    assert result["step"] == 4 and result["loss/train"] == result["loss/train"]  # finite
