@@ -280,7 +280,6 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bw
 // ------------------------------------------------------------------------------------------- QuickGELU
 // g = u * sigmoid(1.702 u) (aligner/encoder/slip.py:359-361);  du = dg * s * (1 + 1.702 u (1 - s)),  s = sigmoid(1.702 u)
 __global__ void __launch_bounds__(256) quickgelu_kernel(const bf16* __restrict__ u, bf16* __restrict__ g, int64_t n8) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
   auto apply = [](const uint4& a) {
     const uint32_t w[4] = {a.x, a.y, a.z, a.w};
     uint32_t o[4];
@@ -291,18 +290,22 @@ __global__ void __launch_bounds__(256) quickgelu_kernel(const bf16* __restrict__
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
   };
-  int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  for (; i + 3 * stride < n8; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
-    const uint4 a = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i);
-    const uint4 b = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i + stride);
-    const uint4 c = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i + 2 * stride);
-    const uint4 d = ld_nc_v4(reinterpret_cast<const uint4*>(u) + i + 3 * stride);
-    st_na_v4(reinterpret_cast<uint4*>(g) + i, apply(a));
-    st_na_v4(reinterpret_cast<uint4*>(g) + i + stride, apply(b));
-    st_na_v4(reinterpret_cast<uint4*>(g) + i + 2 * stride, apply(c));
-    st_na_v4(reinterpret_cast<uint4*>(g) + i + 3 * stride, apply(d));
+  // a CTA walks 16 KiB spans (1024 x 16 bytes): four independent loads in flight per thread, all in one DRAM
+  // neighbourhood (a grid-wide stride between a thread's loads cost 25 % of the bandwidth)
+  const uint4* src = reinterpret_cast<const uint4*>(u);
+  uint4* dst = reinterpret_cast<uint4*>(g);
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * 1024; base < n8; base += static_cast<int64_t>(gridDim.x) * 1024) {
+    const int64_t i = base + threadIdx.x;
+    if (base + 1024 <= n8) {
+      const uint4 a = ld_nc_v4(src + i), b = ld_nc_v4(src + i + 256), c = ld_nc_v4(src + i + 512), d = ld_nc_v4(src + i + 768);
+      st_na_v4(dst + i, apply(a));
+      st_na_v4(dst + i + 256, apply(b));
+      st_na_v4(dst + i + 512, apply(c));
+      st_na_v4(dst + i + 768, apply(d));
+    } else {
+      for (int64_t j = i; j < n8; j += 256) st_na_v4(dst + j, apply(ld_nc_v4(src + j)));
+    }
   }
-  for (; i < n8; i += stride) st_na_v4(reinterpret_cast<uint4*>(g) + i, apply(ld_nc_v4(reinterpret_cast<const uint4*>(u) + i)));
 }
 
 // g_out (optional): also writes g = quickgelu(u), which the weight gradient of the following Linear reads -- one pass
@@ -885,6 +888,30 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+// Split count of a weight-gradient GEMM: (K range, tile) work items are dealt round-robin to the SM pairs, so the
+// launch takes ceil(items / pairs) waves; pick the split whose last wave is fullest (2..4 waves, >= 8 K blocks per item).
+// E.g. out_proj of ViT-B/16 (9 tiles, 74 pairs): 17 splits = 153 items = 3 waves at 69 %, 16 splits = 144 items = 2 waves at 97 %.
+int pick_k_splits(int M, int N, int K) {
+  const int num_k = (K + 63) / 64;
+  const int64_t tiles = static_cast<int64_t>((((M + 127) / 128) + 1) / 2) * ((N + 255) / 256);
+  const int pairs = num_sms() / 2;
+  int best = 1;
+  double best_score = -1.0;
+  for (int sp = 1; sp <= num_k && sp <= 256; ++sp) {
+    if (sp > 1 && num_k / sp < 8) break;
+    const int64_t items = tiles * sp;
+    const int64_t waves = (items + pairs - 1) / pairs;
+    if (waves > 4 && sp > 1) break;
+    double score = static_cast<double>(items) / static_cast<double>(waves * pairs);
+    if (waves < 2) score *= 0.9;  // one wave leaves the pipeline prologue / accumulator drain of every item exposed
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = sp;
+    }
+  }
+  return best;
+}
+
 int grid_for(int64_t work_items, int per_block) {
   const int64_t blocks = (work_items + per_block - 1) / per_block;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
@@ -906,11 +933,7 @@ int fc_gemm_bf16_splitk(const void* A, int64_t lda, const void* B, int64_t ldb, 
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.alpha = alpha;
   const int num_k = (K + 63) / 64;
-  if (k_splits <= 0) {  // fill the SM pairs: items = pair tiles x splits ~ 2 waves
-    const int64_t tiles = static_cast<int64_t>((((M + 127) / 128) + 1) / 2) * ((N + 255) / 256);
-    const int64_t want = (2 * static_cast<int64_t>(num_sms() / 2) + tiles - 1) / tiles;
-    k_splits = static_cast<int>(want < 1 ? 1 : want);
-  }
+  if (k_splits <= 0) k_splits = pick_k_splits(M, N, K);
   p.k_splits = k_splits > num_k ? num_k : k_splits;
   return gemm_bf16_tn(EPI_F32_SPLITK, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb, p,
                       static_cast<cudaStream_t>(stream));
@@ -925,11 +948,7 @@ int fc_gemm_bf16_layout(int epilogue, int a_mn, int b_mn, const void* A, int64_t
   p.a_mn = a_mn != 0; p.b_mn = b_mn != 0;
   if (epilogue == EPI_F32_SPLITK) {
     const int num_k = (K + 63) / 64;
-    if (k_splits <= 0) {
-      const int64_t tiles = static_cast<int64_t>((((M + 127) / 128) + 1) / 2) * ((N + 255) / 256);
-      const int64_t want = (2 * static_cast<int64_t>(num_sms() / 2) + tiles - 1) / tiles;
-      k_splits = static_cast<int>(want < 1 ? 1 : want);
-    }
+    if (k_splits <= 0) k_splits = pick_k_splits(M, N, K);
     p.k_splits = k_splits > num_k ? num_k : k_splits;
   } else {
     FC_REQUIRE(epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESID || epilogue == EPI_F32,
@@ -1001,7 +1020,7 @@ int fc_quickgelu_bf16(const void* u, void* g, int64_t n, void* stream) {
   FC_REQUIRE(u && g && n % 8 == 0, "fc_quickgelu_bf16: null pointer or n %% 8 != 0");
   if (n == 0) return FC_OK;
   ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 13, n, 1, 0, 0.0, 4.0 * n);
-  quickgelu_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  quickgelu_kernel<<<grid_for(n / 8, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(u), static_cast<bf16*>(g), n / 8);
   FC_CHECK_LAUNCH();
   return FC_OK;

@@ -13,8 +13,10 @@ The reference gets the backward pass from torch.autograd.  Here it is an explici
   views into it), with flat fp32 gradient / Adam-moment buffers and a flat bf16 mirror next to it: the optimizer is one
   launch, the gradient all-reduce across GPUs one NCCL call, and ``zero_grad`` one memset;
 * the forward keeps the activations the backward needs (per block: block input, QKV, attention output, post-attention
-  residual, MLP pre-activation = 10 x tokens x width bf16; 74 GB for 2048 frames of ViT-B/16, which is what the 180 GB
-  of HBM are for) -- nothing is recomputed except LayerNorm outputs and QuickGELU values (memory-bound, cheap);
+  residual, MLP pre-activation and both LayerNorm outputs = 12 x tokens x width bf16; 89 GB for 2048 frames of
+  ViT-B/16, which is what the 180 GB of HBM are for) -- nothing is recomputed except QuickGELU values, which the
+  backward kernel emits on its single pass over the pre-activation (``keep_layernorm=False`` drops the LayerNorm
+  outputs and recomputes them: 15 GB less, 2 % slower);
 * the backward GEMMs read their operands IN PLACE through MN-major tcgen05 descriptors: dgrad ``dX = dY W`` takes ``W``
   as the forward pass stores it, wgrad ``dW = dY^T X`` takes ``dY`` and ``X`` as they are and splits K (= the token
   count) across the SMs -- no transposed copies of weights or activations exist (only the patch-embedding weight
@@ -93,8 +95,9 @@ class ClipTrainer:
     """Forward-with-saved-activations, backward and AdamW for one :class:`B200Clip` (the student)."""
 
     def __init__(self, model: B200Clip, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, kernels: Any = None) -> None:
+                 weight_decay: float = 1e-2, kernels: Any = None, keep_layernorm: bool = True) -> None:
         self.model = model
+        self.keep_layernorm = keep_layernorm
         self.cfg = dict(model.config)
         if (3 * self.cfg["vision_patch_size"] ** 2) % 8:
             raise ValueError("training needs 3 * patch_size^2 to be a multiple of 8 (ViT-B/16, ViT-B/32)")
@@ -159,7 +162,7 @@ class ClipTrainer:
             u = K.linear(ln2, wb[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"])
             act = K.quickgelu(u)
             x_out = K.linear(act, wb[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"], resid=x_mid)
-            saved.append((x, qkv, att, x_mid, u))
+            saved.append((x, qkv, att, x_mid, u) + ((ln1, ln2) if self.keep_layernorm else (None, None)))
             x = x_out
         return x
 
@@ -174,7 +177,7 @@ class ClipTrainer:
         K, w, g = self.K, self.w, self.g
         for i in reversed(range(layers)):
             p = f"{prefix}resblocks.{i}."
-            x_in, qkv, att, x_mid, u = saved.pop()
+            x_in, qkv, att, x_mid, u, ln1, ln2 = saved.pop()
             # x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
             # dact first (it does not need quickgelu(u)); then ONE pass over u gives both du and quickgelu(u), which the
             # c_proj weight gradient reads
@@ -184,7 +187,8 @@ class ClipTrainer:
             K.colsum(dx, g[p + "mlp.c_proj.bias"])
             K.wgrad_tn(dx, act, g[p + "mlp.c_proj.weight"])
             del act
-            ln2 = K.layernorm(x_mid, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
+            if ln2 is None:
+                ln2 = K.layernorm(x_mid, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
             dln2 = self._linear_backward(du, ln2, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias")
             del du, dact, ln2
             dx_mid = K.layernorm_bwd(x_mid, dln2, w[p + "ln_2.weight"], g[p + "ln_2.weight"], g[p + "ln_2.bias"],
@@ -192,7 +196,8 @@ class ClipTrainer:
             # x_mid = x_in + out_proj(attention(in_proj(ln_1(x_in))))
             datt = self._linear_backward(dx_mid, att, p + "attn.out_proj.weight", p + "attn.out_proj.bias")
             dqkv = K.attention_bwd(qkv, att, datt, seqs, L, heads, causal)
-            ln1 = K.layernorm(x_in, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
+            if ln1 is None:
+                ln1 = K.layernorm(x_in, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
             dln1 = self._linear_backward(dqkv, ln1, p + "attn.in_proj_weight", p + "attn.in_proj_bias")
             del dqkv, datt, ln1
             dx = K.layernorm_bwd(x_in, dln1, w[p + "ln_1.weight"], g[p + "ln_1.weight"], g[p + "ln_1.bias"],
@@ -300,7 +305,9 @@ class TeacherStudentTrainingModule:
     def __init__(self, encoder, teacher, init_temperature: float = 0.05, labeled_dataset_name: str = "labeled",
                  labeled_dataset_loss_share: Optional[float] = None,
                  dataset_names: Sequence[str] = ("labeled", "unlabeled"), lr: float = 3e-6,
-                 weight_decay: float = 1e-2, group=None, kernels: Any = None) -> None:
+                 weight_decay: float = 1e-2, group=None, kernels: Any = None, fit_temperature: bool = False) -> None:
+        if fit_temperature:  # config/trainer.yaml:20 default is false; the logit scales are constants here
+            raise NotImplementedError("fit_temperature=True (a trainable logit scale) is not implemented")
         self.encoder, self.teacher = encoder, teacher
         self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels)
         self.K = self.trainer.K

@@ -82,6 +82,53 @@ def test_training_step_matches_autograd(dev, names):
     assert float(cos.min()) >= 0.999
 
 
+def test_other_geometry_and_recomputed_layernorm(dev):
+    """ViT-B/32-style patches (5 image tokens: one attention tile), the real 77-token context, LayerNorm outputs
+    recomputed in the backward pass instead of kept: gradients against autograd on the oracle."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder
+    from fitclip_b200.training import TeacherStudentTrainingModule
+    geom = dict(vision_layers=1, transformer_layers=1, image_resolution=64, vision_patch_size=32, context_length=77,
+                vocab_size=512)
+    student, teacher = oracle.clip_vit_b_16(seed=0, **geom), oracle.clip_vit_b_16(seed=1, **geom)
+    ref_student = oracle.RefClipVideoTextEncoder(copy.deepcopy(student)).train()
+    ref_teacher = oracle.RefClipVideoTextEncoder(copy.deepcopy(teacher)).eval()
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=3).to(dev)
+    teach = B200ClipVideoTextEncoder(teacher.state_dict(), num_frames=3).to(dev)
+    module = TeacherStudentTrainingModule(enc, teach)
+    module.trainer.keep_layernorm = False
+    n = 9
+    batch, cpu_batch = _batch(n, 3, 64, 77, 512, dev), _batch(n, 3, 64, 77, 512, "cpu")
+    opt = torch.optim.AdamW(ref_student.model.parameters(), lr=3e-6)
+    ref_loss, ref_grads = oracle.ref_training_step(ref_student, ref_teacher, cpu_batch, [("unlabeled", 0, n)], opt)
+    loss = module.training_step(batch, 0, optimize=False)
+    assert abs(float(loss) - float(ref_loss)) <= 0.02 * abs(float(ref_loss)) + 1e-4
+    top = max(float(v.norm()) for v in ref_grads.values())
+    checked = 0
+    for name, ref in ref_grads.items():
+        if float(ref.norm()) < 1e-3 * top:
+            continue
+        got = module.trainer.g[name].cpu()
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+        assert cos >= 0.98 and abs(float(got.norm()) / float(ref.norm()) - 1) <= 0.06, f"{name}: cos {cos:.4f}"
+        checked += 1
+    assert checked >= 20
+
+
+def test_native_errors_are_raised_not_swallowed(dev):
+    """Bad arguments come back as FitclipError with the library's message (no silent fallback)."""
+    from fitclip_b200 import _lib, train_ops as T
+    x = torch.zeros(8, 12, device=dev, dtype=torch.bfloat16)  # 12 columns: not a multiple of 8
+    with pytest.raises(_lib.FitclipError, match="multiples of 8"):
+        T.colsum(x, torch.zeros(12, device=dev))
+    with pytest.raises(_lib.FitclipError, match="unsupported"):
+        T.attention_bwd(torch.zeros(500, 192, device=dev, dtype=torch.bfloat16),
+                        torch.zeros(500, 64, device=dev, dtype=torch.bfloat16),
+                        torch.zeros(500, 64, device=dev, dtype=torch.bfloat16), 1, 500, 1, False)
+    with pytest.raises(_lib.FitclipError):
+        T.colsum(torch.zeros(8, 16, dtype=torch.bfloat16), torch.zeros(16))  # CPU tensors: no CPU path
+
+
 def test_loss_decreases(dev):
     """A few steps at a large learning rate on one fixed batch: the distillation loss goes down."""
     import oracle

@@ -89,6 +89,18 @@ def test_gradients_and_adamw_match_autograd(names):
         assert enc.model.visual.proj.data_ptr() == tr.w["visual.proj"].data_ptr()
 
 
+def test_recomputed_layernorm_gives_the_same_gradients():
+    student, teacher = make_models()
+    grads = []
+    for keep in (True, False):
+        enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+        module = TeacherStudentTrainingModule(enc, oracle.RefClipVideoTextEncoder(teacher), kernels=TorchKernels())
+        module.trainer.keep_layernorm = keep
+        module.training_step(make_batch(6, seed=2), 0, optimize=False)
+        grads.append(module.trainer.grad.clone())
+    assert torch.equal(grads[0], grads[1])
+
+
 def test_flat_buffers_and_weight_copies():
     student, _ = make_models()
     enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
