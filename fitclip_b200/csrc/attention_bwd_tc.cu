@@ -1,0 +1,407 @@
+// tcgen05 attention BACKWARD for sequences of up to 208 tokens, head dim 64 (the 197-token image and the 77-token
+// causal text sequence of CLIP ViT-B/16) -- training step, SURVEY.md 8f row f3.  Same math as attention_bwd_kernel
+// (train.cu): with P = softmax(q k^T / 8 [+ causal mask]), delta_i = sum_d dO_id O_id:
+//     dV = P^T dO,  dP = dO V^T,  dS = P o (dP - delta),  dQ = dS K / 8,  dK = dS^T Q / 8.
+//
+// One CTA per (sequence, head); Q, K, V, dO of the head are TMA-loaded once (3-D tensor maps: rows beyond the sequence
+// are zero-filled) as K-major 128-byte-swizzled tiles of R = 128 or 256 rows.  All seven products run on the tensor
+// core with accumulators in TMEM; one query (phase A) or key (phase B) row per softmax thread, so row statistics need
+// no cross-thread reduction.
+//   phase A, per 128-query tile:  S = Q_t K^T -> cols [0, NP);  dP = dO_t V^T -> cols [NP, 2 NP)      (NP = L rounded to 16)
+//        softmax threads: row max, row sum, then dS = P o (dP - delta) as bf16 written back over the dP columns
+//        dQ = dS K   (A = dS from TMEM, B = K read MN-major) -> cols [2 NP, 2 NP + 64) -> scaled -> global
+//        the row's log-sum-exp and delta go to shared memory for phase B
+//   phase B, per 128-key tile:    S^T = K_t Q^T -> [0, NP);  dP^T = V_t dO^T -> [NP, 2 NP)
+//        softmax threads: P^T = exp2(S^T c - lse_q) and dS^T = P^T o (dP^T - delta_q), bf16, in place
+//        dV = P^T dO (B = dO MN-major) -> [2 NP, +64);  dK = dS^T Q (B = Q MN-major) -> the dead S^T columns -> global
+// Everything is serialised inside a CTA (no software pipelining yet): MMA batch -> softmax -> MMA batch -> read-out.
+#include <stdlib.h>
+#include <string.h>
+
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace fc {
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int QT = 128;
+constexpr int BWD_THREADS = 160;  // warps 0-3: one row per thread; warp 4: TMA + MMA issue + TMEM allocation
+constexpr uint32_t BWD_TMEM_COLS = 512;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// bf16 tensor viewed as [seqs][L][cols] (cols contiguous); box = 64 columns x box_rows tokens x 1 sequence, SW128.
+int make_tmap_3d(CUtensorMap* tm, const bf16* base, int64_t cols, int64_t L, int64_t seqs, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return FC_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(seqs)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(cols) * 2 * L};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d, attention backward) failed (CUresult %d)", static_cast<int>(r));
+    return FC_ERR_CUDA;
+  }
+  return FC_OK;
+}
+
+__device__ __forceinline__ void store_row64(bf16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], float k) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t(&r)[32] = c < 4 ? a : b;
+    const int o = (c & 3) * 8;
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(r[o + 0]) * k, __uint_as_float(r[o + 1]) * k);
+    u.y = pack_bf16x2(__uint_as_float(r[o + 2]) * k, __uint_as_float(r[o + 3]) * k);
+    u.z = pack_bf16x2(__uint_as_float(r[o + 4]) * k, __uint_as_float(r[o + 5]) * k);
+    u.w = pack_bf16x2(__uint_as_float(r[o + 6]) * k, __uint_as_float(r[o + 7]) * k);
+    reinterpret_cast<uint4*>(dst)[c] = u;
+  }
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                        const bf16* __restrict__ O, const bf16* __restrict__ dO, bf16* __restrict__ dqkv, int L, int NP,
+                        int tiles, int heads, float scale, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int R = tiles * QT;  // rows per resident tile (128 or 256)
+  const int tile_bytes = R * 128;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + tile_bytes;
+  uint8_t* sV = smem + 2 * tile_bytes;
+  uint8_t* sdO = smem + 3 * tile_bytes;
+  float* sLse = reinterpret_cast<float*>(smem + 4 * tile_bytes);
+  float* sDelta = sLse + 256;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sDelta + 256);
+  uint64_t* bar_mma = bar_load + 1;
+  uint64_t* bar_soft = bar_load + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x;
+  const int seq = blockIdx.y;
+  const int D = heads * HD;
+  const int nk16 = NP / 16;                                     // 16-wide column chunks / UMMA_K steps over NP
+  const int DK_COL = (NP / 2 + HD <= NP) ? NP / 2 : 2 * NP + HD;  // dK accumulator: the dead upper half of S^T if it fits
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    mbar_init(bar_soft, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<BWD_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA + MMA thread =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 4 * tile_bytes);
+      tma_load_3d(sQ, &tmQKV, bar_load, head * HD, 0, seq);
+      tma_load_3d(sK, &tmQKV, bar_load, D + head * HD, 0, seq);
+      tma_load_3d(sV, &tmQKV, bar_load, 2 * D + head * HD, 0, seq);
+      tma_load_3d(sdO, &tmDO, bar_load, head * HD, 0, seq);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), do_addr = smem_u32(sdO);
+      const uint32_t idesc_s = umma_idesc_bf16_f32(QT, NP);
+      const uint32_t idesc_o = umma_idesc_bf16_f32_bmn(QT, HD);
+      uint32_t ps = 0;
+      mbar_wait(bar_load, 0);
+      tc_fence_after();
+      // ---------- phase A: query tiles
+      for (int t = 0; t < tiles; ++t) {
+        const uint32_t row_off = t * QT * 128;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + row_off + k * 32), umma_desc_k_sw128(k_addr + k * 32),
+                       idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base + NP, umma_desc_k_sw128(do_addr + row_off + k * 32),
+                       umma_desc_k_sw128(v_addr + k * 32), idesc_s, k != 0);
+        umma_commit(bar_mma);
+        mbar_wait(bar_soft, ps);  // dS (bf16) is in TMEM
+        ps ^= 1;
+        tc_fence_after();
+        for (int k = 0; k < nk16; ++k)
+          umma_bf16_ts(tmem_base + 2 * NP, tmem_base + NP + k * 8, umma_desc_mn_sw128(k_addr + k * 2048), idesc_o,
+                       k != 0);
+        umma_commit(bar_mma);
+        mbar_wait(bar_soft, ps);  // dQ has been read out
+        ps ^= 1;
+        tc_fence_after();
+      }
+      // ---------- phase B: key tiles
+      for (int t = 0; t < tiles; ++t) {
+        const uint32_t row_off = t * QT * 128;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_k_sw128(k_addr + row_off + k * 32), umma_desc_k_sw128(q_addr + k * 32),
+                       idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base + NP, umma_desc_k_sw128(v_addr + row_off + k * 32),
+                       umma_desc_k_sw128(do_addr + k * 32), idesc_s, k != 0);
+        umma_commit(bar_mma);
+        mbar_wait(bar_soft, ps);  // P^T and dS^T (bf16) are in TMEM
+        ps ^= 1;
+        tc_fence_after();
+        for (int k = 0; k < nk16; ++k)
+          umma_bf16_ts(tmem_base + 2 * NP, tmem_base + k * 8, umma_desc_mn_sw128(do_addr + k * 2048), idesc_o, k != 0);
+        for (int k = 0; k < nk16; ++k)
+          umma_bf16_ts(tmem_base + DK_COL, tmem_base + NP + k * 8, umma_desc_mn_sw128(q_addr + k * 2048), idesc_o,
+                       k != 0);
+        umma_commit(bar_mma);
+        mbar_wait(bar_soft, ps);  // dV, dK have been read out
+        ps ^= 1;
+        tc_fence_after();
+      }
+    }
+  } else {
+    // ===================== softmax / read-out warps: one row per thread =====================
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int r = warp * 32 + lane;
+    const int64_t tok0 = static_cast<int64_t>(seq) * L;
+    uint32_t pm = 0;
+    // ---------- phase A
+    for (int t = 0; t < tiles; ++t) {
+      const int row = t * QT + r;
+      const bool valid = row < L;
+      // delta_row = dO_row . O_row from global memory while the first MMAs run
+      float delta = 0.f;
+      if (valid) {
+        const uint4* po = reinterpret_cast<const uint4*>(O + (tok0 + row) * D + head * HD);
+        const uint4* pd = reinterpret_cast<const uint4*>(dO + (tok0 + row) * D + head * HD);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = po[c], b = pd[c];
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(bw[e]);
+            delta = fmaf(x.x, y.x, fmaf(x.y, y.y, delta));
+          }
+        }
+      }
+      const int lim = !valid ? 0 : (CAUSAL ? min(L, row + 1) : L);  // keys [0, lim) are visible to this row
+      // tcgen05.ld / .st are warp-collective: loop bounds are warp-uniform (wlim = the largest lim of the warp), the
+      // per-row limit only masks the arithmetic
+      const int wrow0 = t * QT + warp * 32;
+      const int wlim = wrow0 >= L ? 0 : (CAUSAL ? min(L, wrow0 + 32) : L);
+      const int wchunks = (wlim + 15) / 16;
+      mbar_wait(bar_mma, pm);
+      pm ^= 1;
+      tc_fence_after();
+      float m = -INFINITY, l = 0.f;
+      uint32_t s16[16], d16[16];
+      for (int j = 0; j < wchunks; ++j) {  // pass 1: row maximum
+        tmem_ld_32x32b_x16(trow + j * 16, s16);
+        tmem_ld_wait_fence16(s16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (j * 16 + c < lim) m = fmaxf(m, __uint_as_float(s16[c]));
+      }
+      const float mc = valid ? m * scale_log2 : 0.f;
+      for (int j = 0; j < wchunks; ++j) {  // pass 2: row sum
+        tmem_ld_32x32b_x16(trow + j * 16, s16);
+        tmem_ld_wait_fence16(s16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (j * 16 + c < lim) l += ex2_approx(fmaf(__uint_as_float(s16[c]), scale_log2, -mc));
+      }
+      const float inv_l = valid ? 1.f / l : 0.f;
+      for (int j = 0; j < nk16; ++j) {  // pass 3: dS = P o (dP - delta) -> bf16 over the dP columns (zeros beyond wlim)
+        uint32_t pk[8];
+        if (j < wchunks) {
+          tmem_ld_32x32b_x16(trow + j * 16, s16);
+          tmem_ld_32x32b_x16(trow + NP + j * 16, d16);
+          tmem_ld_wait_fence16(s16);
+          tmem_ld_wait_fence16(d16);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = j * 16 + 2 * c + e;
+              const float p = ex2_approx(fmaf(__uint_as_float(s16[2 * c + e]), scale_log2, -mc)) * inv_l;
+              v[e] = col < lim ? p * (__uint_as_float(d16[2 * c + e]) - delta) : 0.f;
+            }
+            pk[c] = pack_bf16x2(v[0], v[1]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) pk[c] = 0u;
+        }
+        tmem_st_32x32b_x8(trow + NP + j * 8, pk);
+      }
+      tmem_st_wait();
+      sLse[row] = valid ? fmaf(m, scale_log2, log2f(l)) : 0.f;
+      sDelta[row] = delta;
+      tc_fence_before();
+      mbar_arrive(bar_soft);
+      // dQ read-out
+      mbar_wait(bar_mma, pm);
+      pm ^= 1;
+      tc_fence_after();
+      if (wrow0 < L) {  // warp-uniform
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32b_x32(trow + 2 * NP, o0);
+        tmem_ld_32x32b_x32(trow + 2 * NP + 32, o1);
+        tmem_ld_wait_fence(o0);
+        tmem_ld_wait_fence(o1);
+        if (valid) store_row64(dqkv + (tok0 + row) * (3 * D) + head * HD, o0, o1, scale);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_soft);
+    }
+    named_bar_sync(1, 128);  // every row's log-sum-exp / delta is in shared memory
+    // ---------- phase B
+    for (int t = 0; t < tiles; ++t) {
+      const int key = t * QT + r;
+      const bool kvalid = key < L;
+      const int wkey0 = t * QT + warp * 32;  // smallest key of the warp: the warp-uniform causal bound
+      mbar_wait(bar_mma, pm);
+      pm ^= 1;
+      tc_fence_after();
+      uint32_t s16[16], d16[16];
+      for (int j = 0; j < nk16; ++j) {
+        uint32_t pp[8], pd[8];
+        const int q0 = j * 16;
+        if (wkey0 < L && q0 < L && (!CAUSAL || q0 + 15 >= wkey0)) {  // warp-uniform: some (key, query) pair is live
+          tmem_ld_32x32b_x16(trow + q0, s16);
+          tmem_ld_32x32b_x16(trow + NP + q0, d16);
+          tmem_ld_wait_fence16(s16);
+          tmem_ld_wait_fence16(d16);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float pv[2], dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int q = q0 + 2 * c + e;
+              const bool dead = !kvalid || q >= L || (CAUSAL && key > q);
+              const float p = dead ? 0.f : ex2_approx(fmaf(__uint_as_float(s16[2 * c + e]), scale_log2, -sLse[q]));
+              pv[e] = p;
+              dv[e] = p * (__uint_as_float(d16[2 * c + e]) - sDelta[q]);
+            }
+            pp[c] = pack_bf16x2(pv[0], pv[1]);
+            pd[c] = pack_bf16x2(dv[0], dv[1]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) pp[c] = pd[c] = 0u;
+        }
+        tmem_st_32x32b_x8(trow + j * 8, pp);
+        tmem_st_32x32b_x8(trow + NP + j * 8, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_soft);
+      mbar_wait(bar_mma, pm);
+      pm ^= 1;
+      tc_fence_after();
+      if (wkey0 < L) {  // warp-uniform
+        uint32_t o0[32], o1[32];
+        bf16* dst = dqkv + (tok0 + key) * (3 * D) + D + head * HD;
+        tmem_ld_32x32b_x32(trow + DK_COL, o0);
+        tmem_ld_32x32b_x32(trow + DK_COL + 32, o1);
+        tmem_ld_wait_fence(o0);
+        tmem_ld_wait_fence(o1);
+        if (kvalid) store_row64(dst, o0, o1, scale);
+        tmem_ld_32x32b_x32(trow + 2 * NP, o0);
+        tmem_ld_32x32b_x32(trow + 2 * NP + 32, o1);
+        tmem_ld_wait_fence(o0);
+        tmem_ld_wait_fence(o1);
+        if (kvalid) store_row64(dst + D, o0, o1, 1.f);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_soft);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<BWD_TMEM_COLS>(tmem_base);
+  }
+}
+
+template <bool CAUSAL>
+int launch_bwd_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, int64_t seqs, int L, int heads,
+                  cudaStream_t s) {
+  const int tiles = (L + QT - 1) / QT;
+  const int R = tiles * QT;
+  const int smem = 4 * R * 128 + 2 * 256 * 4 + 64;
+  static int configured = 0;
+  if (configured < smem) {
+    FC_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int D = heads * HD;
+  const int NP = (L + 15) / 16 * 16;
+  CUtensorMap tqkv, tdo;
+  int rc;
+  if ((rc = make_tmap_3d(&tqkv, qkv, 3 * D, L, seqs, R))) return rc;
+  if ((rc = make_tmap_3d(&tdo, dO, D, L, seqs, R))) return rc;
+  const float scale = 0.125f, scale_log2 = 0.125f * 1.4426950408889634f;
+  for (int64_t s0 = 0; s0 < seqs; s0 += 65535) {
+    FC_REQUIRE(s0 == 0, "attention backward (tcgen05): more than 65535 sequences per call are not supported");
+    dim3 grid(heads, static_cast<unsigned>(seqs));
+    attention_bwd_tc_kernel<CAUSAL><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, O, dO, dqkv, L, NP, tiles, heads, scale,
+                                                                    scale_log2);
+    FC_CHECK_LAUNCH();
+  }
+  return FC_OK;
+}
+
+}  // namespace
+
+// *handled = 1 when the tcgen05 kernel took the call (L <= 208, 16-byte aligned buffers, <= 65535 sequences).
+// FC_ATTENTION_BWD=mma forces the mma.sync kernel of train.cu (diagnostics / A-B timing).
+int attention_bwd_bf16_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, int64_t seqs, int L, int heads,
+                          int causal, cudaStream_t s, int* handled) {
+  *handled = 0;
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("FC_ATTENTION_BWD");
+    mode = (e && strcmp(e, "tc") == 0) ? 1 : 0;
+  }
+  if (!mode || L > 208 || L < 1 || seqs > 65535) return FC_OK;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(O) & 15) ||
+      (reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(dqkv) & 15))
+    return FC_OK;
+  *handled = 1;
+  return causal ? launch_bwd_tc<true>(qkv, O, dO, dqkv, seqs, L, heads, s)
+                : launch_bwd_tc<false>(qkv, O, dO, dqkv, seqs, L, heads, s);
+}
+
+}  // namespace fc

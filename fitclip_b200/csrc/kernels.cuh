@@ -37,6 +37,10 @@ int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, i
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                       int* handled);
 
+// attention_bwd_tc.cu : tcgen05 attention backward for L <= 208; *handled = 1 when it took the call
+int attention_bwd_bf16_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, int64_t seqs, int L, int heads,
+                          int causal, cudaStream_t s, int* handled);
+
 // rank.cu
 int rank_from_scores(const float* S, int64_t ld, int64_t rows, int64_t cols, const int32_t* target, int64_t* ranks,
                      cudaStream_t s);

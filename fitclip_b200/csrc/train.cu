@@ -1049,6 +1049,11 @@ int fc_attention_bwd_bf16(const void* qkv, const void* out, const void* dout, vo
   const int tiles = (L + 15) / 16;
   ProfScope prof(s, PROF_ATTENTION, 2 + causal, seqs, L, heads, 10.0 * L * L * HD * heads * static_cast<double>(seqs),
                  static_cast<double>(seqs) * L * heads * HD * 2.0 * 8.0);
+  {
+    int handled = 0;
+    const int rc = attention_bwd_bf16_tc(q, o, d, dq, seqs, L, heads, causal, s, &handled);
+    if (rc || handled) return rc;
+  }
   // warps per CTA x CTAs per SM (register cap): FC_ATTN_BWD_CFG = 10 * warps + min_blocks overrides (diagnostics)
   static int cfg_override = -1;
   if (cfg_override < 0) {
