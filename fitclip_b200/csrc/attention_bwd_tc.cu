@@ -8,12 +8,15 @@
 // core with accumulators in TMEM; one query (phase A) or key (phase B) row per softmax thread, so row statistics need
 // no cross-thread reduction.
 //   phase A, per 128-query tile:  S = Q_t K^T -> cols [0, NP);  dP = dO_t V^T -> cols [NP, 2 NP)      (NP = L rounded to 16)
-//        softmax threads: row max, row sum, then dS = P o (dP - delta) as bf16 written back over the dP columns
-//        dQ = dS K   (A = dS from TMEM, B = K read MN-major) -> cols [2 NP, 2 NP + 64) -> scaled -> global
+//        softmax threads: row max, then P~ = exp2(S c - m c), the row sum l and dS~ = P~ o (dP - delta) as bf16 written
+//        back over the dP columns; dQ = dS~ K (A = dS~ from TMEM, B = K read MN-major) -> cols [2 NP, 2 NP + 64)
+//        -> x scale / l -> global   (short sequences, NP < 64: the 64-column accumulators start at NP + 64)
 //        the row's log-sum-exp and delta go to shared memory for phase B
 //   phase B, per 128-key tile:    S^T = K_t Q^T -> [0, NP);  dP^T = V_t dO^T -> [NP, 2 NP)
-//        softmax threads: P^T = exp2(S^T c - lse_q) and dS^T = P^T o (dP^T - delta_q), bf16, in place
-//        dV = P^T dO (B = dO MN-major) -> [2 NP, +64);  dK = dS^T Q (B = Q MN-major) -> the dead S^T columns -> global
+//        softmax threads: P^T = exp2(S^T c - lse_q) and dS^T = P^T o (dP^T - delta_q), bf16
+//        dV = P^T dO (B = dO MN-major) -> [2 NP, +64);  dK = dS^T Q (B = Q MN-major) -> [NP, NP + 64) -> global
+// bf16 results are written over the 16-column fp32 chunk they were computed from (chunk j -> columns 16 j .. 16 j + 15),
+// so no thread overwrites input another thread still has to read, and each UMMA_K step takes its A operand from there.
 // Everything is serialised inside a CTA (no software pipelining yet): MMA batch -> softmax -> MMA batch -> read-out.
 #include <stdlib.h>
 #include <string.h>
@@ -27,7 +30,7 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int QT = 128;
-constexpr int BWD_THREADS = 160;  // warps 0-3: one row per thread; warp 4: TMA + MMA issue + TMEM allocation
+constexpr int BWD_THREADS = 288;  // warps 0-7: two threads per row; warp 8: TMA + MMA issue + TMEM allocation
 constexpr uint32_t BWD_TMEM_COLS = 512;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -68,6 +71,20 @@ int make_tmap_3d(CUtensorMap* tm, const bf16* base, int64_t cols, int64_t L, int
   return FC_OK;
 }
 
+__device__ __forceinline__ void store_row32(bf16* dst, const uint32_t (&a)[16], const uint32_t (&b)[16], float k) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t(&r)[16] = c < 2 ? a : b;
+    const int o = (c & 1) * 8;
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(r[o + 0]) * k, __uint_as_float(r[o + 1]) * k);
+    u.y = pack_bf16x2(__uint_as_float(r[o + 2]) * k, __uint_as_float(r[o + 3]) * k);
+    u.z = pack_bf16x2(__uint_as_float(r[o + 4]) * k, __uint_as_float(r[o + 5]) * k);
+    u.w = pack_bf16x2(__uint_as_float(r[o + 6]) * k, __uint_as_float(r[o + 7]) * k);
+    reinterpret_cast<uint4*>(dst)[c] = u;
+  }
+}
+
 __device__ __forceinline__ void store_row64(bf16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], float k) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -96,7 +113,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   uint8_t* sdO = smem + 3 * tile_bytes;
   float* sLse = reinterpret_cast<float*>(smem + 4 * tile_bytes);
   float* sDelta = sLse + 256;
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sDelta + 256);
+  float* sRed = sDelta + 256;  // [2][2][128]: row max / row sum partials of the two halves
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sRed + 512);
   uint64_t* bar_mma = bar_load + 1;
   uint64_t* bar_soft = bar_load + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
@@ -106,24 +124,25 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const int seq = blockIdx.y;
   const int D = heads * HD;
   const int nk16 = NP / 16;                                     // 16-wide column chunks / UMMA_K steps over NP
-  const int DK_COL = (NP / 2 + HD <= NP) ? NP / 2 : 2 * NP + HD;  // dK accumulator: the dead upper half of S^T if it fits
+  const int DK_COL = NP;  // dK accumulator: over the dP^T columns, which are dead once the softmax threads are through
+  const int ACC_COL = 2 * NP > NP + HD ? 2 * NP : NP + HD;  // dQ / dV accumulator: behind dP (and behind dK for short sequences)
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == 256) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
-    mbar_init(bar_soft, 128);
+    mbar_init(bar_soft, 256);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<BWD_TMEM_COLS>(tmem_slot);
+  if (warp == 8) tmem_alloc<BWD_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA + MMA thread =====================
     if (lane == 0) {
       mbar_expect_tx(bar_load, 4 * tile_bytes);
@@ -153,7 +172,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         ps ^= 1;
         tc_fence_after();
         for (int k = 0; k < nk16; ++k)
-          umma_bf16_ts(tmem_base + 2 * NP, tmem_base + NP + k * 8, umma_desc_mn_sw128(k_addr + k * 2048), idesc_o,
+          umma_bf16_ts(tmem_base + ACC_COL, tmem_base + NP + k * 16, umma_desc_mn_sw128(k_addr + k * 2048), idesc_o,
                        k != 0);
         umma_commit(bar_mma);
         mbar_wait(bar_soft, ps);  // dQ has been read out
@@ -176,9 +195,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         ps ^= 1;
         tc_fence_after();
         for (int k = 0; k < nk16; ++k)
-          umma_bf16_ts(tmem_base + 2 * NP, tmem_base + k * 8, umma_desc_mn_sw128(do_addr + k * 2048), idesc_o, k != 0);
+          umma_bf16_ts(tmem_base + ACC_COL, tmem_base + k * 16, umma_desc_mn_sw128(do_addr + k * 2048), idesc_o, k != 0);
         for (int k = 0; k < nk16; ++k)
-          umma_bf16_ts(tmem_base + DK_COL, tmem_base + NP + k * 8, umma_desc_mn_sw128(q_addr + k * 2048), idesc_o,
+          umma_bf16_ts(tmem_base + DK_COL, tmem_base + k * 16 + 8, umma_desc_mn_sw128(q_addr + k * 2048), idesc_o,
                        k != 0);
         umma_commit(bar_mma);
         mbar_wait(bar_soft, ps);  // dV, dK have been read out
@@ -187,11 +206,19 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       }
     }
   } else {
-    // ===================== softmax / read-out warps: one row per thread =====================
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const int r = warp * 32 + lane;
+    // ===================== softmax / read-out warps: TWO threads per row =====================
+    // warps 0-3 take the first half of a row's column chunks, warps 4-7 the second half (TMEM lane quarter = warp % 4):
+    // with one thread per row only four warps per SM work through the exponentials, one per scheduler, with nothing to
+    // hide their latencies behind (4.53 ms per layer); the row maximum and sum are combined through shared memory.
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int r = quarter * 32 + lane;
     const int64_t tok0 = static_cast<int64_t>(seq) * L;
+    const int nh = (nk16 + 1) / 2;                       // chunks [0, nh) belong to half 0, [nh, nk16) to half 1
+    const int own_lo = half ? nh : 0, own_hi = half ? nk16 : nh;
+    const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     uint32_t pm = 0;
+    uint32_t s0[16], s1[16], d0[16], d1[16];
     // ---------- phase A
     for (int t = 0; t < tiles; ++t) {
       const int row = t * QT + r;
@@ -215,112 +242,172 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const int lim = !valid ? 0 : (CAUSAL ? min(L, row + 1) : L);  // keys [0, lim) are visible to this row
       // tcgen05.ld / .st are warp-collective: loop bounds are warp-uniform (wlim = the largest lim of the warp), the
       // per-row limit only masks the arithmetic
-      const int wrow0 = t * QT + warp * 32;
+      const int wrow0 = t * QT + quarter * 32;
       const int wlim = wrow0 >= L ? 0 : (CAUSAL ? min(L, wrow0 + 32) : L);
-      const int wchunks = (wlim + 15) / 16;
+      const int lo = own_lo, hi = min(own_hi, (wlim + 15) / 16);  // this thread's live chunks [lo, hi)
       mbar_wait(bar_mma, pm);
       pm ^= 1;
       tc_fence_after();
       float m = -INFINITY, l = 0.f;
-      uint32_t s16[16], d16[16];
-      for (int j = 0; j < wchunks; ++j) {  // pass 1: row maximum
-        tmem_ld_32x32b_x16(trow + j * 16, s16);
-        tmem_ld_wait_fence16(s16);
+      // TMEM loads are software-pipelined: chunk j + 1 is requested before chunk j is consumed (a load + wait per chunk
+      // serialises on the TMEM latency: 5.03 ms per layer for the first version of this kernel)
+      {  // pass 1: row maximum
+        auto body = [&](int j, const uint32_t(&b)[16]) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
-          if (j * 16 + c < lim) m = fmaxf(m, __uint_as_float(s16[c]));
+          for (int c = 0; c < 16; ++c)
+            if (j * 16 + c < lim) m = fmaxf(m, __uint_as_float(b[c]));
+        };
+        if (lo < hi) tmem_ld_32x32b_x16(trow + lo * 16, s0);
+        for (int j = lo; j < hi; j += 2) {
+          tmem_ld_wait_fence16(s0);
+          if (j + 1 < hi) tmem_ld_32x32b_x16(trow + (j + 1) * 16, s1);
+          body(j, s0);
+          if (j + 1 < hi) {
+            tmem_ld_wait_fence16(s1);
+            if (j + 2 < hi) tmem_ld_32x32b_x16(trow + (j + 2) * 16, s0);
+            body(j + 1, s1);
+          }
+        }
       }
+      sRed[half * 128 + r] = m;
+      named_bar_sync(2, 256);
+      m = fmaxf(m, sRed[(half ^ 1) * 128 + r]);
       const float mc = valid ? m * scale_log2 : 0.f;
-      for (int j = 0; j < wchunks; ++j) {  // pass 2: row sum
-        tmem_ld_32x32b_x16(trow + j * 16, s16);
-        tmem_ld_wait_fence16(s16);
-#pragma unroll
-        for (int c = 0; c < 16; ++c)
-          if (j * 16 + c < lim) l += ex2_approx(fmaf(__uint_as_float(s16[c]), scale_log2, -mc));
-      }
-      const float inv_l = valid ? 1.f / l : 0.f;
-      for (int j = 0; j < nk16; ++j) {  // pass 3: dS = P o (dP - delta) -> bf16 over the dP columns (zeros beyond wlim)
-        uint32_t pk[8];
-        if (j < wchunks) {
-          tmem_ld_32x32b_x16(trow + j * 16, s16);
-          tmem_ld_32x32b_x16(trow + NP + j * 16, d16);
-          tmem_ld_wait_fence16(s16);
-          tmem_ld_wait_fence16(d16);
+      {  // pass 2: P~ = exp2(S c - m c) (un-normalised), row sum, dS~ = P~ o (dP - delta) -> bf16 over the dP columns;
+         // dQ is linear in P~, so the 1 / l goes into the read-out of dQ
+        auto body = [&](int j, const uint32_t(&bs)[16], const uint32_t(&bd)[16]) {
+          uint32_t pk[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float v[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int col = j * 16 + 2 * c + e;
-              const float p = ex2_approx(fmaf(__uint_as_float(s16[2 * c + e]), scale_log2, -mc)) * inv_l;
-              v[e] = col < lim ? p * (__uint_as_float(d16[2 * c + e]) - delta) : 0.f;
+              const float p = col < lim ? ex2_approx(fmaf(__uint_as_float(bs[2 * c + e]), scale_log2, -mc)) : 0.f;
+              l += p;
+              v[e] = p * (__uint_as_float(bd[2 * c + e]) - delta);
             }
             pk[c] = pack_bf16x2(v[0], v[1]);
           }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) pk[c] = 0u;
+          tmem_st_32x32b_x8(trow + NP + j * 16, pk);  // over the first half of the chunk's own (consumed) dP columns
+        };
+        if (lo < hi) {
+          tmem_ld_32x32b_x16(trow + lo * 16, s0);
+          tmem_ld_32x32b_x16(trow + NP + lo * 16, d0);
         }
-        tmem_st_32x32b_x8(trow + NP + j * 8, pk);
+        for (int j = lo; j < hi; j += 2) {
+          tmem_ld_wait_fence16(s0);
+          tmem_ld_wait_fence16(d0);
+          if (j + 1 < hi) {
+            tmem_ld_32x32b_x16(trow + (j + 1) * 16, s1);
+            tmem_ld_32x32b_x16(trow + NP + (j + 1) * 16, d1);
+          }
+          body(j, s0, d0);
+          if (j + 1 < hi) {
+            tmem_ld_wait_fence16(s1);
+            tmem_ld_wait_fence16(d1);
+            if (j + 2 < hi) {
+              tmem_ld_32x32b_x16(trow + (j + 2) * 16, s0);
+              tmem_ld_32x32b_x16(trow + NP + (j + 2) * 16, d0);
+            }
+            body(j + 1, s1, d1);
+          }
+        }
+        for (int j = max(hi, own_lo); j < own_hi; ++j) tmem_st_32x32b_x8(trow + NP + j * 16, zero);  // keys beyond the limit
       }
       tmem_st_wait();
-      sLse[row] = valid ? fmaf(m, scale_log2, log2f(l)) : 0.f;
-      sDelta[row] = delta;
       tc_fence_before();
       mbar_arrive(bar_soft);
-      // dQ read-out
+      sRed[256 + half * 128 + r] = l;
+      named_bar_sync(2, 256);
+      l += sRed[256 + (half ^ 1) * 128 + r];
+      if (half == 0) {
+        sLse[row] = valid ? fmaf(m, scale_log2, log2f(l)) : 0.f;
+        sDelta[row] = delta;
+      }
+      // dQ read-out: 32 of the 64 columns per thread
       mbar_wait(bar_mma, pm);
       pm ^= 1;
       tc_fence_after();
       if (wrow0 < L) {  // warp-uniform
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32b_x32(trow + 2 * NP, o0);
-        tmem_ld_32x32b_x32(trow + 2 * NP + 32, o1);
-        tmem_ld_wait_fence(o0);
-        tmem_ld_wait_fence(o1);
-        if (valid) store_row64(dqkv + (tok0 + row) * (3 * D) + head * HD, o0, o1, scale);
+        tmem_ld_32x32b_x16(trow + ACC_COL + half * 32, s0);
+        tmem_ld_32x32b_x16(trow + ACC_COL + half * 32 + 16, s1);
+        tmem_ld_wait_fence16(s0);
+        tmem_ld_wait_fence16(s1);
+        if (valid) store_row32(dqkv + (tok0 + row) * (3 * D) + head * HD + half * 32, s0, s1, scale / l);
       }
       tc_fence_before();
       mbar_arrive(bar_soft);
     }
-    named_bar_sync(1, 128);  // every row's log-sum-exp / delta is in shared memory
+    named_bar_sync(1, 256);  // every row's log-sum-exp / delta is in shared memory
     // ---------- phase B
     for (int t = 0; t < tiles; ++t) {
       const int key = t * QT + r;
       const bool kvalid = key < L;
-      const int wkey0 = t * QT + warp * 32;  // smallest key of the warp: the warp-uniform causal bound
+      const int wkey0 = t * QT + quarter * 32;  // smallest key of the warp: the warp-uniform causal bound
       mbar_wait(bar_mma, pm);
       pm ^= 1;
       tc_fence_after();
-      uint32_t s16[16], d16[16];
-      for (int j = 0; j < nk16; ++j) {
-        uint32_t pp[8], pd[8];
-        const int q0 = j * 16;
-        if (wkey0 < L && q0 < L && (!CAUSAL || q0 + 15 >= wkey0)) {  // warp-uniform: some (key, query) pair is live
-          tmem_ld_32x32b_x16(trow + q0, s16);
-          tmem_ld_32x32b_x16(trow + NP + q0, d16);
-          tmem_ld_wait_fence16(s16);
-          tmem_ld_wait_fence16(d16);
+      {
+        // warp-uniform live range of this thread's query chunks (causal: queries before the warp's smallest key are masked)
+        const int jhi = wkey0 < L ? min(own_hi, (L + 15) / 16) : own_lo;
+        const int jlo = min(jhi, max(own_lo, CAUSAL ? wkey0 / 16 : 0));
+        auto body = [&](int j, const uint32_t(&bs)[16], const uint32_t(&bd)[16]) {
+          uint32_t pp[8], pd[8];
+          const float4* lse4 = reinterpret_cast<const float4*>(sLse + j * 16);
+          const float4* dl4 = reinterpret_cast<const float4*>(sDelta + j * 16);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float pv[2], dv[2];
+          for (int g = 0; g < 4; ++g) {
+            const float4 ls = lse4[g], dl = dl4[g];
+            const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int q = q0 + 2 * c + e;
-              const bool dead = !kvalid || q >= L || (CAUSAL && key > q);
-              const float p = dead ? 0.f : ex2_approx(fmaf(__uint_as_float(s16[2 * c + e]), scale_log2, -sLse[q]));
-              pv[e] = p;
-              dv[e] = p * (__uint_as_float(d16[2 * c + e]) - sDelta[q]);
+            for (int h = 0; h < 2; ++h) {
+              float pv[2], dv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = 4 * g + 2 * h + e, q = j * 16 + i;
+                const bool dead = !kvalid || q >= L || (CAUSAL && key > q);
+                const float p = dead ? 0.f : ex2_approx(fmaf(__uint_as_float(bs[i]), scale_log2, -lsv[2 * h + e]));
+                pv[e] = p;
+                dv[e] = p * (__uint_as_float(bd[i]) - dlv[2 * h + e]);
+              }
+              pp[2 * g + h] = pack_bf16x2(pv[0], pv[1]);
+              pd[2 * g + h] = pack_bf16x2(dv[0], dv[1]);
             }
-            pp[c] = pack_bf16x2(pv[0], pv[1]);
-            pd[c] = pack_bf16x2(dv[0], dv[1]);
           }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) pp[c] = pd[c] = 0u;
+          tmem_st_32x32b_x8(trow + j * 16, pp);      // both results go over the chunk's own (consumed) S^T columns:
+          tmem_st_32x32b_x8(trow + j * 16 + 8, pd);  // no thread ever overwrites another thread's unread input
+        };
+        if (jlo < jhi) {
+          tmem_ld_32x32b_x16(trow + jlo * 16, s0);
+          tmem_ld_32x32b_x16(trow + NP + jlo * 16, d0);
         }
-        tmem_st_32x32b_x8(trow + j * 8, pp);
-        tmem_st_32x32b_x8(trow + NP + j * 8, pd);
+        for (int j = jlo; j < jhi; j += 2) {
+          tmem_ld_wait_fence16(s0);
+          tmem_ld_wait_fence16(d0);
+          if (j + 1 < jhi) {
+            tmem_ld_32x32b_x16(trow + (j + 1) * 16, s1);
+            tmem_ld_32x32b_x16(trow + NP + (j + 1) * 16, d1);
+          }
+          body(j, s0, d0);
+          if (j + 1 < jhi) {
+            tmem_ld_wait_fence16(s1);
+            tmem_ld_wait_fence16(d1);
+            if (j + 2 < jhi) {
+              tmem_ld_32x32b_x16(trow + (j + 2) * 16, s0);
+              tmem_ld_32x32b_x16(trow + NP + (j + 2) * 16, d0);
+            }
+            body(j + 1, s1, d1);
+          }
+        }
+        for (int j = own_lo; j < jlo; ++j) {
+          tmem_st_32x32b_x8(trow + j * 16, zero);
+          tmem_st_32x32b_x8(trow + j * 16 + 8, zero);
+        }
+        for (int j = jhi; j < own_hi; ++j) {
+          tmem_st_32x32b_x8(trow + j * 16, zero);
+          tmem_st_32x32b_x8(trow + j * 16 + 8, zero);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -329,27 +416,29 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       pm ^= 1;
       tc_fence_after();
       if (wkey0 < L) {  // warp-uniform
-        uint32_t o0[32], o1[32];
-        bf16* dst = dqkv + (tok0 + key) * (3 * D) + D + head * HD;
-        tmem_ld_32x32b_x32(trow + DK_COL, o0);
-        tmem_ld_32x32b_x32(trow + DK_COL + 32, o1);
-        tmem_ld_wait_fence(o0);
-        tmem_ld_wait_fence(o1);
-        if (kvalid) store_row64(dst, o0, o1, scale);
-        tmem_ld_32x32b_x32(trow + 2 * NP, o0);
-        tmem_ld_32x32b_x32(trow + 2 * NP + 32, o1);
-        tmem_ld_wait_fence(o0);
-        tmem_ld_wait_fence(o1);
-        if (kvalid) store_row64(dst + D, o0, o1, 1.f);
+        bf16* dst = dqkv + (tok0 + key) * (3 * D) + D + head * HD + half * 32;
+        tmem_ld_32x32b_x16(trow + DK_COL + half * 32, s0);
+        tmem_ld_32x32b_x16(trow + DK_COL + half * 32 + 16, s1);
+        tmem_ld_32x32b_x16(trow + ACC_COL + half * 32, d0);
+        tmem_ld_32x32b_x16(trow + ACC_COL + half * 32 + 16, d1);
+        tmem_ld_wait_fence16(s0);
+        tmem_ld_wait_fence16(s1);
+        tmem_ld_wait_fence16(d0);
+        tmem_ld_wait_fence16(d1);
+        if (kvalid) {
+          store_row32(dst, s0, s1, scale);
+          store_row32(dst + D, d0, d1, 1.f);
+        }
       }
       tc_fence_before();
       mbar_arrive(bar_soft);
     }
   }
 
+
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc<BWD_TMEM_COLS>(tmem_base);
   }
@@ -360,7 +449,7 @@ int launch_bwd_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, in
                   cudaStream_t s) {
   const int tiles = (L + QT - 1) / QT;
   const int R = tiles * QT;
-  const int smem = 4 * R * 128 + 2 * 256 * 4 + 64;
+  const int smem = 4 * R * 128 + 4 * 256 * 4 + 64;
   static int configured = 0;
   if (configured < smem) {
     FC_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -393,7 +482,7 @@ int attention_bwd_bf16_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* 
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("FC_ATTENTION_BWD");
-    mode = (e && strcmp(e, "tc") == 0) ? 1 : 0;
+    mode = (e && strcmp(e, "mma") == 0) ? 0 : 1;
   }
   if (!mode || L > 208 || L < 1 || seqs > 65535) return FC_OK;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(O) & 15) ||
