@@ -17,7 +17,8 @@
 //        dV = P^T dO (B = dO MN-major) -> [2 NP, +64);  dK = dS^T Q (B = Q MN-major) -> [NP, NP + 64) -> global
 // bf16 results are written over the 16-column fp32 chunk they were computed from (chunk j -> columns 16 j .. 16 j + 15),
 // so no thread overwrites input another thread still has to read, and each UMMA_K step takes its A operand from there.
-// Everything is serialised inside a CTA (no software pipelining yet): MMA batch -> softmax -> MMA batch -> read-out.
+// Inside a CTA a stage is MMA batch -> softmax -> MMA batch -> read-out; only the S / dP products of the stage behind a
+// phase-A stage overlap that stage's read-out (four mbarriers: S/dP ready, operands ready, accumulators ready, read).
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,7 +32,6 @@ namespace {
 constexpr int HD = 64;
 constexpr int QT = 128;
 constexpr int BWD_THREADS = 288;  // warps 0-7: two threads per row; warp 8: TMA + MMA issue + TMEM allocation
-constexpr uint32_t BWD_TMEM_COLS = 512;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -99,8 +99,10 @@ __device__ __forceinline__ void store_row64(bf16* dst, const uint32_t (&a)[32], 
   }
 }
 
-template <bool CAUSAL>
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+// TMEM_COLS: 512 for the image sequence (S 208 + dP 208 + 64: one CTA per SM), 256 when 2 NP + 64 <= 256 (the text
+// sequence: two co-resident CTAs hide each other's load and read-out phases).
+template <bool CAUSAL, uint32_t TMEM_COLS>
+__global__ void __launch_bounds__(BWD_THREADS, TMEM_COLS == 256 ? 2 : 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const bf16* __restrict__ O, const bf16* __restrict__ dO, bf16* __restrict__ dqkv, int L, int NP,
                         int tiles, int heads, float scale, float scale_log2) {
@@ -115,9 +117,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   float* sDelta = sLse + 256;
   float* sRed = sDelta + 256;  // [2][2][128]: row max / row sum partials of the two halves
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(sRed + 512);
-  uint64_t* bar_mma = bar_load + 1;
-  uint64_t* bar_soft = bar_load + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+  uint64_t* bar_sd = bar_load + 1;   // MMA -> softmax: S / dP (or S^T / dP^T) of a stage are in TMEM
+  uint64_t* bar_sm = bar_load + 2;   // softmax -> MMA: the bf16 operands of the stage are in TMEM
+  uint64_t* bar_acc = bar_load + 3;  // MMA -> read-out: the accumulators of the stage are complete
+  uint64_t* bar_rd = bar_load + 4;   // read-out -> MMA: the accumulators have been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x;
@@ -132,11 +136,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     mbar_init(bar_load, 1);
-    mbar_init(bar_mma, 1);
-    mbar_init(bar_soft, 256);
+    mbar_init(bar_sd, 1);
+    mbar_init(bar_sm, 256);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_rd, 256);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<BWD_TMEM_COLS>(tmem_slot);
+  if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -153,56 +159,51 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), do_addr = smem_u32(sdO);
       const uint32_t idesc_s = umma_idesc_bf16_f32(QT, NP);
       const uint32_t idesc_o = umma_idesc_bf16_f32_bmn(QT, HD);
-      uint32_t ps = 0;
       mbar_wait(bar_load, 0);
       tc_fence_after();
-      // ---------- phase A: query tiles
-      for (int t = 0; t < tiles; ++t) {
-        const uint32_t row_off = t * QT * 128;
+      // stages 0 .. tiles-1: phase A (query tiles), stages tiles .. 2 tiles-1: phase B (key tiles)
+      const int stages = 2 * tiles;
+      auto issue_sd = [&](int st) {
+        const bool pa = st < tiles;
+        const uint32_t row_off = (pa ? st : st - tiles) * QT * 128;
+        const uint32_t a0 = (pa ? q_addr : k_addr) + row_off, b0 = pa ? k_addr : q_addr;
+        const uint32_t a1 = (pa ? do_addr : v_addr) + row_off, b1 = pa ? v_addr : do_addr;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + row_off + k * 32), umma_desc_k_sw128(k_addr + k * 32),
-                       idesc_s, k != 0);
+          umma_bf16_ss(tmem_base, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc_s, k != 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base + NP, umma_desc_k_sw128(do_addr + row_off + k * 32),
-                       umma_desc_k_sw128(v_addr + k * 32), idesc_s, k != 0);
-        umma_commit(bar_mma);
-        mbar_wait(bar_soft, ps);  // dS (bf16) is in TMEM
-        ps ^= 1;
+          umma_bf16_ss(tmem_base + NP, umma_desc_k_sw128(a1 + k * 32), umma_desc_k_sw128(b1 + k * 32), idesc_s, k != 0);
+        umma_commit(bar_sd);
+      };
+      uint32_t p_sm = 0, p_rd = 0;
+      issue_sd(0);
+      for (int st = 0; st < stages; ++st) {
+        mbar_wait(bar_sm, p_sm);  // the stage's bf16 operands are in TMEM
+        p_sm ^= 1;
         tc_fence_after();
-        for (int k = 0; k < nk16; ++k)
-          umma_bf16_ts(tmem_base + ACC_COL, tmem_base + NP + k * 16, umma_desc_mn_sw128(k_addr + k * 2048), idesc_o,
-                       k != 0);
-        umma_commit(bar_mma);
-        mbar_wait(bar_soft, ps);  // dQ has been read out
-        ps ^= 1;
+        if (st < tiles) {  // dQ = dS~ K
+          for (int k = 0; k < nk16; ++k)
+            umma_bf16_ts(tmem_base + ACC_COL, tmem_base + NP + k * 16, umma_desc_mn_sw128(k_addr + k * 2048), idesc_o,
+                         k != 0);
+        } else {  // dV = P^T dO, dK = dS^T Q
+          for (int k = 0; k < nk16; ++k)
+            umma_bf16_ts(tmem_base + ACC_COL, tmem_base + k * 16, umma_desc_mn_sw128(do_addr + k * 2048), idesc_o,
+                         k != 0);
+          for (int k = 0; k < nk16; ++k)
+            umma_bf16_ts(tmem_base + DK_COL, tmem_base + k * 16 + 8, umma_desc_mn_sw128(q_addr + k * 2048), idesc_o,
+                         k != 0);
+        }
+        umma_commit(bar_acc);
+        // The next stage's S / dP products are queued right behind a phase-A stage: the tensor pipe runs in order, so
+        // they overwrite dS~ only after dQ consumed it, and they do not touch the dQ columns, so they overlap the
+        // read-out.  Behind a phase-B stage they would land on the dK accumulator (it sits in the dP^T columns).
+        const bool early = st < tiles && st + 1 < stages;
+        if (early) issue_sd(st + 1);
+        mbar_wait(bar_rd, p_rd);  // the accumulators have been read out
+        p_rd ^= 1;
         tc_fence_after();
-      }
-      // ---------- phase B: key tiles
-      for (int t = 0; t < tiles; ++t) {
-        const uint32_t row_off = t * QT * 128;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base, umma_desc_k_sw128(k_addr + row_off + k * 32), umma_desc_k_sw128(q_addr + k * 32),
-                       idesc_s, k != 0);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base + NP, umma_desc_k_sw128(v_addr + row_off + k * 32),
-                       umma_desc_k_sw128(do_addr + k * 32), idesc_s, k != 0);
-        umma_commit(bar_mma);
-        mbar_wait(bar_soft, ps);  // P^T and dS^T (bf16) are in TMEM
-        ps ^= 1;
-        tc_fence_after();
-        for (int k = 0; k < nk16; ++k)
-          umma_bf16_ts(tmem_base + ACC_COL, tmem_base + k * 16, umma_desc_mn_sw128(do_addr + k * 2048), idesc_o, k != 0);
-        for (int k = 0; k < nk16; ++k)
-          umma_bf16_ts(tmem_base + DK_COL, tmem_base + k * 16 + 8, umma_desc_mn_sw128(q_addr + k * 2048), idesc_o,
-                       k != 0);
-        umma_commit(bar_mma);
-        mbar_wait(bar_soft, ps);  // dV, dK have been read out
-        ps ^= 1;
-        tc_fence_after();
+        if (!early && st + 1 < stages) issue_sd(st + 1);
       }
     }
   } else {
@@ -245,17 +246,28 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const int wrow0 = t * QT + quarter * 32;
       const int wlim = wrow0 >= L ? 0 : (CAUSAL ? min(L, wrow0 + 32) : L);
       const int lo = own_lo, hi = min(own_hi, (wlim + 15) / 16);  // this thread's live chunks [lo, hi)
-      mbar_wait(bar_mma, pm);
-      pm ^= 1;
+      mbar_wait(bar_sd, pm);
       tc_fence_after();
       float m = -INFINITY, l = 0.f;
       // TMEM loads are software-pipelined: chunk j + 1 is requested before chunk j is consumed (a load + wait per chunk
       // serialises on the TMEM latency: 5.03 ms per layer for the first version of this kernel)
       {  // pass 1: row maximum
+        // chunks whose 16 keys are valid and visible to all rows of the warp skip the per-element limit (rows beyond
+        // the sequence then hold garbage statistics, which only ever reach their own, never stored, dQ row)
         auto body = [&](int j, const uint32_t(&b)[16]) {
+          if (j * 16 + 16 <= L && (!CAUSAL || j * 16 + 15 <= wrow0)) {
+            float m1 = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (j * 16 + c < lim) m = fmaxf(m, __uint_as_float(b[c]));
+            for (int c = 0; c < 16; c += 2) {
+              m = fmaxf(m, __uint_as_float(b[c]));
+              m1 = fmaxf(m1, __uint_as_float(b[c + 1]));
+            }
+            m = fmaxf(m, m1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              if (j * 16 + c < lim) m = fmaxf(m, __uint_as_float(b[c]));
+          }
         };
         if (lo < hi) tmem_ld_32x32b_x16(trow + lo * 16, s0);
         for (int j = lo; j < hi; j += 2) {
@@ -277,18 +289,22 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
          // dQ is linear in P~, so the 1 / l goes into the read-out of dQ
         auto body = [&](int j, const uint32_t(&bs)[16], const uint32_t(&bd)[16]) {
           uint32_t pk[8];
+          const bool full = j * 16 + 16 <= L && (!CAUSAL || j * 16 + 15 <= wrow0);  // warp-uniform
+          float l1 = 0.f;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float v[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int col = j * 16 + 2 * c + e;
-              const float p = col < lim ? ex2_approx(fmaf(__uint_as_float(bs[2 * c + e]), scale_log2, -mc)) : 0.f;
-              l += p;
+              float p = ex2_approx(fmaf(__uint_as_float(bs[2 * c + e]), scale_log2, -mc));
+              if (!full && col >= lim) p = 0.f;
+              if (e) l1 += p; else l += p;
               v[e] = p * (__uint_as_float(bd[2 * c + e]) - delta);
             }
             pk[c] = pack_bf16x2(v[0], v[1]);
           }
+          l += l1;
           tmem_st_32x32b_x8(trow + NP + j * 16, pk);  // over the first half of the chunk's own (consumed) dP columns
         };
         if (lo < hi) {
@@ -317,7 +333,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_soft);
+      mbar_arrive(bar_sm);
       sRed[256 + half * 128 + r] = l;
       named_bar_sync(2, 256);
       l += sRed[256 + (half ^ 1) * 128 + r];
@@ -326,7 +342,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         sDelta[row] = delta;
       }
       // dQ read-out: 32 of the 64 columns per thread
-      mbar_wait(bar_mma, pm);
+      mbar_wait(bar_acc, pm);
       pm ^= 1;
       tc_fence_after();
       if (wrow0 < L) {  // warp-uniform
@@ -337,7 +353,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         if (valid) store_row32(dqkv + (tok0 + row) * (3 * D) + head * HD + half * 32, s0, s1, scale / l);
       }
       tc_fence_before();
-      mbar_arrive(bar_soft);
+      mbar_arrive(bar_rd);
     }
     named_bar_sync(1, 256);  // every row's log-sum-exp / delta is in shared memory
     // ---------- phase B
@@ -345,8 +361,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const int key = t * QT + r;
       const bool kvalid = key < L;
       const int wkey0 = t * QT + quarter * 32;  // smallest key of the warp: the warp-uniform causal bound
-      mbar_wait(bar_mma, pm);
-      pm ^= 1;
+      mbar_wait(bar_sd, pm);
       tc_fence_after();
       {
         // warp-uniform live range of this thread's query chunks (causal: queries before the warp's smallest key are masked)
@@ -354,6 +369,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         const int jlo = min(jhi, max(own_lo, CAUSAL ? wkey0 / 16 : 0));
         auto body = [&](int j, const uint32_t(&bs)[16], const uint32_t(&bd)[16]) {
           uint32_t pp[8], pd[8];
+          // warp-uniform: all 16 queries valid and visible to all keys of the warp -> no per-element mask (key rows
+          // beyond the sequence then hold garbage, which only reaches their own, never stored, dK / dV rows)
+          const bool full = j * 16 + 16 <= L && (!CAUSAL || j * 16 >= wkey0 + 31);
           const float4* lse4 = reinterpret_cast<const float4*>(sLse + j * 16);
           const float4* dl4 = reinterpret_cast<const float4*>(sDelta + j * 16);
 #pragma unroll
@@ -366,8 +384,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int i = 4 * g + 2 * h + e, q = j * 16 + i;
-                const bool dead = !kvalid || q >= L || (CAUSAL && key > q);
-                const float p = dead ? 0.f : ex2_approx(fmaf(__uint_as_float(bs[i]), scale_log2, -lsv[2 * h + e]));
+                float p = ex2_approx(fmaf(__uint_as_float(bs[i]), scale_log2, -lsv[2 * h + e]));
+                if (!full && (!kvalid || q >= L || (CAUSAL && key > q))) p = 0.f;
                 pv[e] = p;
                 dv[e] = p * (__uint_as_float(bd[i]) - dlv[2 * h + e]);
               }
@@ -411,8 +429,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_soft);
-      mbar_wait(bar_mma, pm);
+      mbar_arrive(bar_sm);
+      mbar_wait(bar_acc, pm);
       pm ^= 1;
       tc_fence_after();
       if (wkey0 < L) {  // warp-uniform
@@ -431,7 +449,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_soft);
+      mbar_arrive(bar_rd);
     }
   }
 
@@ -440,11 +458,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc<BWD_TMEM_COLS>(tmem_base);
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, uint32_t TMEM_COLS>
 int launch_bwd_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, int64_t seqs, int L, int heads,
                   cudaStream_t s) {
   const int tiles = (L + QT - 1) / QT;
@@ -452,7 +470,7 @@ int launch_bwd_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, in
   const int smem = 4 * R * 128 + 4 * 256 * 4 + 64;
   static int configured = 0;
   if (configured < smem) {
-    FC_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FC_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<CAUSAL, TMEM_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   const int D = heads * HD;
@@ -465,7 +483,7 @@ int launch_bwd_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, in
   for (int64_t s0 = 0; s0 < seqs; s0 += 65535) {
     FC_REQUIRE(s0 == 0, "attention backward (tcgen05): more than 65535 sequences per call are not supported");
     dim3 grid(heads, static_cast<unsigned>(seqs));
-    attention_bwd_tc_kernel<CAUSAL><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, O, dO, dqkv, L, NP, tiles, heads, scale,
+    attention_bwd_tc_kernel<CAUSAL, TMEM_COLS><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, O, dO, dqkv, L, NP, tiles, heads, scale,
                                                                     scale_log2);
     FC_CHECK_LAUNCH();
   }
@@ -489,8 +507,13 @@ int attention_bwd_bf16_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* 
       (reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(dqkv) & 15))
     return FC_OK;
   *handled = 1;
-  return causal ? launch_bwd_tc<true>(qkv, O, dO, dqkv, seqs, L, heads, s)
-                : launch_bwd_tc<false>(qkv, O, dO, dqkv, seqs, L, heads, s);
+  const int NP = (L + 15) / 16 * 16;
+  const bool small = (2 * NP > NP + HD ? 2 * NP : NP + HD) + HD <= 256;  // last accumulator column fits 256 columns
+  if (causal)
+    return small ? launch_bwd_tc<true, 256>(qkv, O, dO, dqkv, seqs, L, heads, s)
+                 : launch_bwd_tc<true, 512>(qkv, O, dO, dqkv, seqs, L, heads, s);
+  return small ? launch_bwd_tc<false, 256>(qkv, O, dO, dqkv, seqs, L, heads, s)
+               : launch_bwd_tc<false, 512>(qkv, O, dO, dqkv, seqs, L, heads, s);
 }
 
 }  // namespace fc

@@ -7,8 +7,9 @@
 //                       wgrad  dW = dY^T . X        -> the tcgen05 GEMM's split-K epilogue (EPI_F32_SPLITK) on
 //                                                      transposed activations (transpose_bf16 below, which also
 //                                                      produces the bias gradient = column sums of dY on the way)
-//   attention backward  mma.sync.m16n8k16, Q/K/V/dO of one (sequence, head) resident in shared memory, two phases
-//                       (query-tile owners produce dQ, key-tile owners produce dK/dV) so no atomics are needed
+//   attention backward  L <= 208: tcgen05 kernel in attention_bwd_tc.cu; longer sequences: mma.sync.m16n8k16 here, Q/K/V/dO
+//                       of one (sequence, head) resident in shared memory, two phases (query-tile owners produce dQ,
+//                       key-tile owners produce dK/dV) so no atomics are needed
 //   memory-bound        LayerNorm backward (+ residual add), QuickGELU forward/backward, pool+normalise backward,
 //                       embedding scatter/sums, loss gradients, fused AdamW over ONE flat parameter buffer.
 #include <math.h>
