@@ -102,7 +102,11 @@ def _ref_attention(qkv, seqs, L, heads, causal):
 
 @pytest.mark.parametrize("seqs,L,heads,causal", [
     (3, 197, 12, False), (5, 77, 8, True), (2, 77, 8, False), (4, 16, 2, True), (3, 50, 4, False), (2, 130, 3, True),
-    (1, 208, 1, False), (7, 1, 2, True), (2, 257, 2, False), (3, 33, 1, True), (40, 197, 3, False)])
+    (1, 208, 1, False), (7, 1, 2, True), (2, 257, 2, False), (3, 33, 1, True), (40, 197, 3, False),
+    # tile / column-layout edges of the tcgen05 kernel: exactly one tile, one row in the second tile, NP = 64 (the
+    # accumulators start at NP + 64 below that), causal across two tiles, many items
+    (2, 128, 2, False), (2, 129, 2, True), (3, 64, 1, True), (2, 17, 3, True), (2, 200, 2, True), (3, 48, 2, False),
+    (300, 77, 8, True)])
 def test_attention_bwd(dev, seqs, L, heads, causal):
     from fitclip_b200 import ops, train_ops as T
     torch.manual_seed(4)
