@@ -31,7 +31,8 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int QT = 128;
-constexpr int BWD_THREADS = 288;  // warps 0-7: two threads per row; warp 8: TMA + MMA issue + TMEM allocation
+// threads: NPARTS softmax threads per row (4 NPARTS warps), then one warp for TMA + MMA issue + TMEM allocation
+constexpr int bwd_threads(int nparts) { return nparts * 128 + 32; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -100,9 +101,13 @@ __device__ __forceinline__ void store_row64(bf16* dst, const uint32_t (&a)[32], 
 }
 
 // TMEM_COLS: 512 for the image sequence (S 208 + dP 208 + 64: one CTA per SM), 256 when 2 NP + 64 <= 256 (the text
-// sequence: two co-resident CTAs hide each other's load and read-out phases).
+// sequence: two co-resident CTAs hide each other's load and read-out).  BWD_NPARTS softmax threads per row: measured on
+// 2048 x 197 x 12 heads, 1 -> 4.53 ms, 2 -> 3.86 ms, 3 -> 4.07 ms per layer (128-register cap, 5/4/4 chunk split, a third
+// partner in the row-statistics exchange): a stage is a serial chain MMA -> softmax -> MMA -> read-out of about equal
+// parts, so more softmax threads stop paying after two.
+constexpr int BWD_NPARTS = 2;
 template <bool CAUSAL, uint32_t TMEM_COLS>
-__global__ void __launch_bounds__(BWD_THREADS, TMEM_COLS == 256 ? 2 : 1)
+__global__ void __launch_bounds__(bwd_threads(BWD_NPARTS), TMEM_COLS == 256 ? 2 : 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const bf16* __restrict__ O, const bf16* __restrict__ dO, bf16* __restrict__ dqkv, int L, int NP,
                         int tiles, int heads, float scale, float scale_log2) {
@@ -115,8 +120,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   uint8_t* sdO = smem + 3 * tile_bytes;
   float* sLse = reinterpret_cast<float*>(smem + 4 * tile_bytes);
   float* sDelta = sLse + 256;
-  float* sRed = sDelta + 256;  // [2][2][128]: row max / row sum partials of the two halves
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sRed + 512);
+  constexpr int NPARTS = BWD_NPARTS;  // softmax threads per row
+  constexpr int SOFT_THREADS = NPARTS * 128;
+  constexpr int T_WARP = NPARTS * 4;
+  float* sRed = sDelta + 256;  // [2][NPARTS][128]: row max / row sum partials of the threads of a row
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sRed + 2 * 3 * 128);
   uint64_t* bar_sd = bar_load + 1;   // MMA -> softmax: S / dP (or S^T / dP^T) of a stage are in TMEM
   uint64_t* bar_sm = bar_load + 2;   // softmax -> MMA: the bf16 operands of the stage are in TMEM
   uint64_t* bar_acc = bar_load + 3;  // MMA -> read-out: the accumulators of the stage are complete
@@ -132,23 +140,23 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const int ACC_COL = 2 * NP > NP + HD ? 2 * NP : NP + HD;  // dQ / dV accumulator: behind dP (and behind dK for short sequences)
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 256) {
+  if (threadIdx.x == SOFT_THREADS) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     mbar_init(bar_load, 1);
     mbar_init(bar_sd, 1);
-    mbar_init(bar_sm, 256);
+    mbar_init(bar_sm, SOFT_THREADS);
     mbar_init(bar_acc, 1);
-    mbar_init(bar_rd, 256);
+    mbar_init(bar_rd, SOFT_THREADS);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == T_WARP) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == T_WARP) {
     // ===================== TMA + MMA thread =====================
     if (lane == 0) {
       mbar_expect_tx(bar_load, 4 * tile_bytes);
@@ -207,16 +215,16 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       }
     }
   } else {
-    // ===================== softmax / read-out warps: TWO threads per row =====================
-    // warps 0-3 take the first half of a row's column chunks, warps 4-7 the second half (TMEM lane quarter = warp % 4):
-    // with one thread per row only four warps per SM work through the exponentials, one per scheduler, with nothing to
-    // hide their latencies behind (4.53 ms per layer); the row maximum and sum are combined through shared memory.
-    const int quarter = warp & 3, half = warp >> 2;
+    // ===================== softmax / read-out warps: NPARTS threads per row =====================
+    // warps 4 p .. 4 p + 3 take part p of a row's column chunks (TMEM lane quarter = warp % 4): with one thread per row
+    // only four warps per SM work through the exponentials, one per scheduler, with nothing to hide their latencies
+    // behind (4.53 ms per layer; two per row 3.99); the row maximum and sum are combined through shared memory.
+    const int quarter = warp & 3, part = warp >> 2;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int r = quarter * 32 + lane;
     const int64_t tok0 = static_cast<int64_t>(seq) * L;
-    const int nh = (nk16 + 1) / 2;                       // chunks [0, nh) belong to half 0, [nh, nk16) to half 1
-    const int own_lo = half ? nh : 0, own_hi = half ? nk16 : nh;
+    const int nh = (nk16 + NPARTS - 1) / NPARTS;         // chunks [p nh, (p + 1) nh) belong to part p
+    const int own_lo = min(part * nh, nk16), own_hi = min(own_lo + nh, nk16);
     const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     uint32_t pm = 0;
     uint32_t s0[16], s1[16], d0[16], d1[16];
@@ -281,9 +289,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
         }
       }
-      sRed[half * 128 + r] = m;
-      named_bar_sync(2, 256);
-      m = fmaxf(m, sRed[(half ^ 1) * 128 + r]);
+      sRed[part * 128 + r] = m;
+      named_bar_sync(2, SOFT_THREADS);
+#pragma unroll
+      for (int p = 0; p < NPARTS; ++p) m = fmaxf(m, sRed[p * 128 + r]);
       const float mc = valid ? m * scale_log2 : 0.f;
       {  // pass 2: P~ = exp2(S c - m c) (un-normalised), row sum, dS~ = P~ o (dP - delta) -> bf16 over the dP columns;
          // dQ is linear in P~, so the 1 / l goes into the read-out of dQ
@@ -334,28 +343,30 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_sm);
-      sRed[256 + half * 128 + r] = l;
-      named_bar_sync(2, 256);
-      l += sRed[256 + (half ^ 1) * 128 + r];
-      if (half == 0) {
+      sRed[384 + part * 128 + r] = l;
+      named_bar_sync(2, SOFT_THREADS);
+      l = 0.f;
+#pragma unroll
+      for (int p = 0; p < NPARTS; ++p) l += sRed[384 + p * 128 + r];
+      if (part == 0) {
         sLse[row] = valid ? fmaf(m, scale_log2, log2f(l)) : 0.f;
         sDelta[row] = delta;
       }
-      // dQ read-out: 32 of the 64 columns per thread
+      // dQ read-out: 32 of the 64 columns per thread (parts 0 and 1)
       mbar_wait(bar_acc, pm);
       pm ^= 1;
       tc_fence_after();
-      if (wrow0 < L) {  // warp-uniform
-        tmem_ld_32x32b_x16(trow + ACC_COL + half * 32, s0);
-        tmem_ld_32x32b_x16(trow + ACC_COL + half * 32 + 16, s1);
+      if (wrow0 < L && part < 2) {  // warp-uniform
+        tmem_ld_32x32b_x16(trow + ACC_COL + part * 32, s0);
+        tmem_ld_32x32b_x16(trow + ACC_COL + part * 32 + 16, s1);
         tmem_ld_wait_fence16(s0);
         tmem_ld_wait_fence16(s1);
-        if (valid) store_row32(dqkv + (tok0 + row) * (3 * D) + head * HD + half * 32, s0, s1, scale / l);
+        if (valid) store_row32(dqkv + (tok0 + row) * (3 * D) + head * HD + part * 32, s0, s1, scale / l);
       }
       tc_fence_before();
       mbar_arrive(bar_rd);
     }
-    named_bar_sync(1, 256);  // every row's log-sum-exp / delta is in shared memory
+    named_bar_sync(1, SOFT_THREADS);  // every row's log-sum-exp / delta is in shared memory
     // ---------- phase B
     for (int t = 0; t < tiles; ++t) {
       const int key = t * QT + r;
@@ -433,12 +444,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       mbar_wait(bar_acc, pm);
       pm ^= 1;
       tc_fence_after();
-      if (wkey0 < L) {  // warp-uniform
-        bf16* dst = dqkv + (tok0 + key) * (3 * D) + D + head * HD + half * 32;
-        tmem_ld_32x32b_x16(trow + DK_COL + half * 32, s0);
-        tmem_ld_32x32b_x16(trow + DK_COL + half * 32 + 16, s1);
-        tmem_ld_32x32b_x16(trow + ACC_COL + half * 32, d0);
-        tmem_ld_32x32b_x16(trow + ACC_COL + half * 32 + 16, d1);
+      if (wkey0 < L && part < 2) {  // warp-uniform
+        bf16* dst = dqkv + (tok0 + key) * (3 * D) + D + head * HD + part * 32;
+        tmem_ld_32x32b_x16(trow + DK_COL + part * 32, s0);
+        tmem_ld_32x32b_x16(trow + DK_COL + part * 32 + 16, s1);
+        tmem_ld_32x32b_x16(trow + ACC_COL + part * 32, d0);
+        tmem_ld_32x32b_x16(trow + ACC_COL + part * 32 + 16, d1);
         tmem_ld_wait_fence16(s0);
         tmem_ld_wait_fence16(s1);
         tmem_ld_wait_fence16(d0);
@@ -456,7 +467,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == T_WARP) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -467,7 +478,7 @@ int launch_bwd_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, in
                   cudaStream_t s) {
   const int tiles = (L + QT - 1) / QT;
   const int R = tiles * QT;
-  const int smem = 4 * R * 128 + 4 * 256 * 4 + 64;
+  const int smem = 4 * R * 128 + 2 * 256 * 4 + 2 * 3 * 128 * 4 + 64;
   static int configured = 0;
   if (configured < smem) {
     FC_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<CAUSAL, TMEM_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -483,7 +494,7 @@ int launch_bwd_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, in
   for (int64_t s0 = 0; s0 < seqs; s0 += 65535) {
     FC_REQUIRE(s0 == 0, "attention backward (tcgen05): more than 65535 sequences per call are not supported");
     dim3 grid(heads, static_cast<unsigned>(seqs));
-    attention_bwd_tc_kernel<CAUSAL, TMEM_COLS><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, O, dO, dqkv, L, NP, tiles, heads, scale,
+    attention_bwd_tc_kernel<CAUSAL, TMEM_COLS><<<grid, bwd_threads(BWD_NPARTS), smem, s>>>(tqkv, tdo, O, dO, dqkv, L, NP, tiles, heads, scale,
                                                                     scale_log2);
     FC_CHECK_LAUNCH();
   }
