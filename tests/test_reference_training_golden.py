@@ -1,0 +1,94 @@
+"""The training step against what the REFERENCE's own code computes (tests/golden/reference_training.pt, frozen by
+tests/golden/make_reference_training_golden.py from aligner/teacher_student.py ``training_step`` / ``training_step_end``,
+aligner/loss.py, torch.autograd and torch.optim.AdamW, third-party imports stubbed):
+
+* CPU: the training oracle (oracle/train_ref.py) reproduces loss, all 61 gradients and the AdamW update;
+* CPU: the explicit trainer with torch stand-ins for the kernels reproduces them too (orchestration vs reference code);
+* GPU: the CUDA training path, within the bf16 tolerances of tests/test_gpu_training.py."""
+import os
+
+import pytest
+import torch
+
+import oracle
+from fitclip_b200 import B200ClipVideoTextEncoder
+from fitclip_b200.training import TeacherStudentTrainingModule
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_training.pt")
+SECTIONS = [("labeled", 0, 4), ("unlabeled", 4, 10)]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLDEN)
+
+
+def _batch(gold, dev="cpu"):
+    video, ids = gold["video"].to(dev), gold["input_ids"].to(dev)
+    return {"video_student": video, "video_teacher": video, "text_student": {"input_ids": ids},
+            "text_teacher": {"input_ids": ids}, "dataset": list(gold["dataset"])}
+
+
+def _models(gold):
+    student, teacher = oracle.CLIP(**gold["config"]).float(), oracle.CLIP(**gold["config"]).float()
+    student.load_state_dict(gold["student_state_dict"])
+    teacher.load_state_dict(gold["teacher_state_dict"])
+    return student.train(), teacher.eval()
+
+
+def test_reference_code_trains_every_student_parameter(gold):
+    assert gold["dataset"] == ["labeled"] * 4 + ["unlabeled"] * 6 and len(gold["grads"]) == 61
+    assert not any("logit_scale" in k or k.startswith("teacher.") for k in gold["trainable"])  # fit_temperature=False
+    assert set(gold["logged"]) >= {"loss/train_labeled", "loss/train_unlabeled", "loss/train"}
+    total = 0.5 * float(gold["logged"]["loss/train_labeled"]) + 0.5 * float(gold["logged"]["loss/train_unlabeled"])
+    assert abs(total - float(gold["loss"])) <= 1e-5 * abs(total)  # dataset_loss_share = 1/2 each (teacher_student.py:60-61)
+
+
+def test_oracle_matches_reference_training_code(gold):
+    student, teacher = _models(gold)
+    ref_student, ref_teacher = oracle.RefClipVideoTextEncoder(student, 2), oracle.RefClipVideoTextEncoder(teacher, 2)
+    opt = torch.optim.AdamW(ref_student.model.parameters(), lr=3e-6)
+    loss, grads = oracle.ref_training_step(ref_student, ref_teacher, _batch(gold), SECTIONS, opt,
+                                           init_temperature=gold["init_temperature"])
+    assert abs(float(loss) - float(gold["loss"])) <= 1e-5 * abs(float(gold["loss"]))
+    assert set(grads) == set(gold["grads"])
+    for name, ref in gold["grads"].items():
+        err, scale = (grads[name] - ref).abs().max().item(), ref.abs().max().item()
+        assert err <= 1e-4 * scale + 1e-7, f"{name}: {err:.3e} vs {scale:.3e}"
+    after = ref_student.model.state_dict()
+    for name, ref in gold["student_after_step"].items():
+        assert torch.allclose(after[name], ref, rtol=0, atol=3.1e-6), name  # one AdamW step moves a weight by <= lr = 3e-6
+
+
+def test_trainer_orchestration_matches_reference_training_code(gold):
+    from torch_kernels import TorchKernels
+    student, teacher = _models(gold)
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    module = TeacherStudentTrainingModule(enc, oracle.RefClipVideoTextEncoder(teacher, 2),
+                                          init_temperature=gold["init_temperature"], kernels=TorchKernels())
+    loss = module.training_step(_batch(gold), 0, optimize=False)
+    assert abs(float(loss) - float(gold["loss"])) <= 1e-4 * abs(float(gold["loss"]))
+    for name, ref in gold["grads"].items():
+        err, scale = (module.trainer.g[name] - ref).abs().max().item(), ref.abs().max().item()
+        assert err <= 3e-4 * scale + 1e-6, f"{name}: {err:.3e} vs {scale:.3e}"
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_matches_reference_training_code(gold, dev):
+    student, teacher = _models(gold)
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2).to(dev)
+    teach = B200ClipVideoTextEncoder(teacher.state_dict(), num_frames=2).to(dev)
+    module = TeacherStudentTrainingModule(enc, teach, init_temperature=gold["init_temperature"])
+    loss = module.training_step(_batch(gold, dev), 0, optimize=False)
+    assert abs(float(loss) - float(gold["loss"])) <= 0.02 * abs(float(gold["loss"])), (float(loss), float(gold["loss"]))
+    top = max(float(v.norm()) for v in gold["grads"].values())
+    checked = 0
+    for name, ref in gold["grads"].items():
+        if float(ref.norm()) < 1e-3 * top:
+            continue  # rounding-noise gradients (attention key biases)
+        got = module.trainer.g[name].cpu()
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+        ratio = float(got.norm()) / float(ref.norm())
+        assert cos >= 0.98 and abs(ratio - 1) <= 0.06, f"{name}: cos {cos:.4f} norm ratio {ratio:.4f}"
+        checked += 1
+    assert checked >= 40
