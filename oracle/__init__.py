@@ -13,7 +13,9 @@ in-tree twin of the CLIP text tower (``aligner/encoder/slip.py:350-480``), ``wis
 ``teacher_student_nce_loss``, ``Rank`` / ``MedianRank``, the eval frame sampler, and the evaluation flows of
 ``TextVideoRetrievalLightningModule``, ``VideoTextClassificationLightningModule`` and ``TeacherStudentLightningModule``
 (on a stub ``pl.LightningModule``) -- ``tests/test_reference_golden.py`` checks this oracle (CPU) and the CUDA path (GPU)
-against them.  The rest is pinned against (a) independent
+against them.  The training step (``train_ref.py``) is pinned the same way: ``tests/golden/make_reference_training_golden.py``
+runs the reference's ``training_step`` / ``training_step_end`` + autograd + AdamW and ``tests/test_reference_training_golden.py``
+checks the oracle and the CUDA path against the frozen loss / gradients / update.  The rest is pinned against (a) independent
 implementations in the image -- ``transformers.CLIPModel`` for both towers (tests/test_oracle_clip.py), torchvision for
 the eval transform (tests/test_oracle_preprocess.py) -- and (b) seeded golden vectors frozen under ``tests/golden/`` by
 ``tests/golden/make_golden.py``; **the vision tower and the torchmetrics definitions stay "parity unpinned"** in the
