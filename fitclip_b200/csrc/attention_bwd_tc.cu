@@ -89,20 +89,6 @@ __device__ __forceinline__ void store_row32(bf16* dst, const uint32_t (&a)[16], 
   }
 }
 
-__device__ __forceinline__ void store_row64(bf16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], float k) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t(&r)[32] = c < 4 ? a : b;
-    const int o = (c & 3) * 8;
-    uint4 u;
-    u.x = pack_bf16x2(__uint_as_float(r[o + 0]) * k, __uint_as_float(r[o + 1]) * k);
-    u.y = pack_bf16x2(__uint_as_float(r[o + 2]) * k, __uint_as_float(r[o + 3]) * k);
-    u.z = pack_bf16x2(__uint_as_float(r[o + 4]) * k, __uint_as_float(r[o + 5]) * k);
-    u.w = pack_bf16x2(__uint_as_float(r[o + 6]) * k, __uint_as_float(r[o + 7]) * k);
-    reinterpret_cast<uint4*>(dst)[c] = u;
-  }
-}
-
 // TMEM_COLS: 512 for the image sequence (S 208 + dP 208 + 64: one CTA per SM), 256 when 2 NP + 64 <= 256 (the text
 // sequence: two co-resident CTAs hide each other's load and read-out).  BWD_NPARTS softmax threads per row: measured on
 // 2048 x 197 x 12 heads, 1 -> 4.53 ms, 2 -> 3.86 ms, 3 -> 4.07 ms per layer (128-register cap, 5/4/4 chunk split, a third
