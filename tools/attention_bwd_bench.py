@@ -1,5 +1,6 @@
 """Times fc_attention_bwd_bf16 on the two CLIP sequence shapes (CUDA events, 20 launches after 3 warm-ups).
-FC_ATTN_BWD_CFG=10*warps+min_blocks selects the kernel configuration (read once per process)."""
+Default: the tcgen05 kernel (attention_bwd_tc.cu).  FC_ATTENTION_BWD=mma selects the mma.sync kernel of train.cu, whose
+configuration FC_ATTN_BWD_CFG=10*warps+min_blocks overrides (both read once per process)."""
 import os
 import sys
 
@@ -24,5 +25,6 @@ for seqs, L, heads, causal in ((256, 197, 12, False), (2048, 197, 12, False), (5
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1e3
     flops = 10.0 * L * L * 64 * heads * seqs
-    print(f"[cfg {os.environ.get('FC_ATTN_BWD_CFG', 'default')}] attention_bwd seqs={seqs} L={L} heads={heads} "
+    which = os.environ.get("FC_ATTENTION_BWD", "tc") + ("/" + os.environ["FC_ATTN_BWD_CFG"] if "FC_ATTN_BWD_CFG" in os.environ else "")
+    print(f"[{which}] attention_bwd seqs={seqs} L={L} heads={heads} "
           f"causal={causal}: {us:9.1f} us  {flops / us / 1e6:7.1f} TFLOP/s (5 products)")
