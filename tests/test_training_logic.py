@@ -193,3 +193,22 @@ def test_checkpoint_resume_is_bit_exact(tmp_path):
     bad["state"] = {k: v for k, v in list(bad["state"].items())[1:]}
     with pytest.raises(RuntimeError, match="optimizer state mismatch"):
         mod_c.trainer.load_state_dict(bad)
+
+
+def test_labeled_dataset_loss_share():
+    """``labeled_dataset_loss_share=0.3`` -> shares {labeled: 0.3, unlabeled: 0.7} (teacher_student.py:62-66)."""
+    student, teacher = make_models()
+    ref_student = oracle.RefClipVideoTextEncoder(copy.deepcopy(student))
+    ref_teacher = oracle.RefClipVideoTextEncoder(teacher)
+    names = ["labeled"] * 3 + ["unlabeled"] * 5
+    batch = make_batch(8, seed=4, names=names)
+    opt = torch.optim.AdamW(ref_student.model.parameters(), lr=1e-3)
+    ref_loss, ref_grads = oracle.ref_training_step(ref_student, ref_teacher, batch, sections_of(names, 8), opt,
+                                                   shares={"labeled": 0.3, "unlabeled": 0.7})
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    module = TeacherStudentTrainingModule(enc, ref_teacher, labeled_dataset_loss_share=0.3, kernels=TorchKernels())
+    assert module.dataset_loss_share == {"labeled": 0.3, "unlabeled": 0.7}
+    loss = module.training_step(batch, 0, optimize=False)
+    assert torch.allclose(loss, ref_loss, rtol=1e-4, atol=1e-5)
+    for name, ref in ref_grads.items():
+        assert (module.trainer.g[name] - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-6, name
