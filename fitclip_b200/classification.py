@@ -43,7 +43,9 @@ class VideoTextClassificationModule(nn.Module):
         self.similarity_terms = similarity_terms
         self.metrics: Dict[str, Rank] = {"a1": Accuracy(process_group=group), "a5": Accuracy(top_k=5, process_group=group),
                                          "mr": MedianRank(process_group=group)}
-        self.metrics_by_class = ({f"a1_{k}": Accuracy(process_group=group) for k in range(self.label_count)}
+        # per-class accuracy (:62-66): (rank, label) pairs are kept in two "cat" states and reduced ONCE per epoch, so
+        # every rank issues the same collectives whatever classes its shard happened to contain
+        self.metrics_by_class = ({"rank": Rank(process_group=group), "label": Rank(process_group=group)}
                                  if return_metrics_by_class else None)
 
     def _on_start(self) -> None:
@@ -69,14 +71,25 @@ class VideoTextClassificationModule(nn.Module):
             metric.update_from_ranks(ranks, scores.shape[1])
             logged[name] = metric._compute_from(ranks)
         if self.metrics_by_class is not None:
-            for r, y in zip(ranks.tolist(), label_id.tolist()):
-                self.metrics_by_class[f"a1_{y}"].update_from_ranks(torch.tensor([r], device=ranks.device), scores.shape[1])
+            self.metrics_by_class["rank"].update_from_ranks(ranks, scores.shape[1])
+            self.metrics_by_class["label"].update_from_ranks(label_id.to(ranks.device), self.label_count)
         return logged
 
     def validation_epoch_end(self, _outputs=None) -> Dict[str, torch.Tensor]:
         result = {name: metric.compute() for name, metric in self.metrics.items()}
         if self.metrics_by_class is not None:
-            result.update({k: m.compute() for k, m in self.metrics_by_class.items() if m.ranks})
+            by_class = self.metrics_by_class
+            if not by_class["rank"].ranks:  # a rank whose shard was empty still takes part in the two gathers
+                device = next(self.encoder.parameters()).device
+                for m in by_class.values():
+                    m.update_from_ranks(torch.empty(0, dtype=torch.int64, device=device), self.label_count)
+            ranks, labels = by_class["rank"].compute(), by_class["label"].compute()
+            hits = torch.bincount(labels[ranks < 1], minlength=self.label_count).to(torch.float32)
+            seen = torch.bincount(labels, minlength=self.label_count)
+            for k in torch.nonzero(seen).flatten().tolist():  # classes without samples log nothing, as in the reference
+                result[f"a1_{k}"] = hits[k] / seen[k]
+            for m in by_class.values():
+                m.reset()
         for metric in self.metrics.values():
             metric.reset()
         return result

@@ -405,9 +405,9 @@ int fc_model_create(const fc_config* cfg, fc_model** out) {
   m->patch_cols = 3 * c.vision_patch_size * c.vision_patch_size;
   m->patch_dim = (m->patch_cols + 7) / 8 * 8;
   if (m->L_img > 768 || c.context_length > 768) {
-    delete m;
     set_error("fc_model_create: sequence length above 768 tokens is not supported (image %d, text %d)", m->L_img,
               c.context_length);
+    delete m;
     return FC_ERR_INVALID;
   }
   m->maxF = c.max_frames_per_pass > 0 ? c.max_frames_per_pass : 512;

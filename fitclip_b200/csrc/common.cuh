@@ -88,6 +88,15 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+// same without .nc: for buffers the kernel may also WRITE (an output that aliases the input row by row)
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
 __device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)

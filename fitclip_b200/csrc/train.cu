@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 constexpr int LNB_WARPS = 4;
 
 template <int LNB_CHUNKS>
-__global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+__global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* dy,
                                                      const float* __restrict__ gamma, const bf16* add, bf16* dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      int64_t rows, int D, float eps) {
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bw
       const int c = lane + 32 * i;
       if (c < chunks) {
         nx[i] = ld_nc_v4(xr + c);
-        nd[i] = ld_nc_v4(dr + c);
+        nd[i] = ld_stream_v4(dr + c);  // dx may alias dy (training.py backward_video): no non-coherent load
       }
     }
   };

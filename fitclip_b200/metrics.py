@@ -45,17 +45,19 @@ class Rank:
             raise RuntimeError("compute() called before update()")
         ranks = torch.cat(self.ranks)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
-            # dist_reduce_fx="cat" (metrics.py:13); shards may be uneven, so gather sizes first
+            # dist_reduce_fx="cat" (metrics.py:13); shards may be uneven: one size gather (one host read), one padded
+            # data gather
             world = dist.get_world_size(self.process_group)
-            n = torch.tensor([ranks.numel()], device=ranks.device)
-            sizes = [torch.zeros_like(n) for _ in range(world)]
-            dist.all_gather(sizes, n, group=self.process_group)
-            cap = int(max(s.item() for s in sizes))
+            n = torch.tensor([ranks.numel()], device=ranks.device, dtype=torch.int64)
+            sizes_t = torch.empty(world, device=ranks.device, dtype=torch.int64)
+            dist.all_gather_into_tensor(sizes_t, n, group=self.process_group)
+            sizes = sizes_t.tolist()
+            cap = max(sizes)
             padded = torch.zeros(cap, dtype=ranks.dtype, device=ranks.device)
             padded[:ranks.numel()] = ranks
-            parts = [torch.zeros_like(padded) for _ in range(world)]
-            dist.all_gather(parts, padded, group=self.process_group)
-            ranks = torch.cat([p[:int(s.item())] for p, s in zip(parts, sizes)])
+            parts = torch.empty(world * cap, dtype=ranks.dtype, device=ranks.device)
+            dist.all_gather_into_tensor(parts, padded, group=self.process_group)
+            ranks = torch.cat([parts[r * cap:r * cap + v] for r, v in enumerate(sizes)])
         return ranks
 
     def _compute_from(self, ranks: torch.Tensor) -> torch.Tensor:
@@ -63,6 +65,13 @@ class Rank:
 
     def compute(self) -> torch.Tensor:
         return self._compute_from(self._all_ranks())
+
+    def compute_local(self) -> torch.Tensor:
+        """``compute()`` without the cross-rank "cat": for state that is already global on every rank (the ranks
+        :func:`fitclip_b200.retrieval.retrieval_ranks` returns)."""
+        if not self.ranks:
+            raise RuntimeError("compute_local() called before update()")
+        return self._compute_from(torch.cat(self.ranks))
 
     def reset(self) -> None:
         self.ranks = []

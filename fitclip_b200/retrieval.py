@@ -27,6 +27,9 @@ from .api import TYPE_OUTPUT, VideoTextEncoder
 from .metrics import MedianRank, Rank, Recall
 
 
+NO_GROUP = False  # `group=NO_GROUP`: treat the inputs as complete -- no collective even if a process group exists
+
+
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous shard [lo, hi) of n items for `rank`: ceil(n / world) per rank, last shards may be short/empty."""
     per = -(-n // world)
@@ -34,54 +37,96 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def _world(group) -> Tuple[int, int]:
-    if dist.is_available() and dist.is_initialized():
+    if group is not NO_GROUP and dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
     return 1, 0
 
 
-def all_gather_rows(x: torch.Tensor, group=None) -> Tuple[torch.Tensor, List[int]]:
-    """Concatenate per-rank row blocks of different heights (pad to the tallest, gather, strip).
-    Returns the gathered tensor and the per-rank heights."""
+def _gather_sizes(counts: Sequence[int], device: torch.device, group) -> List[List[int]]:
+    """ONE collective + ONE host read for all the per-rank counts a call needs: -> [rank][i]."""
     world, _ = _world(group)
+    mine = torch.tensor(list(counts), device=device, dtype=torch.int64)
+    out = torch.empty(world * len(counts), device=device, dtype=torch.int64)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.view(world, len(counts)).tolist()
+
+
+def all_gather_rows(x: torch.Tensor, group=None, sizes: Optional[Sequence[int]] = None,
+                    total: Optional[int] = None) -> Tuple[torch.Tensor, List[int]]:
+    """Concatenate per-rank row blocks of different heights. Returns the gathered tensor and the per-rank heights.
+
+    ``total``: the blocks are the :func:`shard_bounds` shards of ``total`` rows -- heights are known analytically, the
+    padded gather buffer IS the concatenation (no size exchange, no host synchronisation, no strip copies: every shard
+    but the last non-empty one is full).  ``sizes``: heights known to the caller.  Neither: one size all-gather + one
+    host read."""
+    world, rank = _world(group)
     if world == 1:
         return x, [x.shape[0]]
-    n = torch.tensor([x.shape[0]], device=x.device, dtype=torch.int64)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    x = x.contiguous()
+    if total is not None:
+        per = -(-total // world)
+        sizes = [shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world)]
+        if x.shape[0] != sizes[rank]:
+            raise ValueError(f"rank {rank} holds {x.shape[0]} rows, shard_bounds({total}, {world}, {rank}) has {sizes[rank]}")
+        if x.shape[0] != per:
+            padded = x.new_zeros((per, *x.shape[1:]))
+            padded[:x.shape[0]] = x
+            x = padded
+        out = x.new_empty((world * per, *x.shape[1:]))
+        dist.all_gather_into_tensor(out, x, group=group)
+        return out[:total], sizes
+    if sizes is None:
+        sizes = [s[0] for s in _gather_sizes([x.shape[0]], x.device, group)]
+    sizes = [int(v) for v in sizes]
     cap = max(sizes)
-    padded = x.new_zeros((cap, *x.shape[1:]))
-    padded[:x.shape[0]] = x
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded.contiguous(), group=group)
-    return torch.cat([p[:s] for p, s in zip(parts, sizes)]), sizes
+    if x.shape[0] != cap:
+        padded = x.new_zeros((cap, *x.shape[1:]))
+        padded[:x.shape[0]] = x
+        x = padded
+    out = x.new_empty((world * cap, *x.shape[1:]))  # (world * cap, ...): the shape gloo's all-gather accepts too
+    dist.all_gather_into_tensor(out, x, group=group)
+    if all(v == cap for v in sizes):
+        return out, sizes
+    return torch.cat([out[r * cap:r * cap + v] for r, v in enumerate(sizes)]), sizes
 
 
 def retrieval_ranks(text_local: torch.Tensor, video_local: torch.Tensor, group=None, terms: int = 3,
                     target_local: Optional[torch.Tensor] = None,
-                    similarity_factory: Callable[..., Any] = ops.Similarity) -> torch.Tensor:
+                    similarity_factory: Callable[..., Any] = ops.Similarity,
+                    totals: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """0-based rank of every query's target video among ALL videos, int64 ``(Nt_total,)``, same on every rank.
 
     ``text_local (nt_r, E)`` / ``video_local (nv_r, E)``: this rank's fp32 embeddings, contiguous shards in rank
     order.  ``target_local``: global video index per local query (default: query i <-> video i).
+    ``totals = (Nt_total, Nv_total)``: the shards are the :func:`shard_bounds` shards of those totals, so every size and
+    offset is known analytically and the call issues no size exchange and no host synchronisation (the launch queue
+    keeps running); without it the two local counts travel in ONE small all-gather with one host read.
+    ``group=NO_GROUP``: inputs are complete, no communication.
     ``similarity_factory`` exists so the host-side sharding logic can be exercised without a GPU (tests only)."""
     world, rank = _world(group)
-    text_all, _ = all_gather_rows(text_local.contiguous(), group)
-    if world > 1:
-        nv = torch.tensor([video_local.shape[0]], device=video_local.device, dtype=torch.int64)
-        sizes = [torch.zeros_like(nv) for _ in range(world)]
-        dist.all_gather(sizes, nv, group=group)
-        col_offset = int(sum(int(s.item()) for s in sizes[:rank]))
+    if world > 1 and totals is not None:
+        text_all, _ = all_gather_rows(text_local, group, total=totals[0])
+        col_offset, hi = shard_bounds(totals[1], world, rank)
+        if video_local.shape[0] != hi - col_offset:
+            raise ValueError(f"rank {rank} holds {video_local.shape[0]} videos, its shard of {totals[1]} has {hi - col_offset}")
+        text_sizes = None
+    elif world > 1:
+        counts = _gather_sizes([text_local.shape[0], video_local.shape[0]], text_local.device, group)
+        text_sizes = [c[0] for c in counts]
+        text_all, _ = all_gather_rows(text_local, group, sizes=text_sizes)
+        col_offset = sum(c[1] for c in counts[:rank])
     else:
-        col_offset = 0
+        text_all, col_offset, text_sizes = text_local.contiguous(), 0, None
     if target_local is None:
         target = torch.arange(text_all.shape[0], device=text_all.device, dtype=torch.int32)
+    elif world > 1 and totals is not None:
+        target, _ = all_gather_rows(target_local.to(torch.int32), group, total=totals[0])
     else:
-        target, _ = all_gather_rows(target_local.to(torch.int32).contiguous(), group)
+        target, _ = all_gather_rows(target_local.to(torch.int32).contiguous(), group, sizes=text_sizes)
     nt = text_all.shape[0]
     if video_local.shape[0] > 0:
-        sim = similarity_factory(text_all, video_local.contiguous(), terms)
-        tscore = sim.target_scores(target, col_offset)
+        sim = similarity_factory(text_all.contiguous(), video_local.contiguous(), terms)
+        tscore = sim.target_scores(target.contiguous(), col_offset)
     else:  # an empty shard still has to take part in the collectives
         sim = None
         tscore = torch.zeros(nt, device=text_all.device, dtype=torch.float32)
@@ -108,16 +153,14 @@ def retrieval_topk(text_local: torch.Tensor, video_local: torch.Tensor, k: int =
     the ``world x k`` candidates per query are all-gathered and merged with the same top-k kernel.  ``k`` may exceed a
     shard's (or the gallery's) size: missing slots are ``-inf`` / ``-1``."""
     world, rank = _world(group)
-    text_all, _ = all_gather_rows(text_local.contiguous(), group)
+    if world > 1:
+        counts = _gather_sizes([text_local.shape[0], video_local.shape[0]], text_local.device, group)
+        text_all, _ = all_gather_rows(text_local, group, sizes=[c[0] for c in counts])
+        col_offset = sum(c[1] for c in counts[:rank])
+    else:
+        text_all, col_offset = text_local.contiguous(), 0
     dev = text_all.device
     nt, nv_local = text_all.shape[0], video_local.shape[0]
-    if world > 1:
-        nv = torch.tensor([nv_local], device=dev, dtype=torch.int64)
-        sizes = [torch.zeros_like(nv) for _ in range(world)]
-        dist.all_gather(sizes, nv, group=group)
-        col_offset = int(sum(int(s.item()) for s in sizes[:rank]))
-    else:
-        col_offset = 0
     values = torch.full((nt, k), float("-inf"), device=dev, dtype=torch.float32)
     indices = torch.full((nt, k), -1, device=dev, dtype=torch.int64)
     kl = min(k, nv_local)
@@ -132,12 +175,12 @@ def retrieval_topk(text_local: torch.Tensor, video_local: torch.Tensor, k: int =
     if world == 1:
         return values, indices
     # merge: candidates ordered by rank = by ascending column offset, so "first among equals" is the lowest video index
-    all_v = [torch.empty_like(values) for _ in range(world)]
-    all_i = [torch.empty_like(indices) for _ in range(world)]
-    dist.all_gather(all_v, values, group=group)
-    dist.all_gather(all_i, indices, group=group)
-    cand_v = torch.cat(all_v, dim=1).contiguous()
-    cand_i = torch.cat(all_i, dim=1)
+    all_v = values.new_empty((world * nt, k))
+    all_i = indices.new_empty((world * nt, k))
+    dist.all_gather_into_tensor(all_v, values, group=group)
+    dist.all_gather_into_tensor(all_i, indices, group=group)
+    cand_v = all_v.view(world, nt, k).permute(1, 0, 2).reshape(nt, world * k).contiguous()
+    cand_i = all_i.view(world, nt, k).permute(1, 0, 2).reshape(nt, world * k)
     best_v, pos = topk_fn(cand_v, k)
     return best_v, torch.gather(cand_i, 1, pos.to(torch.int64))
 
@@ -149,10 +192,24 @@ def metrics_from_ranks(ranks: torch.Tensor, num_candidates: int) -> Dict[str, to
 
 
 class TextVideoRetrievalModule(nn.Module):
-    """Lightning-free twin of ``TextVideoRetrievalLightningModule`` for ``command=evaluate`` / ``predict``."""
+    """Lightning-free twin of ``TextVideoRetrievalLightningModule`` for ``command=evaluate`` / ``predict``.
+
+    Multi-process protocol: step outputs stay LOCAL (each rank keeps the embeddings of its own samples); the per-batch
+    ``loss/val`` is computed on the batch gathered across ranks like the reference (``text_video_retrieval.py:44-58``),
+    and ``validation_epoch_end`` hands the local shards to :func:`retrieval_ranks` with ``self.group``, which shards the
+    similarity by video columns -- every rank ends up with the same global ranks and derives the metrics from them
+    locally.  (The reference gathers in ``validation_step_end`` and evaluates the full matrix on every rank.)
+
+    ``dataset_names`` with more than one name selects the reference's multi-dataset mode
+    (``text_video_retrieval.py:28-37,84-93``): ``validation_step`` receives a ``dataloader_idx``, every metric is cloned
+    per dataset under ``f"{metric}_{dataset}"``, ``loss/val_{dataset}`` is logged per dataset and ``validation_epoch_end``
+    takes one output list per dataset."""
 
     def __init__(self, encoder: VideoTextEncoder, init_temperature: float = 0.05, min_temperature: float = 0.001,
-                 fit_temperature: bool = True, compute_rank: bool = False, group=None, similarity_terms: int = 3) -> None:
+                 fit_temperature: bool = True, compute_rank: bool = False, group=None, similarity_terms: int = 3,
+                 dataset_names: Optional[Sequence[str]] = None,
+                 similarity_factory: Callable[..., Any] = ops.Similarity,
+                 nce_loss_fn: Callable[[torch.Tensor], torch.Tensor] = ops.nce_loss) -> None:
         super().__init__()
         self.encoder = encoder
         # video_text_module.py:32-34
@@ -160,13 +217,23 @@ class TextVideoRetrievalModule(nn.Module):
         self.max_logit_scale = nn.Parameter(torch.tensor([-math.log(min_temperature)]), requires_grad=False)
         self.group = group
         self.similarity_terms = similarity_terms
-        self.metrics: Dict[str, Rank] = {"r1": Recall(), "r5": Recall(top_k=5), "r10": Recall(top_k=10),
-                                         "mr": MedianRank()}
+        self._similarity_factory = similarity_factory  # injectable so the host logic runs without a GPU (tests only)
+        self._nce_loss = nce_loss_fn
+        metrics: Dict[str, Rank] = {"r1": Recall(), "r5": Recall(top_k=5), "r10": Recall(top_k=10),
+                                    "mr": MedianRank()}
         if compute_rank:
-            self.metrics["rank"] = Rank()
+            metrics["rank"] = Rank()
+        self.dataset_names = list(dataset_names) if dataset_names else None
+        self.multiple_datasets = self.dataset_names is not None and len(self.dataset_names) > 1
+        if self.multiple_datasets:
+            assert all("_" not in name for name in self.dataset_names), \
+                "Underscores in dataset names are problematic because of how we get their corresponding metrics."
+            self.metrics: Dict[str, Rank] = {f"{name}_{dataset_name}": metric.clone()
+                                             for dataset_name in self.dataset_names for name, metric in metrics.items()}
+        else:
+            self.metrics = metrics
         self.logged: Dict[str, Any] = {}
-        self._loss_sum = 0.0
-        self._loss_weight = 0
+        self._loss: Dict[str, List[float]] = {}  # key -> [weighted sum, weight]
 
     def forward(self, batch: MutableMapping[str, Any], _batch_idx: int = 0) -> TYPE_OUTPUT:
         batch.pop("video_id", None)  # video_text_module.py:38-41
@@ -179,39 +246,53 @@ class TextVideoRetrievalModule(nn.Module):
         return self._step(batch, batch_idx), dataloader_idx
 
     def validation_step_end(self, output) -> TYPE_OUTPUT:
-        (encoded_video, encoded_text), _ = output
-        return self._validation_dataset_step_end((encoded_video, encoded_text))
+        step_output, dataloader_idx = output
+        assert self.multiple_datasets == (dataloader_idx is not None)  # text_video_retrieval.py:62-63
+        dataset_name = self.dataset_names[dataloader_idx] if self.multiple_datasets else None
+        return self._validation_dataset_step_end(step_output, dataset_name=dataset_name)
 
-    def _validation_dataset_step_end(self, output: TYPE_OUTPUT) -> TYPE_OUTPUT:
+    def _validation_dataset_step_end(self, output: TYPE_OUTPUT, dataset_name: Optional[str] = None) -> TYPE_OUTPUT:
         # text_video_retrieval.py:44-58: gather the batch across ranks, scaled B x B scores, NCE loss
         encoded_video, _ = all_gather_rows(output[0].contiguous(), self.group)
         encoded_text, _ = all_gather_rows(output[1].contiguous(), self.group)
         batch_size = len(encoded_video)
-        scale = float(self.logit_scale.exp())
+        scale = float(self.logit_scale.detach().exp())
         # `logit_scale * V @ T.T` == (logit_scale * V) @ T.T: rows = videos here
-        scores = ops.Similarity(encoded_video, encoded_text, self.similarity_terms).scores(alpha=scale)
-        loss = ops.nce_loss(scores)
-        self._loss_sum += float(loss) * batch_size  # PL's batch-size weighted mean of `loss/val`
-        self._loss_weight += batch_size
-        return encoded_video, encoded_text
+        scores = self._similarity_factory(encoded_video, encoded_text, self.similarity_terms).scores(alpha=scale)
+        loss = self._nce_loss(scores)
+        key = "loss/val" + ("" if dataset_name is None else f"_{dataset_name}")
+        acc = self._loss.setdefault(key, [0.0, 0])  # PL's batch-size weighted mean of the logged value
+        acc[0] += float(loss) * batch_size
+        acc[1] += batch_size
+        return output[0], output[1]  # local shards: retrieval_ranks does the sharded evaluation at epoch end
 
-    def _validate_dataset(self, outputs: Sequence[TYPE_OUTPUT]) -> Dict[str, torch.Tensor]:
+    def _validate_dataset(self, outputs: Sequence[TYPE_OUTPUT], dataset_name: Optional[str] = None
+                          ) -> Dict[str, torch.Tensor]:
         # text_video_retrieval.py:67-83, fused: ranks straight from the embeddings
+        assert self.multiple_datasets == (dataset_name is not None)
         encoded_videos, encoded_texts = (torch.cat(x) for x in zip(*outputs))
-        ranks = retrieval_ranks(encoded_texts, encoded_videos, group=None, terms=self.similarity_terms)
-        n_videos = encoded_videos.shape[0]
+        ranks = retrieval_ranks(encoded_texts, encoded_videos, group=self.group, terms=self.similarity_terms,
+                                similarity_factory=self._similarity_factory)
+        n_videos = int(ranks.numel())  # query i <-> video i: the global gallery is as large as the global query set
         result = {}
         for name, metric in self.metrics.items():
-            metric.reset()
-            metric.update_from_ranks(ranks, n_videos)
-            result[name] = metric.compute()
+            if not dataset_name or name.endswith(f"_{dataset_name}"):
+                metric.reset()
+                metric.update_from_ranks(ranks, n_videos)
+                result[name] = metric.compute_local()  # the ranks are already global: no second reduction
         return result
 
-    def validation_epoch_end(self, outputs: Sequence[TYPE_OUTPUT]) -> Dict[str, Any]:
-        result = self._validate_dataset(outputs)
-        if self._loss_weight:
-            result["loss/val"] = self._loss_sum / self._loss_weight
-        self._loss_sum, self._loss_weight = 0.0, 0
+    def validation_epoch_end(self, outputs) -> Dict[str, Any]:
+        result: Dict[str, Any] = {}
+        if self.multiple_datasets:
+            for name, dataset_output in zip(self.dataset_names, outputs):  # text_video_retrieval.py:86-91
+                result.update(self._validate_dataset(dataset_output, dataset_name=name))
+        else:
+            result.update(self._validate_dataset(outputs))
+        for key, (total, weight) in self._loss.items():
+            if weight:
+                result[key] = total / weight
+        self._loss = {}
         self.logged = result
         return result
 

@@ -308,7 +308,9 @@ def train(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> Dict
     for i, batch in enumerate(data.train_batches(device, steps)):
         losses.append(model.training_step(batch, i))
     losses = [float(x) for x in losses]  # one device read-back at the end
-    encoders["student"].model.check_inputs()
+    model.trainer.check_inputs()  # the student's training forward (its own err_flag, not the eval engine's)
+    if hasattr(encoders["teacher"].model, "check_inputs"):
+        encoders["teacher"].model.check_inputs()
     return {"loss/train": losses[-1], "step": len(losses), "losses": losses}
 
 

@@ -137,40 +137,14 @@ class ClipTrainer:
     def zero_grad(self) -> None:
         self.grad.zero_()
 
-    # ------------------------------------------------------------------------------------------------ checkpoints
-    def state_dict(self) -> Dict[str, Any]:
-        """Optimizer state in the layout of ``torch.optim.AdamW.state_dict()`` restricted to what resuming needs: the step
-        count and the two moment buffers per parameter NAME (the reference checkpoints through Lightning's
-        ``ModelCheckpoint``, ``config/trainer/callbacks/default_teacher_student.yaml``; the model weights themselves are
-        the module's own ``state_dict()``, whose tensors are views into the flat buffer)."""
-        off, state = 0, {}
-        for name, p in self.w.items():
-            n = p.numel()
-            state[name] = {"exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
-                           "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
-            off += (n + 63) // 64 * 64
-        return {"step": self.step_count, "state": state,
-                "hparams": {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps,
-                            "weight_decay": self.weight_decay}}
-
-    def load_state_dict(self, sd: Mapping[str, Any]) -> None:
-        missing = set(self.w) - set(sd["state"])
-        unexpected = set(sd["state"]) - set(self.w)
-        if missing or unexpected:  # strict, like Module.load_state_dict (aligner/wise.py:21-22 relies on strictness too)
-            raise RuntimeError(f"optimizer state mismatch: missing {sorted(missing)[:3]} unexpected {sorted(unexpected)[:3]}")
-        off = 0
-        for name, p in self.w.items():
-            n = p.numel()
-            self.exp_avg[off:off + n].copy_(sd["state"][name]["exp_avg"].reshape(-1))
-            self.exp_avg_sq[off:off + n].copy_(sd["state"][name]["exp_avg_sq"].reshape(-1))
-            off += (n + 63) // 64 * 64
-        self.step_count = int(sd["step"])
-        hp = sd.get("hparams", {})
-        self.lr, self.eps, self.weight_decay = hp.get("lr", self.lr), hp.get("eps", self.eps), \
-            hp.get("weight_decay", self.weight_decay)
-        self.betas = tuple(hp.get("betas", self.betas))
-        self.refresh_weight_copies()  # the module's weights may have been loaded just before
-        self.model._engine.signature = None
+    def check_inputs(self) -> None:
+        """Synchronises and raises if a token id fed to the training forward was out of range: ``text_embed_kernel``
+        clamps such an id to token 0 and raises the flag, ``token_scatter_kernel`` drops its gradient -- torch's embedding
+        lookup in the reference would have raised.  Resets the flag."""
+        flag = getattr(self.K, "err_flag", None)
+        if flag is not None and bool(flag.any().item()):
+            flag.zero_()
+            raise _lib.FitclipError(-3, "training step: token id out of range (text_embed clamped it to 0)")
 
     def optimizer_step(self, group=None) -> None:
         """All-reduce(SUM) of the flat gradient across ``group`` (each rank holds the gradient of the GLOBAL-batch loss

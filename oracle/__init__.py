@@ -21,11 +21,12 @@ the eval transform (tests/test_oracle_preprocess.py) -- and (b) seeded golden ve
 ``tests/golden/make_golden.py``; **the vision tower and the torchmetrics definitions stay "parity unpinned"** in the
 sense of the task statement.
 """
-from .clip_ref import CLIP, build_model, clip_vit_b_16, tokenize_synthetic  # noqa: F401
+from .clip_ref import CLIP, build_model, clip_vit_b_16, perturb_trained_like, tokenize_synthetic  # noqa: F401
 from .encoder_ref import RefClipVideoTextEncoder  # noqa: F401
 from .metrics_ref import (ref_accuracy_at_k, ref_median_rank, ref_rank, ref_recall_at_k,  # noqa: F401
                           ref_retrieval_metrics, ref_stable_rank)
 from .wise_ref import ref_wise, ref_wise_state_dict  # noqa: F401
 from .preprocess_ref import ref_eval_transform, ref_resized_size  # noqa: F401
 from .loss_ref import ref_nce_loss, ref_teacher_student_nce_loss  # noqa: F401
+from .bf16_emulation import bf16_stream_model  # noqa: F401
 from .train_ref import ref_training_loss, ref_training_step  # noqa: F401

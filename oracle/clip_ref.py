@@ -197,10 +197,68 @@ VIT_B_16 = dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_wi
                 transformer_layers=12)  # config/encoder/clip_from_scratch_vit_b_16.yaml:7-16
 
 
-def clip_vit_b_16(seed: int = 0, **overrides) -> CLIP:
-    """Random-init ViT-B/16 (the benchmark weights: no network, no checkpoints). ``overrides`` shrink it for tests."""
+def perturb_trained_like(model: nn.Module, seed: int = 0, stress: bool = False) -> nn.Module:
+    """Moves the parameters that every init path leaves at an identity value (LayerNorm gamma = 1 / beta = 0,
+    ``in_proj_bias`` = ``out_proj.bias`` = 0) to where a trained checkpoint has them, so that parity tests exercise the
+    LayerNorm-folding arithmetic (``W diag(gamma)``, ``b + W beta``, the column-sum term) and the attention bias adds
+    with non-trivial values: gamma ~ U(0.2, 3), beta ~ N(0, 0.5), attention biases ~ N(0, 0.1).
+
+    ``stress`` adds what pretrained CLIP checkpoints are known for, at magnitudes a bf16 residual stream still carries
+    (calibrated with a CPU emulation that rounds the stream to bf16: cosine >= 0.9995 vs fp32; putting the x10 gammas on
+    the SAME channels as the x60 writers compounds to a x600 loop gain per block that not even the reference's fp16 GPU
+    path survives): four "massive activation" channels per tower (the ``out_proj`` / ``c_proj`` rows that write them
+    x60, their LayerNorm gammas x0.3 as trained models have them), four other channels with gamma x10 on every
+    LayerNorm of the stream, and a DC offset on three token rows before the first LayerNorm (+20 on positional-embedding
+    rows of the image tower, which has ``ln_pre``; +4 on the text tower, whose stream starts at the 0.02-scale token
+    embeddings) -- what punishes an ``E[x^2] - mean^2`` variance.  Test infrastructure (``oracle/__init__.py``); in place."""
+    g = torch.Generator().manual_seed(1_000_003 + seed)
+
+    def rand(shape, lo, hi):
+        return lo + (hi - lo) * torch.rand(shape, generator=g)
+
+    def randn(shape, std):
+        return std * torch.randn(shape, generator=g)
+
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            parent, _, leaf = name.rpartition(".")
+            is_ln = parent.rsplit(".", 1)[-1] in ("ln_1", "ln_2", "ln_pre", "ln_post", "ln_final")
+            if is_ln and leaf == "weight":
+                p.copy_(rand(p.shape, 0.2, 3.0))
+            elif is_ln and leaf == "bias":
+                p.copy_(randn(p.shape, 0.5))
+            elif name.endswith("attn.in_proj_bias") or name.endswith("attn.out_proj.bias"):
+                p.copy_(randn(p.shape, 0.1))
+        if stress:
+            for visual, width, dc in ((True, model.visual.conv1.weight.shape[0], 20.0),
+                                      (False, model.transformer.width, 4.0)):
+                perm = torch.randperm(width, generator=g)
+                gamma_channels, massive_channels = perm[:4], perm[4:8]
+                for name, p in model.named_parameters():
+                    if name.startswith("visual.") != visual:
+                        continue
+                    parent, _, leaf = name.rpartition(".")
+                    if parent.rsplit(".", 1)[-1] in ("ln_1", "ln_2", "ln_pre") and leaf == "weight":
+                        p[gamma_channels] *= 10.0
+                        p[massive_channels] *= 0.3
+                    elif name.endswith("attn.out_proj.weight") or name.endswith("mlp.c_proj.weight"):
+                        p[massive_channels] *= 60.0
+                pos = model.visual.positional_embedding if visual else model.positional_embedding
+                rows = torch.randperm(pos.shape[0], generator=g)[:3]
+                pos[rows] += dc
+    return model
+
+
+def clip_vit_b_16(seed: int = 0, trained_like: bool = True, stress: bool = False, **overrides) -> CLIP:
+    """Random-init ViT-B/16 (the benchmark weights: no network, no checkpoints). ``overrides`` shrink it for tests.
+    ``trained_like`` (default) applies :func:`perturb_trained_like` on top of the reference's init so that no LayerNorm
+    or attention bias sits at its identity value; ``trained_like=False`` is the bare ``CLIP.__init__`` state
+    (``config/encoder/clip_from_scratch_vit_b_16.yaml``)."""
     torch.manual_seed(seed)
-    return CLIP(**{**VIT_B_16, **overrides}).float().eval()
+    model = CLIP(**{**VIT_B_16, **overrides}).float().eval()
+    if trained_like:
+        perturb_trained_like(model, seed, stress)
+    return model
 
 
 def tokenize_synthetic(count: int, length: int | tuple[int, int] = 77, seed: int = 4321, context_length: int = 77,

@@ -59,6 +59,11 @@ def _worker(rank, world, port, n, ties, out_dir):
         assert torch.equal(gathered, t) and sum(sizes) == n
         expect = oracle.ref_stable_rank(t @ v.T, torch.arange(n))
         assert torch.equal(ranks, expect), (rank, ranks.tolist(), expect.tolist())
+        # analytic shard sizes (totals=): same result with no size exchange / host read
+        ranks2 = retrieval_ranks(t[lo:hi], v[lo:hi], similarity_factory=CpuSimilarity, totals=(n, n))
+        assert torch.equal(ranks2, expect), (rank, ranks2.tolist())
+        gathered2, sizes2 = all_gather_rows(t[lo:hi], total=n)
+        assert torch.equal(gathered2, t) and sizes2 == sizes
         # distributed top-k: local top-k per column slab, all-gather of the candidates, merge.  (Not on the tied case:
         # the CPU stand-in's per-slab matmuls differ from the full matmul in the last bit, which reorders exact ties; the
         # GPU kernel computes a score identically wherever its tile lies -- tests/test_gpu_multi.py covers ties.)
@@ -128,3 +133,54 @@ def test_metric_state_cat_and_explicit_targets(tmp_path):
     mp.spawn(_metric_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
     outs = [torch.load(tmp_path / f"m_{r}.pt") for r in range(3)]
     assert all(torch.equal(o, outs[0]) for o in outs)
+
+
+class _StubEncoder(torch.nn.Module):
+    """Deterministic CPU stand-in for a VideoTextEncoder: 'video' / 'text' are already embeddings."""
+
+    def forward(self, video, text):
+        return video, text["input_ids"]
+
+
+def _cpu_metrics_from_ranks(ranks, num_candidates):
+    recall = torch.stack([(ranks < k).float().mean() for k in (1, 5, 10)])
+    return recall, ranks.median() + 1, ranks.float().mean() + 1
+
+
+def _module_worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fitclip_b200 import TextVideoRetrievalModule, ops
+        ops.metrics_from_ranks = _cpu_metrics_from_ranks  # the metric reduction kernel needs a GPU; same contract
+        g = torch.Generator().manual_seed(5)
+        t = torch.nn.functional.normalize(torch.randn(n, 16, generator=g), dim=-1)
+        v = torch.nn.functional.normalize(t + 0.7 * torch.randn(n, 16, generator=g), dim=-1)
+        module = TextVideoRetrievalModule(_StubEncoder(), compute_rank=True, similarity_factory=CpuSimilarity,
+                                          nce_loss_fn=oracle.ref_nce_loss)
+        lo, hi = shard_bounds(n, world, rank)
+        outputs = []
+        for b in range(lo, hi, 5):  # batches of 5 of this rank's shard; every rank runs the same number of steps
+            e = min(hi, b + 5)
+            batch = {"video": v[b:e], "text": {"input_ids": t[b:e]}, "video_id": list(range(b, e))}
+            outputs.append(module.validation_step_end(module.validation_step(batch, len(outputs))))
+        result = module.validation_epoch_end(outputs)
+        torch.save({k: torch.as_tensor(x) for k, x in result.items()}, os.path.join(out_dir, f"mod_{world}_{rank}.pt"))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def test_retrieval_module_two_ranks_equals_single_process(tmp_path):
+    """with a process group, the module must not gather twice -- world=2 metrics == single-process
+    metrics (r1/r5/r10/mr and the full rank list), identical on both ranks."""
+    n = 40  # two shards of 20 = four batches of 5 per rank
+    mp.spawn(_module_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    _module_worker(0, 1, 0, n, str(tmp_path))
+    single = torch.load(tmp_path / "mod_1_0.pt")
+    for r in range(2):
+        got = torch.load(tmp_path / f"mod_2_{r}.pt")
+        for k in ("r1", "r5", "r10", "mr", "rank"):
+            assert torch.equal(got[k], single[k]), (r, k, got[k], single[k])
+    assert 0.0 < float(single["r1"]) < 1.0  # a non-degenerate case

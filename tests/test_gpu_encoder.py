@@ -1,7 +1,10 @@
 """End-to-end encoder parity: B200ClipVideoTextEncoder (bf16 tensor-core path) vs the fp32 CPU oracle, same seeded
-weights and inputs.  Tolerances: cosine >= 0.999 per vector; max-abs and mean-centred relative
-L2 error are printed and bounded loosely (random-init embeddings are nearly collinear, so the centred error is the
-sensitive number)."""
+weights and inputs.  Weights are the oracle's trained-like perturbation (no LayerNorm gamma / beta or attention bias at its identity
+value), so the LayerNorm folding (W diag(gamma), b + W beta, column sums) and the bias adds run with real values.
+Tolerances: cosine >= 0.999 per vector and, tighter, ~2-3x what was measured on the B200 /
+what a bf16 residual stream explains (oracle.bf16_stream_model: the fp32 oracle with ONLY the stream rounded to bf16):
+max-abs <= 5e-3 on unit-norm embeddings, mean-centred relative L2 error <= 0.1 (random-init embeddings are nearly
+collinear, so the centred error is the sensitive number), and error(CUDA) <= 3 x error(bf16-stream emulation) + 1e-3."""
 import copy
 
 import pytest
@@ -46,9 +49,9 @@ def test_encode_video_matches_oracle(models, dev):
         got = enc.encode_video(video.to(dev)).cpu()
     assert got.shape == (6, 512) and got.dtype == torch.float32
     cos, max_abs, centred = _report("video", got, expect)
-    assert cos >= 0.999
-    assert max_abs <= 2e-2
-    assert centred <= 0.25
+    assert cos >= 0.9995
+    assert max_abs <= 5e-3
+    assert centred <= 0.1
 
 
 def test_encode_text_matches_oracle(models, dev):
@@ -59,10 +62,77 @@ def test_encode_text_matches_oracle(models, dev):
         expect = ref.encode_text({"input_ids": ids})
         got = enc.encode_text({"input_ids": ids.to(dev)}).cpu()
     cos, max_abs, centred = _report("text", got, expect)
-    assert cos >= 0.999
-    assert max_abs <= 2e-2
-    assert centred <= 0.25
+    assert cos >= 0.9995
+    assert max_abs <= 5e-3
+    assert centred <= 0.1
     assert torch.allclose(got.norm(dim=-1), torch.ones(16), atol=1e-5)
+
+
+def _truncate(state_dict, vision_layers, text_layers):
+    """The first `vision_layers` / `text_layers` residual blocks of a CLIP state dict (heads and embeddings kept)."""
+    out = {}
+    for k, v in state_dict.items():
+        if ".resblocks." in k:
+            idx = int(k.split(".resblocks.")[1].split(".")[0])
+            if idx >= (vision_layers if k.startswith("visual.") else text_layers):
+                continue
+        out[k] = v
+    return out
+
+
+@pytest.mark.parametrize("stress", [False, True], ids=["trained_like", "stress"])
+def test_per_depth_activations_match_oracle(dev, stress):
+    """SURVEY.md section 7 hard part 5 (per-layer activation checks): the residual stream after k blocks, read through
+    ln_post / ln_final + projection, for k = 1, 2, 4, 8, 12 -- so an error that a later block would wash out (or that
+    only accumulates with depth) is seen where it arises.  Weights are the trained-like perturbation (no LayerNorm or
+    attention bias at its identity value); `stress` adds outlier channels, x10 gammas and +20 DC rows."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder
+    full = oracle.clip_vit_b_16(seed=2, stress=stress).state_dict()
+    video = torch.randn(3, 2, 3, 224, 224, generator=torch.Generator().manual_seed(21))
+    ids = oracle.tokenize_synthetic(6, (4, 77), seed=22)
+    worst = {}
+    for depth in (1, 2, 4, 8, 12):
+        sd = _truncate(full, depth, depth)
+        model = oracle.build_model(sd)
+        ref = oracle.RefClipVideoTextEncoder(copy.deepcopy(model), num_frames=2)
+        emu = oracle.RefClipVideoTextEncoder(oracle.bf16_stream_model(model), num_frames=2)
+        enc = B200ClipVideoTextEncoder(sd, num_frames=2).to(dev)
+        with torch.inference_mode():
+            ev, et = ref(video, {"input_ids": ids})
+            mv, mt = emu(video, {"input_ids": ids})
+            gv, gt = enc(video.to(dev), {"input_ids": ids.to(dev)})
+        tag = f"depth {depth}{' (stress)' if stress else ''}"
+        cv, ct = _report(f"{tag} video", gv.cpu(), ev), _report(f"{tag} text", gt.cpu(), et)
+        bv, bt = _report(f"{tag} video, bf16-stream emulation", mv, ev), _report(f"{tag} text, bf16-stream emulation", mt, et)
+        worst[depth] = (cv, ct)
+        assert cv[0] >= 0.9995 and ct[0] >= 0.9995, (depth, cv, ct)
+        assert cv[1] <= 5e-3 and ct[1] <= 5e-3, (depth, cv, ct)
+        assert cv[2] <= 0.1 and ct[2] <= 0.1, (depth, cv, ct)
+        assert cv[1] <= 3 * bv[1] + 1e-3 and ct[1] <= 3 * bt[1] + 1e-3, (depth, cv, bv, ct, bt)
+
+
+def test_stress_weights_full_depth(dev):
+    """Pretrained-like stress case at full ViT-B/16 depth: residual outlier channels (x60 writers, x10 gammas), +20 DC
+    offset on three token rows of each tower, random gamma / beta / attention biases everywhere."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder
+    model = oracle.clip_vit_b_16(seed=5, stress=True)
+    ref = oracle.RefClipVideoTextEncoder(copy.deepcopy(model))
+    emu = oracle.RefClipVideoTextEncoder(oracle.bf16_stream_model(model))
+    enc = B200ClipVideoTextEncoder(model.state_dict(), num_frames=4).to(dev)
+    video = torch.randn(4, 4, 3, 224, 224, generator=torch.Generator().manual_seed(31))
+    ids = oracle.tokenize_synthetic(12, (4, 77), seed=32)
+    with torch.inference_mode():
+        ev, et = ref(video, {"input_ids": ids})
+        mv, mt = emu(video, {"input_ids": ids})
+        gv, gt = enc(video.to(dev), {"input_ids": ids.to(dev)})
+    cv, ct = _report("stress video", gv.cpu(), ev), _report("stress text", gt.cpu(), et)
+    bv, bt = _report("stress video, bf16-stream emulation", mv, ev), _report("stress text, bf16-stream emulation", mt, et)
+    assert cv[0] >= 0.9995 and ct[0] >= 0.9995
+    assert cv[1] <= 8e-3 and ct[1] <= 8e-3
+    assert cv[2] <= 0.1 and ct[2] <= 0.1
+    assert cv[1] <= 3 * bv[1] + 1e-3 and ct[1] <= 3 * bt[1] + 1e-3
 
 
 def test_forward_tuple_and_int64_ids_and_bf16_frames(models, dev):
@@ -167,8 +237,8 @@ def test_other_clip_geometries(dev, name):
         gv, gt = enc(video.to(dev), {"input_ids": ids.to(dev)})
     cos_v, max_v, _ = _report(f"{name} video", gv.cpu(), ev)
     cos_t, max_t, _ = _report(f"{name} text", gt.cpu(), et)
-    assert cos_v >= 0.999 and cos_t >= 0.999
-    assert max_v <= 2e-2 and max_t <= 2e-2
+    assert cos_v >= 0.9995 and cos_t >= 0.9995
+    assert max_v <= 5e-3 and max_t <= 5e-3
 
 
 def test_unsupported_geometry_is_refused(dev):

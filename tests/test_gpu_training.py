@@ -140,3 +140,24 @@ def test_loss_decreases(dev):
     batch = _batch(16, 2, 64, 24, 512, dev)
     losses = [float(module.training_step(batch, i)) for i in range(6)]
     assert losses[-1] < losses[0], losses
+
+
+def test_out_of_range_token_ids_are_reported(dev):
+    """a bad token id on the TRAINING path (text_embed clamps it, token_scatter drops its gradient) must
+    surface through ClipTrainer.check_inputs -- the reference's embedding lookup would have raised."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder, _lib
+    from fitclip_b200.training import TeacherStudentTrainingModule
+    enc = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0, **GEOM).state_dict(), num_frames=2).to(dev)
+    teach = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=1, **GEOM).state_dict(), num_frames=2).to(dev)
+    module = TeacherStudentTrainingModule(enc, teach)
+    batch = _batch(8, 2, 64, 24, 512, dev)
+    module.training_step(batch, 0)
+    module.trainer.check_inputs()  # clean batch: no error
+    bad = batch["text_student"]["input_ids"].clone()
+    bad[3, 2] = 60000
+    batch["text_student"] = {"input_ids": bad}  # the teacher keeps the clean ids
+    module.training_step(batch, 1)
+    with pytest.raises(_lib.FitclipError, match="token id out of range"):
+        module.trainer.check_inputs()
+    module.trainer.check_inputs()  # the flag was reset
