@@ -47,6 +47,20 @@ constexpr int STG_BYTES = 4 * 32 * 128;    // 4 warps x (32 rows x 128 B) output
                        // 8 = no pass 2 at all, 16 = no epilogue
 #endif
 constexpr int ATT_THREADS = 160;           // warps 0-3 softmax/epilogue, warp 4 TMA + MMA + TMEM alloc
+// ---- second-generation kernel (attention_tc2_kernel): softmax warpgroup + EPILOGUE warpgroup + TMA/MMA warp
+constexpr int ATT2_THREADS = 288;          // warps 0-3 softmax, warps 4-7 epilogue (same lane quadrants), warp 8 TMA + MMA
+#ifndef ATT2_POLY
+#define ATT2_POLY 4  // of every 16 column pairs of a x32 chunk, this many take exp2 on the FMA pipe (degree-3 polynomial,
+                     // Cody-Waite split, packed fp32x2) instead of the MUFU: 0 = none, 4 = 25 %, 8 = 50 %
+#endif
+#ifndef ATT2_REGS_SOFTMAX
+// setmaxnreg targets (multiples of 8).  Registers move inside a CTA's own launch allocation, so
+// 128 * SOFTMAX + 128 * EPILOGUE + 32 * (launch count, kept by the TMA/MMA warp) must not exceed 288 * (registers per
+// thread at launch) -- checked on the host
+// against cudaFuncGetAttributes before the first launch (an unsatisfiable setmaxnreg.inc would spin forever).
+#define ATT2_REGS_SOFTMAX 120
+#define ATT2_REGS_EPILOGUE 72
+#endif
 
 template <int KP>
 struct AttSmem {
@@ -451,6 +465,397 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// exp2 of two non-positive arguments on the FMA pipe (no MUFU): Cody-Waite split x = n + f with n = round(x) taken from
+// the low mantissa bits of x + 1.5 * 2^23, degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max relative error
+// 7.7e-5, far below the bf16 rounding of P), and 2^n applied by adding n << 23 to the exponent field.  Arguments are
+// clamped at -126 (the result would be a denormal; everything that small is irrelevant to a row whose maximum is 1).
+__device__ __forceinline__ void ex2_poly_x2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  x2 = pack_f32x2(x0, x1);
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f), nmagic = pack_f32x2(-12582912.f, -12582912.f);
+  const uint64_t r2 = add_f32x2(x2, magic);                 // bits: 0x4B400000 + n
+  const uint64_t n2 = add_f32x2(r2, nmagic);                // n as a float
+  const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.f, -1.f), x2);
+  uint64_t q2 = fma_f32x2(pack_f32x2(0.05508868f, 0.05508868f), f2, pack_f32x2(0.24260405f, 0.24260405f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.69327623f, 0.69327623f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.99992895f, 0.99992895f));
+  float r0, r1, q0, q1;
+  unpack_f32x2(r2, r0, r1);
+  unpack_f32x2(q2, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));  // (0x4B400000 + n) << 23 == n << 23 (mod 2^32)
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
+
+template <int KP>
+struct Att2Smem {
+  using B = AttSmem<KP>;
+  static constexpr int OFF_L = B::OFF_BAR + 128;  // float[2][128]: row sums handed from the softmax to the epilogue warps
+  static constexpr int BYTES = OFF_L + 2 * 128 * 4;
+};
+
+// Second-generation kernel for the un-masked image sequence: the work split of attention_tc_kernel plus a dedicated
+// EPILOGUE warpgroup.  In the first kernel a softmax warp spends a third of every item waiting for P.V and reading out /
+// scaling / storing O (1570 of 6100 cycles) with only two warps per scheduler to hide it; here warps 4-7 (the same TMEM
+// lane quadrants as warps 0-3) do that, the softmax warps go straight from the last P chunk of item i to S(i+1), and
+// the scheduler has four warps to pick from.  Registers are re-balanced with setmaxnreg (softmax 152, epilogue 88,
+// TMA/MMA 40).  A fraction of the exponentials runs on the FMA pipe (ex2_poly_x2): the MUFU pipe is the busiest unit.
+template <int KP, int NPH>
+__global__ void __launch_bounds__(ATT2_THREADS, 2)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                     const __grid_constant__ CUtensorMap tmO, int L, int heads, int tiles, int num_items,
+                     float scale_log2) {
+  using S = AttSmem<KP>;
+  using S2 = Att2Smem<KP>;
+  static_assert(KP % 32 == 16 && KP >= 48 && KP <= 208, "padded key count: whole x32 chunks plus one 16-key tail");
+  static_assert(!ATT_DIRECT_STORE, "the epilogue warpgroup stores through the staging tile");
+  constexpr int KMAIN = KP - 16;
+  constexpr int O_COL = KMAIN;
+  constexpr int KHALF = NPH == 2 ? 64 : 96;
+  constexpr uint32_t TMEM_COLS = O_COL + HD <= 128 ? 128 : 256;
+  static_assert(KP / 2 <= O_COL && O_COL + HD <= 256, "P / O column ranges must not overlap");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* kq_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* v_full = kq_full + 1;
+  uint64_t* s_full = kq_full + 2;
+  uint64_t* p_full = kq_full + 3;
+  uint64_t* o_full = kq_full + 4;
+  uint64_t* o_empty = kq_full + 5;
+  uint64_t* t_full = kq_full + 6;
+  uint64_t* p_half = kq_full + 7;   // [2]
+  uint64_t* l_full = kq_full + 10;  // row sums of item it are in l_buf[it & 1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 9);
+  float* l_buf = reinterpret_cast<float*>(smem + S2::OFF_L);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = heads * HD;
+  const bool flip_ok = (gridDim.x & 1) == 0 && tiles == 2;
+
+  griddep_launch_dependents();
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 256) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
+    mbar_init(kq_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
+    mbar_init(t_full, 1);
+    mbar_init(p_half, 128);
+    mbar_init(p_half + 1, 128);
+    mbar_init(l_full, 128);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+
+  if (warp == 8) {
+    // ===================== TMA + MMA thread (identical protocol to attention_tc_kernel) =====================
+    // (keeps its launch-time registers: setmaxnreg is a warpgroup-wide instruction and this warp is alone in its group)
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(QT, KMAIN);
+      constexpr uint32_t idesc_t = umma_idesc_bf16_f32(QT, 16);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_f32_bmn(QT, HD);
+      const uint32_t q_addr = smem_u32(smem + S::OFF_Q);
+      const uint32_t k_addr = smem_u32(smem + S::OFF_K);
+      const uint32_t v_addr = smem_u32(smem + S::OFF_V);
+      auto load_qk = [&](const ItemCursor& c, int n) {
+        const int tile = flip_ok ? (c.t ^ (n & 1)) : c.t;
+        mbar_expect_tx(kq_full, Q_BYTES + S::KV_BYTES);
+        tma_load_3d(smem + S::OFF_Q, &tmQ, kq_full, c.head * HD, tile * QT, c.seq);
+        tma_load_3d(smem + S::OFF_K, &tmKV, kq_full, D + c.head * HD, 0, c.seq);
+      };
+      auto load_v = [&](const ItemCursor& c) {
+        mbar_expect_tx(v_full, S::KV_BYTES);
+        tma_load_3d(smem + S::OFF_V, &tmKV, v_full, 2 * D + c.head * HD, 0, c.seq);
+      };
+      auto issue_s_main = [&]() {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s,
+                       k != 0);
+        umma_commit(s_full);
+      };
+      auto issue_s_tail = [&]() {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base + KMAIN, umma_desc_k_sw128(q_addr + k * 32),
+                       umma_desc_k_sw128(k_addr + KMAIN * 128 + k * 32), idesc_t, k != 0);
+        umma_commit(t_full);
+      };
+      ItemCursor cv, cqk;
+      cv.init(blockIdx.x, gridDim.x, tiles, heads);
+      cqk = cv;
+      if (static_cast<int>(blockIdx.x) < num_items) {
+        load_qk(cqk, 0);
+        load_v(cv);
+        cqk.advance();
+        cv.advance();
+        mbar_wait(kq_full, 0);
+        tc_fence_after();
+        issue_s_main();
+        issue_s_tail();
+        mbar_wait(t_full, 0);
+        if (static_cast<int>(blockIdx.x + gridDim.x) < num_items) load_qk(cqk, 1);
+        cqk.advance();
+      }
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int next = item + gridDim.x, next2 = next + gridDim.x;
+        const bool has_next = next < num_items;
+        mbar_wait(v_full, ph);
+#pragma unroll
+        for (int part = 0; part < NPH; ++part) {
+          mbar_wait(p_half + part, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = part * (KHALF / 16); k < (part + 1) * (KHALF / 16); ++k)
+            umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
+        }
+        mbar_wait(p_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = NPH * (KHALF / 16); k < KP / 16; ++k)
+          umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
+        umma_commit(o_full);
+        if (has_next) {
+          mbar_wait(kq_full, ph ^ 1);
+          tc_fence_after();
+          issue_s_main();
+        }
+        mbar_wait(o_full, ph);  // V tile is free again
+        if (has_next) {
+          load_v(cv);
+          cv.advance();
+          mbar_wait(o_empty, ph);  // the epilogue warps have read O(it): the tail columns may be overwritten
+          tc_fence_after();
+          issue_s_tail();
+          mbar_wait(t_full, ph ^ 1);
+          if (next2 < num_items) load_qk(cqk, it + 2);
+          cqk.advance();
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps: O / l -> bf16 -> staging tile -> TMA store =====================
+    setmaxnreg_dec<ATT2_REGS_EPILOGUE>();
+    const int q = warp - 4;  // TMEM lane quadrant = warp % 4
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* stg_ptr = smem + S::OFF_STG + q * (32 * 128);
+    const uint32_t stg_row = smem_u32(stg_ptr) + lane * 128;
+    const int sw = lane & 7;
+    ItemCursor cur;
+    cur.init(blockIdx.x, gridDim.x, tiles, heads);
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it, cur.advance()) {
+      const uint32_t ph = it & 1;
+      const int tile = flip_ok ? (cur.t ^ (it & 1)) : cur.t;
+      const int row0 = tile * QT + q * 32;
+      const bool active = row0 < L;
+      mbar_wait(l_full, ph);  // arrived before p_full, hence before P.V was even issued: returns at once; orders the l read
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      if (active) {
+        const float inv = 1.f / l_buf[(it & 1) * 128 + q * 32 + lane];
+        const uint64_t inv2 = pack_f32x2(inv, inv);
+        // two halves of 32 columns, each scaled and packed to bf16 as soon as it arrives (32 + 16 live registers)
+        uint32_t pk[2][16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(trow + O_COL + 32 * h, o);
+          tmem_ld_wait_fence(o);
+          if (h == 1) {
+            tc_fence_before();
+            mbar_arrive(o_empty);  // O(it) is in registers: the MMA thread may overwrite the tail columns
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a, b;
+            unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1])), inv2), a, b);
+            pk[h][e] = pack_bf16x2(a, b);
+          }
+        }
+        if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous store has finished reading its staging tile
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t(&pp)[16] = pk[c >> 2];
+          const int o = (c & 3) * 4;
+          st_shared_v4(stg_row + ((c ^ sw) << 4), make_uint4(pp[o], pp[o + 1], pp[o + 2], pp[o + 3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO, stg_ptr, cur.head * HD, row0, cur.seq);  // rows >= L are clipped by the tensor map
+          bulk_commit_group();
+        }
+      } else {
+        tc_fence_before();
+        mbar_arrive(o_empty);
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();
+  } else {
+    // ===================== softmax warps (one query row per thread): S -> P, row sums =====================
+    setmaxnreg_inc<ATT2_REGS_SOFTMAX>();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    constexpr int NFULL = KP / 32;
+    static_assert(NPH == 0 || (KHALF % 32 == 0 && NPH * (KHALF / 32) < NFULL), "early hand-overs must end on chunk boundaries");
+    ItemCursor cur;
+    cur.init(blockIdx.x, gridDim.x, tiles, heads);
+    int it = 0;
+    FC_T(long long tq[7] = {0, 0, 0, 0, 0, 0, 0}; long long n_it = 0; const long long t_begin = clock64();)
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it, cur.advance()) {
+      const uint32_t ph = it & 1;
+      const int tile = flip_ok ? (cur.t ^ (it & 1)) : cur.t;
+      const int row0 = tile * QT + warp * 32;
+      const bool active = row0 < L;
+      const int lim = L;  // un-masked: every row attends to keys [0, L)
+      FC_T(long long t0 = clock64(); long long t1;)
+      mbar_wait(s_full, ph);
+      FC_T(t1 = clock64(); tq[1] += t1 - t0; t0 = t1; ++n_it;)
+      tc_fence_after();
+      float l = 1.f;
+      float m = -INFINITY;
+      if (active) {
+        float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        constexpr int DEPTH = 2;
+        uint32_t r[DEPTH][32];
+#pragma unroll
+        for (int j = 0; j < DEPTH && j < NFULL; ++j) tmem_ld_32x32b_x32(trow + j * 32, r[j]);
+#pragma unroll
+        for (int j = 0; j < NFULL; ++j) {
+          tmem_ld_wait_fence(r[j % DEPTH]);
+          const uint32_t(&rc)[32] = r[j % DEPTH];
+          if ((j + 1) * 32 <= lim) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
+              m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
+              m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
+              m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (j * 32 + c < lim) m = fmaxf(m, __uint_as_float(rc[c]));
+          }
+          if (j + DEPTH < NFULL) tmem_ld_32x32b_x32(trow + (j + DEPTH) * 32, r[j % DEPTH]);
+        }
+        m = fmaxf(max3(m, m1, m2), m3);
+      }
+      FC_T(t1 = clock64(); tq[2] += t1 - t0; t0 = t1;)
+      mbar_wait(t_full, ph);
+      FC_T(t1 = clock64(); tq[3] += t1 - t0; t0 = t1;)
+      tc_fence_after();
+      if (active) {
+        uint32_t r16[16];
+        tmem_ld_32x32b_x16(trow + NFULL * 32, r16);
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(trow, r[0]);
+        tmem_ld_wait_fence16(r16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (NFULL * 32 + c < lim) m = fmaxf(m, __uint_as_float(r16[c]));
+        const float mc = m * scale_log2;
+        const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nmc2 = pack_f32x2(-mc, -mc);
+        uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
+        uint32_t pk_tail[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float p0 = 0.f, p1 = 0.f;
+          if (NFULL * 32 + 2 * c < lim) {  // compile-time per c only when lim is; L is a runtime value: a uniform branch
+            float x0, x1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r16[2 * c]), __uint_as_float(r16[2 * c + 1])), sc2, nmc2),
+                         x0, x1);
+            p0 = ex2_approx(x0);
+            p1 = NFULL * 32 + 2 * c + 1 < lim ? ex2_approx(x1) : 0.f;
+          }
+          l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+          pk_tail[c] = pack_bf16x2(p0, p1);
+        }
+#pragma unroll
+        for (int j = 0; j < NFULL; ++j) {
+          tmem_ld_wait_fence(r[j & 1]);
+          if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
+          uint32_t pk[16];
+          const bool full = (j + 1) * 32 <= lim;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
+                                          sc2, nmc2);
+            float p0, p1;
+            // ATT2_POLY of every 16 pairs take the FMA-pipe exp2, spread evenly so both pipes stay fed
+            if (ATT2_POLY > 0 && (c * ATT2_POLY) % 16 < ATT2_POLY) {
+              ex2_poly_x2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f32x2(x2, x0, x1);
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
+            if (!full) {
+              if (j * 32 + 2 * c >= lim) p0 = 0.f;
+              if (j * 32 + 2 * c + 1 >= lim) p1 = 0.f;
+            }
+            if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+            else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
+            pk[c] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x32b_x16(trow + j * 16, pk);
+          if (NPH > 0 && (j + 1) % (KHALF / 32) == 0 && (j + 1) / (KHALF / 32) <= NPH) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_half + (j + 1) / (KHALF / 32) - 1);
+          }
+        }
+        tmem_st_32x32b_x8(trow + NFULL * 16, pk_tail);
+        tmem_st_wait();
+        float la, lb;
+        unpack_f32x2(add_f32x2(l2a, l2b), la, lb);
+        l = la + lb;
+      } else {
+#pragma unroll
+        for (int part = 0; part < NPH; ++part) mbar_arrive(p_half + part);
+      }
+      l_buf[(it & 1) * 128 + threadIdx.x] = l;
+      mbar_arrive(l_full);  // release: the epilogue thread of this row reads l after its acquire-wait on l_full
+      tc_fence_before();
+      mbar_arrive(p_full);
+      FC_T(t1 = clock64(); tq[4] += t1 - t0; t0 = t1;)
+    }
+    FC_T(if (threadIdx.x == 0) {
+      atomicAdd(&g_att_timing[0], static_cast<unsigned long long>(clock64() - t_begin));
+      for (int i = 1; i < 7; ++i) atomicAdd(&g_att_timing[i], static_cast<unsigned long long>(tq[i]));
+      atomicAdd(&g_att_timing[7], static_cast<unsigned long long>(n_it));
+    })
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -527,6 +932,49 @@ int launch_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaSt
   return FC_OK;
 }
 
+template <int KP, int NPH>
+int launch_tc2(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaStream_t s) {
+  using S2 = Att2Smem<KP>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncAttributes fa;
+    FC_CUDA(cudaFuncGetAttributes(&fa, attention_tc2_kernel<KP, NPH>));
+    FC_REQUIRE(128 * ATT2_REGS_SOFTMAX + 128 * ATT2_REGS_EPILOGUE + 32 * fa.numRegs <= ATT2_THREADS * fa.numRegs &&
+                   ATT2_REGS_EPILOGUE <= fa.numRegs && ATT2_REGS_SOFTMAX >= fa.numRegs,
+               "attention_tc2: setmaxnreg plan (%d/%d) does not fit the %d registers per thread the kernel launches with",
+               ATT2_REGS_SOFTMAX, ATT2_REGS_EPILOGUE, fa.numRegs);
+    FC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<KP, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::BYTES));
+    configured = true;
+  }
+  const int D = heads * HD;
+  CUtensorMap tq, tkv, to;
+  int rc;
+  if ((rc = make_tmap_3d(&tq, qkv, 3 * D, L, seqs, QT))) return rc;
+  if ((rc = make_tmap_3d(&tkv, qkv, 3 * D, L, seqs, KP))) return rc;
+  if ((rc = make_tmap_3d(&to, out, D, L, seqs, 32))) return rc;
+  const int tiles = (L + QT - 1) / QT;
+  const int64_t items64 = seqs * heads * tiles;
+  FC_REQUIRE(items64 < (int64_t(1) << 31), "attention: too many work items");
+  const int items = static_cast<int>(items64);
+  int grid = 2 * num_sms();
+  if (grid > items) grid = items;
+  if (tiles == 2 && (grid & 1)) grid -= 1;
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(ATT2_THREADS);
+  cfg.dynamicSmemBytes = S2::BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  note_launch();
+  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc2_kernel<KP, NPH>, tq, tkv, to, L, heads, tiles, items, scale_log2));
+  return FC_OK;
+}
+
 }  // namespace
 
 #ifdef FC_GEMM_TIMING
@@ -546,9 +994,11 @@ extern "C" __attribute__((visibility("default"))) int fc_debug_att_timing(unsign
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                       int* handled) {
   *handled = 0;
-  static int disabled = -1;
+  static int disabled = -1, gen1 = 0;
   if (disabled < 0) {
-    const char* e = getenv("FC_ATTENTION");  // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels
+    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=tc1 the first-generation tcgen05 kernel
+    const char* e = getenv("FC_ATTENTION");
+    gen1 = (e && strcmp(e, "tc1") == 0) ? 1 : 0;
     disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
   }
   if (disabled) return FC_OK;
@@ -558,6 +1008,7 @@ int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads
   FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "attention: buffers must be 16-byte aligned");
   *handled = 1;
+  if (image && !gen1) return launch_tc2<208, ATT_PHALF>(qkv, out, seqs, L, heads, s);
   if (image) return launch_tc<208, false, ATT_PHALF>(qkv, out, seqs, L, heads, s);
   return launch_tc<80, true, 0>(qkv, out, seqs, L, heads, s);
 }
