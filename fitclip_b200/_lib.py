@@ -48,6 +48,7 @@ SIGNATURES = {
     "fc_model_ready": (C.c_int, [_p]),
     "fc_model_workspace_bytes": (_i64, [_p]),
     "fc_encode_video": (C.c_int, [_p, _p, C.c_int, _i64, _i32, _p, _p, _p]),
+    "fc_encode_video_uint8": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "fc_encode_text": (C.c_int, [_p, _p, _i64, _p, _p]),
     "fc_model_check": (C.c_int, [_p, _p]),
     "fc_preprocess_frames": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, C.c_int, _p]),

@@ -294,11 +294,12 @@ static int finalize(fc_model* m, cudaStream_t s) {
 }
 
 // CLIP.encode_image for F frames -> un-normalised features feat[F, E]   ([3P] VisionTransformer.forward)
+// `frames` == nullptr: the patch matrix of the F frames is already in m->big (fc_encode_video_uint8)
 static int vision_pass(fc_model* m, const void* frames, int dtype, int64_t F, float* feat, cudaStream_t s) {
   const fc_config& c = m->cfg;
   const int W = c.vision_width, L = m->L_img, G = m->grid;
   int rc;
-  if ((rc = im2col_patches(frames, dtype, m->big, F, c.image_resolution, c.vision_patch_size, s))) return rc;
+  if (frames && (rc = im2col_patches(frames, dtype, m->big, F, c.image_resolution, c.vision_patch_size, s))) return rc;
   GemmParams p;
   p.M = static_cast<int>(F * G * G); p.N = W; p.K = m->patch_dim; p.C = m->x; p.ldc = W;
   p.pos = m->vpos; p.patches_per_frame = G * G;
@@ -499,6 +500,37 @@ int fc_encode_video(fc_model* m, const void* frames, int dtype, int64_t videos, 
                               cudaMemcpyDeviceToDevice, s));
     rc = pool_normalize(m->feat, out_video + v0 * c.embed_dim, nullptr, nv, T, c.embed_dim, 1.f, s);
     if (rc) return rc;
+  }
+  return FC_OK;
+}
+
+int fc_encode_video_uint8(fc_model* m, const uint8_t* frames, int64_t videos, int32_t T, int32_t H, int32_t W,
+                          const float* mean, const float* std, float* out_video, float* out_frames, void* stream) {
+  FC_REQUIRE(m && ((out_video && frames) || videos == 0) && mean && std, "fc_encode_video_uint8: null argument");
+  FC_REQUIRE(videos >= 0 && T >= 1 && H > 0 && W > 0, "fc_encode_video_uint8: bad shape videos=%lld T=%d H=%d W=%d",
+             static_cast<long long>(videos), T, H, W);
+  FC_REQUIRE(T <= m->maxF, "fc_encode_video_uint8: frames_per_video=%d exceeds max_frames_per_pass=%d", T, m->maxF);
+  if (!fc_model_ready(m)) return FC_ERR_STATE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int frc = finalize(m, s)) return frc;
+  const fc_config& c = m->cfg;
+  const int64_t frame_bytes = int64_t(3) * H * W;
+  const int64_t max_vids = m->maxF / T;
+  const int64_t n_passes = (videos + max_vids - 1) / max_vids;
+  const int64_t vids_per_pass = n_passes ? (videos + n_passes - 1) / n_passes : 1;
+  for (int64_t v0 = 0; v0 < videos; v0 += vids_per_pass) {
+    const int64_t nv = std::min(vids_per_pass, videos - v0);
+    const int64_t F = nv * T;
+    // eval transform fused into the patch gather: uint8 -> /255 -> bicubic resize -> crop -> normalise -> bf16 patch rows
+    if (m->patch_dim != m->patch_cols)  // padded patch rows (ViT-L/14: 588 -> 592): the pad columns must be zero
+      FC_CUDA(cudaMemsetAsync(m->big, 0, static_cast<size_t>(F) * m->grid * m->grid * m->patch_dim * sizeof(bf16), s));
+    int rc = preprocess_to_patches(frames + v0 * T * frame_bytes, F, H, W, c.image_resolution, c.vision_patch_size, mean,
+                                   std, m->big, m->patch_dim, s);
+    if (rc) return rc;
+    if ((rc = vision_pass(m, nullptr, FC_BF16, F, m->feat, s))) return rc;
+    if (out_frames)
+      FC_CUDA(cudaMemcpyAsync(out_frames + v0 * T * c.embed_dim, m->feat, F * c.embed_dim * 4, cudaMemcpyDeviceToDevice, s));
+    if ((rc = pool_normalize(m->feat, out_video + v0 * c.embed_dim, nullptr, nv, T, c.embed_dim, 1.f, s))) return rc;
   }
   return FC_OK;
 }

@@ -30,6 +30,9 @@ int split_bf16(const float* in, bf16* out, int64_t rows, int D, int mode, int te
 // preprocess.cu : uint8 (F,H,W,3) -> [x/255 -> bicubic resize (shorter side = size) -> centre crop -> normalise] -> (F,3,size,size)
 int preprocess_frames(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
                       void* out, int out_dtype, cudaStream_t s);
+// uint8 frames -> the bf16 patch matrix [F * (size/patch)^2, ldp] the patch-embedding GEMM reads (no NCHW intermediate)
+int preprocess_to_patches(const uint8_t* frames, int64_t F, int H, int W, int size, int patch, const float* mean,
+                          const float* stdv, bf16* patches, int ldp, cudaStream_t s);
 
 // attention.cu : out[s*L + l, h*64 + d] = softmax(q k^T / 8 [+ causal mask]) v, qkv rows are [q | k | v] of width 3*D
 int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s);

@@ -30,6 +30,7 @@ struct PreParams {
   int size;        // output side
   float scale_h, scale_w;
   float mean[3], stdv[3];
+  int P, G, ldp;   // PATCH mode: patch size, patches per side, row stride of the patch matrix (elements)
 };
 
 template <typename TOut>
@@ -44,7 +45,11 @@ __device__ __forceinline__ void store_px<bf16>(bf16* p, float v) { *p = __float2
 // (4 pixels x RGB): they are fetched as four aligned 32-bit words and realigned with funnel shifts -- 16 loads per
 // output pixel instead of 48 byte loads (the kernel is LSU-bound, not HBM-bound: neighbouring threads re-read the
 // same lines from L1).  Pixels whose taps are clamped at the left / right border take the byte path.
-template <typename TOut>
+// PATCH = true writes the result straight into the patch-embedding GEMM's A operand instead of an NCHW image: pixel
+// (c, oy, ox) of frame f lands in row f*G*G + (oy/P)*G + ox/P, column c*P*P + (oy%P)*P + ox%P of the bf16 patch matrix
+// (the layout im2col_kernel produces, elementwise.cu) -- the normalised frame never exists in memory.  The P
+// consecutive pixels of a patch row are P consecutive bf16 (full 32-byte sectors for P = 16).
+template <typename TOut, bool PATCH>
 __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ in, TOut* __restrict__ out,
                                                          int64_t frames, const PreParams p) {
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,16 +95,24 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
 #pragma unroll
     for (int c = 0; c < 3; ++c) acc[c] = fmaf(r[c], cy[i], acc[c]);
   }
-  const int64_t plane = static_cast<int64_t>(p.size) * p.size;
-  TOut* dst = out + f * 3 * plane + static_cast<int64_t>(oy) * p.size + ox;
+  if (PATCH) {
+    const int py = oy / p.P, px = ox / p.P;
+    TOut* dst = out + ((f * p.G + py) * p.G + px) * static_cast<int64_t>(p.ldp) + (oy - py * p.P) * p.P + (ox - px * p.P);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) store_px<TOut>(dst + c * plane, (acc[c] - p.mean[c]) / p.stdv[c]);
+    for (int c = 0; c < 3; ++c) store_px<TOut>(dst + c * p.P * p.P, (acc[c] - p.mean[c]) / p.stdv[c]);
+  } else {
+    const int64_t plane = static_cast<int64_t>(p.size) * p.size;
+    TOut* dst = out + f * 3 * plane + static_cast<int64_t>(oy) * p.size + ox;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) store_px<TOut>(dst + c * plane, (acc[c] - p.mean[c]) / p.stdv[c]);
+  }
 }
 
 }  // namespace
 
-int preprocess_frames(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
-                      void* out, int out_dtype, cudaStream_t s) {
+// patch > 0: `out` is the bf16 patch matrix [F * (size/patch)^2, ldp] (see preprocess_kernel<.., true>)
+static int preprocess_impl(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
+                           void* out, int out_dtype, int patch, int ldp, cudaStream_t s) {
   FC_REQUIRE(frames && out && mean && stdv, "preprocess: null pointer");
   FC_REQUIRE(F >= 0 && H > 0 && W > 0 && size > 0, "preprocess: bad shape F=%lld H=%d W=%d size=%d",
              static_cast<long long>(F), H, W, size);
@@ -127,17 +140,35 @@ int preprocess_frames(const uint8_t* frames, int64_t F, int H, int W, int size, 
     p.stdv[c] = stdv[c];
     FC_REQUIRE(stdv[c] != 0.f, "preprocess: std[%d] is zero", c);
   }
-  ProfScope prof(s, PROF_OTHER, 1, F, H, W, 0.0,
+  p.P = patch;
+  p.G = patch > 0 ? size / patch : 0;
+  p.ldp = ldp;
+  ProfScope prof(s, PROF_OTHER, patch > 0 ? 2 : 1, F, H, W, 0.0,
                  static_cast<double>(F) * (3.0 * H * W + 3.0 * size * size * (out_dtype == FC_DTYPE_F32 ? 4 : 2)));
   dim3 grid((size + 255) / 256, size, static_cast<unsigned>(F));
-  if (out_dtype == FC_DTYPE_F32)
-    preprocess_kernel<float><<<grid, 256, 0, s>>>(frames, static_cast<float*>(out), F, p);
-  else if (out_dtype == FC_DTYPE_BF16)
-    preprocess_kernel<bf16><<<grid, 256, 0, s>>>(frames, static_cast<bf16*>(out), F, p);
-  else
+  if (patch > 0) {
+    FC_REQUIRE(out_dtype == FC_DTYPE_BF16 && size % patch == 0 && ldp >= 3 * patch * patch,
+               "preprocess (patch mode): bf16 output, size %% patch == 0 and ldp >= 3 * patch^2 required");
+    preprocess_kernel<bf16, true><<<grid, 256, 0, s>>>(frames, static_cast<bf16*>(out), F, p);
+  } else if (out_dtype == FC_DTYPE_F32) {
+    preprocess_kernel<float, false><<<grid, 256, 0, s>>>(frames, static_cast<float*>(out), F, p);
+  } else if (out_dtype == FC_DTYPE_BF16) {
+    preprocess_kernel<bf16, false><<<grid, 256, 0, s>>>(frames, static_cast<bf16*>(out), F, p);
+  } else {
     FC_REQUIRE(false, "preprocess: output dtype must be fp32 (0) or bf16 (1), got %d", out_dtype);
+  }
   FC_CHECK_LAUNCH();
   return FC_OK;
+}
+
+int preprocess_frames(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
+                      void* out, int out_dtype, cudaStream_t s) {
+  return preprocess_impl(frames, F, H, W, size, mean, stdv, out, out_dtype, 0, 0, s);
+}
+
+int preprocess_to_patches(const uint8_t* frames, int64_t F, int H, int W, int size, int patch, const float* mean,
+                          const float* stdv, bf16* patches, int ldp, cudaStream_t s) {
+  return preprocess_impl(frames, F, H, W, size, mean, stdv, patches, FC_DTYPE_BF16, patch, ldp, s);
 }
 
 }  // namespace fc

@@ -168,6 +168,24 @@ class B200Clip(nn.Module):
                                                    _lib.ptr(out), None, _lib.stream_ptr(video.device)))
         return out
 
+    def encode_video_uint8_pooled(self, video: torch.Tensor, mean, std) -> torch.Tensor:
+        """raw frames (B, T, H, W, 3) uint8 -> (B, E): eval transform fused into the patch gather + the encoder, one
+        native call (``fc_encode_video_uint8``)."""
+        if not video.is_cuda:
+            raise _lib.FitclipError(-101, "B200Clip needs CUDA tensors: there is no CPU path")
+        if video.dtype != torch.uint8 or video.dim() != 5 or video.shape[-1] != 3:
+            raise ValueError(f"expected uint8 frames of shape (B, T, H, W, 3), got {video.dtype} {tuple(video.shape)}")
+        B, T, H, W = video.shape[:4]
+        video = video.contiguous()
+        out = torch.empty(B, self.config["embed_dim"], device=video.device, dtype=torch.float32)
+        handle = self._native(video.device)
+        m3 = (C.c_float * 3)(*[float(v) for v in mean])
+        s3 = (C.c_float * 3)(*[float(v) for v in std])
+        with torch.cuda.device(video.device):
+            _lib.check(_lib.load().fc_encode_video_uint8(handle, _lib.ptr(video), B, T, H, W, m3, s3, _lib.ptr(out), None,
+                                                         _lib.stream_ptr(video.device)))
+        return out
+
     def encode_image(self, image: torch.Tensor) -> torch.Tensor:
         """``CLIP.encode_image``: (F, 3, R, R) -> un-normalised (F, E) fp32."""
         if not image.is_cuda:
@@ -239,11 +257,14 @@ class B200ClipVideoTextEncoder(VideoTextEncoder):
         # clip_video_text_encoder.py:80-89 -- fused natively: encode_image, x/||x|| per frame, mean over frames
         return self.model.encode_video_pooled(video)
 
-    def encode_video_uint8(self, video: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    def encode_video_uint8(self, video: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         """Raw decoded frames ``(B, T, H, W, 3)`` uint8 on the GPU -> ``(B, E)``: the eval transform
-        (``get_eval_transform``, clip_video_text_encoder.py:124-133) runs as one CUDA kernel in front of the encoder
-        instead of on DataLoader workers.  ``dtype`` is the precision of the normalised frames handed to the patch
-        embedding (the tensor cores consume bf16 either way)."""
+        (``get_eval_transform``, clip_video_text_encoder.py:124-133) runs on the GPU in front of the encoder instead of
+        on DataLoader workers.  Default (``dtype=None``): fused -- the transform writes bf16 patch rows straight into
+        the patch-embedding GEMM's operand, no normalised frame is ever stored.  ``dtype=torch.float32 / bfloat16``:
+        the two-step path through an NCHW intermediate of that precision (``fc_preprocess_frames``)."""
+        if dtype is None:
+            return self.model.encode_video_uint8_pooled(video, CLIP_MEAN, CLIP_STD)
         from . import ops
         frames = ops.preprocess_frames(video, self.model.visual.input_resolution, CLIP_MEAN, CLIP_STD, dtype)
         return self.model.encode_video_pooled(frames)

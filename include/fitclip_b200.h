@@ -120,6 +120,14 @@ FC_API int fc_model_check(fc_model* m, void* stream);
 FC_API int fc_preprocess_frames(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size,
                                 const float* mean, const float* std, void* out, int out_dtype, void* stream);
 
+/* The two steps above in one call, for raw decoded frames: uint8 (videos*frames_per_video, H, W, 3) -> eval transform
+ * (same arithmetic as fc_preprocess_frames) written STRAIGHT into the bf16 patch matrix of the patch-embedding GEMM
+ * (the normalised NCHW frame never exists in memory) -> fc_encode_video's path.  Replaces the CPU DataLoader transform
+ * of clip_video_text_encoder.py:124-133 + encode_video (:80-89); 4x fewer host->device bytes than fp32 frames. */
+FC_API int fc_encode_video_uint8(fc_model* m, const uint8_t* frames, int64_t videos, int32_t frames_per_video, int32_t H,
+                                 int32_t W, const float* mean, const float* std, float* out_video, float* out_frames,
+                                 void* stream);
+
 /* ---- pooling / WiSE ---------------------------------------------------------------------------------------------
  * out[b] = scale * mean_t( x[b*T+t] / ||x[b*T+t]||_2 ), fp32 (clip_video_text_encoder.py:85-89; T = 1 is the text
  * normalisation of :94).  out_bf16 may be NULL. */

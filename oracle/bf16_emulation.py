@@ -28,4 +28,6 @@ def bf16_stream_model(model: nn.Module) -> nn.Module:
             block.forward = forward
     m.visual.ln_pre.register_forward_pre_hook(lambda mod, args: (_rb(args[0]),))
     m.visual.ln_pre.register_forward_hook(lambda mod, args, out: _rb(out))
+    # the text stream starts at token + positional embedding (no ln_pre): stored in bf16 as well
+    m.transformer.register_forward_pre_hook(lambda mod, args: (_rb(args[0]),))
     return m

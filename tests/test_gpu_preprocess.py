@@ -49,6 +49,12 @@ def test_encode_video_uint8_equals_transform_then_encode(dev):
     a = enc.encode_video_uint8(raw, dtype=torch.float32)
     b = enc.encode_video(ops.preprocess_frames(raw, 224, MEAN, STD))
     assert torch.equal(a, b)
+    # fused path (row f1 as specified): the transform writes bf16 patch rows straight into the patch-embedding GEMM's
+    # operand -- bit-identical to transform -> bf16 NCHW frame -> im2col, for several frame sizes / patch sizes
+    fused = enc.encode_video_uint8(raw)
+    assert torch.equal(fused, enc.encode_video_uint8(raw, dtype=torch.bfloat16))
+    tall = torch.randint(0, 256, (2, 2, 360, 250, 3), dtype=torch.uint8, generator=g).to(dev)
+    assert torch.equal(enc.encode_video_uint8(tall), enc.encode_video_uint8(tall, dtype=torch.bfloat16))
     # and against the CPU path: hook on the CPU -> oracle encoder
     ref_enc = oracle.RefClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0, vision_layers=1, transformer_layers=1))
     frames = torch.stack([oracle.ref_eval_transform(v, 224, MEAN, STD) for v in raw.cpu()])
@@ -64,3 +70,16 @@ def test_preprocess_rejects_bad_input(dev):
         ops.preprocess_frames(torch.zeros(1, 8, 8, 3, device=dev), 224, MEAN, STD)  # not uint8
     with pytest.raises(_lib.FitclipError):
         ops.preprocess_frames(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), 224, MEAN, STD)  # CPU tensor
+
+
+def test_fused_uint8_path_other_patch_sizes(dev):
+    """ViT-B/32 (32-pixel patches) and ViT-L/14 (14-pixel patches, patch rows padded 588 -> 592 with zero columns)."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder
+    g = torch.Generator().manual_seed(6)
+    raw = torch.randint(0, 256, (2, 2, 256, 300, 3), dtype=torch.uint8, generator=g).to(dev)
+    for cfg in (dict(vision_patch_size=32, vision_layers=1, transformer_layers=1),
+                dict(embed_dim=768, vision_patch_size=14, vision_width=1024, vision_layers=1, transformer_width=768,
+                     transformer_heads=12, transformer_layers=1)):
+        enc = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=3, **cfg).state_dict(), num_frames=2).to(dev)
+        assert torch.equal(enc.encode_video_uint8(raw), enc.encode_video_uint8(raw, dtype=torch.bfloat16)), cfg

@@ -71,7 +71,11 @@ def step_baseline(out, steps, do_compile):
     model = oracle.clip_vit_b_16(seed=0)
     sd = model.state_dict()
     ours = B200ClipVideoTextEncoder(sd, num_frames=4).to(dev)
-    lib = oracle.RefClipVideoTextEncoder(model.to(dev).bfloat16())
+    model = model.to(dev).bfloat16()
+    for mod in model.modules():  # like clip.model.convert_weights: LayerNorms keep fp32 parameters (their forward casts)
+        if isinstance(mod, torch.nn.LayerNorm):
+            mod.float()
+    lib = oracle.RefClipVideoTextEncoder(model)
     gd = torch.Generator(device=dev).manual_seed(1234)
     frames = torch.randn(1000, 4, 3, 224, 224, device=dev, generator=gd)
     ids = oracle.tokenize_synthetic(1000, 77, seed=4321).to(dev)
@@ -110,7 +114,11 @@ def step_baseline(out, steps, do_compile):
         if do_compile:
             try:
                 t0 = time.time()
-                comp = oracle.RefClipVideoTextEncoder(torch.compile(lib.model))
+                import copy
+                cm = copy.deepcopy(lib.model)
+                cm.visual = torch.compile(cm.visual)          # the towers are what encode_image / encode_text call
+                cm.transformer = torch.compile(cm.transformer)
+                comp = oracle.RefClipVideoTextEncoder(cm)
                 ms_comp = timed(lambda: lib_step(comp), steps, warmup=2)
                 rec.update(torch_bf16_compile_ms=ms_comp, torch_bf16_compile_videos_per_s=1e6 / ms_comp,
                            speedup_vs_torch_compile=ms_comp / ms_ours, compile_seconds=time.time() - t0)
