@@ -82,13 +82,16 @@ def test_cuda_training_step_matches_reference_training_code(gold, dev):
     loss = module.training_step(_batch(gold, dev), 0, optimize=False)
     assert abs(float(loss) - float(gold["loss"])) <= 0.02 * abs(float(gold["loss"])), (float(loss), float(gold["loss"]))
     top = max(float(v.norm()) for v in gold["grads"].values())
-    checked = 0
+    checked, bad = 0, []
     for name, ref in gold["grads"].items():
         if float(ref.norm()) < 1e-3 * top:
             continue  # rounding-noise gradients (attention key biases)
         got = module.trainer.g[name].cpu()
         cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
         ratio = float(got.norm()) / float(ref.norm())
-        assert cos >= 0.98 and abs(ratio - 1) <= 0.06, f"{name}: cos {cos:.4f} norm ratio {ratio:.4f}"
+        print(f"grad {name}: cos {cos:.5f} norm ratio {ratio:.4f}")
+        if not (cos >= 0.98 and abs(ratio - 1) <= 0.06):
+            bad.append(f"{name}: cos {cos:.4f} norm ratio {ratio:.4f}")
         checked += 1
+    assert not bad, bad
     assert checked >= 40
