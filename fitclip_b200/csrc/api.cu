@@ -504,6 +504,13 @@ int fc_encode_video(fc_model* m, const void* frames, int dtype, int64_t videos, 
   return FC_OK;
 }
 
+int fc_preprocess_to_patches(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size, int32_t patch,
+                             const float* mean, const float* std, void* patches, int64_t ldp, void* stream) {
+  FC_REQUIRE(ldp > 0 && ldp < (int64_t(1) << 31), "fc_preprocess_to_patches: bad row stride");
+  return preprocess_to_patches(frames, n, H, W, size, patch, mean, std, static_cast<bf16*>(patches),
+                               static_cast<int>(ldp), static_cast<cudaStream_t>(stream));
+}
+
 int fc_encode_video_uint8(fc_model* m, const uint8_t* frames, int64_t videos, int32_t T, int32_t H, int32_t W,
                           const float* mean, const float* std, float* out_video, float* out_frames, void* stream) {
   FC_REQUIRE(m && ((out_video && frames) || videos == 0) && mean && std, "fc_encode_video_uint8: null argument");

@@ -25,6 +25,7 @@
 
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace fc {
 
@@ -50,16 +51,19 @@ constexpr int ATT_THREADS = 160;           // warps 0-3 softmax/epilogue, warp 4
 // ---- second-generation kernel (attention_tc2_kernel): softmax warpgroup + EPILOGUE warpgroup + TMA/MMA warp
 constexpr int ATT2_THREADS = 288;          // warps 0-3 softmax, warps 4-7 epilogue (same lane quadrants), warp 8 TMA + MMA
 #ifndef ATT2_POLY
-#define ATT2_POLY 4  // of every 16 column pairs of a x32 chunk, this many take exp2 on the FMA pipe (degree-3 polynomial,
+#define ATT2_POLY 0  // of every 16 column pairs of a x32 chunk, this many take exp2 on the FMA pipe (degree-3 polynomial,
                      // Cody-Waite split, packed fp32x2) instead of the MUFU: 0 = none, 4 = 25 %, 8 = 50 %
+#endif
+#ifndef ATT2_SPLIT_S
+#define ATT2_SPLIT_S 0  // 1: S = Q.K^T of the main keys in two column halves with separate commits (row max starts earlier)
 #endif
 #ifndef ATT2_REGS_SOFTMAX
 // setmaxnreg targets (multiples of 8).  Registers move inside a CTA's own launch allocation, so
 // 128 * SOFTMAX + 128 * EPILOGUE + 32 * (launch count, kept by the TMA/MMA warp) must not exceed 288 * (registers per
 // thread at launch) -- checked on the host
 // against cudaFuncGetAttributes before the first launch (an unsatisfiable setmaxnreg.inc would spin forever).
-#define ATT2_REGS_SOFTMAX 120
-#define ATT2_REGS_EPILOGUE 72
+#define ATT2_REGS_SOFTMAX 128
+#define ATT2_REGS_EPILOGUE 64
 #endif
 
 template <int KP>
@@ -532,6 +536,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* t_full = kq_full + 6;
   uint64_t* p_half = kq_full + 7;   // [2]
   uint64_t* l_full = kq_full + 10;  // row sums of item it are in l_buf[it & 1]
+  uint64_t* s_full_b = kq_full + 11;  // ATT2_SPLIT_S: the upper half of the main S columns (keys KMAIN/2 .. KMAIN)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 9);
   float* l_buf = reinterpret_cast<float*>(smem + S2::OFF_L);
 
@@ -555,6 +560,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(p_half, 128);
     mbar_init(p_half + 1, 128);
     mbar_init(l_full, 128);
+    mbar_init(s_full_b, 1);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -585,11 +591,27 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_load_3d(smem + S::OFF_V, &tmKV, v_full, 2 * D + c.head * HD, 0, c.seq);
       };
       auto issue_s_main = [&]() {
+        if (ATT2_SPLIT_S) {
+          // two column halves with their own commits: the row-max pass starts on keys [0, KMAIN/2) while the tensor
+          // core still works on the upper half
+          constexpr uint32_t idesc_h = umma_idesc_bf16_f32(QT, KMAIN / 2);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s,
-                       k != 0);
-        umma_commit(s_full);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_h,
+                         k != 0);
+          umma_commit(s_full);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16_ss(tmem_base + KMAIN / 2, umma_desc_k_sw128(q_addr + k * 32),
+                         umma_desc_k_sw128(k_addr + (KMAIN / 2) * 128 + k * 32), idesc_h, k != 0);
+          umma_commit(s_full_b);
+        } else {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s,
+                         k != 0);
+          umma_commit(s_full);
+        }
       };
       auto issue_s_tail = [&]() {
 #pragma unroll
@@ -674,8 +696,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (active) {
         const float inv = 1.f / l_buf[(it & 1) * 128 + q * 32 + lane];
         const uint64_t inv2 = pack_f32x2(inv, inv);
-        // two halves of 32 columns, each scaled and packed to bf16 as soon as it arrives (32 + 16 live registers)
-        uint32_t pk[2][16];
+        if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous store has finished reading its staging tile
+        __syncwarp();
+        // two halves of 32 columns, each scaled, packed to bf16 and staged as soon as it arrives (32 + 16 live registers)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t o[32];
@@ -685,20 +708,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tc_fence_before();
             mbar_arrive(o_empty);  // O(it) is in registers: the MMA thread may overwrite the tail columns
           }
+          uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float a, b;
             unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1])), inv2), a, b);
-            pk[h][e] = pack_bf16x2(a, b);
+            pk[e] = pack_bf16x2(a, b);
           }
-        }
-        if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous store has finished reading its staging tile
-        __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t(&pp)[16] = pk[c >> 2];
-          const int o = (c & 3) * 4;
-          st_shared_v4(stg_row + ((c ^ sw) << 4), make_uint4(pp[o], pp[o + 1], pp[o + 2], pp[o + 3]));
+          for (int c = 0; c < 4; ++c)
+            st_shared_v4(stg_row + (((4 * h + c) ^ sw) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -744,18 +763,17 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int j = 0; j < NFULL; ++j) {
           tmem_ld_wait_fence(r[j % DEPTH]);
           const uint32_t(&rc)[32] = r[j % DEPTH];
-          if ((j + 1) * 32 <= lim) {
+          if (ATT2_SPLIT_S && j == NFULL / 2 - DEPTH) {  // the loads issued from here on touch the upper half of S
+            mbar_wait(s_full_b, ph);
+            tc_fence_after();
+          }
+          // no masks in the main chunks: the dispatcher only sends sequences with KP - 16 < L <= KP here
 #pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
-              m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
-              m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
-              m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (j * 32 + c < lim) m = fmaxf(m, __uint_as_float(rc[c]));
+          for (int c = 0; c < 32; c += 8) {
+            m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
+            m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
+            m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
+            m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
           }
           if (j + DEPTH < NFULL) tmem_ld_32x32b_x32(trow + (j + DEPTH) * 32, r[j % DEPTH]);
         }
@@ -796,7 +814,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_ld_wait_fence(r[j & 1]);
           if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
           uint32_t pk[16];
-          const bool full = (j + 1) * 32 <= lim;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
@@ -810,10 +827,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               unpack_f32x2(x2, x0, x1);
               p0 = ex2_approx(x0);
               p1 = ex2_approx(x1);
-            }
-            if (!full) {
-              if (j * 32 + 2 * c >= lim) p0 = 0.f;
-              if (j * 32 + 2 * c + 1 >= lim) p1 = 0.f;
             }
             if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
             else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
@@ -857,385 +870,12 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Third-generation kernel for the un-masked 193..208-token image sequence: TWO THREADS PER QUERY ROW.
-// ncu on attention_tc2_kernel (profiles/r2_ncu_attention_tc2_*.csv): the softmax warps sit 34 % of their time waiting
-// for S(i+1), because S(i+1) can only be written over P(i) once P(i).V has run -- a fixed ~1200-cycle chain per item
-// that two CTAs per SM (all the 512 TMEM columns allow) cannot hide while each warp needs ~3600 cycles of softmax per
-// item; XU busy 38 %, issue 43 %.  The chain cannot be shortened, so the softmax is: warps q and q + 4 share TMEM lane
-// quadrant q and each takes HALF of the row's keys (warp q: keys 0..95, warp q + 4: keys 96..191 and the 16-key tail),
-// exchanging the half-row maximum and sum through shared memory (one 64-thread named barrier each), and each reads out,
-// scales and stages 32 of the 64 O columns.  Per item the softmax phase halves while the chain stays, and every
-// scheduler has four softmax warps to interleave (MUFU-bound stretches of one with the chain latency of another).
-// No masks in the main chunks: 192 < L guarantees the first 192 keys are valid; only the tail is masked.
-constexpr int ATT3_THREADS = 288;  // warps 0-7 softmax + epilogue (quadrant = warp % 4, key half = warp / 4), warp 8 TMA + MMA
-#ifndef ATT3_POLY
-#define ATT3_POLY 4
-#endif
-
-template <int KP>
-struct Att3Smem {
-  using B = AttSmem<KP>;
-  static constexpr int OFF_X = B::OFF_BAR + 128;      // float[2][128] half-row maxima, float[2][128] half-row sums
-  static constexpr int BYTES = OFF_X + 4 * 128 * 4;
-};
-
-template <int KP, int POLY>
-__global__ void __launch_bounds__(ATT3_THREADS, 2)
-attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                     const __grid_constant__ CUtensorMap tmO, int L, int heads, int tiles, int num_items,
-                     float scale_log2) {
-  using S = AttSmem<KP>;
-  using S3 = Att3Smem<KP>;
-  static_assert(KP == 208, "two-threads-per-row kernel: 6 chunks of 32 keys + a 16-key tail");
-  static_assert(!ATT_DIRECT_STORE, "the epilogue stores through the staging tile");
-  constexpr int KMAIN = KP - 16;  // 192
-  constexpr int O_COL = KMAIN;
-  constexpr uint32_t TMEM_COLS = 256;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* kq_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* v_full = kq_full + 1;
-  uint64_t* s_full = kq_full + 2;
-  uint64_t* p_full = kq_full + 3;
-  uint64_t* o_full = kq_full + 4;
-  uint64_t* o_empty = kq_full + 5;
-  uint64_t* t_full = kq_full + 6;
-  uint64_t* p_half = kq_full + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 9);
-  float* mx = reinterpret_cast<float*>(smem + S3::OFF_X);  // [2][128]
-  float* ls = mx + 256;                                    // [2][128]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = heads * HD;
-  const bool flip_ok = (gridDim.x & 1) == 0 && tiles == 2;
-
-  griddep_launch_dependents();
-  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 256) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmKV);
-    tma_prefetch_desc(&tmO);
-    mbar_init(kq_full, 1);
-    mbar_init(v_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 256);
-    mbar_init(t_full, 1);
-    mbar_init(p_half, 256);
-    fence_barrier_init();
-  }
-  if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  griddep_wait();
-
-  if (warp == 8) {
-    // ===================== TMA + MMA thread =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(QT, KMAIN);
-      constexpr uint32_t idesc_t = umma_idesc_bf16_f32(QT, 16);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16_f32_bmn(QT, HD);
-      const uint32_t q_addr = smem_u32(smem + S::OFF_Q);
-      const uint32_t k_addr = smem_u32(smem + S::OFF_K);
-      const uint32_t v_addr = smem_u32(smem + S::OFF_V);
-      auto load_qk = [&](const ItemCursor& c, int n) {
-        const int tile = flip_ok ? (c.t ^ (n & 1)) : c.t;
-        mbar_expect_tx(kq_full, Q_BYTES + S::KV_BYTES);
-        tma_load_3d(smem + S::OFF_Q, &tmQ, kq_full, c.head * HD, tile * QT, c.seq);
-        tma_load_3d(smem + S::OFF_K, &tmKV, kq_full, D + c.head * HD, 0, c.seq);
-      };
-      auto load_v = [&](const ItemCursor& c) {
-        mbar_expect_tx(v_full, S::KV_BYTES);
-        tma_load_3d(smem + S::OFF_V, &tmKV, v_full, 2 * D + c.head * HD, 0, c.seq);
-      };
-      auto issue_s_main = [&]() {
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s,
-                       k != 0);
-        umma_commit(s_full);
-      };
-      auto issue_s_tail = [&]() {
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base + KMAIN, umma_desc_k_sw128(q_addr + k * 32),
-                       umma_desc_k_sw128(k_addr + KMAIN * 128 + k * 32), idesc_t, k != 0);
-        umma_commit(t_full);
-      };
-      // O += P[:, 16 k .. 16 k + 16) . V[16 k .. 16 k + 16, :]
-      auto pv = [&](int k, bool acc) {
-        umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, acc);
-      };
-      ItemCursor cv, cqk;
-      cv.init(blockIdx.x, gridDim.x, tiles, heads);
-      cqk = cv;
-      if (static_cast<int>(blockIdx.x) < num_items) {
-        load_qk(cqk, 0);
-        load_v(cv);
-        cqk.advance();
-        cv.advance();
-        mbar_wait(kq_full, 0);
-        tc_fence_after();
-        issue_s_main();
-        issue_s_tail();
-        mbar_wait(t_full, 0);
-        if (static_cast<int>(blockIdx.x + gridDim.x) < num_items) load_qk(cqk, 1);
-        cqk.advance();
-      }
-      int it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const uint32_t ph = it & 1;
-        const int next = item + gridDim.x, next2 = next + gridDim.x;
-        const bool has_next = next < num_items;
-        mbar_wait(v_full, ph);
-        mbar_wait(p_half, ph);  // both halves have written the P of their first two chunks: keys 0..63 and 96..159
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pv(k, k != 0);
-#pragma unroll
-        for (int k = 6; k < 10; ++k) pv(k, true);
-        mbar_wait(p_full, ph);  // all of P is in TMEM: keys 64..95, 160..191 and the tail
-        tc_fence_after();
-        pv(4, true);
-        pv(5, true);
-        pv(10, true);
-        pv(11, true);
-        pv(12, true);
-        umma_commit(o_full);
-        if (has_next) {
-          mbar_wait(kq_full, ph ^ 1);
-          tc_fence_after();
-          issue_s_main();
-        }
-        mbar_wait(o_full, ph);  // V tile is free again
-        if (has_next) {
-          load_v(cv);
-          cv.advance();
-          mbar_wait(o_empty, ph);
-          tc_fence_after();
-          issue_s_tail();
-          mbar_wait(t_full, ph ^ 1);
-          if (next2 < num_items) load_qk(cqk, it + 2);
-          cqk.advance();
-        }
-      }
-    }
-  } else {
-    // ===================== softmax + epilogue warps: row = quadrant * 32 + lane, key half = warp / 4 =====================
-    const int q = warp & 3, h = warp >> 2;
-    const int rowq = q * 32 + lane;  // row within the 128-row tile
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t bar_id = 1 + q;   // named barrier of the warp pair (q, q + 4)
-    uint8_t* stg_ptr = smem + S::OFF_STG + q * (32 * 128);
-    const uint32_t stg_row = smem_u32(stg_ptr) + lane * 128;
-    const int sw = lane & 7;
-    const int c0 = 3 * h;  // first x32 chunk of this thread's key half
-    ItemCursor cur;
-    cur.init(blockIdx.x, gridDim.x, tiles, heads);
-    int it = 0;
-    FC_T(long long tq[7] = {0, 0, 0, 0, 0, 0, 0}; long long n_it = 0; const long long t_begin = clock64();)
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it, cur.advance()) {
-      const uint32_t ph = it & 1;
-      const int tile = flip_ok ? (cur.t ^ (it & 1)) : cur.t;
-      const int row0 = tile * QT + q * 32;
-      const bool active = row0 < L;  // uniform over the warp pair
-      FC_T(long long t0 = clock64(); long long t1;)
-      mbar_wait(s_full, ph);
-      FC_T(t1 = clock64(); tq[1] += t1 - t0; t0 = t1; ++n_it;)
-      tc_fence_after();
-      float l = 0.f;
-      if (active) {
-        // ---- pass 1: maximum over this thread's 96 keys (all keys < 192 are valid: no masks), in x16 pieces with two
-        // loads in flight (the 96-register budget of 2 CTAs x 9 warps rules out x32 double buffering: ptxas then sinks the
-        // prefetch behind the compute and every chunk pays the full TMEM latency)
-        float m = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        {
-          uint32_t r[2][16];
-          tmem_ld_32x32b_x16(trow + c0 * 32, r[0]);
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            tmem_ld_wait_fence16(r[j & 1]);  // (tcgen05.wait::ld waits for every outstanding load, so the prefetch follows it)
-            if (j + 1 < 6) tmem_ld_32x32b_x16(trow + c0 * 32 + (j + 1) * 16, r[(j + 1) & 1]);
-            const uint32_t(&rc)[16] = r[j & 1];
-#pragma unroll
-            for (int c = 0; c < 16; c += 8) {
-              m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
-              m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
-              m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
-              m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
-            }
-          }
-        }
-        m = fmaxf(max3(m, m1, m2), m3);
-        FC_T(t1 = clock64(); tq[2] += t1 - t0; t0 = t1;)
-        uint32_t r16[16];
-        if (h == 1) {  // the upper half also owns the 16-key tail (keys 192..207, valid below L)
-          mbar_wait(t_full, ph);
-          tc_fence_after();
-          tmem_ld_32x32b_x16(trow + KMAIN, r16);
-          tmem_ld_wait_fence16(r16);
-#pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (KMAIN + c < L) m = fmaxf(m, __uint_as_float(r16[c]));
-        }
-        FC_T(t1 = clock64(); tq[3] += t1 - t0; t0 = t1;)
-        mx[h * 128 + rowq] = m;
-        named_bar_sync(bar_id, 64);
-        m = fmaxf(m, mx[(h ^ 1) * 128 + rowq]);
-        // ---- pass 2: P = exp2((s - m) * scale * log2e) for this thread's keys, bf16, written over the dead S columns
-        uint32_t r[2][16];
-        tmem_ld_32x32b_x16(trow + c0 * 32, r[0]);
-        const float mc = m * scale_log2;
-        const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nmc2 = pack_f32x2(-mc, -mc);
-        uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
-        uint32_t pk_tail[8];
-        if (h == 1) {  // tail first (it waits in registers: the early P.V writes O over the tail's S columns)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float x0, x1;
-            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r16[2 * c]), __uint_as_float(r16[2 * c + 1])), sc2, nmc2),
-                         x0, x1);
-            const float p0 = KMAIN + 2 * c < L ? ex2_approx(x0) : 0.f;
-            const float p1 = KMAIN + 2 * c + 1 < L ? ex2_approx(x1) : 0.f;
-            l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
-            pk_tail[c] = pack_bf16x2(p0, p1);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {  // six x16 pieces of this thread's 96 keys, the next one in flight
-          tmem_ld_wait_fence16(r[j & 1]);
-          if (j + 1 < 6) tmem_ld_32x32b_x16(trow + c0 * 32 + (j + 1) * 16, r[(j + 1) & 1]);  // in flight during the math below
-          uint32_t pk[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
-                                          sc2, nmc2);
-            float p0, p1;
-            if (POLY > 0 && (c * POLY) % 16 < POLY) {  // POLY of every 16 pairs take the FMA-pipe exp2, spread evenly
-              ex2_poly_x2(x2, p0, p1);
-            } else {
-              float x0, x1;
-              unpack_f32x2(x2, x0, x1);
-              p0 = ex2_approx(x0);
-              p1 = ex2_approx(x1);
-            }
-            if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
-            else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
-            pk[c] = pack_bf16x2(p0, p1);
-          }
-          tmem_st_32x32b_x8(trow + c0 * 16 + j * 8, pk);
-          if (j == 3) {  // keys [0, 64) / [96, 160) of P are complete: the tensor core may start on them
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(p_half);
-          }
-        }
-        if (h == 1) tmem_st_32x32b_x8(trow + 6 * 16, pk_tail);
-        tmem_st_wait();
-        float la, lb;
-        unpack_f32x2(add_f32x2(l2a, l2b), la, lb);
-        l = la + lb;
-        ls[h * 128 + rowq] = l;  // read by the partner after the pair barrier in the epilogue
-      } else {
-        mbar_arrive(p_half);
-      }
-      tc_fence_before();
-      mbar_arrive(p_full);
-      FC_T(t1 = clock64(); tq[4] += t1 - t0; t0 = t1;)
-
-      // ---- epilogue: this thread's 32 of the row's 64 O columns
-      mbar_wait(o_full, ph);
-      FC_T(t1 = clock64(); tq[5] += t1 - t0; t0 = t1;)
-      tc_fence_after();
-      if (active) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(trow + O_COL + 32 * h, o);
-        tmem_ld_wait_fence(o);
-        tc_fence_before();
-        mbar_arrive(o_empty);
-        if (h == 0 && lane == 0) bulk_wait_group_read<0>();  // the pair's previous store has finished reading its staging tile
-        named_bar_sync(bar_id, 64);  // partner's row sum is visible; the staging tile is free
-        const float inv = 1.f / (l + ls[(h ^ 1) * 128 + rowq]);
-        const uint64_t inv2 = pack_f32x2(inv, inv);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[8 * c + 2 * e]), __uint_as_float(o[8 * c + 2 * e + 1])), inv2),
-                         v[2 * e], v[2 * e + 1]);
-          st_shared_v4(stg_row + (((4 * h + c) ^ sw) << 4),
-                       make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                  pack_bf16x2(v[6], v[7])));
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 64);  // both halves of the 32 x 64 tile are staged
-        if (h == 0 && lane == 0) {
-          tma_store_3d(&tmO, stg_ptr, cur.head * HD, row0, cur.seq);  // rows >= L are clipped by the tensor map
-          bulk_commit_group();
-        }
-      } else {
-        tc_fence_before();
-        mbar_arrive(o_empty);
-      }
-      FC_T(t1 = clock64(); tq[6] += t1 - t0;)
-    }
-    FC_T(if (threadIdx.x == 0) {
-      atomicAdd(&g_att_timing[0], static_cast<unsigned long long>(clock64() - t_begin));
-      for (int i = 1; i < 7; ++i) atomicAdd(&g_att_timing[i], static_cast<unsigned long long>(tq[i]));
-      atomicAdd(&g_att_timing[7], static_cast<unsigned long long>(n_it));
-    })
-    if (h == 0 && lane == 0) bulk_wait_group<0>();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) {
-    tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
-  }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 // bf16 tensor viewed as [seqs][L][cols] (cols contiguous); box = 64 columns x box_rows tokens x 1 sequence, SW128.
 int make_tmap_3d(CUtensorMap* tm, const bf16* base, int64_t cols, int64_t L, int64_t seqs, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return FC_ERR_CUDA;
-  }
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(seqs)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(cols) * 2 * L};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(3d) failed (CUresult %d) cols=%lld L=%lld seqs=%lld", static_cast<int>(r),
-              static_cast<long long>(cols), static_cast<long long>(L), static_cast<long long>(seqs));
-    return FC_ERR_CUDA;
-  }
-  return FC_OK;
+  const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(L), static_cast<uint64_t>(seqs)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(cols) * 2, static_cast<uint64_t>(cols) * 2 * L};
+  const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
+  return tmap_bf16_sw128(tm, base, 3, dims, strides, box);
 }
 
 template <int KP, bool CAUSAL, int NPH>
@@ -1318,43 +958,6 @@ int launch_tc2(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaS
   return FC_OK;
 }
 
-template <int KP>
-int launch_tc3(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaStream_t s) {
-  using S3 = Att3Smem<KP>;
-  static bool configured = false;
-  if (!configured) {
-    FC_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<KP, ATT3_POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3::BYTES));
-    configured = true;
-  }
-  const int D = heads * HD;
-  CUtensorMap tq, tkv, to;
-  int rc;
-  if ((rc = make_tmap_3d(&tq, qkv, 3 * D, L, seqs, QT))) return rc;
-  if ((rc = make_tmap_3d(&tkv, qkv, 3 * D, L, seqs, KP))) return rc;
-  if ((rc = make_tmap_3d(&to, out, D, L, seqs, 32))) return rc;
-  const int tiles = (L + QT - 1) / QT;
-  const int64_t items64 = seqs * heads * tiles;
-  FC_REQUIRE(items64 < (int64_t(1) << 31), "attention: too many work items");
-  const int items = static_cast<int>(items64);
-  int grid = 2 * num_sms();
-  if (grid > items) grid = items;
-  if (tiles == 2 && (grid & 1)) grid -= 1;
-  const float scale_log2 = 0.125f * 1.4426950408889634f;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(ATT3_THREADS);
-  cfg.dynamicSmemBytes = S3::BYTES;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  note_launch();
-  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc3_kernel<KP, ATT3_POLY>, tq, tkv, to, L, heads, tiles, items, scale_log2));
-  return FC_OK;
-}
-
 }  // namespace
 
 #ifdef FC_GEMM_TIMING
@@ -1374,23 +977,21 @@ extern "C" __attribute__((visibility("default"))) int fc_debug_att_timing(unsign
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                       int* handled) {
   *handled = 0;
-  static int disabled = -1, gen1 = 0, gen2 = 0;
+  static int disabled = -1, gen1 = 0;
   if (disabled < 0) {
-    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=tc1 / tc2 the earlier tcgen05 kernels
+    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=tc1 the first-generation tcgen05 kernel
     const char* e = getenv("FC_ATTENTION");
     gen1 = (e && strcmp(e, "tc1") == 0) ? 1 : 0;
-    gen2 = (e && strcmp(e, "tc2") == 0) ? 1 : 0;
     disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
   }
   if (disabled) return FC_OK;
-  const bool image = !causal && L > 192 && L <= 208;
+  const bool image = !causal && L > 192 && L <= 208;  // (attention_tc2_kernel relies on L > KP - 16: unmasked main chunks)
   const bool text = causal && L > 64 && L <= 80;
   if (!image && !text) return FC_OK;
   FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "attention: buffers must be 16-byte aligned");
   *handled = 1;
-  if (image && !gen1 && !gen2) return launch_tc3<208>(qkv, out, seqs, L, heads, s);
-  if (image && gen2) return launch_tc2<208, ATT_PHALF>(qkv, out, seqs, L, heads, s);
+  if (image && !gen1) return launch_tc2<208, ATT_PHALF>(qkv, out, seqs, L, heads, s);
   if (image) return launch_tc<208, false, ATT_PHALF>(qkv, out, seqs, L, heads, s);
   return launch_tc<80, true, 0>(qkv, out, seqs, L, heads, s);
 }

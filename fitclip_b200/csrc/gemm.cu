@@ -36,6 +36,7 @@
 
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace fc {
 
@@ -656,66 +657,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-// ---- host side: tensor maps + launch ----
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
+// ---- host side: tensor maps (memoised per (pointer, shape): tmap.cuh) + launch ----
 // rows x cols bf16 matrix, cols contiguous, row stride ld elements; box = box_rows x 64 elements, 128B swizzle.
 int make_tmap(CUtensorMap* tm, const bf16* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return FC_ERR_CUDA;
-  }
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(bf16)};
-  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld ld=%lld", static_cast<int>(r),
-              static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld));
-    return FC_ERR_CUDA;
-  }
-  return FC_OK;
+  const uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(ld) * sizeof(bf16)};
+  const uint32_t box[2] = {BK, static_cast<uint32_t>(box_rows)};
+  return tmap_bf16_sw128(tm, base, 2, dims, strides, box);
 }
 
 // MN-major operand: stored [k_rows][mn_cols] with mn contiguous; box = 64 (MN) x 64 (K rows), 128B swizzle.
 int make_tmap_mn(CUtensorMap* tm, const bf16* base, int64_t k_rows, int64_t mn_cols, int64_t ld) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return FC_ERR_CUDA;
-  }
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(mn_cols), static_cast<cuuint64_t>(k_rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(bf16)};
-  cuuint32_t box[2] = {64, BK};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled (MN-major) failed (CUresult %d) k=%lld mn=%lld ld=%lld", static_cast<int>(r),
-              static_cast<long long>(k_rows), static_cast<long long>(mn_cols), static_cast<long long>(ld));
-    return FC_ERR_CUDA;
-  }
-  return FC_OK;
+  const uint64_t dims[2] = {static_cast<uint64_t>(mn_cols), static_cast<uint64_t>(k_rows)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(ld) * sizeof(bf16)};
+  const uint32_t box[2] = {64, BK};
+  return tmap_bf16_sw128(tm, base, 2, dims, strides, box);
 }
 
 template <int EPI, int MAJ = 0>

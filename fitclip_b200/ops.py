@@ -77,6 +77,25 @@ def preprocess_frames(frames: torch.Tensor, size: int, mean, std, dtype: torch.d
     return out.reshape(*lead, 3, size, size)
 
 
+def preprocess_to_patches(frames: torch.Tensor, size: int, patch: int, mean, std) -> torch.Tensor:
+    """uint8 ``(n, H, W, 3)`` frames -> the bf16 patch matrix ``(n * (size/patch)**2, 3 * patch * patch)`` of the ViT patch
+    embedding (column order ``(c, ky, kx)`` = ``conv1.weight.reshape(width, -1)``): the eval transform of
+    :func:`preprocess_frames` fused with the patch gather."""
+    import ctypes as C
+    dev = _dev(frames)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+        raise ValueError(f"expected uint8 frames of shape (n, H, W, 3), got {frames.dtype} {tuple(frames.shape)}")
+    n, H, W = frames.shape[:3]
+    g = size // patch
+    out = torch.empty(n * g * g, 3 * patch * patch, device=dev, dtype=torch.bfloat16)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    with torch.cuda.device(dev):
+        check(_lib.load().fc_preprocess_to_patches(ptr(frames.contiguous()), n, H, W, size, patch, m3, s3, ptr(out),
+                                                   out.stride(0), stream_ptr(dev)))
+    return out
+
+
 def pool_normalize(x: torch.Tensor, frames_per_row: int, scale: float = 1.0) -> torch.Tensor:
     """``x (B*T, D)`` fp32 -> ``(B, D)``: L2-normalise every row, mean over each group of T rows
     (``aligner/encoder/clip_video_text_encoder.py:85-89``)."""

@@ -120,6 +120,12 @@ FC_API int fc_model_check(fc_model* m, void* stream);
 FC_API int fc_preprocess_frames(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size,
                                 const float* mean, const float* std, void* out, int out_dtype, void* stream);
 
+/* Same transform, written as the bf16 patch matrix of the ViT patch embedding instead of an NCHW image: pixel (c, y, x)
+ * of frame f -> row f*G*G + (y/patch)*G + x/patch, column c*patch*patch + (y%patch)*patch + x%patch, G = size/patch,
+ * row stride ldp elements (>= 3*patch*patch; pad columns are NOT written) -- conv1.weight.reshape(width, -1)'s column
+ * order, i.e. the A operand of the patch-embedding GEMM (VisionTransformer.forward's conv1 as a GEMM). */
+FC_API int fc_preprocess_to_patches(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size, int32_t patch,
+                                    const float* mean, const float* std, void* patches, int64_t ldp, void* stream);
 /* The two steps above in one call, for raw decoded frames: uint8 (videos*frames_per_video, H, W, 3) -> eval transform
  * (same arithmetic as fc_preprocess_frames) written STRAIGHT into the bf16 patch matrix of the patch-embedding GEMM
  * (the normalised NCHW frame never exists in memory) -> fc_encode_video's path.  Replaces the CPU DataLoader transform

@@ -72,6 +72,22 @@ def test_preprocess_rejects_bad_input(dev):
         ops.preprocess_frames(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), 224, MEAN, STD)  # CPU tensor
 
 
+@pytest.mark.parametrize("patch", [16, 32, 14])
+def test_preprocess_to_patches_equals_unfold_of_the_frames(dev, patch):
+    """The fused transform + patch gather against torch's unfold of the two-step result (bit-exact: same arithmetic,
+    another store address)."""
+    from fitclip_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    raw = torch.randint(0, 256, (5, 240, 320, 3), dtype=torch.uint8, generator=g).to(dev)
+    frames = ops.preprocess_frames(raw, 224, MEAN, STD, torch.bfloat16)              # (5, 3, 224, 224)
+    expect = torch.nn.functional.unfold(frames.float(), kernel_size=patch, stride=patch)  # (5, 3*P*P, G*G)
+    expect = expect.transpose(1, 2).reshape(-1, 3 * patch * patch).bfloat16()
+    got = ops.preprocess_to_patches(raw, 224, patch, MEAN, STD)
+    assert got.shape == expect.shape
+    bad = (got != expect).nonzero()
+    assert bad.numel() == 0, (bad[:8].tolist(), got[bad[0, 0], bad[0, 1]].item(), expect[bad[0, 0], bad[0, 1]].item())
+
+
 def test_fused_uint8_path_other_patch_sizes(dev):
     """ViT-B/32 (32-pixel patches) and ViT-L/14 (14-pixel patches, patch rows padded 588 -> 592 with zero columns)."""
     import oracle

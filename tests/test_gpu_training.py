@@ -65,7 +65,7 @@ def test_training_step_matches_autograd(dev, names):
         got = tr.g[name].cpu()
         cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
         ratio = float(got.norm()) / rn
-        assert cos >= 0.98 and abs(ratio - 1) <= 0.06, f"{name}: cos {cos:.4f} norm ratio {ratio:.4f}"
+        assert cos >= 0.995 and abs(ratio - 1) <= 0.08, f"{name}: cos {cos:.4f} norm ratio {ratio:.4f}"
         checked += 1
     assert checked >= 40
     # optimizer on identical gradients (Adam amplifies rounding noise of near-zero gradients into +-lr steps)
@@ -110,7 +110,7 @@ def test_other_geometry_and_recomputed_layernorm(dev):
             continue
         got = module.trainer.g[name].cpu()
         cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
-        assert cos >= 0.98 and abs(float(got.norm()) / float(ref.norm()) - 1) <= 0.06, f"{name}: cos {cos:.4f}"
+        assert cos >= 0.995 and abs(float(got.norm()) / float(ref.norm()) - 1) <= 0.08, f"{name}: cos {cos:.4f}"
         checked += 1
     assert checked >= 20
 

