@@ -305,7 +305,9 @@ int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, i
                  static_cast<double>(seqs) * L * heads * HD * 2.0 * 4.0);
   {
     int handled = 0;
-    const int rc = attention_bf16_tc(qkv, out, seqs, L, heads, causal, s, &handled);
+    int rc = attention_bf16_tc(qkv, out, seqs, L, heads, causal, s, &handled);
+    if (rc || handled) return rc;
+    rc = attention_bf16_tc_long(qkv, out, seqs, L, heads, causal, s, &handled);
     if (rc || handled) return rc;
   }
   if (L > 208) return launch_long(qkv, out, seqs, L, heads, causal, s);  // ViT-L/14: 257, ViT-L/14@336: 577

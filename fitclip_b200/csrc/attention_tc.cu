@@ -736,7 +736,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     setmaxnreg_inc<ATT2_REGS_SOFTMAX>();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     constexpr int NFULL = KP / 32;
-    static_assert(NPH == 0 || (KHALF % 32 == 0 && NPH * (KHALF / 32) < NFULL), "early hand-overs must end on chunk boundaries");
+    static_assert(NFULL % 2 == 0 && (NPH == 0 || (KHALF == 64 && 2 * NPH < NFULL)),
+                  "chunk pairs: an even number of x32 chunks, early hand-overs every 64 keys");
     ItemCursor cur;
     cur.init(blockIdx.x, gridDim.x, tiles, heads);
     int it = 0;
@@ -754,28 +755,34 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float l = 1.f;
       float m = -INFINITY;
       if (active) {
+        // Rolled over chunk PAIRS (#pragma unroll 1): register use is fixed at two x32 buffers and the code stays small --
+        // fully unrolled, ptxas hoists loads across chunks until it spills (measured: 73.4 vs 70.3 us).  No masks in the
+        // main chunks: the dispatcher only sends sequences with KP - 16 < L <= KP here.
         float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        constexpr int DEPTH = 2;
-        uint32_t r[DEPTH][32];
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(trow, r[0]);
+        tmem_ld_32x32b_x32(trow + 32, r[1]);
+#pragma unroll 1
+        for (int jj = 0; jj < NFULL; jj += 2) {
 #pragma unroll
-        for (int j = 0; j < DEPTH && j < NFULL; ++j) tmem_ld_32x32b_x32(trow + j * 32, r[j]);
+          for (int u = 0; u < 2; ++u) {
+            tmem_ld_wait_fence(r[u]);
+            const uint32_t(&rc)[32] = r[u];
 #pragma unroll
-        for (int j = 0; j < NFULL; ++j) {
-          tmem_ld_wait_fence(r[j % DEPTH]);
-          const uint32_t(&rc)[32] = r[j % DEPTH];
-          if (ATT2_SPLIT_S && j == NFULL / 2 - DEPTH) {  // the loads issued from here on touch the upper half of S
-            mbar_wait(s_full_b, ph);
-            tc_fence_after();
+            for (int c = 0; c < 32; c += 8) {
+              m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
+              m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
+              m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
+              m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
+            }
+            if (jj + 2 + u < NFULL) {
+              if (ATT2_SPLIT_S && jj == 0 && u == 1) {  // chunk 3 is the first one of the upper half of S
+                mbar_wait(s_full_b, ph);
+                tc_fence_after();
+              }
+              tmem_ld_32x32b_x32(trow + (jj + 2 + u) * 32, r[u]);
+            }
           }
-          // no masks in the main chunks: the dispatcher only sends sequences with KP - 16 < L <= KP here
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
-            m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
-            m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
-            m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
-          }
-          if (j + DEPTH < NFULL) tmem_ld_32x32b_x32(trow + (j + DEPTH) * 32, r[j % DEPTH]);
         }
         m = fmaxf(max3(m, m1, m2), m3);
       }
@@ -809,34 +816,37 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
           pk_tail[c] = pack_bf16x2(p0, p1);
         }
+#pragma unroll 1
+        for (int jj = 0; jj < NFULL; jj += 2) {  // chunk pairs = 64 keys = one early hand-over of P
 #pragma unroll
-        for (int j = 0; j < NFULL; ++j) {
-          tmem_ld_wait_fence(r[j & 1]);
-          if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
-          uint32_t pk[16];
+          for (int u = 0; u < 2; ++u) {
+            tmem_ld_wait_fence(r[u]);
+            if (jj + u + 1 < NFULL) tmem_ld_32x32b_x32(trow + (jj + u + 1) * 32, r[u ^ 1]);
+            uint32_t pk[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
-                                          sc2, nmc2);
-            float p0, p1;
-            // ATT2_POLY of every 16 pairs take the FMA-pipe exp2, spread evenly so both pipes stay fed
-            if (ATT2_POLY > 0 && (c * ATT2_POLY) % 16 < ATT2_POLY) {
-              ex2_poly_x2(x2, p0, p1);
-            } else {
-              float x0, x1;
-              unpack_f32x2(x2, x0, x1);
-              p0 = ex2_approx(x0);
-              p1 = ex2_approx(x1);
+            for (int c = 0; c < 16; ++c) {
+              const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[u][2 * c]), __uint_as_float(r[u][2 * c + 1])), sc2,
+                                            nmc2);
+              float p0, p1;
+              // ATT2_POLY of every 16 pairs take the FMA-pipe exp2, spread evenly so both pipes stay fed
+              if (ATT2_POLY > 0 && (c * ATT2_POLY) % 16 < ATT2_POLY) {
+                ex2_poly_x2(x2, p0, p1);
+              } else {
+                float x0, x1;
+                unpack_f32x2(x2, x0, x1);
+                p0 = ex2_approx(x0);
+                p1 = ex2_approx(x1);
+              }
+              if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+              else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
+              pk[c] = pack_bf16x2(p0, p1);
             }
-            if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
-            else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
-            pk[c] = pack_bf16x2(p0, p1);
+            tmem_st_32x32b_x16(trow + (jj + u) * 16, pk);
           }
-          tmem_st_32x32b_x16(trow + j * 16, pk);
-          if (NPH > 0 && (j + 1) % (KHALF / 32) == 0 && (j + 1) / (KHALF / 32) <= NPH) {
-            tmem_st_wait();
+          if (NPH > 0 && jj / 2 < NPH) {
+            tmem_st_wait();  // 64 more keys of P are complete: let the tensor core start on them
             tc_fence_before();
-            mbar_arrive(p_half + (j + 1) / (KHALF / 32) - 1);
+            mbar_arrive(p_half + jj / 2);
           }
         }
         tmem_st_32x32b_x8(trow + NFULL * 16, pk_tail);
@@ -972,8 +982,8 @@ extern "C" __attribute__((visibility("default"))) int fc_debug_att_timing(unsign
 }
 #endif
 
-// tcgen05 path: un-masked sequences of 193..208 tokens (the ViT-B/16 image sequence, 197) and causal sequences of
-// 65..80 tokens (the CLIP text sequence, 77). *handled = 1 when it took the call.
+// tcgen05 path for every sequence of up to 208 tokens, masked or not (ViT-B/16 image 197, ViT-B/32 image 50, CLIP text 77
+// causal, ...). *handled = 1 when it took the call.
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                       int* handled) {
   *handled = 0;
@@ -985,14 +995,20 @@ int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads
     disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
   }
   if (disabled) return FC_OK;
-  const bool image = !causal && L > 192 && L <= 208;  // (attention_tc2_kernel relies on L > KP - 16: unmasked main chunks)
-  const bool text = causal && L > 64 && L <= 80;
-  if (!image && !text) return FC_OK;
+  if (L > 208) return FC_OK;  // longer un-masked sequences: attention_tc_long.cu; longer causal ones: mma.sync kernels
   FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "attention: buffers must be 16-byte aligned");
   *handled = 1;
-  if (image && !gen1) return launch_tc2<208, ATT_PHALF>(qkv, out, seqs, L, heads, s);
-  if (image) return launch_tc<208, false, ATT_PHALF>(qkv, out, seqs, L, heads, s);
+  // padded key counts: 80 (CLIP text 77 causal; ViT-B/32 image 50), 144, 208 (ViT-B/16 image 197).  The kernels mask
+  // keys >= L generically; attention_tc2_kernel relies on L > KP - 16 (un-masked main chunks).
+  if (!causal) {
+    if (L > 192 && !gen1) return launch_tc2<208, ATT_PHALF>(qkv, out, seqs, L, heads, s);
+    if (L > 144) return launch_tc<208, false, ATT_PHALF>(qkv, out, seqs, L, heads, s);
+    if (L > 80) return launch_tc<144, false, 0>(qkv, out, seqs, L, heads, s);
+    return launch_tc<80, false, 0>(qkv, out, seqs, L, heads, s);
+  }
+  if (L > 144) return launch_tc<208, true, 0>(qkv, out, seqs, L, heads, s);
+  if (L > 80) return launch_tc<144, true, 0>(qkv, out, seqs, L, heads, s);
   return launch_tc<80, true, 0>(qkv, out, seqs, L, heads, s);
 }
 

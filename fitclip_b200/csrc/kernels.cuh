@@ -39,6 +39,9 @@ int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, i
 // attention_tc.cu : tcgen05 path for the un-masked 193..208-token case; *handled = 1 when it took the call
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                       int* handled);
+// tcgen05 kernel for un-masked sequences of 209..768 tokens (key-block loop, online softmax): attention_tc_long.cu
+int attention_bf16_tc_long(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
+                           int* handled);
 
 // attention_bwd_tc.cu : tcgen05 attention backward for L <= 208; *handled = 1 when it took the call
 int attention_bwd_bf16_tc(const bf16* qkv, const bf16* O, const bf16* dO, bf16* dqkv, int64_t seqs, int L, int heads,

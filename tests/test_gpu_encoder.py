@@ -266,3 +266,28 @@ def test_parameters_created_under_inference_mode(dev):
         out = merged.encode_video(video)
         assert out.shape == (2, 512) and torch.isfinite(out).all()
         assert not torch.equal(out, a.encode_video(video))
+
+
+def test_vit_l_14_full_depth(dev):
+    """Row f4 at full depth: ViT-L/14 (config/encoder/clip_vit_l_14.yaml: 24 x 1024-wide vision blocks, 257 image tokens
+    on the tcgen05 key-block attention kernel, 588-wide patch rows padded to 592; 12 x 768-wide text blocks), trained-like
+    weights, against the fp32 oracle and the bf16-stream emulation."""
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder
+    cfg = dict(embed_dim=768, vision_patch_size=14, vision_width=1024, vision_layers=24, transformer_width=768,
+               transformer_heads=12)
+    model = oracle.clip_vit_b_16(seed=4, **cfg)
+    ref = oracle.RefClipVideoTextEncoder(copy.deepcopy(model), num_frames=2)
+    emu = oracle.RefClipVideoTextEncoder(oracle.bf16_stream_model(model), num_frames=2)
+    enc = B200ClipVideoTextEncoder(model.state_dict(), num_frames=2).to(dev)
+    video = torch.randn(3, 2, 3, 224, 224, generator=torch.Generator().manual_seed(41))
+    ids = oracle.tokenize_synthetic(6, (4, 77), seed=42)
+    with torch.inference_mode():
+        ev, et = ref(video, {"input_ids": ids})
+        mv, mt = emu(video, {"input_ids": ids})
+        gv, gt = enc(video.to(dev), {"input_ids": ids.to(dev)})
+    cv, ct = _report("ViT-L/14 video", gv.cpu(), ev), _report("ViT-L/14 text", gt.cpu(), et)
+    bv, bt = _report("ViT-L/14 video, bf16-stream emulation", mv, ev), _report("ViT-L/14 text, bf16-stream emulation", mt, et)
+    assert cv[0] >= 0.9995 and ct[0] >= 0.9995
+    assert cv[1] <= 5e-3 and ct[1] <= 5e-3
+    assert cv[1] <= 3 * bv[1] + 1e-3 and ct[1] <= 3 * bt[1] + 1e-3

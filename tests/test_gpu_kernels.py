@@ -41,7 +41,13 @@ def _ref_attention(qkv, seqs, L, heads, causal):
     # long sequences (key blocks of 64 streamed past a 128-row query chunk): ViT-L/14 257, ViT-L/14@336 577
     (3, 257, 16, False), (2, 577, 4, False), (2, 300, 2, True), (1, 768, 1, True), (2, 209, 3, False),
     # the causal text sequence on the tcgen05 kernel (65..80 tokens), many items per persistent CTA
-    (300, 77, 8, True), (9, 65, 2, True), (11, 80, 3, True), (64, 64, 2, True)])
+    (300, 77, 8, True), (9, 65, 2, True), (11, 80, 3, True), (64, 64, 2, True),
+    # every length up to 208 runs on the tcgen05 kernels (padded key counts 80 / 144 / 208), masked or not:
+    # ViT-B/32's 50-token image sequence, lengths at and around the padding boundaries
+    (200, 50, 12, False), (6, 33, 2, False), (9, 100, 3, False), (9, 144, 2, False), (5, 145, 2, False), (4, 192, 3, False),
+    (5, 145, 2, True), (3, 160, 2, True), (2, 208, 2, True), (6, 81, 1, True), (5, 48, 2, True),
+    # tcgen05 key-block kernel (un-masked 209..768 tokens): many items per CTA, exact multiples of the block, the maximum
+    (40, 257, 16, False), (10, 577, 16, False), (3, 768, 2, False), (5, 256, 4, False), (6, 385, 3, False), (4, 384, 2, False)])
 def test_attention(dev, seqs, L, heads, causal):
     from fitclip_b200 import ops
     torch.manual_seed(1)
