@@ -205,6 +205,45 @@ def webvid_leg(encoder, device, rank, world, group, n_total, barrier) -> dict:
             "inputs": "500-video resident pool, per-chunk affine map inside the timed region; resident token ids"}
 
 
+def train_leg(teacher, device, videos: int, steps: int = 3) -> dict:
+    """BASELINE configs[4] as a TRAINING step: `videos` videos x 4 frames + as many captions per
+    step; student ViT-B/16 forward with saved activations + backward + AdamW, frozen teacher forward (the evaluation
+    engine the bench already holds).  One warm-up step, `steps` timed ones, CUDA events; N = 1 only."""
+    import torch
+
+    from fitclip_b200 import B200ClipVideoTextEncoder, _lib
+    from fitclip_b200._init import init_clip_state_dict
+    from fitclip_b200.training import TeacherStudentTrainingModule
+    student = B200ClipVideoTextEncoder(init_clip_state_dict(seed=3), num_frames=FRAMES).to(device)
+    module = TeacherStudentTrainingModule(student, teacher)
+    g = torch.Generator(device=device).manual_seed(99)
+    video = torch.randn(videos, FRAMES, 3, 224, 224, device=device, generator=g)
+    ids = torch.randint(1, 49405, (videos, CTX), device=device, generator=g, dtype=torch.int32)
+    ids[:, 0], ids[:, -1] = 49406, 49407
+    batch = {"video_student": video, "video_teacher": video, "text_student": {"input_ids": ids},
+             "text_teacher": {"input_ids": ids}}
+    torch.cuda.reset_peak_memory_stats(device)
+    losses = [float(module.training_step(batch, 0))]
+    torch.cuda.synchronize(device)
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = module.training_step(batch, i + 1)
+    e1.record()
+    torch.cuda.synchronize(device)
+    module.trainer.check_inputs()
+    losses.append(float(loss))
+    ms = e0.elapsed_time(e1) / steps
+    fwd = videos * FRAMES * FLOP_PER_FRAME + videos * FLOP_PER_CAPTION
+    algorithmic = 4 * fwd  # teacher forward + student forward + student backward (2x)
+    return {"workload": f"teacher-student training step: {videos} videos x {FRAMES} frames + {videos} captions, student "
+                        f"fwd + bwd + AdamW and frozen-teacher fwd, ViT-B/16", "steps": steps, "ms_per_step": ms,
+            "videos_per_s": videos / ms * 1e3, "algorithmic_tflop_per_step": algorithmic / 1e12,
+            "achieved_tflops": algorithmic / ms / 1e9, "gpu_launches_per_step": (_lib.launch_count() - launches0) // steps,
+            "peak_memory_gb": torch.cuda.max_memory_allocated(device) / 1e9, "losses_first_last": losses}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -346,6 +385,10 @@ def run_ours(args) -> None:
             del frames, h_frames, bufs
             torch.cuda.empty_cache()
             webvid = webvid_leg(encoder, device, rank, world, group, args.webvid_videos, barrier)
+        torch.cuda.empty_cache()
+    train = None
+    if world == 1 and args.train_videos > 0:  # row f3 (outside inference_mode: the trainer writes parameters in place)
+        train = train_leg(encoder, device, args.train_videos)
 
     if rank == 0:
         peak, sustained, hbm, src = measured_peaks()
@@ -414,7 +457,10 @@ def run_ours(args) -> None:
                     webvid["metrics_equal_single_gpu"] = webvid["metrics"] == one["metrics"]
                     webvid["single_gpu_reference"] = {"videos_per_s": one["videos_per_s"], "metrics": one["metrics"],
                                                       "file": "profiles/r2_webvid_1gpu.json"}
-            line["extra"] = {"webvid": webvid}
+            line.setdefault("extra", {})["webvid"] = webvid
+        if train is not None:
+            train["roofline_frac"] = train["achieved_tflops"] / peak
+            line.setdefault("extra", {})["train_step"] = train
         line["cpu_baseline"] = cpu_baseline(sample_videos=args.cpu_sample)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -496,6 +542,8 @@ def main() -> None:
     ap.add_argument("--webvid-videos", type=int, default=100_000,
                     help="gallery size of the BASELINE configs[3] leg (100k videos x 8 frames, split over the ranks; "
                          "reported under extra.webvid, outside the K timed steps); 0 skips it")
+    ap.add_argument("--train-videos", type=int, default=512,
+                    help="videos per step of the teacher-student TRAINING leg (row f3; extra.train_step, N = 1 only); 0 skips it")
     ap.add_argument("--cpu-sample", type=int, default=128,
                     help="videos in the bounded CPU-baseline sample (128 videos x 4 frames + 128 captions: 10-30 s of CPU work)")
     args = ap.parse_args()

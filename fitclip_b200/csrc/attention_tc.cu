@@ -54,16 +54,13 @@ constexpr int ATT2_THREADS = 288;          // warps 0-3 softmax, warps 4-7 epilo
 #define ATT2_POLY 0  // of every 16 column pairs of a x32 chunk, this many take exp2 on the FMA pipe (degree-3 polynomial,
                      // Cody-Waite split, packed fp32x2) instead of the MUFU: 0 = none, 4 = 25 %, 8 = 50 %
 #endif
-#ifndef ATT2_SPLIT_S
-#define ATT2_SPLIT_S 0  // 1: S = Q.K^T of the main keys in two column halves with separate commits (row max starts earlier)
-#endif
 #ifndef ATT2_REGS_SOFTMAX
 // setmaxnreg targets (multiples of 8).  Registers move inside a CTA's own launch allocation, so
 // 128 * SOFTMAX + 128 * EPILOGUE + 32 * (launch count, kept by the TMA/MMA warp) must not exceed 288 * (registers per
 // thread at launch) -- checked on the host
 // against cudaFuncGetAttributes before the first launch (an unsatisfiable setmaxnreg.inc would spin forever).
-#define ATT2_REGS_SOFTMAX 128
-#define ATT2_REGS_EPILOGUE 64
+#define ATT2_REGS_SOFTMAX 120
+#define ATT2_REGS_EPILOGUE 72
 #endif
 
 template <int KP>
@@ -536,7 +533,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* t_full = kq_full + 6;
   uint64_t* p_half = kq_full + 7;   // [2]
   uint64_t* l_full = kq_full + 10;  // row sums of item it are in l_buf[it & 1]
-  uint64_t* s_full_b = kq_full + 11;  // ATT2_SPLIT_S: the upper half of the main S columns (keys KMAIN/2 .. KMAIN)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 9);
   float* l_buf = reinterpret_cast<float*>(smem + S2::OFF_L);
 
@@ -560,7 +556,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(p_half, 128);
     mbar_init(p_half + 1, 128);
     mbar_init(l_full, 128);
-    mbar_init(s_full_b, 1);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -591,27 +586,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_load_3d(smem + S::OFF_V, &tmKV, v_full, 2 * D + c.head * HD, 0, c.seq);
       };
       auto issue_s_main = [&]() {
-        if (ATT2_SPLIT_S) {
-          // two column halves with their own commits: the row-max pass starts on keys [0, KMAIN/2) while the tensor
-          // core still works on the upper half
-          constexpr uint32_t idesc_h = umma_idesc_bf16_f32(QT, KMAIN / 2);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_h,
-                         k != 0);
-          umma_commit(s_full);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16_ss(tmem_base + KMAIN / 2, umma_desc_k_sw128(q_addr + k * 32),
-                         umma_desc_k_sw128(k_addr + (KMAIN / 2) * 128 + k * 32), idesc_h, k != 0);
-          umma_commit(s_full_b);
-        } else {
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s,
-                         k != 0);
-          umma_commit(s_full);
-        }
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s,
+                       k != 0);
+        umma_commit(s_full);
       };
       auto issue_s_tail = [&]() {
 #pragma unroll
@@ -696,9 +675,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (active) {
         const float inv = 1.f / l_buf[(it & 1) * 128 + q * 32 + lane];
         const uint64_t inv2 = pack_f32x2(inv, inv);
-        if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous store has finished reading its staging tile
-        __syncwarp();
-        // two halves of 32 columns, each scaled, packed to bf16 and staged as soon as it arrives (32 + 16 live registers)
+        // two halves of 32 columns, each scaled and packed to bf16 as soon as it arrives (32 + 16 live registers)
+        uint32_t pk[2][16];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t o[32];
@@ -708,16 +686,20 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tc_fence_before();
             mbar_arrive(o_empty);  // O(it) is in registers: the MMA thread may overwrite the tail columns
           }
-          uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float a, b;
             unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1])), inv2), a, b);
-            pk[e] = pack_bf16x2(a, b);
+            pk[h][e] = pack_bf16x2(a, b);
           }
+        }
+        if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous store has finished reading its staging tile
+        __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            st_shared_v4(stg_row + (((4 * h + c) ^ sw) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t(&pp)[16] = pk[c >> 2];
+          const int o = (c & 3) * 4;
+          st_shared_v4(stg_row + ((c ^ sw) << 4), make_uint4(pp[o], pp[o + 1], pp[o + 2], pp[o + 3]));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -736,8 +718,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     setmaxnreg_inc<ATT2_REGS_SOFTMAX>();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     constexpr int NFULL = KP / 32;
-    static_assert(NFULL % 2 == 0 && (NPH == 0 || (KHALF == 64 && 2 * NPH < NFULL)),
-                  "chunk pairs: an even number of x32 chunks, early hand-overs every 64 keys");
+    static_assert(NPH == 0 || (KHALF % 32 == 0 && NPH * (KHALF / 32) < NFULL), "early hand-overs must end on chunk boundaries");
     ItemCursor cur;
     cur.init(blockIdx.x, gridDim.x, tiles, heads);
     int it = 0;
@@ -755,19 +736,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float l = 1.f;
       float m = -INFINITY;
       if (active) {
-        // Rolled over chunk PAIRS (#pragma unroll 1): register use is fixed at two x32 buffers and the code stays small --
-        // fully unrolled, ptxas hoists loads across chunks until it spills (measured: 73.4 vs 70.3 us).  No masks in the
-        // main chunks: the dispatcher only sends sequences with KP - 16 < L <= KP here.
         float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        uint32_t r[2][32];
-        tmem_ld_32x32b_x32(trow, r[0]);
-        tmem_ld_32x32b_x32(trow + 32, r[1]);
-#pragma unroll 1
-        for (int jj = 0; jj < NFULL; jj += 2) {
+        constexpr int DEPTH = 2;
+        uint32_t r[DEPTH][32];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            tmem_ld_wait_fence(r[u]);
-            const uint32_t(&rc)[32] = r[u];
+        for (int j = 0; j < DEPTH && j < NFULL; ++j) tmem_ld_32x32b_x32(trow + j * 32, r[j]);
+#pragma unroll
+        for (int j = 0; j < NFULL; ++j) {
+          tmem_ld_wait_fence(r[j % DEPTH]);
+          const uint32_t(&rc)[32] = r[j % DEPTH];
+          if ((j + 1) * 32 <= lim) {
 #pragma unroll
             for (int c = 0; c < 32; c += 8) {
               m = max3(m, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
@@ -775,14 +753,12 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
               m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
             }
-            if (jj + 2 + u < NFULL) {
-              if (ATT2_SPLIT_S && jj == 0 && u == 1) {  // chunk 3 is the first one of the upper half of S
-                mbar_wait(s_full_b, ph);
-                tc_fence_after();
-              }
-              tmem_ld_32x32b_x32(trow + (jj + 2 + u) * 32, r[u]);
-            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (j * 32 + c < lim) m = fmaxf(m, __uint_as_float(rc[c]));
           }
+          if (j + DEPTH < NFULL) tmem_ld_32x32b_x32(trow + (j + DEPTH) * 32, r[j % DEPTH]);
         }
         m = fmaxf(max3(m, m1, m2), m3);
       }
@@ -816,37 +792,39 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
           pk_tail[c] = pack_bf16x2(p0, p1);
         }
-#pragma unroll 1
-        for (int jj = 0; jj < NFULL; jj += 2) {  // chunk pairs = 64 keys = one early hand-over of P
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            tmem_ld_wait_fence(r[u]);
-            if (jj + u + 1 < NFULL) tmem_ld_32x32b_x32(trow + (jj + u + 1) * 32, r[u ^ 1]);
-            uint32_t pk[16];
+        for (int j = 0; j < NFULL; ++j) {
+          tmem_ld_wait_fence(r[j & 1]);
+          if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
+          uint32_t pk[16];
+          const bool full = (j + 1) * 32 <= lim;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[u][2 * c]), __uint_as_float(r[u][2 * c + 1])), sc2,
-                                            nmc2);
-              float p0, p1;
-              // ATT2_POLY of every 16 pairs take the FMA-pipe exp2, spread evenly so both pipes stay fed
-              if (ATT2_POLY > 0 && (c * ATT2_POLY) % 16 < ATT2_POLY) {
-                ex2_poly_x2(x2, p0, p1);
-              } else {
-                float x0, x1;
-                unpack_f32x2(x2, x0, x1);
-                p0 = ex2_approx(x0);
-                p1 = ex2_approx(x1);
-              }
-              if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
-              else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
-              pk[c] = pack_bf16x2(p0, p1);
+          for (int c = 0; c < 16; ++c) {
+            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
+                                          sc2, nmc2);
+            float p0, p1;
+            // ATT2_POLY of every 16 pairs take the FMA-pipe exp2, spread evenly so both pipes stay fed
+            if (ATT2_POLY > 0 && (c * ATT2_POLY) % 16 < ATT2_POLY) {
+              ex2_poly_x2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f32x2(x2, x0, x1);
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
             }
-            tmem_st_32x32b_x16(trow + (jj + u) * 16, pk);
+            if (!full) {
+              if (j * 32 + 2 * c >= lim) p0 = 0.f;
+              if (j * 32 + 2 * c + 1 >= lim) p1 = 0.f;
+            }
+            if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+            else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
+            pk[c] = pack_bf16x2(p0, p1);
           }
-          if (NPH > 0 && jj / 2 < NPH) {
-            tmem_st_wait();  // 64 more keys of P are complete: let the tensor core start on them
+          tmem_st_32x32b_x16(trow + j * 16, pk);
+          if (NPH > 0 && (j + 1) % (KHALF / 32) == 0 && (j + 1) / (KHALF / 32) <= NPH) {
+            tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(p_half + jj / 2);
+            mbar_arrive(p_half + (j + 1) / (KHALF / 32) - 1);
           }
         }
         tmem_st_32x32b_x8(trow + NFULL * 16, pk_tail);

@@ -89,8 +89,10 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
   if (warp == 4) {
     // ===================== TMA + MMA thread =====================
     if (lane == 0 && my_items > 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(QT, KB);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32_bmn(QT, HD);
+      // key columns block j really needs: the keys that exist, rounded up to the MMA's N granularity (16).  The last
+      // block of a 257-token sequence holds ONE key: S, softmax and P.V then cost 16 columns instead of 128.
+      auto ncols_of = [&](int j) { return (min(KB, L - j * KB) + 15) & ~15; };
       const uint32_t q_addr = smem_u32(smem + S::OFF_Q);
       const int total_blocks = my_items * nkb;
       // block g of this CTA belongs to item blockIdx.x + (g / nkb) * gridDim.x, key block g % nkb
@@ -113,8 +115,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
       };
       auto issue_pv = [&](int g, bool accumulate) {  // O (+)= P_g . V_g
         const uint32_t v_addr = smem_u32(smem + S::OFF_V + (g & 1) * TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < KB / 16; ++k)
+        const int nk = ncols_of(g % nkb) / 16;
+        for (int k = 0; k < nk; ++k)
           umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv,
                        accumulate || k != 0);
         umma_commit(kv_empty + (g & 1));  // K_g / V_g may be overwritten once these MMAs (and S_g before them) are done
@@ -138,6 +140,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
         }
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem + S::OFF_K + (g & 1) * TILE_BYTES);
+        const uint32_t idesc_s = umma_idesc_bf16_f32(QT, ncols_of(j));
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0);
@@ -173,13 +176,16 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
         tc_fence_after();
         if (active) {
           const int valid = min(KB, L - j * KB);  // keys of this block that exist (>= 1)
+          const int nch = (valid + 31) >> 5;     // x32 chunks that hold at least one of them (S has (valid + 15) & ~15 columns;
+                                                 // the upper half of a half-written last chunk is stale TMEM, masked below)
           // ---- pass 1: block maximum
           float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
           uint32_t r[2][32];
           tmem_ld_32x32b_x32(trow, r[0]);
-          tmem_ld_32x32b_x32(trow + 32, r[1]);
+          if (nch > 1) tmem_ld_32x32b_x32(trow + 32, r[1]);
 #pragma unroll
           for (int c4 = 0; c4 < KB / 32; ++c4) {
+            if (c4 >= nch) break;
             tmem_ld_wait_fence(r[c4 & 1]);
             const uint32_t(&rc)[32] = r[c4 & 1];
             if ((c4 + 1) * 32 <= valid) {
@@ -195,7 +201,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
               for (int c = 0; c < 32; ++c)
                 if (c4 * 32 + c < valid) m0 = fmaxf(m0, __uint_as_float(rc[c]));
             }
-            if (c4 + 2 < KB / 32) tmem_ld_32x32b_x32(trow + (c4 + 2) * 32, r[c4 & 1]);
+            if (c4 + 2 < nch) tmem_ld_32x32b_x32(trow + (c4 + 2) * 32, r[c4 & 1]);
           }
           const float m_new = fmaxf(fmaxf(max3(m0, m1, m2), m3), m_run);
           // rescale factor of everything accumulated so far; the first block has nothing to rescale (m_run = -inf)
@@ -209,8 +215,9 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
           uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
 #pragma unroll
           for (int c4 = 0; c4 < KB / 32; ++c4) {
+            if (c4 >= nch) break;
             tmem_ld_wait_fence(r[c4 & 1]);
-            if (c4 + 1 < KB / 32) tmem_ld_32x32b_x32(trow + (c4 + 1) * 32, r[(c4 + 1) & 1]);
+            if (c4 + 1 < nch) tmem_ld_32x32b_x32(trow + (c4 + 1) * 32, r[(c4 + 1) & 1]);
             uint32_t pk[16];
             const bool full = (c4 + 1) * 32 <= valid;
 #pragma unroll

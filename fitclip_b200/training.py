@@ -314,15 +314,27 @@ class TeacherStudentTrainingModule:
     def __init__(self, encoder, teacher, init_temperature: float = 0.05, labeled_dataset_name: str = "labeled",
                  labeled_dataset_loss_share: Optional[float] = None,
                  dataset_names: Sequence[str] = ("labeled", "unlabeled"), lr: float = 3e-6,
-                 weight_decay: float = 1e-2, group=None, kernels: Any = None, fit_temperature: bool = False) -> None:
-        if fit_temperature:  # config/trainer.yaml:20 default is false; the logit scales are constants here
-            raise NotImplementedError("fit_temperature=True (a trainable logit scale) is not implemented")
+                 weight_decay: float = 1e-2, group=None, kernels: Any = None, fit_temperature: bool = False,
+                 min_temperature: float = 0.001) -> None:
         self.encoder, self.teacher = encoder, teacher
         self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels)
         self.K = self.trainer.K
         self.group = group
         self.logit_scale = -math.log(init_temperature)                # video_text_module.py:32
         self.teacher_student_logit_scale = self.logit_scale          # teacher_student.py:70-71
+        self.max_logit_scale = -math.log(min_temperature)             # video_text_module.py:34
+        # fit_temperature (video_text_module.py:32, teacher_student.py:70-71; config/trainer.yaml:20 defaults to false):
+        # the two log-space scales become parameters of the same AdamW group, clamped at max_logit_scale after every
+        # optimizer step (video_text_module.py:93-97, teacher_student.py:211-215).  They live in one 2-element device
+        # tensor [logit_scale, teacher_student_logit_scale]; their gradients come from the B x B score matrices the
+        # step builds anyway, so this path costs one host read of two floats per step.
+        self.fit_temperature = fit_temperature
+        if fit_temperature:
+            device = self.trainer.flat.device
+            self.temps = torch.full((2,), self.logit_scale, device=device, dtype=torch.float32)
+            self.temps_grad = torch.zeros_like(self.temps)
+            self.temps_m = torch.zeros_like(self.temps)
+            self.temps_v = torch.zeros_like(self.temps)
         self.labeled_dataset_name = labeled_dataset_name
         names = list(dataset_names)
         if labeled_dataset_loss_share is None:                        # teacher_student.py:60-66
@@ -354,6 +366,9 @@ class TeacherStudentTrainingModule:
             tt_local = self.teacher.encode_text(batch["text_teacher"])
         n_local = v_local.shape[0]
         # _dataset_step_end (:142-173): gather across ranks (sections are per-rank contiguous, so gather per section)
+        if self.fit_temperature:
+            self.logit_scale, self.teacher_student_logit_scale = self.temps.tolist()
+            self.temps_grad.zero_()
         scale, ts_scale = math.exp(self.logit_scale), math.exp(self.teacher_student_logit_scale)
         dv = torch.zeros_like(v_local)
         dt = torch.zeros_like(t_local)
@@ -372,6 +387,10 @@ class TeacherStudentTrainingModule:
                 teacher_scores = K.sgemm(tv, tt, trans_b=True, alpha=ts_scale)
                 loss, dscores = K.loss_fwd_bwd(scores, teacher_scores, gscale=share * ts_scale ** 2)
                 loss = loss * (share * ts_scale ** 2)
+                if self.fit_temperature:
+                    self.temps_grad[1] += self._teacher_scale_grad(scores, teacher_scores, loss, share * ts_scale ** 2)
+            if self.fit_temperature:  # scores = exp(logit_scale) * V T^T  =>  dL/d logit_scale = sum(dL/dscores * scores)
+                self.temps_grad[0] += (dscores * scores).sum()
             total = loss if total is None else total + loss
             # scores = scale * V T^T:  dV = scale * dS T,  dT = scale * dS^T V; keep this rank's rows
             n = hi - lo
@@ -381,4 +400,35 @@ class TeacherStudentTrainingModule:
         tr.backward_video(dv)
         if optimize:
             tr.optimizer_step(self.group)
+            if self.fit_temperature:
+                self._temperature_step()
         return total
+
+    @staticmethod
+    def _teacher_scale_grad(scores: torch.Tensor, teacher_scores: torch.Tensor, weighted_loss: torch.Tensor,
+                            weight: float) -> torch.Tensor:
+        """d/d ts of ``weight(ts) * KL(scores, teacher_scores(ts))`` with ``teacher_scores = exp(ts) * M`` and
+        ``weight = share * exp(ts)^2`` (teacher_student.py:156-158): the product rule gives ``2 * weighted_loss`` plus the
+        path through the teacher's soft targets, ``weight * sum(dKL/dT * T)`` with, per softmax direction,
+        ``dKL/dT = p * (a - sum_line(p * a)) / B``, ``p = softmax(T)``, ``a = log p - log softmax(scores)``."""
+        B = scores.shape[0]
+        through_targets = scores.new_zeros(())
+        for dim in (1, 0):
+            logp, logq = torch.log_softmax(teacher_scores, dim), torch.log_softmax(scores, dim)
+            p, a = logp.exp(), logp - logq
+            d = p * (a - (p * a).sum(dim, keepdim=True)) / B
+            through_targets = through_targets + (d * teacher_scores).sum()
+        return 2 * weighted_loss.reshape(()) + weight * through_targets
+
+    def _temperature_step(self) -> None:
+        """AdamW on the two log-space scales with the trainer's hyper-parameters (one parameter group in the reference,
+        ``aligner/cli.py:126-134``), then the clamp of ``optimizer_step`` (video_text_module.py:93-97)."""
+        tr = self.trainer
+        b1, b2 = tr.betas
+        step = tr.step_count  # already advanced by ClipTrainer.optimizer_step
+        self.temps.mul_(1 - tr.lr * tr.weight_decay)
+        self.temps_m.mul_(b1).add_(self.temps_grad, alpha=1 - b1)
+        self.temps_v.mul_(b2).addcmul_(self.temps_grad, self.temps_grad, value=1 - b2)
+        denom = self.temps_v.sqrt() / (1 - b2 ** step) ** 0.5 + tr.eps
+        self.temps.addcdiv_(self.temps_m, denom, value=-tr.lr / (1 - b1 ** step))
+        self.temps.clamp_(max=self.max_logit_scale)

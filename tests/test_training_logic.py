@@ -180,3 +180,50 @@ def test_labeled_dataset_loss_share():
     assert torch.allclose(loss, ref_loss, rtol=1e-4, atol=1e-5)
     for name, ref in ref_grads.items():
         assert (module.trainer.g[name] - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-6, name
+
+
+def test_fit_temperature_matches_autograd_and_clamps():
+    """``fit_temperature=True`` (video_text_module.py:32, teacher_student.py:70-71): the two log-space scales are
+    parameters of the same AdamW group; gradients vs. torch.autograd on the reference's loss expression
+    (teacher_student.py:142-173, 176-183), one AdamW step vs. torch.optim.AdamW, then the clamp of ``optimizer_step``
+    (video_text_module.py:93-97, teacher_student.py:211-215)."""
+    import math
+    student, teacher = make_models()
+    ref_student = oracle.RefClipVideoTextEncoder(copy.deepcopy(student))
+    ref_teacher = oracle.RefClipVideoTextEncoder(teacher)
+    names = ["labeled"] * 3 + ["unlabeled"] * 5
+    batch = make_batch(8, seed=6, names=names)
+    # ---- reference arithmetic with autograd: logit scales as nn.Parameters
+    ls = torch.nn.Parameter(torch.tensor([-math.log(0.05)]))
+    ts = torch.nn.Parameter(ls.detach().clone())
+    params = list(ref_student.model.parameters()) + [ls, ts]
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    v, t = ref_student(batch["video_student"], batch["text_student"])
+    with torch.no_grad():
+        tv, tt = ref_teacher(batch["video_teacher"], batch["text_teacher"])
+    total = 0.0
+    for name, lo, hi in sections_of(names, 8):
+        scores = ls.exp() * v[lo:hi] @ t[lo:hi].T
+        if name == "labeled":
+            loss = oracle.ref_nce_loss(scores)
+        else:
+            teacher_scores = ts.exp() * tv[lo:hi] @ tt[lo:hi].T
+            loss = oracle.ref_teacher_student_nce_loss(scores, teacher_scores, reduction="batchmean") * ts.exp() ** 2
+        total = total + loss * 0.5
+    total.backward()
+    opt.step()
+    # ---- the trainer
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    module = TeacherStudentTrainingModule(enc, ref_teacher, lr=1e-3, kernels=TorchKernels(), fit_temperature=True)
+    loss = module.training_step(batch, 0)
+    assert torch.allclose(loss, total.detach(), rtol=1e-4, atol=1e-5)
+    assert abs(float(module.temps_grad[0]) - float(ls.grad)) <= 2e-4 * abs(float(ls.grad)) + 1e-6
+    assert abs(float(module.temps_grad[1]) - float(ts.grad)) <= 2e-4 * abs(float(ts.grad)) + 1e-6
+    assert abs(float(module.temps[0]) - float(ls)) <= 1e-5 and abs(float(module.temps[1]) - float(ts)) <= 1e-5
+    # the next step uses the UPDATED scales
+    module.training_step(batch, 1, optimize=False)
+    assert abs(module.logit_scale - float(ls)) <= 1e-5 and abs(module.teacher_student_logit_scale - float(ts)) <= 1e-5
+    # ---- clamp: a scale pushed past max_logit_scale = -log(min_temperature) comes back to it
+    module.temps.fill_(module.max_logit_scale + 1.0)
+    module.training_step(batch, 2)
+    assert float(module.temps.max()) <= module.max_logit_scale + 1e-6
