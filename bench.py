@@ -323,56 +323,72 @@ def run_ours(args) -> None:
         h_frames, h_ids = synthetic_inputs(rank, device, pinned=True)
         chunk = 250  # videos per H2D chunk; copies run on a side stream and overlap the previous chunk's encode
         copy_stream = torch.cuda.Stream(device)
-        bufs = [torch.empty(chunk, FRAMES, 3, 224, 224, device=device) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
-
         n_chunks = VIDEOS_PER_GPU // chunk
-
-        def issue_copy(i):
-            b = i % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[b])
-                bufs[b].copy_(h_frames[i * chunk:(i + 1) * chunk], non_blocking=True)
-                ready[b].record(copy_stream)
-
-        def step_e2e():
-            """Steady-state streaming: chunk i+1 is copied while chunk i is encoded, and the first chunk of the NEXT
-            step starts streaming in while this step finishes (text encode, ranks, metrics, D2H) -- what a prefetching
-            data loader does.  Every step issues exactly n_chunks H2D chunk copies."""
-            main = torch.cuda.current_stream(device)
-            outs = []
-            for i in range(n_chunks):
-                if i + 1 < n_chunks:
-                    issue_copy(i + 1)
-                b = i % 2
-                main.wait_event(ready[b])
-                outs.append(encoder.encode_video(bufs[b]))
-                freed[b].record(main)
-            issue_copy(0)  # next step's first chunk
-            d_ids = h_ids.to(device, non_blocking=True)
-            t = encoder.encode_text({"input_ids": d_ids})
-            ranks = retrieval_ranks(t, torch.cat(outs), group=group, totals=(n_total, n_total))
-            m = metrics_from_ranks(ranks, n_total)
-            return {k: x.cpu() for k, x in m.items()}  # D2H read of the step's result
-
         assert n_chunks % 2 == 0
-        for b in range(2):
-            freed[b].record(torch.cuda.current_stream(device))
-        issue_copy(0)
-        for _ in range(2):
-            m_e2e = step_e2e()
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            m_e2e = step_e2e()
-        torch.cuda.current_stream(device).wait_event(ready[0])  # the last prefetch counts towards the timed region
-        e1.record()
-        barrier()
-        ms2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e_ms = ms2.item() / args.steps
+
+        def time_e2e(h_video, encode):
+            """Steady-state streaming of `h_video` (pinned host frames, any dtype) through `encode`: chunk i+1 is copied
+            while chunk i is encoded, and the first chunk of the NEXT step starts streaming in while this step finishes
+            (text encode, ranks, metrics, D2H) -- what a prefetching data loader does.  Every step issues exactly
+            n_chunks H2D chunk copies."""
+            bufs = [torch.empty((chunk, *h_video.shape[1:]), device=device, dtype=h_video.dtype) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            freed = [torch.cuda.Event() for _ in range(2)]
+
+            def issue_copy(i):
+                b = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[b])
+                    bufs[b].copy_(h_video[i * chunk:(i + 1) * chunk], non_blocking=True)
+                    ready[b].record(copy_stream)
+
+            def step():
+                main = torch.cuda.current_stream(device)
+                outs = []
+                for i in range(n_chunks):
+                    if i + 1 < n_chunks:
+                        issue_copy(i + 1)
+                    b = i % 2
+                    main.wait_event(ready[b])
+                    outs.append(encode(bufs[b]))
+                    freed[b].record(main)
+                issue_copy(0)  # next step's first chunk
+                d_ids = h_ids.to(device, non_blocking=True)
+                t = encoder.encode_text({"input_ids": d_ids})
+                ranks = retrieval_ranks(t, torch.cat(outs), group=group, totals=(n_total, n_total))
+                m = metrics_from_ranks(ranks, n_total)
+                return {k: x.cpu() for k, x in m.items()}  # D2H read of the step's result
+
+            for b in range(2):
+                freed[b].record(torch.cuda.current_stream(device))
+            issue_copy(0)
+            for _ in range(2):
+                step()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            torch.cuda.current_stream(device).wait_event(ready[0])  # the last prefetch counts towards the timed region
+            e1.record()
+            barrier()
+            t_ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            return t_ms.item() / args.steps
+
+        e2e_ms = time_e2e(h_frames, encoder.encode_video)
+        h2d_bytes = int(h_frames.numel() * 4 + h_ids.numel() * 4)
+        # the reference's real input: decoded uint8 frames (here 240 x 320 RGB); its DataLoader workers run the eval
+        # transform on the CPU (clip_video_text_encoder.py:124-133), here it is fused into the patch gather on the GPU
+        gu = torch.Generator().manual_seed(4321 + rank)
+        h_u8 = torch.empty(VIDEOS_PER_GPU, FRAMES, 240, 320, 3, dtype=torch.uint8, pin_memory=True)
+        h_u8.random_(0, 256, generator=gu)
+        e2e_u8_ms = time_e2e(h_u8, encoder.encode_video_uint8)
+        e2e_uint8 = {"value": n_total / (e2e_u8_ms * 1e-3), "unit": "videos/s", "ms_per_step": e2e_u8_ms,
+                     "h2d_bytes_per_step": int(h_u8.numel() + h_ids.numel() * 4), "d2h_bytes_per_step": 3 * 4 + 8,
+                     "input": "uint8 decoded frames 240x320x3 from pinned host memory; eval transform (bicubic resize, "
+                              "crop, normalise) fused into the patch gather (fc_encode_video_uint8)"}
+        del h_u8
 
         # ---- outside every timed region: multi-GPU integer-rank equality (BASELINE.md section 4 gate) ----
         ranks_equal = None
@@ -380,9 +396,8 @@ def run_ours(args) -> None:
             ranks_equal = rank_equality_check(encoder, frames, ids, n_total, world, rank, group, device)
         # ---- BASELINE configs[3] (the north_star target): 100k videos x 8 frames + 100k captions, STRONG scaling ----
         webvid = None
-        h2d_bytes = int(h_frames.numel() * 4 + h_ids.numel() * 4)
         if args.webvid_videos > 0:
-            del frames, h_frames, bufs
+            del frames, h_frames
             torch.cuda.empty_cache()
             webvid = webvid_leg(encoder, device, rank, world, group, args.webvid_videos, barrier)
         torch.cuda.empty_cache()
@@ -438,6 +453,7 @@ def run_ours(args) -> None:
                                         for r in shapes[:8]]},
             "metrics": {k: float(v) for k, v in metrics.items()},
         }
+        line.setdefault("extra", {})["e2e_uint8"] = e2e_uint8
         if ranks_equal is not None:
             line["ranks_equal_single_gpu"] = ranks_equal["equal"] and ranks_equal["equal_uneven"]
             line["ranks_equal_detail"] = ranks_equal

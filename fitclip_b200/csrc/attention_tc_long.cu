@@ -45,6 +45,77 @@ struct LongSmem {
   static constexpr int BYTES = OFF_BAR + 128;
 };
 
+// Softmax of one key block for one query row (thread): returns the block's contribution to the row sum and updates the
+// running maximum; P goes to TMEM as bf16 over the S columns already read.  FULL: all 128 keys of the block exist (every
+// block but the last): fully unrolled, no masks.  !FULL: `valid` < 128 keys exist; S has (valid + 15) & ~15 columns, only
+// the x32 chunks that hold a valid key are touched, stale columns are masked.
+template <bool FULL>
+__device__ __forceinline__ void softmax_block(uint32_t trow, int valid, bool first, float scale_log2, float& m_run,
+                                              float& l, float& alpha, bool& moved) {
+  const int nch = FULL ? KB / 32 : (valid + 31) >> 5;
+  // ---- pass 1: block maximum
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  uint32_t r[2][32];
+  tmem_ld_32x32b_x32(trow, r[0]);
+  if (FULL || nch > 1) tmem_ld_32x32b_x32(trow + 32, r[1]);
+#pragma unroll
+  for (int c4 = 0; c4 < KB / 32; ++c4) {
+    if (!FULL && c4 >= nch) break;
+    tmem_ld_wait_fence(r[c4 & 1]);
+    const uint32_t(&rc)[32] = r[c4 & 1];
+    if (FULL || (c4 + 1) * 32 <= valid) {
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) {
+        m0 = max3(m0, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
+        m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
+        m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
+        m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c4 * 32 + c < valid) m0 = fmaxf(m0, __uint_as_float(rc[c]));
+    }
+    if (c4 + 2 < nch) tmem_ld_32x32b_x32(trow + (c4 + 2) * 32, r[c4 & 1]);
+  }
+  const float m_new = fmaxf(fmaxf(max3(m0, m1, m2), m3), m_run);
+  // rescale factor of everything accumulated so far; the first block has nothing to rescale (m_run = -inf)
+  alpha = first ? 0.f : ex2_approx((m_run - m_new) * scale_log2);
+  moved = !first && m_new > m_run;
+  m_run = m_new;
+  // ---- pass 2: P = exp2((s - m) c) -> bf16 -> TMEM
+  tmem_ld_32x32b_x32(trow, r[0]);
+  const float mc = m_new * scale_log2;
+  const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nmc2 = pack_f32x2(-mc, -mc);
+  uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
+#pragma unroll
+  for (int c4 = 0; c4 < KB / 32; ++c4) {
+    if (!FULL && c4 >= nch) break;
+    tmem_ld_wait_fence(r[c4 & 1]);
+    if (c4 + 1 < nch) tmem_ld_32x32b_x32(trow + (c4 + 1) * 32, r[(c4 + 1) & 1]);
+    uint32_t pk[16];
+    const bool full = FULL || (c4 + 1) * 32 <= valid;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float x0, x1;
+      unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[c4 & 1][2 * c]), __uint_as_float(r[c4 & 1][2 * c + 1])), sc2, nmc2),
+                   x0, x1);
+      float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+      if (!full) {
+        if (c4 * 32 + 2 * c >= valid) p0 = 0.f;
+        if (c4 * 32 + 2 * c + 1 >= valid) p1 = 0.f;
+      }
+      if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
+      else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
+      pk[c] = pack_bf16x2(p0, p1);
+    }
+    tmem_st_32x32b_x16(trow + c4 * 16, pk);
+  }
+  float la, lb;
+  unpack_f32x2(add_f32x2(l2a, l2b), la, lb);
+  l = l * alpha + la + lb;
+}
+
 __global__ void __launch_bounds__(LONG_THREADS, 2)
 attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmO, int L,
                          int heads, int tiles, int nkb, int num_items, float scale_log2) {
@@ -116,9 +187,16 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
       auto issue_pv = [&](int g, bool accumulate) {  // O (+)= P_g . V_g
         const uint32_t v_addr = smem_u32(smem + S::OFF_V + (g & 1) * TILE_BYTES);
         const int nk = ncols_of(g % nkb) / 16;
-        for (int k = 0; k < nk; ++k)
-          umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv,
-                       accumulate || k != 0);
+        if (nk == KB / 16) {
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k)
+            umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv,
+                         accumulate || k != 0);
+        } else {
+          for (int k = 0; k < nk; ++k)
+            umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv,
+                         accumulate || k != 0);
+        }
         umma_commit(kv_empty + (g & 1));  // K_g / V_g may be overwritten once these MMAs (and S_g before them) are done
       };
       load_kv(0);
@@ -176,70 +254,10 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
         tc_fence_after();
         if (active) {
           const int valid = min(KB, L - j * KB);  // keys of this block that exist (>= 1)
-          const int nch = (valid + 31) >> 5;     // x32 chunks that hold at least one of them (S has (valid + 15) & ~15 columns;
-                                                 // the upper half of a half-written last chunk is stale TMEM, masked below)
-          // ---- pass 1: block maximum
-          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-          uint32_t r[2][32];
-          tmem_ld_32x32b_x32(trow, r[0]);
-          if (nch > 1) tmem_ld_32x32b_x32(trow + 32, r[1]);
-#pragma unroll
-          for (int c4 = 0; c4 < KB / 32; ++c4) {
-            if (c4 >= nch) break;
-            tmem_ld_wait_fence(r[c4 & 1]);
-            const uint32_t(&rc)[32] = r[c4 & 1];
-            if ((c4 + 1) * 32 <= valid) {
-#pragma unroll
-              for (int c = 0; c < 32; c += 8) {
-                m0 = max3(m0, __uint_as_float(rc[c]), __uint_as_float(rc[c + 1]));
-                m1 = max3(m1, __uint_as_float(rc[c + 2]), __uint_as_float(rc[c + 3]));
-                m2 = max3(m2, __uint_as_float(rc[c + 4]), __uint_as_float(rc[c + 5]));
-                m3 = max3(m3, __uint_as_float(rc[c + 6]), __uint_as_float(rc[c + 7]));
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (c4 * 32 + c < valid) m0 = fmaxf(m0, __uint_as_float(rc[c]));
-            }
-            if (c4 + 2 < nch) tmem_ld_32x32b_x32(trow + (c4 + 2) * 32, r[c4 & 1]);
-          }
-          const float m_new = fmaxf(fmaxf(max3(m0, m1, m2), m3), m_run);
-          // rescale factor of everything accumulated so far; the first block has nothing to rescale (m_run = -inf)
-          const float alpha = j == 0 ? 0.f : ex2_approx((m_run - m_new) * scale_log2);
-          const bool moved = j > 0 && m_new > m_run;
-          m_run = m_new;
-          // ---- pass 2: P = exp2((s - m) c) -> bf16 -> TMEM over the S columns already read
-          tmem_ld_32x32b_x32(trow, r[0]);
-          const float mc = m_new * scale_log2;
-          const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nmc2 = pack_f32x2(-mc, -mc);
-          uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
-#pragma unroll
-          for (int c4 = 0; c4 < KB / 32; ++c4) {
-            if (c4 >= nch) break;
-            tmem_ld_wait_fence(r[c4 & 1]);
-            if (c4 + 1 < nch) tmem_ld_32x32b_x32(trow + (c4 + 1) * 32, r[(c4 + 1) & 1]);
-            uint32_t pk[16];
-            const bool full = (c4 + 1) * 32 <= valid;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              float x0, x1;
-              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[c4 & 1][2 * c]), __uint_as_float(r[c4 & 1][2 * c + 1])),
-                                     sc2, nmc2),
-                           x0, x1);
-              float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-              if (!full) {
-                if (c4 * 32 + 2 * c >= valid) p0 = 0.f;
-                if (c4 * 32 + 2 * c + 1 >= valid) p1 = 0.f;
-              }
-              if (c & 1) l2b = add_f32x2(l2b, pack_f32x2(p0, p1));
-              else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
-              pk[c] = pack_bf16x2(p0, p1);
-            }
-            tmem_st_32x32b_x16(trow + c4 * 16, pk);
-          }
-          float la, lb;
-          unpack_f32x2(add_f32x2(l2a, l2b), la, lb);
-          l = l * alpha + la + lb;
+          float alpha;
+          bool moved;
+          if (valid == KB) softmax_block<true>(trow, valid, j == 0, scale_log2, m_run, l, alpha, moved);
+          else softmax_block<false>(trow, valid, j == 0, scale_log2, m_run, l, alpha, moved);
           // ---- O <- a O where a row's maximum moved (s_full of this block implies P_{j-1}.V_{j-1} has completed)
           if (__any_sync(0xffffffffu, moved)) {
             const uint64_t a2 = pack_f32x2(alpha, alpha);
