@@ -184,3 +184,43 @@ def test_retrieval_module_two_ranks_equals_single_process(tmp_path):
         for k in ("r1", "r5", "r10", "mr", "rank"):
             assert torch.equal(got[k], single[k]), (r, k, got[k], single[k])
     assert 0.0 < float(single["r1"]) < 1.0  # a non-degenerate case
+
+
+def test_retrieval_module_multiple_datasets():
+    """``dataset_names`` with two names (text_video_retrieval.py:28-37, 60-65, 84-93): ``validation_step`` carries a
+    ``dataloader_idx``, every metric is cloned per dataset under ``{metric}_{dataset}``, ``loss/val_{dataset}`` is logged
+    per dataset, ``validation_epoch_end`` takes one output list per dataset -- each dataset's numbers equal a
+    single-dataset module fed that dataset alone."""
+    from fitclip_b200 import TextVideoRetrievalModule, ops
+    ops_backup = ops.metrics_from_ranks
+    ops.metrics_from_ranks = _cpu_metrics_from_ranks
+    try:
+        g = torch.Generator().manual_seed(11)
+        data = {}
+        for name, n in (("msrvtt", 25), ("didemo", 15)):
+            t = torch.nn.functional.normalize(torch.randn(n, 16, generator=g), dim=-1)
+            v = torch.nn.functional.normalize(t + 0.8 * torch.randn(n, 16, generator=g), dim=-1)
+            data[name] = (v, t)
+        kw = dict(similarity_factory=CpuSimilarity, nce_loss_fn=oracle.ref_nce_loss)
+        multi = TextVideoRetrievalModule(_StubEncoder(), dataset_names=list(data), **kw)
+        assert multi.multiple_datasets and set(multi.metrics) == {f"{m}_{d}" for d in data for m in ("r1", "r5", "r10", "mr")}
+        outputs = []
+        for idx, (name, (v, t)) in enumerate(data.items()):
+            outs = []
+            for b in range(0, len(v), 5):
+                batch = {"video": v[b:b + 5], "text": {"input_ids": t[b:b + 5]}}
+                outs.append(multi.validation_step_end(multi.validation_step(batch, len(outs), dataloader_idx=idx)))
+            outputs.append(outs)
+        result = multi.validation_epoch_end(outputs)
+        for name, (v, t) in data.items():
+            single = TextVideoRetrievalModule(_StubEncoder(), **kw)
+            outs = [single.validation_step_end(single.validation_step(
+                {"video": v[b:b + 5], "text": {"input_ids": t[b:b + 5]}}, 0)) for b in range(0, len(v), 5)]
+            expect = single.validation_epoch_end(outs)
+            for m in ("r1", "r5", "r10", "mr"):
+                assert torch.equal(torch.as_tensor(result[f"{m}_{name}"]), torch.as_tensor(expect[m])), (name, m)
+            assert abs(result[f"loss/val_{name}"] - expect["loss/val"]) < 1e-6
+        with pytest.raises(AssertionError):  # a dataloader_idx is mandatory in multi-dataset mode (:62-63)
+            multi.validation_step_end(multi.validation_step({"video": v[:2], "text": {"input_ids": t[:2]}}, 0))
+    finally:
+        ops.metrics_from_ranks = ops_backup
