@@ -269,7 +269,9 @@ def run_ours(args) -> None:
 
     # random-init ViT-B/16, identical on every rank (config/encoder/clip_from_scratch_vit_b_16.yaml)
     model = oracle.clip_vit_b_16(seed=0)
-    encoder = B200ClipVideoTextEncoder(model.state_dict(), num_frames=FRAMES).to(device)
+    from fitclip_b200 import B200Clip
+    encoder = B200ClipVideoTextEncoder(B200Clip(model.state_dict(), max_frames_per_pass=args.frames_per_pass),
+                                       num_frames=FRAMES).to(device)
     del model
     frames, ids = synthetic_inputs(rank, device, pinned=False)
     n_total = VIDEOS_PER_GPU * world
@@ -431,7 +433,8 @@ def run_ours(args) -> None:
             "dtype": "bf16", "data": "synthetic (random-init CLIP ViT-B/16, N(0,1) frames, random token ids)",
             "config": {"workload": WORKLOAD, "videos_per_gpu": VIDEOS_PER_GPU, "frames_per_video": FRAMES,
                        "captions_per_gpu": CAPTIONS_PER_GPU, "gallery": n_total, "similarity": "split-bf16 x3",
-                       "l2": "inputs (2.4 GB/GPU) exceed L2; no explicit flush", "parallelism": f"dp{world}"},
+                       "l2": "inputs (2.4 GB/GPU) exceed L2; no explicit flush", "parallelism": f"dp{world}",
+                       "frames_per_pass": encoder.model.max_frames_per_pass},
             "queries_per_sec": n_total / (ms_per_step * 1e-3),
             "e2e_roofline_frac": step_flops / (ms_per_step * 1e-3) / (peak * 1e12),
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "videos/s",
@@ -558,6 +561,8 @@ def main() -> None:
     ap.add_argument("--webvid-videos", type=int, default=100_000,
                     help="gallery size of the BASELINE configs[3] leg (100k videos x 8 frames, split over the ranks; "
                          "reported under extra.webvid, outside the K timed steps); 0 skips it")
+    ap.add_argument("--frames-per-pass", type=int, default=None,
+                    help="frames per internal encoder pass (default: the library's token budget, ~2000 frames of ViT-B/16)")
     ap.add_argument("--train-videos", type=int, default=512,
                     help="videos per step of the teacher-student TRAINING leg (row f3; extra.train_step, N = 1 only); 0 skips it")
     ap.add_argument("--cpu-sample", type=int, default=128,

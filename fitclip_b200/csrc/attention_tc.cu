@@ -509,7 +509,7 @@ struct Att2Smem {
 // lane quadrants as warps 0-3) do that, the softmax warps go straight from the last P chunk of item i to S(i+1), and
 // the scheduler has four warps to pick from.  Registers are re-balanced with setmaxnreg (softmax 152, epilogue 88,
 // TMA/MMA 40).  A fraction of the exponentials runs on the FMA pipe (ex2_poly_x2): the MUFU pipe is the busiest unit.
-template <int KP, int NPH, bool DESC>
+template <int KP, int NPH>
 __global__ void __launch_bounds__(ATT2_THREADS, 2)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const __grid_constant__ CUtensorMap tmO, int L, int heads, int tiles, int num_items,
@@ -523,13 +523,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int KHALF = NPH == 2 ? 64 : 96;
   constexpr uint32_t TMEM_COLS = O_COL + HD <= 128 ? 128 : 256;
   static_assert(KP / 2 <= O_COL && O_COL + HD <= 256, "P / O column ranges must not overlap");
-  // DESC: the exp pass walks the S chunks in DESCENDING key order and writes P into the UPPER columns -- k-block k
-  // (16 keys) at column P_BASE + 8 k, the tail's P at P_BASE - 8 -- so that after the pass the low columns [0, KLO) hold
-  // nothing: S(i+1) of the first KLO keys is issued at p_full, IN FRONT of the last P(i).V MMAs, and the row-max pass of
-  // item i+1 starts while the tensor core still finishes item i (S of the remaining keys follows behind P.V as before).
-  constexpr int P_BASE = DESC ? KMAIN / 2 : 0;
-  constexpr int KLO = 64;
-  static_assert(!DESC || (KP == 208 && NPH == 2), "descending layout: 6 chunks + tail, hand-overs every 64 keys");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* kq_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* v_full = kq_full + 1;
@@ -540,7 +533,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* t_full = kq_full + 6;
   uint64_t* p_half = kq_full + 7;   // [2]
   uint64_t* l_full = kq_full + 10;  // row sums of item it are in l_buf[it & 1]
-  uint64_t* s_hi = kq_full + 11;    // DESC: S of keys [KLO, KMAIN) is in TMEM (s_full then covers keys [0, KLO) only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kq_full + 9);
   float* l_buf = reinterpret_cast<float*>(smem + S2::OFF_L);
 
@@ -564,7 +556,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(p_half, 128);
     mbar_init(p_half + 1, 128);
     mbar_init(l_full, 128);
-    mbar_init(s_hi, 1);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -601,29 +592,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                        k != 0);
         umma_commit(s_full);
       };
-      // DESC: keys [0, KLO) -> columns [0, KLO) (s_full), keys [KLO, KMAIN) -> columns [KLO, KMAIN) (s_hi)
-      auto issue_s_lo = [&]() {
-        constexpr uint32_t idesc_lo = umma_idesc_bf16_f32(QT, KLO);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_lo,
-                       k != 0);
-        umma_commit(s_full);
-      };
-      auto issue_s_hi = [&]() {
-        constexpr uint32_t idesc_hi = umma_idesc_bf16_f32(QT, KMAIN - KLO);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base + KLO, umma_desc_k_sw128(q_addr + k * 32),
-                       umma_desc_k_sw128(k_addr + KLO * 128 + k * 32), idesc_hi, k != 0);
-        umma_commit(s_hi);
-      };
-      // O (+)= P[:, 16 k .. 16 k + 16) . V[16 k .. 16 k + 16, :]; DESC: P of k-block k sits at column P_BASE + 8 k, the tail's
-      // (k = KP / 16 - 1) at P_BASE - 8
-      auto pv = [&](int k, bool acc) {
-        const uint32_t pcol = !DESC ? k * 8 : (k == KP / 16 - 1 ? P_BASE - 8 : P_BASE + k * 8);
-        umma_bf16_ts(tmem_base + O_COL, tmem_base + pcol, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, acc);
-      };
       auto issue_s_tail = [&]() {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
@@ -641,12 +609,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         cv.advance();
         mbar_wait(kq_full, 0);
         tc_fence_after();
-        if (DESC) {
-          issue_s_lo();
-          issue_s_hi();
-        } else {
-          issue_s_main();
-        }
+        issue_s_main();
         issue_s_tail();
         mbar_wait(t_full, 0);
         if (static_cast<int>(blockIdx.x + gridDim.x) < num_items) load_qk(cqk, 1);
@@ -658,47 +621,24 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int next = item + gridDim.x, next2 = next + gridDim.x;
         const bool has_next = next < num_items;
         mbar_wait(v_full, ph);
-        if (!DESC) {
 #pragma unroll
-          for (int part = 0; part < NPH; ++part) {
-            mbar_wait(p_half + part, ph);
-            tc_fence_after();
-#pragma unroll
-            for (int k = part * (KHALF / 16); k < (part + 1) * (KHALF / 16); ++k) pv(k, k != 0);
-          }
-          mbar_wait(p_full, ph);
+        for (int part = 0; part < NPH; ++part) {
+          mbar_wait(p_half + part, ph);
           tc_fence_after();
 #pragma unroll
-          for (int k = NPH * (KHALF / 16); k < KP / 16; ++k) pv(k, k != 0);
-          umma_commit(o_full);
-          if (has_next) {
-            mbar_wait(kq_full, ph ^ 1);
-            tc_fence_after();
-            issue_s_main();
-          }
-        } else {
-          // P arrives from the high keys down: keys [128, 192) after the first hand-over, [64, 128) after the second,
-          // [0, 64) and the tail at p_full
-          mbar_wait(p_half, ph);
-          tc_fence_after();
+          for (int k = part * (KHALF / 16); k < (part + 1) * (KHALF / 16); ++k)
+            umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
+        }
+        mbar_wait(p_full, ph);
+        tc_fence_after();
 #pragma unroll
-          for (int k = 8; k < 12; ++k) pv(k, k != 8);
-          mbar_wait(p_half + 1, ph);
+        for (int k = NPH * (KHALF / 16); k < KP / 16; ++k)
+          umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv, k != 0);
+        umma_commit(o_full);
+        if (has_next) {
+          mbar_wait(kq_full, ph ^ 1);
           tc_fence_after();
-#pragma unroll
-          for (int k = 4; k < 8; ++k) pv(k, true);
-          mbar_wait(p_full, ph);
-          tc_fence_after();
-          if (has_next) {  // columns [0, KLO) are dead now: S(it+1) of the first keys goes in FRONT of the last P.V MMAs
-            mbar_wait(kq_full, ph ^ 1);
-            tc_fence_after();
-            issue_s_lo();
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) pv(k, true);
-          pv(12, true);
-          umma_commit(o_full);
-          if (has_next) issue_s_hi();  // behind P.V in the tensor pipe's order: P(it) has been consumed
+          issue_s_main();
         }
         mbar_wait(o_full, ph);  // V tile is free again
         if (has_next) {
@@ -818,13 +758,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int c = 0; c < 32; ++c)
               if (j * 32 + c < lim) m = fmaxf(m, __uint_as_float(rc[c]));
           }
-          if (j + DEPTH < NFULL) {
-            if (DESC && (j + DEPTH) * 32 == KLO) {  // the first chunk of the upper keys
-              mbar_wait(s_hi, ph);
-              tc_fence_after();
-            }
-            tmem_ld_32x32b_x32(trow + (j + DEPTH) * 32, r[j % DEPTH]);
-          }
+          if (j + DEPTH < NFULL) tmem_ld_32x32b_x32(trow + (j + DEPTH) * 32, r[j % DEPTH]);
         }
         m = fmaxf(max3(m, m1, m2), m3);
       }
@@ -836,7 +770,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t r16[16];
         tmem_ld_32x32b_x16(trow + NFULL * 32, r16);
         uint32_t r[2][32];
-        tmem_ld_32x32b_x32(trow + (DESC ? (NFULL - 1) * 32 : 0), r[0]);
+        tmem_ld_32x32b_x32(trow, r[0]);
         tmem_ld_wait_fence16(r16);
 #pragma unroll
         for (int c = 0; c < 16; ++c)
@@ -859,15 +793,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk_tail[c] = pack_bf16x2(p0, p1);
         }
 #pragma unroll
-        for (int t = 0; t < NFULL; ++t) {
-          const int j = DESC ? NFULL - 1 - t : t;  // S chunk (32 keys) handled at step t
-          tmem_ld_wait_fence(r[t & 1]);
-          if (t + 1 < NFULL) tmem_ld_32x32b_x32(trow + (DESC ? j - 1 : j + 1) * 32, r[(t + 1) & 1]);
+        for (int j = 0; j < NFULL; ++j) {
+          tmem_ld_wait_fence(r[j & 1]);
+          if (j + 1 < NFULL) tmem_ld_32x32b_x32(trow + (j + 1) * 32, r[(j + 1) & 1]);
           uint32_t pk[16];
           const bool full = (j + 1) * 32 <= lim;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[t & 1][2 * c]), __uint_as_float(r[t & 1][2 * c + 1])),
+            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[j & 1][2 * c]), __uint_as_float(r[j & 1][2 * c + 1])),
                                           sc2, nmc2);
             float p0, p1;
             // ATT2_POLY of every 16 pairs take the FMA-pipe exp2, spread evenly so both pipes stay fed
@@ -887,14 +820,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             else l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
             pk[c] = pack_bf16x2(p0, p1);
           }
-          tmem_st_32x32b_x16(trow + P_BASE + j * 16, pk);
-          if (NPH > 0 && (t + 1) % (KHALF / 32) == 0 && (t + 1) / (KHALF / 32) <= NPH) {
+          tmem_st_32x32b_x16(trow + j * 16, pk);
+          if (NPH > 0 && (j + 1) % (KHALF / 32) == 0 && (j + 1) / (KHALF / 32) <= NPH) {
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(p_half + (t + 1) / (KHALF / 32) - 1);
+            mbar_arrive(p_half + (j + 1) / (KHALF / 32) - 1);
           }
         }
-        tmem_st_32x32b_x8(trow + (DESC ? P_BASE - 8 : NFULL * 16), pk_tail);
+        tmem_st_32x32b_x8(trow + NFULL * 16, pk_tail);
         tmem_st_wait();
         float la, lb;
         unpack_f32x2(add_f32x2(l2a, l2b), la, lb);
@@ -970,18 +903,18 @@ int launch_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaSt
   return FC_OK;
 }
 
-template <int KP, int NPH, bool DESC>
+template <int KP, int NPH>
 int launch_tc2(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaStream_t s) {
   using S2 = Att2Smem<KP>;
   static bool configured = false;
   if (!configured) {
     cudaFuncAttributes fa;
-    FC_CUDA(cudaFuncGetAttributes(&fa, attention_tc2_kernel<KP, NPH, DESC>));
+    FC_CUDA(cudaFuncGetAttributes(&fa, attention_tc2_kernel<KP, NPH>));
     FC_REQUIRE(128 * ATT2_REGS_SOFTMAX + 128 * ATT2_REGS_EPILOGUE + 32 * fa.numRegs <= ATT2_THREADS * fa.numRegs &&
                    ATT2_REGS_EPILOGUE <= fa.numRegs && ATT2_REGS_SOFTMAX >= fa.numRegs,
                "attention_tc2: setmaxnreg plan (%d/%d) does not fit the %d registers per thread the kernel launches with",
                ATT2_REGS_SOFTMAX, ATT2_REGS_EPILOGUE, fa.numRegs);
-    FC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<KP, NPH, DESC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::BYTES));
+    FC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<KP, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::BYTES));
     configured = true;
   }
   const int D = heads * HD;
@@ -1009,7 +942,7 @@ int launch_tc2(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaS
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   note_launch();
-  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc2_kernel<KP, NPH, DESC>, tq, tkv, to, L, heads, tiles, items, scale_log2));
+  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc2_kernel<KP, NPH>, tq, tkv, to, L, heads, tiles, items, scale_log2));
   return FC_OK;
 }
 
@@ -1032,13 +965,11 @@ extern "C" __attribute__((visibility("default"))) int fc_debug_att_timing(unsign
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                       int* handled) {
   *handled = 0;
-  static int disabled = -1, gen1 = 0, gen2a = 0;
+  static int disabled = -1, gen1 = 0;
   if (disabled < 0) {
-    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=tc1 the first-generation tcgen05 kernel,
-    // FC_ATTENTION=tc2a the second-generation kernel with the ascending P layout
+    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=tc1 the first-generation tcgen05 kernel
     const char* e = getenv("FC_ATTENTION");
     gen1 = (e && strcmp(e, "tc1") == 0) ? 1 : 0;
-    gen2a = (e && strcmp(e, "tc2a") == 0) ? 1 : 0;
     disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
   }
   if (disabled) return FC_OK;
@@ -1049,10 +980,7 @@ int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads
   // padded key counts: 80 (CLIP text 77 causal; ViT-B/32 image 50), 144, 208 (ViT-B/16 image 197).  The kernels mask
   // keys >= L generically; attention_tc2_kernel relies on L > KP - 16 (un-masked main chunks).
   if (!causal) {
-    if (L > 192 && !gen1) {
-      if (gen2a) return launch_tc2<208, ATT_PHALF, false>(qkv, out, seqs, L, heads, s);
-      return launch_tc2<208, ATT_PHALF, true>(qkv, out, seqs, L, heads, s);
-    }
+    if (L > 192 && !gen1) return launch_tc2<208, ATT_PHALF>(qkv, out, seqs, L, heads, s);
     if (L > 144) return launch_tc<208, false, ATT_PHALF>(qkv, out, seqs, L, heads, s);
     if (L > 80) return launch_tc<144, false, 0>(qkv, out, seqs, L, heads, s);
     return launch_tc<80, false, 0>(qkv, out, seqs, L, heads, s);
