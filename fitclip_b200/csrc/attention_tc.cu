@@ -965,14 +965,15 @@ extern "C" __attribute__((visibility("default"))) int fc_debug_att_timing(unsign
 int attention_bf16_tc(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                       int* handled) {
   *handled = 0;
-  static int disabled = -1, gen1 = 0;
-  if (disabled < 0) {
-    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=tc1 the first-generation tcgen05 kernel
+  // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, =tc1 the first-generation tcgen05 kernel for the image
+  // sequence, =long the key-block kernel (attention_tc_long.cu) for every un-masked length
+  static int mode = -1;  // 0 default, 1 tc1, 2 mma, 3 long
+  if (mode < 0) {
     const char* e = getenv("FC_ATTENTION");
-    gen1 = (e && strcmp(e, "tc1") == 0) ? 1 : 0;
-    disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+    mode = !e ? 0 : strcmp(e, "tc1") == 0 ? 1 : strcmp(e, "mma") == 0 ? 2 : strcmp(e, "long") == 0 ? 3 : 0;
   }
-  if (disabled) return FC_OK;
+  const bool gen1 = mode == 1;
+  if (mode == 2 || (mode == 3 && !causal)) return FC_OK;
   if (L > 208) return FC_OK;  // longer un-masked sequences: attention_tc_long.cu; longer causal ones: mma.sync kernels
   FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "attention: buffers must be 16-byte aligned");

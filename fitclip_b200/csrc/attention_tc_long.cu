@@ -30,18 +30,25 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int QT = 128;   // query rows per tile
-constexpr int KB = 128;   // keys per block
-constexpr int TILE_BYTES = 128 * 128;  // a [128 x 64] bf16 tile, 128-byte rows
+constexpr int Q_BYTES = 128 * 128;     // a [128 x 64] bf16 tile, 128-byte rows
 constexpr int LONG_THREADS = 160;      // warps 0-3 softmax / epilogue, warp 4 TMA + MMA + TMEM alloc
-constexpr int O_COL = 128;
-constexpr uint32_t TMEM_COLS = 256;
+#ifndef ATT_LONG_KB
+#define ATT_LONG_KB 128  // keys per block: 128 (256 TMEM columns, 2 CTAs per SM) or 64 (128 columns, 3 CTAs per SM)
+#endif
 
-struct LongSmem {
+// KB keys per block: S in TMEM columns [0, KB), P (bf16) over [0, KB / 2), O in [KB, KB + 64)
+template <int KB>
+struct LongCfg {
+  static_assert(KB == 64 || KB == 128, "key block: 64 or 128");
+  static constexpr int KV_BYTES = KB * 128;               // a [KB x 64] bf16 tile
+  static constexpr int O_COL = KB;
+  static constexpr uint32_t TMEM_COLS = KB == 128 ? 256 : 128;
+  static constexpr int CTAS_PER_SM = KB == 128 ? 2 : 3;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = TILE_BYTES;                 // 2 stages
-  static constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;     // 2 stages
-  static constexpr int OFF_STG = OFF_V + 2 * TILE_BYTES;   // 4 warps x (32 rows x 128 B)
-  static constexpr int OFF_BAR = OFF_STG + TILE_BYTES;
+  static constexpr int OFF_K = Q_BYTES;                    // 2 stages
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;       // 2 stages
+  static constexpr int OFF_STG = OFF_V + 2 * KV_BYTES;     // 4 warps x (32 rows x 128 B)
+  static constexpr int OFF_BAR = OFF_STG + Q_BYTES;
   static constexpr int BYTES = OFF_BAR + 128;
 };
 
@@ -49,7 +56,7 @@ struct LongSmem {
 // running maximum; P goes to TMEM as bf16 over the S columns already read.  FULL: all 128 keys of the block exist (every
 // block but the last): fully unrolled, no masks.  !FULL: `valid` < 128 keys exist; S has (valid + 15) & ~15 columns, only
 // the x32 chunks that hold a valid key are touched, stale columns are masked.
-template <bool FULL>
+template <int KB, bool FULL>
 __device__ __forceinline__ void softmax_block(uint32_t trow, int valid, bool first, float scale_log2, float& m_run,
                                               float& l, float& alpha, bool& moved) {
   const int nch = FULL ? KB / 32 : (valid + 31) >> 5;
@@ -57,7 +64,7 @@ __device__ __forceinline__ void softmax_block(uint32_t trow, int valid, bool fir
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
   uint32_t r[2][32];
   tmem_ld_32x32b_x32(trow, r[0]);
-  if (FULL || nch > 1) tmem_ld_32x32b_x32(trow + 32, r[1]);
+  if (KB > 32 && (FULL || nch > 1)) tmem_ld_32x32b_x32(trow + 32, r[1]);
 #pragma unroll
   for (int c4 = 0; c4 < KB / 32; ++c4) {
     if (!FULL && c4 >= nch) break;
@@ -116,10 +123,15 @@ __device__ __forceinline__ void softmax_block(uint32_t trow, int valid, bool fir
   l = l * alpha + la + lb;
 }
 
-__global__ void __launch_bounds__(LONG_THREADS, 2)
-attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmO, int L,
-                         int heads, int tiles, int nkb, int num_items, float scale_log2) {
-  using S = LongSmem;
+template <int KB>
+__global__ void __launch_bounds__(LONG_THREADS, LongCfg<KB>::CTAS_PER_SM)
+attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmKV,
+                         const __grid_constant__ CUtensorMap tmO, int L, int heads, int tiles, int nkb, int num_items,
+                         float scale_log2) {
+  using S = LongCfg<KB>;
+  constexpr int O_COL = S::O_COL;
+  constexpr uint32_t TMEM_COLS = S::TMEM_COLS;
+  constexpr int TILE_BYTES = S::KV_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* kv_full = q_full + 1;   // [2]
@@ -139,6 +151,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   if (threadIdx.x == 128) {
     tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmO);
     mbar_init(q_full, 1);
     mbar_init(kv_full, 1);
@@ -181,8 +194,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
         const int st = g & 1;
         mbar_wait(kv_empty + st, ((g >> 1) & 1) ^ 1);  // first use of a stage: passes at once
         mbar_expect_tx(kv_full + st, 2 * TILE_BYTES);
-        tma_load_3d(smem + S::OFF_K + st * TILE_BYTES, &tmQK, kv_full + st, D + head * HD, j * KB, seq);
-        tma_load_3d(smem + S::OFF_V + st * TILE_BYTES, &tmQK, kv_full + st, 2 * D + head * HD, j * KB, seq);
+        tma_load_3d(smem + S::OFF_K + st * TILE_BYTES, &tmKV, kv_full + st, D + head * HD, j * KB, seq);
+        tma_load_3d(smem + S::OFF_V + st * TILE_BYTES, &tmKV, kv_full + st, 2 * D + head * HD, j * KB, seq);
       };
       auto issue_pv = [&](int g, bool accumulate) {  // O (+)= P_g . V_g
         const uint32_t v_addr = smem_u32(smem + S::OFF_V + (g & 1) * TILE_BYTES);
@@ -206,7 +219,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
         if (j == 0) {
           // Q of the previous item is free: its last S MMA completed before the softmax threads arrived on p_full, and
           // that arrival was waited for below before this point was reached
-          mbar_expect_tx(q_full, TILE_BYTES);
+          mbar_expect_tx(q_full, Q_BYTES);
           tma_load_3d(smem + S::OFF_Q, &tmQK, q_full, head * HD, t * QT, seq);
         }
         mbar_wait(kv_full + (g & 1), (g >> 1) & 1);
@@ -256,8 +269,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
           const int valid = min(KB, L - j * KB);  // keys of this block that exist (>= 1)
           float alpha;
           bool moved;
-          if (valid == KB) softmax_block<true>(trow, valid, j == 0, scale_log2, m_run, l, alpha, moved);
-          else softmax_block<false>(trow, valid, j == 0, scale_log2, m_run, l, alpha, moved);
+          if (valid == KB) softmax_block<KB, true>(trow, valid, j == 0, scale_log2, m_run, l, alpha, moved);
+          else softmax_block<KB, false>(trow, valid, j == 0, scale_log2, m_run, l, alpha, moved);
           // ---- O <- a O where a row's maximum moved (s_full of this block implies P_{j-1}.V_{j-1} has completed)
           if (__any_sync(0xffffffffu, moved)) {
             const uint64_t a2 = pack_f32x2(alpha, alpha);
@@ -341,36 +354,41 @@ int make_tmap_3d(CUtensorMap* tm, const bf16* base, int64_t cols, int64_t L, int
 int attention_bf16_tc_long(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
                            int* handled) {
   *handled = 0;
-  static int disabled = -1;
+  static int disabled = -1, forced = 0;
   if (disabled < 0) {
-    const char* e = getenv("FC_ATTENTION");  // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels
+    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=long this kernel for every un-masked length
+    const char* e = getenv("FC_ATTENTION");
     disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+    forced = (e && strcmp(e, "long") == 0) ? 1 : 0;
   }
-  if (disabled || causal || L <= 208 || L > 768) return FC_OK;
+  if (disabled || causal || (L <= 208 && !forced) || L > 768) return FC_OK;
   FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "attention: buffers must be 16-byte aligned");
   *handled = 1;
+  constexpr int KB = ATT_LONG_KB;
+  using Cfg = LongCfg<KB>;
   static bool configured = false;
   if (!configured) {
-    FC_CUDA(cudaFuncSetAttribute(attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LongSmem::BYTES));
+    FC_CUDA(cudaFuncSetAttribute(attention_tc_long_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
     configured = true;
   }
   const int D = heads * HD;
-  CUtensorMap tqk, to;
+  CUtensorMap tqk, tkv, to;
   int rc;
-  if ((rc = make_tmap_3d(&tqk, qkv, 3 * D, L, seqs, 128))) return rc;  // Q tiles and K / V blocks: 128 rows x 64 columns
+  if ((rc = make_tmap_3d(&tqk, qkv, 3 * D, L, seqs, 128))) return rc;  // Q tiles: 128 rows x 64 columns
+  if ((rc = make_tmap_3d(&tkv, qkv, 3 * D, L, seqs, KB))) return rc;   // K / V blocks: KB rows x 64 columns
   if ((rc = make_tmap_3d(&to, out, D, L, seqs, 32))) return rc;
   const int tiles = (L + QT - 1) / QT, nkb = (L + KB - 1) / KB;
   const int64_t items64 = seqs * heads * tiles;
   FC_REQUIRE(items64 * nkb < (int64_t(1) << 30), "attention: too many work items");
   const int items = static_cast<int>(items64);
-  int grid = 2 * num_sms();
+  int grid = Cfg::CTAS_PER_SM * num_sms();
   if (grid > items) grid = items;
   const float scale_log2 = 0.125f * 1.4426950408889634f;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(LONG_THREADS);
-  cfg.dynamicSmemBytes = LongSmem::BYTES;
+  cfg.dynamicSmemBytes = Cfg::BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -378,7 +396,7 @@ int attention_bf16_tc_long(const bf16* qkv, bf16* out, int64_t seqs, int L, int 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   note_launch();
-  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_long_kernel, tqk, to, L, heads, tiles, nkb, items, scale_log2));
+  FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_long_kernel<KB>, tqk, tkv, to, L, heads, tiles, nkb, items, scale_log2));
   return FC_OK;
 }
 

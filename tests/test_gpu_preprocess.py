@@ -99,3 +99,21 @@ def test_fused_uint8_path_other_patch_sizes(dev):
                      transformer_heads=12, transformer_layers=1)):
         enc = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=3, **cfg).state_dict(), num_frames=2).to(dev)
         assert torch.equal(enc.encode_video_uint8(raw), enc.encode_video_uint8(raw, dtype=torch.bfloat16)), cfg
+
+
+def test_fused_path_argument_errors(dev):
+    import oracle
+    from fitclip_b200 import B200ClipVideoTextEncoder, _lib, ops
+    with pytest.raises(ValueError):
+        ops.preprocess_to_patches(torch.zeros(1, 8, 8, 3, device=dev), 224, 16, MEAN, STD)          # not uint8
+    with pytest.raises(_lib.FitclipError):
+        ops.preprocess_to_patches(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), 224, 16, MEAN, STD)   # CPU tensor
+    with pytest.raises(_lib.FitclipError, match="size % patch"):
+        ops.preprocess_to_patches(torch.zeros(1, 8, 8, 3, dtype=torch.uint8, device=dev), 224, 15, MEAN, STD)
+    enc = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0, vision_layers=1, transformer_layers=1).state_dict(),
+                                   num_frames=2).to(dev)
+    with pytest.raises(ValueError):
+        enc.encode_video_uint8(torch.zeros(1, 2, 3, 32, 32, dtype=torch.uint8, device=dev))          # channels-first
+    with pytest.raises(_lib.FitclipError):
+        enc.encode_video_uint8(torch.zeros(1, 2, 32, 32, 3, dtype=torch.uint8))                       # CPU tensor
+    assert enc.encode_video_uint8(torch.zeros(0, 2, 32, 32, 3, dtype=torch.uint8, device=dev)).shape == (0, 512)

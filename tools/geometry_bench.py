@@ -9,6 +9,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fitclip_b200 import _lib as _libmod  # noqa: E402
+
+if os.environ.get("FITCLIP_VARIANT"):  # A/B runs against a `make VARIANT=name` build of the library
+    _libmod.LIB_PATH = _libmod.LIB_PATH.replace("libfitclip_b200.so", "libfitclip_b200_%s.so" % os.environ["FITCLIP_VARIANT"])
 import oracle  # noqa: E402
 from fitclip_b200 import B200ClipVideoTextEncoder, metrics_from_ranks, ops, retrieval_ranks  # noqa: E402
 
