@@ -12,6 +12,8 @@ from typing import Optional
 import torch
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfitclip_b200.so")
+if os.environ.get("FITCLIP_VARIANT"):  # diagnostics: an experiment build of the SAME library (`make VARIANT=name EXTRA=-D...`)
+    LIB_PATH = LIB_PATH.replace("libfitclip_b200.so", "libfitclip_b200_%s.so" % os.environ["FITCLIP_VARIANT"])
 
 
 class FitclipError(RuntimeError):
