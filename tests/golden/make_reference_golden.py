@@ -276,6 +276,23 @@ def main() -> None:
         "r1_restated": next(v for n, v, _ in logged if n == "r1"), "r5_restated": next(v for n, v, _ in logged if n == "r5"),
         "encoded_videos": torch.cat([o[0] for o in outputs]).clone(), "encoded_texts": torch.cat([o[1] for o in outputs]).clone()}
 
+    # ---- the same flow with TWO datasets (text_video_retrieval.py:28-37, 60-65, 84-93): per-dataset metric clones,
+    # `dataloader_idx`, `loss/val_{name}`; dataset "a" = all 12 samples, dataset "b" = samples 1..11 (Recall(top_k=10) needs more than 10
+    # candidates per dataset, as torchmetrics does), one batch each
+    multi = TextVideoRetrievalLightningModule(encoder=enc1, init_temperature=0.015, fit_temperature=False,
+                                              dataset_names=["a", "b"])
+    multi_outputs = []
+    with torch.inference_mode():
+        for idx, (lo, hi) in enumerate(((0, 12), (1, 12))):
+            batch = {"video": video[lo:hi], "text": {"input_ids": ids[lo:hi]}}
+            multi_outputs.append([multi.validation_step_end(multi.validation_step(batch, 0, idx))])
+        multi.validation_epoch_end(multi_outputs)
+    out["retrieval_multi"] = {
+        "splits": [(0, 12), (1, 12)], "dataset_names": ["a", "b"],
+        "logged": {n: (v.clone() if isinstance(v, torch.Tensor) else v) for n, v, _ in multi.logged
+                   if n.startswith("loss/val") or n.startswith("mr_")},
+        "logged_names": sorted({n for n, _, _ in multi.logged})}
+
     # ---- zero-shot classification flow (video_text_classification.py:30-140)
     labels = ["archery", "baby crawling", "cutting in kitchen", "drumming", "fencing", "golf swing", "knitting"]
     templates = ["a video of a person {}.", "{} in action", "someone is {} here"]

@@ -227,6 +227,62 @@ def test_cuda_retrieval_module_matches_reference_module(ref, dev):
     assert abs(float(exact["r1"]) - float(r["r1_restated"])) < 1e-7 and abs(float(exact["r5"]) - float(r["r5_restated"])) < 1e-7
 
 
+def _multi_dataset_flow(module, encode_inputs, ref):
+    """Drives a TextVideoRetrievalModule the way the golden script drove the reference's module in multi-dataset mode."""
+    m = ref["retrieval_multi"]
+    outputs = []
+    for idx, (lo, hi) in enumerate(m["splits"]):
+        batch = encode_inputs(lo, hi)
+        outputs.append([module.validation_step_end(module.validation_step(batch, 0, idx))])
+    return module.validation_epoch_end(outputs)
+
+
+def test_multi_dataset_module_matches_reference_module_on_cpu(ref):
+    """Multi-dataset validation (text_video_retrieval.py:28-37, 60-65, 84-93) against what the REFERENCE'S module logged:
+    our module's host logic on the reference's own (oracle) embeddings with CPU stand-ins for the kernels -- metric names,
+    per-dataset MdR exactly, per-dataset loss/val to fp32 precision."""
+    from fitclip_b200 import TextVideoRetrievalModule, ops
+    from test_distributed_gloo import CpuSimilarity, _StubEncoder, _cpu_metrics_from_ranks
+    m, r = ref["retrieval_multi"], ref["retrieval"]
+    backup = ops.metrics_from_ranks
+    ops.metrics_from_ranks = _cpu_metrics_from_ranks
+    try:
+        module = TextVideoRetrievalModule(_StubEncoder(), init_temperature=r["init_temperature"], fit_temperature=False,
+                                          dataset_names=m["dataset_names"], similarity_factory=CpuSimilarity,
+                                          nce_loss_fn=oracle.ref_nce_loss)
+        result = _multi_dataset_flow(module, lambda lo, hi: {"video": r["encoded_videos"][lo:hi],
+                                                             "text": {"input_ids": r["encoded_texts"][lo:hi]}}, ref)
+    finally:
+        ops.metrics_from_ranks = backup
+    assert sorted(result) == m["logged_names"]
+    for name in m["dataset_names"]:
+        assert int(result[f"mr_{name}"]) == int(m["logged"][f"mr_{name}"])
+        assert abs(float(result[f"loss/val_{name}"]) - float(m["logged"][f"loss/val_{name}"])) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_multi_dataset_module_matches_reference_module(ref, dev):
+    from fitclip_b200 import B200ClipVideoTextEncoder, TextVideoRetrievalModule
+    m, r = ref["retrieval_multi"], ref["retrieval"]
+    enc = B200ClipVideoTextEncoder(ref["state_dict_1"], num_frames=3).to(dev)
+    module = TextVideoRetrievalModule(enc, init_temperature=r["init_temperature"], fit_temperature=False,
+                                      dataset_names=m["dataset_names"]).to(dev)
+    with torch.inference_mode():
+        result = _multi_dataset_flow(module, lambda lo, hi: {"video": ref["video"][lo:hi].to(dev),
+                                                             "text": {"input_ids": ref["input_ids"][lo:hi].to(dev)}}, ref)
+    assert sorted(result) == m["logged_names"]
+    for name in m["dataset_names"]:  # bf16 encoder vs fp32 reference at scale 66.7
+        expect = float(m["logged"][f"loss/val_{name}"])
+        assert abs(float(result[f"loss/val_{name}"]) - expect) <= 3e-2 * abs(expect)
+    # the epoch-end logic on the REFERENCE'S embeddings: exact per-dataset MdR
+    module2 = TextVideoRetrievalModule(enc, init_temperature=r["init_temperature"], fit_temperature=False,
+                                       dataset_names=m["dataset_names"]).to(dev)
+    for name, (lo, hi) in zip(m["dataset_names"], m["splits"]):
+        exact = module2._validate_dataset([(r["encoded_videos"][lo:hi].to(dev), r["encoded_texts"][lo:hi].to(dev))],
+                                          dataset_name=name)
+        assert int(exact[f"mr_{name}"]) == int(m["logged"][f"mr_{name}"])
+
+
 @pytest.mark.gpu
 def test_cuda_classification_module_matches_reference_module(ref, dev):
     from fitclip_b200 import B200ClipVideoTextEncoder, ops
