@@ -14,81 +14,104 @@ namespace {
 // ------------------------------------------------------------------------------------------- LayerNorm (K2)
 // One warp per row; the row lives in registers (D <= 1024): one HBM read, one HBM write. fp32 statistics, eps inside
 // the sqrt, two-pass (mean, then centred variance) like ATen's CPU kernel within rounding.
+// Round 2: warps walk rows with a grid stride -- gamma / beta stay in registers (the one-row-per-warp version re-read 6 KB
+// of gamma / beta from L1 for every 1.5 KB row) and the NEXT row's 16-byte chunks are requested before the current row's
+// two shuffle reductions start, so every warp always has loads in flight.
 constexpr int LN_MAX_CHUNKS = 4;  // 4 x 32 lanes x 8 bf16 = 1024
+constexpr int LN_WARPS = 8;
 
-__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* x, bf16* y,  // may alias (ln_pre runs in place)
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, int64_t rows, int D,
-                                                             int64_t ldx, int64_t ldy, float eps,
-                                                             float* __restrict__ stats_out) {
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+template <int CH>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf16* x, bf16* y,  // may alias (ln_pre runs in place)
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, int64_t rows, int D,
+                                                                     int64_t ldx, int64_t ldy, float eps,
+                                                                     float* __restrict__ stats_out) {
   const int lane = threadIdx.x & 31;
   const int chunks = D >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
-  float v[LN_MAX_CHUNKS][8];
-  float sum = 0.f;
+  const float inv_d = 1.f / static_cast<float>(D);
+  float gg[CH][8], bb[CH][8];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-    const int c = lane + 32 * i;
-    if (c < chunks) {
-      const uint4 u = xr[c];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = unpack_bf16x2(w[t]);
-        v[i][2 * t] = f.x;
-        v[i][2 * t + 1] = f.y;
-        sum += f.x + f.y;
-      }
-    }
-  }
-  const float mean = warp_sum(sum) / static_cast<float>(D);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-    if (lane + 32 * i < chunks) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float d = v[i][t] - mean;
-        sq += d * d;
-      }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
-  uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
-  float o1 = 0.f, o2 = 0.f;  // sum / sum of squares of the OUTPUT row (consumed by a folded-LayerNorm GEMM)
-#pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+  for (int i = 0; i < CH; ++i) {
     const int c = lane + 32 * i;
     if (c < chunks) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float r[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        r[t] = (v[i][t] - mean) * rstd * gg[t] + bb[t];
-        o1 += r[t];
-        o2 = fmaf(r[t], r[t], o2);
-      }
-      uint4 o;
-      o.x = pack_bf16x2(r[0], r[1]);
-      o.y = pack_bf16x2(r[2], r[3]);
-      o.z = pack_bf16x2(r[4], r[5]);
-      o.w = pack_bf16x2(r[6], r[7]);
-      yr[c] = o;
+      gg[i][0] = g0.x; gg[i][1] = g0.y; gg[i][2] = g0.z; gg[i][3] = g0.w;
+      gg[i][4] = g1.x; gg[i][5] = g1.y; gg[i][6] = g1.z; gg[i][7] = g1.w;
+      bb[i][0] = b0.x; bb[i][1] = b0.y; bb[i][2] = b0.z; bb[i][3] = b0.w;
+      bb[i][4] = b1.x; bb[i][5] = b1.y; bb[i][6] = b1.z; bb[i][7] = b1.w;
     }
   }
-  if (stats_out != nullptr) {  // layout [rows, D/64, 2]: everything in part 0, zeros elsewhere
-    o1 = warp_sum(o1);
-    o2 = warp_sum(o2);
-    const int parts = D >> 6;
-    float2* so = reinterpret_cast<float2*>(stats_out) + row * parts;
-    for (int pi = lane; pi < parts; pi += 32) so[pi] = pi == 0 ? make_float2(o1, o2) : make_float2(0.f, 0.f);
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * LN_WARPS;
+  int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  uint4 nx[CH];
+  auto fetch = [&](int64_t r) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (lane + 32 * i < chunks) nx[i] = ld_stream_v4(xr + lane + 32 * i);  // plain (coherent) loads: y may alias x
+  };
+  if (row < rows) fetch(row);
+  for (; row < rows; row += nwarps) {
+    float v[CH][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (lane + 32 * i < chunks) {
+        const uint32_t w[4] = {nx[i].x, nx[i].y, nx[i].z, nx[i].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16x2(w[t]);
+          v[i][2 * t] = f.x;
+          v[i][2 * t + 1] = f.y;
+          sum += f.x + f.y;
+        }
+      }
+    }
+    if (row + nwarps < rows) fetch(row + nwarps);  // in flight during the reductions and the stores below
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (lane + 32 * i < chunks) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float d = v[i][t] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
+    float o1 = 0.f, o2 = 0.f;  // sum / sum of squares of the OUTPUT row (consumed by a folded-LayerNorm GEMM)
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < chunks) {
+        float r[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          r[t] = (v[i][t] - mean) * rstd * gg[i][t] + bb[i][t];
+          o1 += r[t];
+          o2 = fmaf(r[t], r[t], o2);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(r[0], r[1]);
+        o.y = pack_bf16x2(r[2], r[3]);
+        o.z = pack_bf16x2(r[4], r[5]);
+        o.w = pack_bf16x2(r[6], r[7]);
+        st_na_v4(yr + c, o);
+      }
+    }
+    if (stats_out != nullptr) {  // layout [rows, D/64, 2]: everything in part 0, zeros elsewhere
+      o1 = warp_sum(o1);
+      o2 = warp_sum(o2);
+      const int parts = D >> 6;
+      float2* so = reinterpret_cast<float2*>(stats_out) + row * parts;
+      for (int pi = lane; pi < parts; pi += 32) so[pi] = pi == 0 ? make_float2(o1, o2) : make_float2(0.f, 0.f);
+    }
   }
 }
 
@@ -528,9 +551,14 @@ int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float
              "layernorm: D=%d must be a multiple of 8 and <= 1024", D);
   if (rows == 0) return FC_OK;
   ProfScope prof(s, PROF_LAYERNORM, 0, rows, D, 0, 0.0, 4.0 * rows * D);
-  const int wpb = 8;
-  layernorm_bf16_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(x, y, gamma, beta, rows, D,
-                                                                                          ldx, ldy, eps, stats_out);
+  // persistent-style grid: up to 4 blocks per SM (register use of the CH = 3 instantiation allows 2-3), rows by grid stride
+  const int64_t want = (rows + LN_WARPS - 1) / LN_WARPS;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, int64_t(4) * num_sms()));
+  const int ch = (D + 255) / 256;
+  if (ch == 1) layernorm_bf16_kernel<1><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
+  else if (ch == 2) layernorm_bf16_kernel<2><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
+  else if (ch == 3) layernorm_bf16_kernel<3><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
+  else layernorm_bf16_kernel<4><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 constexpr int LNB_WARPS = 4;
 
 template <int LNB_CHUNKS>
-__global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* dy,
+__global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* dy,
                                                      const float* __restrict__ gamma, const bf16* add, bf16* dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      int64_t rows, int D, float eps) {
@@ -157,16 +157,21 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bw
     for (int t = 0; t < 8; ++t) ag[i][t] = ab[i][t] = 0.f;
   // The next row's x / dy are requested before this row's reductions start, so a warp always has loads in flight
   // (without the prefetch its loads and its shuffle reductions serialise: 0.36 of the copy peak).
-  uint4 nx[LNB_CHUNKS], nd[LNB_CHUNKS];
+  // (round 2: the residual-gradient row `add` is prefetched with them -- it used to be requested at the top of the row's
+  // own iteration and its HBM latency was only partly covered by the four reductions; two blocks of 4 warps per SM with all
+  // three arrays of the next row in flight instead of three blocks with two)
+  uint4 nx[LNB_CHUNKS], nd[LNB_CHUNKS], na[LNB_CHUNKS];
   auto fetch = [&](int64_t r) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + r * D);
     const uint4* dr = reinterpret_cast<const uint4*>(dy + r * D);
+    const uint4* ar = reinterpret_cast<const uint4*>(add + r * D);
 #pragma unroll
     for (int i = 0; i < LNB_CHUNKS; ++i) {
       const int c = lane + 32 * i;
       if (c < chunks) {
         nx[i] = ld_nc_v4(xr + c);
         nd[i] = ld_stream_v4(dr + c);  // dx may alias dy (training.py backward_video): no non-coherent load
+        if (add) na[i] = ld_stream_v4(ar + c);  // (dx may alias add as well)
       }
     }
   };
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bw
           dv[i][2 * t + 1] = b.y;
           sum += a.x + a.y;
         }
-        if (add) av[i] = *(reinterpret_cast<const uint4*>(add + row * D) + c);  // consumed after the reductions
+        if (add) av[i] = na[i];  // consumed after the reductions
       }
     }
     if (row + nwarps < rows) fetch(row + nwarps);
@@ -880,17 +885,46 @@ __global__ void __launch_bounds__(256) token_scatter_kernel(const int32_t* __res
 // ------------------------------------------------------------------------------------------- AdamW
 // torch.optim.AdamW (config/trainer.yaml:22-24: lr 3e-6, betas (0.9, 0.999), eps 1e-8, weight_decay 0.01), one launch
 // over the flat fp32 parameter buffer; also refreshes the bf16 copy the GEMMs read.
+// Four parameters per thread and iteration: 16-byte streaming loads of p / g / m / v (nothing is re-used: keep it out of
+// L1), 16-byte stores, one 8-byte store of the bf16 mirror -- the scalar version (4-byte accesses, one element in flight per
+// thread) ran at 0.56 of the copy peak.
+__device__ __forceinline__ float adamw_one(float& p, float g, float& m, float& v, float lr, float beta1, float beta2, float eps,
+                                           float decay, float step_size, float bc2_sqrt) {
+  p *= decay;
+  m = beta1 * m + (1.f - beta1) * g;
+  v = beta2 * v + (1.f - beta2) * g * g;
+  p -= step_size * (m / (sqrtf(v) / bc2_sqrt + eps));
+  return p;
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v,
                                                     bf16* __restrict__ p_bf16, int64_t n, float lr, float beta1,
                                                     float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
-    const float gi = g[i];
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= (lr / bc1) * (mi / denom);
+  const float decay = 1.f - lr * wd, step_size = lr / bc1;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += stride) {
+    uint4 pu = ld_stream_v4(reinterpret_cast<const uint4*>(p) + i);
+    const uint4 gu = ld_nc_v4(reinterpret_cast<const uint4*>(g) + i);
+    uint4 mu = ld_stream_v4(reinterpret_cast<const uint4*>(m) + i);
+    uint4 vu = ld_stream_v4(reinterpret_cast<const uint4*>(v) + i);
+    float pf[4] = {__uint_as_float(pu.x), __uint_as_float(pu.y), __uint_as_float(pu.z), __uint_as_float(pu.w)};
+    const float gf[4] = {__uint_as_float(gu.x), __uint_as_float(gu.y), __uint_as_float(gu.z), __uint_as_float(gu.w)};
+    float mf[4] = {__uint_as_float(mu.x), __uint_as_float(mu.y), __uint_as_float(mu.z), __uint_as_float(mu.w)};
+    float vf[4] = {__uint_as_float(vu.x), __uint_as_float(vu.y), __uint_as_float(vu.z), __uint_as_float(vu.w)};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) adamw_one(pf[t], gf[t], mf[t], vf[t], lr, beta1, beta2, eps, decay, step_size, bc2_sqrt);
+    st_na_v4(reinterpret_cast<uint4*>(p) + i, make_uint4(__float_as_uint(pf[0]), __float_as_uint(pf[1]), __float_as_uint(pf[2]), __float_as_uint(pf[3])));
+    st_na_v4(reinterpret_cast<uint4*>(m) + i, make_uint4(__float_as_uint(mf[0]), __float_as_uint(mf[1]), __float_as_uint(mf[2]), __float_as_uint(mf[3])));
+    st_na_v4(reinterpret_cast<uint4*>(v) + i, make_uint4(__float_as_uint(vf[0]), __float_as_uint(vf[1]), __float_as_uint(vf[2]), __float_as_uint(vf[3])));
+    if (p_bf16)
+      *reinterpret_cast<uint2*>(p_bf16 + 4 * i) = make_uint2(pack_bf16x2(pf[0], pf[1]), pack_bf16x2(pf[2], pf[3]));
+  }
+  // tail (n not a multiple of 4) and unaligned callers never happen for the trainer's flat buffers; kept for the generic op
+  for (int64_t i = 4 * n4 + static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adamw_one(pi, g[i], mi, vi, lr, beta1, beta2, eps, decay, step_size, bc2_sqrt);
     p[i] = pi;
     m[i] = mi;
     v[i] = vi;
@@ -1171,7 +1205,10 @@ int fc_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, in
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
   const float bc2s = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
   ProfScope prof(static_cast<cudaStream_t>(stream), PROF_OTHER, 15, n, 1, 0, 0.0, (p_bf16 ? 30.0 : 28.0) * n);
-  adamw_kernel<<<grid_for(n, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FC_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+               reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
+             "fc_adamw_step: buffers must be 16-byte aligned (the bf16 mirror 8-byte)");
+  adamw_kernel<<<grid_for(n, 4096), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, static_cast<bf16*>(p_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
   FC_CHECK_LAUNCH();
   return FC_OK;

@@ -74,3 +74,27 @@ nt = nv = 16384
 s = torch.randn(nt, nv, device=dev)
 tgt = torch.arange(nt, device=dev, dtype=torch.int32)
 report("rank_from_scores_kernel", 4.0 * nt * nv, timed(lambda: ops.rank_from_scores(s, tgt)), "16384 x 16384 fp32 scores (1.07 GB)")
+del s, tgt
+
+# ---- training-step kernels (row f3)
+from fitclip_b200 import train_ops as T  # noqa: E402
+
+# AdamW over the ViT-B/16 parameter count: p, g, m, v read (16 B), p, m, v written (12 B), bf16 mirror written (2 B)
+n = 149_620_736
+p_, g_, m_, v_ = (torch.randn(n, device=dev) * 0.01 for _ in range(4))
+v_.abs_()
+pb = torch.empty(n, device=dev, dtype=torch.bfloat16)
+report("adamw_kernel", 30.0 * n, timed(lambda: T.adamw_step(p_, g_, m_, v_, 3, lr=3e-6, p_bf16=pb)),
+       "149.6 M parameters: fp32 p / g / m / v in, p / m / v + bf16 mirror out")
+del p_, g_, m_, v_, pb
+
+# LayerNorm backward with the residual gradient added: x, dy, add read (6 B), dx written (2 B) per element
+rows, D = 512 * 197, 768
+x = torch.randn(rows, D, device=dev).bfloat16()
+dy = torch.randn(rows, D, device=dev).bfloat16()
+add = torch.randn(rows, D, device=dev).bfloat16()
+gam = torch.ones(D, device=dev)
+dgam, dbet = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+dx = torch.empty_like(x)
+report("ln_bwd_kernel", 8.0 * rows * D, timed(lambda: T.layernorm_bwd(x, dy, gam, dgam, dbet, add=add, out=dx)),
+       "100864 rows x 768: x, dy, residual gradient in, dx out (+ dgamma / dbeta)")
