@@ -14,9 +14,9 @@ namespace {
 // ------------------------------------------------------------------------------------------- LayerNorm (K2)
 // One warp per row; the row lives in registers (D <= 1024): one HBM read, one HBM write. fp32 statistics, eps inside
 // the sqrt, two-pass (mean, then centred variance) like ATen's CPU kernel within rounding.
-// Round 2: warps walk rows with a grid stride -- gamma / beta stay in registers (the one-row-per-warp version re-read 6 KB
-// of gamma / beta from L1 for every 1.5 KB row) and the NEXT row's 16-byte chunks are requested before the current row's
-// two shuffle reductions start, so every warp always has loads in flight.
+// Round 2: warps walk rows with a grid stride, gamma / beta come from shared memory (the one-row-per-warp version re-read
+// 6 KB of gamma / beta from L1 for every 1.5 KB row) and the rows TWO strides ahead are requested before the current row's
+// shuffle reductions start, so every warp always has two rows of loads in flight.
 constexpr int LN_MAX_CHUNKS = 4;  // 4 x 32 lanes x 8 bf16 = 1024
 constexpr int LN_WARPS = 8;
 
@@ -29,38 +29,37 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf1
   const int lane = threadIdx.x & 31;
   const int chunks = D >> 3;
   const float inv_d = 1.f / static_cast<float>(D);
-  float gg[CH][8], bb[CH][8];
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const int c = lane + 32 * i;
-    if (c < chunks) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
-      gg[i][0] = g0.x; gg[i][1] = g0.y; gg[i][2] = g0.z; gg[i][3] = g0.w;
-      gg[i][4] = g1.x; gg[i][5] = g1.y; gg[i][6] = g1.z; gg[i][7] = g1.w;
-      bb[i][0] = b0.x; bb[i][1] = b0.y; bb[i][2] = b0.z; bb[i][3] = b0.w;
-      bb[i][4] = b1.x; bb[i][5] = b1.y; bb[i][6] = b1.z; bb[i][7] = b1.w;
-    }
+  // gamma / beta: staged once per (persistent) block in shared memory -- in registers they cost 48 of them at D = 768 and a
+  // block per SM; re-read from L1 for every row (round 1) they were 6 KB of traffic per 1.5 KB row
+  __shared__ __align__(16) float s_gamma[CH * 256], s_beta[CH * 256];
+  for (int k = threadIdx.x; k < CH * 256; k += LN_WARPS * 32) {
+    s_gamma[k] = k < D ? gamma[k] : 0.f;
+    s_beta[k] = k < D ? beta[k] : 0.f;
   }
+  __syncthreads();
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * LN_WARPS;
   int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
-  uint4 nx[CH];
-  auto fetch = [&](int64_t r) {
+  // two rows ahead: 2 blocks x 8 warps per SM (125 registers at D = 768) with ONE row in flight each are 24 KB per SM, which
+  // caps the kernel near 4.6 TB/s at ~700 ns of HBM latency; two rows in flight lift the cap
+  uint4 nx[2][CH];
+  auto fetch = [&](int64_t r, int slot) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
 #pragma unroll
     for (int i = 0; i < CH; ++i)
-      if (lane + 32 * i < chunks) nx[i] = ld_stream_v4(xr + lane + 32 * i);  // plain (coherent) loads: y may alias x
+      if (lane + 32 * i < chunks) nx[slot][i] = ld_stream_v4(xr + lane + 32 * i);  // plain (coherent) loads: y may alias x
   };
-  if (row < rows) fetch(row);
-  for (; row < rows; row += nwarps) {
+  if (row < rows) fetch(row, 0);
+  if (row + nwarps < rows) fetch(row + nwarps, 1);
+  int slot = 0;
+#pragma unroll 2
+  for (; row < rows; row += nwarps, slot ^= 1) {
     float v[CH][8];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       if (lane + 32 * i < chunks) {
-        const uint32_t w[4] = {nx[i].x, nx[i].y, nx[i].z, nx[i].w};
+        const uint4 q4 = slot ? nx[1][i] : nx[0][i];
+        const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 f = unpack_bf16x2(w[t]);
@@ -70,7 +69,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf1
         }
       }
     }
-    if (row + nwarps < rows) fetch(row + nwarps);  // in flight during the reductions and the stores below
+    if (row + 2 * nwarps < rows) {  // refill the slot just consumed: in flight during the next TWO rows' work
+      if (slot) fetch(row + 2 * nwarps, 1);
+      else fetch(row + 2 * nwarps, 0);
+    }
     const float mean = warp_sum(sum) * inv_d;
     float sq = 0.f;
 #pragma unroll
@@ -90,10 +92,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf1
     for (int i = 0; i < CH; ++i) {
       const int c = lane + 32 * i;
       if (c < chunks) {
+        const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + c * 8), g1 = *reinterpret_cast<const float4*>(s_gamma + c * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_beta + c * 8), b1 = *reinterpret_cast<const float4*>(s_beta + c * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float r[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          r[t] = (v[i][t] - mean) * rstd * gg[i][t] + bb[i][t];
+          r[t] = (v[i][t] - mean) * rstd * gg[t] + bb[t];
           o1 += r[t];
           o2 = fmaf(r[t], r[t], o2);
         }

@@ -137,9 +137,13 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 // One warp per row (same register layout as layernorm_bf16_kernel: lane owns 16-byte chunks lane + 32 i), warps walk
 // rows with a grid stride and keep their dgamma/dbeta partials in registers; one block reduction + atomics at the end.
 constexpr int LNB_WARPS = 4;
+#ifndef LNB_PREFETCH_ADD
+#define LNB_PREFETCH_ADD 0  // 1: prefetch the residual-gradient row with x / dy as well (185 registers: 2 blocks per SM) --
+                           // measured SLOWER (2965 vs 3613 GB/s standalone, 24.0 vs 19.5 ms in the step): occupancy wins
+#endif
 
 template <int LNB_CHUNKS>
-__global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* dy,
+__global__ void __launch_bounds__(LNB_WARPS * 32, (LNB_PREFETCH_ADD || LNB_CHUNKS == 4) ? 2 : 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* dy,
                                                      const float* __restrict__ gamma, const bf16* add, bf16* dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      int64_t rows, int D, float eps) {
@@ -157,9 +161,8 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(const bf16* _
     for (int t = 0; t < 8; ++t) ag[i][t] = ab[i][t] = 0.f;
   // The next row's x / dy are requested before this row's reductions start, so a warp always has loads in flight
   // (without the prefetch its loads and its shuffle reductions serialise: 0.36 of the copy peak).
-  // (round 2: the residual-gradient row `add` is prefetched with them -- it used to be requested at the top of the row's
-  // own iteration and its HBM latency was only partly covered by the four reductions; two blocks of 4 warps per SM with all
-  // three arrays of the next row in flight instead of three blocks with two)
+  // (the residual-gradient row `add` is requested at the top of the row's own iteration and consumed after the four
+  // reductions; prefetching it too costs a block per SM and loses -- see LNB_PREFETCH_ADD)
   uint4 nx[LNB_CHUNKS], nd[LNB_CHUNKS], na[LNB_CHUNKS];
   auto fetch = [&](int64_t r) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + r * D);
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(const bf16* _
       if (c < chunks) {
         nx[i] = ld_nc_v4(xr + c);
         nd[i] = ld_stream_v4(dr + c);  // dx may alias dy (training.py backward_video): no non-coherent load
-        if (add) na[i] = ld_stream_v4(ar + c);  // (dx may alias add as well)
+        if (LNB_PREFETCH_ADD && add) na[i] = ld_stream_v4(ar + c);  // (dx may alias add as well)
       }
     }
   };
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(const bf16* _
           dv[i][2 * t + 1] = b.y;
           sum += a.x + a.y;
         }
-        if (add) av[i] = na[i];  // consumed after the reductions
+        if (add) av[i] = LNB_PREFETCH_ADD ? na[i] : ld_stream_v4(reinterpret_cast<const uint4*>(add + row * D) + c);
       }
     }
     if (row + nwarps < rows) fetch(row + nwarps);

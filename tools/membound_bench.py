@@ -51,6 +51,12 @@ y = torch.empty_like(x)
 report("layernorm_bf16_kernel", 4.0 * rows * D, timed(lambda: ops.layernorm_bf16(x, g, be, out=y)),
        "100864 rows x 768 (one 512-frame pass); 155 MB in + 155 MB out")
 del x, y
+rows = 2000 * 197  # the pass size the engine actually runs (token budget: ~2000 frames of ViT-B/16)
+x = torch.randn(rows, D, device=dev).bfloat16()
+y = torch.empty_like(x)
+report("layernorm_bf16_kernel (2000-frame pass)", 4.0 * rows * D, timed(lambda: ops.layernorm_bf16(x, g, be, out=y)),
+       "394000 rows x 768; 605 MB in + 605 MB out")
+del x, y
 
 # K8 pool + normalise: fp32 (B*T, 512) -> (B, 512)
 B, T = 200_000, 8
