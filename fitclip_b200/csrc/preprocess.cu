@@ -43,7 +43,7 @@ __device__ __forceinline__ void store_px<bf16>(bf16* p, float v) { *p = __float2
 // One thread = one output pixel (all three channels); consecutive threads walk an output row, so the three channel
 // planes are written with fully coalesced stores.  The four horizontal taps of a source row are 12 consecutive bytes
 // (4 pixels x RGB): they are fetched as four aligned 32-bit words and realigned with funnel shifts -- 16 loads per
-// output pixel instead of 48 byte loads (the kernel is LSU-bound, not HBM-bound: neighbouring threads re-read the
+// output pixel instead of 48 byte loads (the kernel is LSU / ALU-bound, not HBM-bound: neighbouring threads re-read the
 // same lines from L1).  Pixels whose taps are clamped at the left / right border take the byte path.
 // PATCH = true writes the result straight into the patch-embedding GEMM's A operand instead of an NCHW image: pixel
 // (c, oy, ox) of frame f lands in row f*G*G + (oy/P)*G + ox/P, column c*P*P + (oy%P)*P + ox%P of the bf16 patch matrix
@@ -81,8 +81,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
       const uint32_t v[3] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh)};
 #pragma unroll
       for (int k = 0; k < 12; ++k) {  // byte k = pixel k / 3, channel k % 3
-        const float t = static_cast<float>((v[k >> 2] >> ((k & 3) * 8)) & 0xffu) * inv255;
-        r[k % 3] = fmaf(t, cx[k / 3], r[k % 3]);
+        // uint8 -> fp32 WITHOUT the I2F instruction (it runs on the quarter-rate XU pipe, and 48 of them per output pixel
+        // were the kernel's bound): one PRMT drops the byte into the mantissa of 2^23, one FADD removes the 2^23 -- exact
+        const float t = __uint_as_float(__byte_perm(v[k >> 2], 0x4B000000u, 0x7440u | (k & 3))) - 8388608.f;
+        r[k % 3] = fmaf(t * inv255, cx[k / 3], r[k % 3]);
       }
     } else {
 #pragma unroll
