@@ -95,9 +95,13 @@ class ClipTrainer:
     """Forward-with-saved-activations, backward and AdamW for one :class:`B200Clip` (the student)."""
 
     def __init__(self, model: B200Clip, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, kernels: Any = None, keep_layernorm: bool = True) -> None:
+                 weight_decay: float = 1e-2, kernels: Any = None, keep_layernorm: bool = True,
+                 keep_activation: bool = True) -> None:
         self.model = model
         self.keep_layernorm = keep_layernorm
+        # keep QuickGELU(u) from the forward (+ 2 B per MLP-hidden element: 30 GB at 2048 frames of ViT-B/16, 133 GB peak)
+        # instead of re-emitting it from the backward's pass over u: that pass then writes 2 B per element less
+        self.keep_activation = keep_activation
         self.cfg = dict(model.config)
         if (3 * self.cfg["vision_patch_size"] ** 2) % 8:
             raise ValueError("training needs 3 * patch_size^2 to be a multiple of 8 (ViT-B/16, ViT-B/32)")
@@ -171,7 +175,8 @@ class ClipTrainer:
             u = K.linear(ln2, wb[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"])
             act = K.quickgelu(u)
             x_out = K.linear(act, wb[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"], resid=x_mid)
-            saved.append((x, qkv, att, x_mid, u) + ((ln1, ln2) if self.keep_layernorm else (None, None)))
+            saved.append((x, qkv, att, x_mid, u) + ((ln1, ln2) if self.keep_layernorm else (None, None))
+                         + ((act,) if self.keep_activation else (None,)))
             x = x_out
         return x
 
@@ -186,13 +191,16 @@ class ClipTrainer:
         K, w, g = self.K, self.w, self.g
         for i in reversed(range(layers)):
             p = f"{prefix}resblocks.{i}."
-            x_in, qkv, att, x_mid, u, ln1, ln2 = saved.pop()
+            x_in, qkv, att, x_mid, u, ln1, ln2, act = saved.pop()
             # x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
-            # dact first (it does not need quickgelu(u)); then ONE pass over u gives both du and quickgelu(u), which the
-            # c_proj weight gradient reads
+            # dact first (it does not need quickgelu(u)); then ONE pass over u gives du -- and, unless the forward kept it,
+            # quickgelu(u), which the c_proj weight gradient reads
             dact = K.linear_nt(dx, self.wb[p + "mlp.c_proj.weight"])
-            act = K.empty_like(u)
-            du = K.quickgelu_bwd(u, dact, out=dact, g_out=act)
+            if act is None:
+                act = K.empty_like(u)
+                du = K.quickgelu_bwd(u, dact, out=dact, g_out=act)
+            else:
+                du = K.quickgelu_bwd(u, dact, out=dact)
             K.colsum(dx, g[p + "mlp.c_proj.bias"])
             K.wgrad_tn(dx, act, g[p + "mlp.c_proj.weight"])
             del act
