@@ -422,7 +422,9 @@ def run_ours(args) -> None:
         step_flops = VIDEOS_PER_GPU * FRAMES * FLOP_PER_FRAME + CAPTIONS_PER_GPU * FLOP_PER_CAPTION \
             + 2.0 * n_total * VIDEOS_PER_GPU * 512
         traffic = None
-        traffic_path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+        traffic_path = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")  # the fc1 launch at the pass size run here
+        if not os.path.exists(traffic_path):
+            traffic_path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
         if os.path.exists(traffic_path):  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from ncu --set full
             with open(traffic_path) as f:
                 traffic = json.load(f)

@@ -1,5 +1,6 @@
-"""One short pass of the hot path for ncu: 256 frames (one vision pass), 984 captions (one text pass), similarity+rank.
-Usage: python tools/profile_step.py [passes]"""
+"""One short pass of the hot path for ncu: `videos` x 4 frames (one vision pass when <= ~500 videos), 984 captions (one
+text pass), similarity+rank.
+Usage: python tools/profile_step.py [passes [videos]]     (videos = 500 is the 2000-frame pass the bench runs)"""
 import os
 import sys
 
@@ -12,7 +13,8 @@ from fitclip_b200 import B200ClipVideoTextEncoder, metrics_from_ranks, retrieval
 passes = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 dev = torch.device("cuda:0")
 enc = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0).state_dict()).to(dev)
-video = torch.randn(64, 4, 3, 224, 224, device=dev)
+videos = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+video = torch.randn(videos, 4, 3, 224, 224, device=dev)
 ids = oracle.tokenize_synthetic(984, 77).to(dev)
 with torch.inference_mode():
     for _ in range(passes):
