@@ -253,8 +253,9 @@ class TextVideoRetrievalModule(nn.Module):
 
     def _validation_dataset_step_end(self, output: TYPE_OUTPUT, dataset_name: Optional[str] = None) -> TYPE_OUTPUT:
         # text_video_retrieval.py:44-58: gather the batch across ranks, scaled B x B scores, NCE loss
-        encoded_video, _ = all_gather_rows(output[0].contiguous(), self.group)
-        encoded_text, _ = all_gather_rows(output[1].contiguous(), self.group)
+        assert len(output[0]) == len(output[1]), "retrieval batches pair every video with one caption"
+        encoded_video, sizes = all_gather_rows(output[0].contiguous(), self.group)
+        encoded_text, _ = all_gather_rows(output[1].contiguous(), self.group, sizes=sizes)  # same sizes: one exchange
         batch_size = len(encoded_video)
         scale = float(self.logit_scale.detach().exp())
         # `logit_scale * V @ T.T` == (logit_scale * V) @ T.T: rows = videos here
