@@ -3,11 +3,12 @@
 // ViT-L/14@336: 577 tokens, clip_vit_l_14_336px.yaml).  Reference arithmetic: nn.MultiheadAttention(need_weights=False)
 // in ResidualAttentionBlock (twin aligner/encoder/slip.py:378-380).
 //
-// A row of S no longer fits the 256 TMEM columns a CTA gets (two CTAs per SM), so keys are walked in blocks of 128 with
-// an ONLINE softmax:
+// A row of S no longer fits the 256 TMEM columns a CTA gets (two CTAs per SM), so keys are walked in blocks of KB = 192
+// (128 for 209..256 tokens, where 192 saves no block) with an ONLINE softmax; written out for KB = 128:
 //   work item   (sequence, head, 128-row query tile); persistent CTAs, 2 per SM
-//   TMA         Q tile once per item; K / V blocks [128 x 64] double-buffered (2 stages each), 3-D tensor maps: rows
-//               beyond the sequence are zero-filled on load and clipped on store
+//   TMA         Q tile once per item; K / V blocks [KB x 64], each with its own full / empty barriers (double-buffered for
+//               KB = 128, single for 192), 3-D tensor maps: rows beyond the sequence are zero-filled on load and clipped
+//               on store
 //   MMA         S_j = Q K_j^T   (M = 128, N = 128, fp32, TMEM cols [0, 128))
 //   softmax     one query row per thread: m' = max(m, rowmax(S_j)), P_j = exp2((S_j - m') c) as bf16 over the dead S
 //               columns, l = l a + rowsum(P_j) with a = exp2((m - m') c); if any row of the warp moved its maximum,
@@ -32,22 +33,23 @@ constexpr int HD = 64;
 constexpr int QT = 128;   // query rows per tile
 constexpr int Q_BYTES = 128 * 128;     // a [128 x 64] bf16 tile, 128-byte rows
 constexpr int LONG_THREADS = 160;      // warps 0-3 softmax / epilogue, warp 4 TMA + MMA + TMEM alloc
-#ifndef ATT_LONG_KB
-#define ATT_LONG_KB 128  // keys per block: 128 (256 TMEM columns, 2 CTAs per SM) or 64 (128 columns, 3 CTAs per SM)
-#endif
 
-// KB keys per block: S in TMEM columns [0, KB), P (bf16) over [0, KB / 2), O in [KB, KB + 64)
+// KB keys per block: S in TMEM columns [0, KB), P (bf16) over [0, KB / 2), O in [KB, KB + 64).
+//   KB = 128: 256 TMEM columns (192 used), K / V double-buffered, 2 CTAs per SM
+//   KB = 192: all 256 columns, K / V single-buffered (80 KB of shared memory keeps 2 CTAs per SM): 257 tokens are 2 key
+//             blocks instead of 3, 577 are 4 instead of 5 -- the per-item chain S -> softmax -> P.V is that much shorter
 template <int KB>
 struct LongCfg {
-  static_assert(KB == 64 || KB == 128, "key block: 64 or 128");
+  static_assert(KB == 128 || KB == 192, "key block: 128 or 192");
+  static constexpr int STAGES = KB == 128 ? 2 : 1;
   static constexpr int KV_BYTES = KB * 128;               // a [KB x 64] bf16 tile
   static constexpr int O_COL = KB;
-  static constexpr uint32_t TMEM_COLS = KB == 128 ? 256 : 128;
-  static constexpr int CTAS_PER_SM = KB == 128 ? 2 : 3;
+  static constexpr uint32_t TMEM_COLS = 256;
+  static constexpr int CTAS_PER_SM = 2;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = Q_BYTES;                    // 2 stages
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;       // 2 stages
-  static constexpr int OFF_STG = OFF_V + 2 * KV_BYTES;     // 4 warps x (32 rows x 128 B)
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
+  static constexpr int OFF_STG = OFF_V + STAGES * KV_BYTES;  // 4 warps x (32 rows x 128 B)
   static constexpr int OFF_BAR = OFF_STG + Q_BYTES;
   static constexpr int BYTES = OFF_BAR + 128;
 };
@@ -134,12 +136,15 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
   constexpr int TILE_BYTES = S::KV_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* kv_full = q_full + 1;   // [2]
-  uint64_t* kv_empty = q_full + 3;  // [2]
-  uint64_t* s_full = q_full + 5;
-  uint64_t* p_full = q_full + 6;
-  uint64_t* o_full = q_full + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 8);
+  uint64_t* k_full = q_full + 1;    // [2]
+  uint64_t* k_empty = q_full + 3;   // [2]
+  uint64_t* v_full = q_full + 5;    // [2]
+  uint64_t* v_empty = q_full + 7;   // [2]
+  uint64_t* s_full = q_full + 9;
+  uint64_t* p_full = q_full + 10;
+  uint64_t* o_full = q_full + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 12);
+  constexpr int ST = S::STAGES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * HD;
@@ -154,10 +159,12 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmO);
     mbar_init(q_full, 1);
-    mbar_init(kv_full, 1);
-    mbar_init(kv_full + 1, 1);
-    mbar_init(kv_empty, 1);
-    mbar_init(kv_empty + 1, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(k_empty + i, 1);
+      mbar_init(v_full + i, 1);
+      mbar_init(v_empty + i, 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
@@ -188,17 +195,29 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
         head = sh % heads;
         seq = sh / heads;
       };
-      auto load_kv = [&](int g) {
+      // K and V have their own full / empty barriers: K_g is free once S_g has completed, V_g once P_g.V_g has -- with one
+      // stage (KB = 192) K_{g+1} streams in under softmax(g) and V_{g+1} under S_{g+1} + softmax(g+1)
+      auto load_k = [&](int g) {
         int t, head, seq, j;
         coords(g, t, head, seq, j);
-        const int st = g & 1;
-        mbar_wait(kv_empty + st, ((g >> 1) & 1) ^ 1);  // first use of a stage: passes at once
-        mbar_expect_tx(kv_full + st, 2 * TILE_BYTES);
-        tma_load_3d(smem + S::OFF_K + st * TILE_BYTES, &tmKV, kv_full + st, D + head * HD, j * KB, seq);
-        tma_load_3d(smem + S::OFF_V + st * TILE_BYTES, &tmKV, kv_full + st, 2 * D + head * HD, j * KB, seq);
+        const int st = g % ST;
+        mbar_wait(k_empty + st, ((g / ST) & 1) ^ 1);  // first use of a stage: passes at once
+        mbar_expect_tx(k_full + st, TILE_BYTES);
+        tma_load_3d(smem + S::OFF_K + st * TILE_BYTES, &tmKV, k_full + st, D + head * HD, j * KB, seq);
+      };
+      auto load_v = [&](int g) {
+        int t, head, seq, j;
+        coords(g, t, head, seq, j);
+        const int st = g % ST;
+        mbar_wait(v_empty + st, ((g / ST) & 1) ^ 1);
+        mbar_expect_tx(v_full + st, TILE_BYTES);
+        tma_load_3d(smem + S::OFF_V + st * TILE_BYTES, &tmKV, v_full + st, 2 * D + head * HD, j * KB, seq);
       };
       auto issue_pv = [&](int g, bool accumulate) {  // O (+)= P_g . V_g
-        const uint32_t v_addr = smem_u32(smem + S::OFF_V + (g & 1) * TILE_BYTES);
+        const int st = g % ST;
+        mbar_wait(v_full + st, (g / ST) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem + S::OFF_V + st * TILE_BYTES);
         const int nk = ncols_of(g % nkb) / 16;
         if (nk == KB / 16) {
 #pragma unroll
@@ -210,19 +229,21 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
             umma_bf16_ts(tmem_base + O_COL, tmem_base + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_pv,
                          accumulate || k != 0);
         }
-        umma_commit(kv_empty + (g & 1));  // K_g / V_g may be overwritten once these MMAs (and S_g before them) are done
+        umma_commit(v_empty + st);  // V_g may be overwritten once these MMAs are done
       };
-      load_kv(0);
+      load_k(0);
+      load_v(0);
       for (int g = 0; g < total_blocks; ++g) {
         int t, head, seq, j;
         coords(g, t, head, seq, j);
+        const int st = g % ST;
         if (j == 0) {
           // Q of the previous item is free: its last S MMA completed before the softmax threads arrived on p_full, and
           // that arrival was waited for below before this point was reached
           mbar_expect_tx(q_full, Q_BYTES);
           tma_load_3d(smem + S::OFF_Q, &tmQK, q_full, head * HD, t * QT, seq);
         }
-        mbar_wait(kv_full + (g & 1), (g >> 1) & 1);
+        mbar_wait(k_full + st, (g / ST) & 1);
         if (j == 0) mbar_wait(q_full, (g / nkb) & 1);
         if (j > 0) {
           mbar_wait(p_full, (g - 1) & 1);  // P_{g-1} is in TMEM and O has been rescaled
@@ -230,15 +251,22 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_
           issue_pv(g - 1, j - 1 > 0);
         }
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(smem + S::OFF_K + (g & 1) * TILE_BYTES);
+        const uint32_t k_addr = smem_u32(smem + S::OFF_K + st * TILE_BYTES);
         const uint32_t idesc_s = umma_idesc_bf16_f32(QT, ncols_of(j));
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0);
         umma_commit(s_full);
-        // prefetch the next block into the other stage: it was last used by block g - 1, whose P.V has just been issued
-        // (kv_empty of that stage completes with it) -- the wait must come after that issue
-        if (g + 1 < total_blocks) load_kv(g + 1);
+        umma_commit(k_empty + st);  // K_g may be overwritten once S_g is done
+        // Loads for later blocks.  Each wait on an empty barrier below is for MMAs that have already been ISSUED (P.V of
+        // block g - 1 above or in the previous iteration's tail, S of block g just now), never for one still to come.
+        if (ST == 1) {
+          if (g > 0) load_v(g);                     // the V stage was released by P_{g-1}.V_{g-1}
+          if (g + 1 < total_blocks) load_k(g + 1);  // the K stage is released by S_g
+        } else if (g + 1 < total_blocks) {
+          load_k(g + 1);  // stage (g + 1) % 2 was used by block g - 1
+          load_v(g + 1);
+        }
         if (j == nkb - 1) {  // last key block of the item
           mbar_wait(p_full, g & 1);
           tc_fence_after();
@@ -348,24 +376,8 @@ int make_tmap_3d(CUtensorMap* tm, const bf16* base, int64_t cols, int64_t L, int
   return tmap_bf16_sw128(tm, base, 3, dims, strides, box);
 }
 
-}  // namespace
-
-// Un-masked sequences of 209..768 tokens. *handled = 1 when it took the call.
-int attention_bf16_tc_long(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
-                           int* handled) {
-  *handled = 0;
-  static int disabled = -1, forced = 0;
-  if (disabled < 0) {
-    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=long this kernel for every un-masked length
-    const char* e = getenv("FC_ATTENTION");
-    disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
-    forced = (e && strcmp(e, "long") == 0) ? 1 : 0;
-  }
-  if (disabled || causal || (L <= 208 && !forced) || L > 768) return FC_OK;
-  FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-             "attention: buffers must be 16-byte aligned");
-  *handled = 1;
-  constexpr int KB = ATT_LONG_KB;
+template <int KB>
+int launch_long(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, cudaStream_t s) {
   using Cfg = LongCfg<KB>;
   static bool configured = false;
   if (!configured) {
@@ -398,6 +410,33 @@ int attention_bf16_tc_long(const bf16* qkv, bf16* out, int64_t seqs, int L, int 
   note_launch();
   FC_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_long_kernel<KB>, tqk, tkv, to, L, heads, tiles, nkb, items, scale_log2));
   return FC_OK;
+}
+
+}  // namespace
+
+// Un-masked sequences of 209..768 tokens. *handled = 1 when it took the call.
+int attention_bf16_tc_long(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s,
+                           int* handled) {
+  *handled = 0;
+  static int disabled = -1, forced = 0;
+  if (disabled < 0) {
+    // diagnostics: FC_ATTENTION=mma forces the mma.sync kernels, FC_ATTENTION=long this kernel for every un-masked length
+    const char* e = getenv("FC_ATTENTION");
+    disabled = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+    forced = (e && strcmp(e, "long") == 0) ? 1 : 0;
+  }
+  if (disabled || causal || (L <= 208 && !forced) || L > 768) return FC_OK;
+  FC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "attention: buffers must be 16-byte aligned");
+  *handled = 1;
+  // 192-key blocks wherever they save a block (every length above 256); FC_ATT_LONG_KB=128|192 overrides for measurements
+  static int kb_env = -1;
+  if (kb_env < 0) {
+    const char* e = getenv("FC_ATT_LONG_KB");
+    kb_env = e ? atoi(e) : 0;
+  }
+  const int kb = kb_env == 128 || kb_env == 192 ? kb_env : ((L + 191) / 192 < (L + 127) / 128 ? 192 : 128);
+  return kb == 192 ? launch_long<192>(qkv, out, seqs, L, heads, s) : launch_long<128>(qkv, out, seqs, L, heads, s);
 }
 
 }  // namespace fc
