@@ -6,6 +6,7 @@ from .encoder import B200Clip, B200ClipVideoTextEncoder, load_clip_model  # noqa
 from .metrics import Accuracy, MeanRank, MedianRank, Rank, Recall  # noqa: F401
 from .retrieval import (TextVideoRetrievalModule, metrics_from_ranks, retrieval_ranks, retrieval_topk,  # noqa: F401
                         shard_bounds)
+from .slip_encoder import B200SlipClip, B200SlipVideoTextEncoder, load_slip_model  # noqa: F401
 from .teacher_student import TeacherStudentScoringModule  # noqa: F401
 from .training import ClipTrainer, TeacherStudentTrainingModule  # noqa: F401
 from .wise import wise, wise_state_dict  # noqa: F401

@@ -69,3 +69,45 @@ def init_clip_state_dict(seed: int = 0, embed_dim: int = 512, image_resolution: 
     sd["text_projection"] = torch.randn(t, embed_dim, generator=g) * t ** -0.5
     sd["logit_scale"] = torch.tensor(math.log(1 / 0.07))
     return sd
+
+
+def init_slip_state_dict(seed: int = 0, embed_dim: int = 512, image_resolution: int = 224, vision_layers: int = 12,
+                         vision_width: int = 768, vision_patch_size: int = 16, context_length: int = 77,
+                         vocab_size: int = 49408, transformer_width: int = 512, transformer_heads: int = 8,
+                         transformer_layers: int = 12) -> Dict[str, torch.Tensor]:
+    """SLIP-layout state dict as ``CLIP_VITB16()`` leaves it (``aligner/encoder/slip.py:595-600``): timm's
+    ``VisionTransformer`` init for the image tower (``trunc_normal_(std=0.02)`` -- cut at +-2 absolute, i.e. a plain normal in
+    practice -- for ``pos_embed`` and every Linear weight,
+    zero biases, unit LayerNorms, ``cls_token`` ~ N(0, 1e-6); the patch convolution keeps PyTorch's default), the normal
+    inits of ``slip.py:438-452`` for the text tower and the two projections."""
+    assert transformer_heads * 64 == transformer_width and vision_width % 64 == 0, "the native kernels use head dim 64"
+    g = torch.Generator().manual_seed(seed)
+
+    def trunc(*shape):
+        return torch.nn.init.trunc_normal_(torch.empty(*shape), std=0.02, generator=g)
+
+    sd: Dict[str, torch.Tensor] = {}
+    w, t = vision_width, transformer_width
+    tokens = (image_resolution // vision_patch_size) ** 2 + 1
+    bound = 1.0 / math.sqrt(3 * vision_patch_size ** 2)
+    sd["positional_embedding"] = torch.randn(context_length, t, generator=g) * 0.01
+    sd["image_projection"] = torch.randn(w, embed_dim, generator=g) * w ** -0.5
+    sd["text_projection"] = torch.randn(t, embed_dim, generator=g) * t ** -0.5
+    sd["logit_scale"] = torch.tensor(math.log(1 / 0.07))
+    sd["visual.cls_token"] = torch.randn(1, 1, w, generator=g) * 1e-6
+    sd["visual.pos_embed"] = trunc(1, tokens, w)
+    sd["visual.patch_embed.proj.weight"] = (torch.rand(w, 3, vision_patch_size, vision_patch_size, generator=g) * 2 - 1) * bound
+    sd["visual.patch_embed.proj.bias"] = (torch.rand(w, generator=g) * 2 - 1) * bound
+    for i in range(vision_layers):
+        p = f"visual.blocks.{i}."
+        for name, (o, k) in (("attn.qkv", (3 * w, w)), ("attn.proj", (w, w)), ("mlp.fc1", (4 * w, w)), ("mlp.fc2", (w, 4 * w))):
+            sd[p + name + ".weight"], sd[p + name + ".bias"] = trunc(o, k), torch.zeros(o)
+        for ln in ("norm1", "norm2"):
+            sd[p + ln + ".weight"], sd[p + ln + ".bias"] = torch.ones(w), torch.zeros(w)
+    sd["visual.norm.weight"], sd["visual.norm.bias"] = torch.ones(w), torch.zeros(w)
+    stds = (t ** -0.5, (t ** -0.5) * ((2 * transformer_layers) ** -0.5), (2 * t) ** -0.5)
+    for i in range(transformer_layers):
+        _block(sd, f"transformer.resblocks.{i}.", t, g, text_std=stds)
+    sd["token_embedding.weight"] = torch.randn(vocab_size, t, generator=g) * 0.02
+    sd["ln_final.weight"], sd["ln_final.bias"] = torch.ones(t), torch.zeros(t)
+    return sd

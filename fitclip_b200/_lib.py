@@ -26,7 +26,10 @@ class fc_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "embed_dim", "image_resolution", "vision_layers", "vision_width", "vision_patch_size", "context_length",
         "vocab_size", "transformer_width", "transformer_heads", "transformer_layers", "max_frames_per_pass",
-        "max_texts_per_pass")]
+        "max_texts_per_pass", "vision_tower")]
+
+
+TOWER_OPENAI, TOWER_TIMM = 0, 1
 
 
 class fc_profile_record(C.Structure):

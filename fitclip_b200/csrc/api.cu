@@ -221,8 +221,10 @@ static void plan_model(fc_model* m, ArenaPlan& plan, bool assign) {
   }
   one("visual.class_embedding", reinterpret_cast<void**>(&m->cls), W, false);
   one("visual.positional_embedding", reinterpret_cast<void**>(&m->vpos), int64_t(m->L_img) * W, false);
-  one("visual.ln_pre.weight", reinterpret_cast<void**>(&m->ln_pre_g), W, false);
-  one("visual.ln_pre.bias", reinterpret_cast<void**>(&m->ln_pre_b), W, false);
+  if (c.vision_tower == FC_TOWER_OPENAI) {  // timm's VisionTransformer has no LayerNorm in front of its blocks
+    one("visual.ln_pre.weight", reinterpret_cast<void**>(&m->ln_pre_g), W, false);
+    one("visual.ln_pre.bias", reinterpret_cast<void**>(&m->ln_pre_b), W, false);
+  }
   one("visual.ln_post.weight", reinterpret_cast<void**>(&m->ln_post_g), W, false);
   one("visual.ln_post.bias", reinterpret_cast<void**>(&m->ln_post_b), W, false);
   one("visual.proj", reinterpret_cast<void**>(&m->vproj), int64_t(W) * E, false);
@@ -255,8 +257,9 @@ static void plan_model(fc_model* m, ArenaPlan& plan, bool assign) {
 }
 
 // The residual stream x arrives with its row statistics in `stats_a` ([rows, W/64, 2] partial sums / sums of squares).
+// act / eps: EPI_LN_BIAS_QGELU and 1e-5 for the OpenAI towers, EPI_LN_BIAS_GELU and 1e-6 for timm's VisionTransformer.
 static int run_blocks(const std::vector<Block>& blocks, bf16* x, bf16* y, bf16* big, float* stats_a, float* stats_b,
-                      int64_t seqs, int L, int W, int heads, int causal, cudaStream_t s) {
+                      int64_t seqs, int L, int W, int heads, int causal, int act, float eps, cudaStream_t s) {
   const int64_t rows64 = seqs * L;
   FC_REQUIRE(rows64 < (int64_t(1) << 31), "too many tokens in one pass");
   const int rows = static_cast<int>(rows64);
@@ -266,7 +269,7 @@ static int run_blocks(const std::vector<Block>& blocks, bf16* x, bf16* y, bf16* 
     // x = x + out_proj(attention(ln_1(x)))                      (slip.py:383); ln_1 folded into the QKV GEMM
     GemmParams p;
     p.M = rows; p.N = 3 * W; p.K = W; p.C = big; p.ldc = 3 * W; p.bias = b.qkv_bf;
-    p.ln_stats = stats_a; p.ln_parts = parts; p.colsum = b.qkv_cs;
+    p.ln_stats = stats_a; p.ln_parts = parts; p.colsum = b.qkv_cs; p.ln_eps = eps;
     if ((rc = gemm_bf16_tn(EPI_LN_BIAS, x, W, b.qkv_w, W, p, s))) return rc;
     if ((rc = attention_bf16(big, y, seqs, L, heads, causal, s))) return rc;
     p = GemmParams();
@@ -275,8 +278,8 @@ static int run_blocks(const std::vector<Block>& blocks, bf16* x, bf16* y, bf16* 
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                  (slip.py:384); ln_2 folded into the fc1 GEMM
     p = GemmParams();
     p.M = rows; p.N = 4 * W; p.K = W; p.C = big; p.ldc = 4 * W; p.bias = b.fc_bf;
-    p.ln_stats = stats_b; p.ln_parts = parts; p.colsum = b.fc_cs;
-    if ((rc = gemm_bf16_tn(EPI_LN_BIAS_QGELU, x, W, b.fc_w, W, p, s))) return rc;
+    p.ln_stats = stats_b; p.ln_parts = parts; p.colsum = b.fc_cs; p.ln_eps = eps;
+    if ((rc = gemm_bf16_tn(act, x, W, b.fc_w, W, p, s))) return rc;
     p = GemmParams();
     p.M = rows; p.N = W; p.K = 4 * W; p.C = x; p.ldc = W; p.bias = b.proj_b; p.resid = x; p.ldr = W; p.stats_out = stats_a;
     if ((rc = gemm_bf16_tn(EPI_BIAS_RESID, big, 4 * W, b.proj_w, 4 * W, p, s))) return rc;
@@ -305,9 +308,17 @@ static int vision_pass(fc_model* m, const void* frames, int dtype, int64_t F, fl
   p.pos = m->vpos; p.patches_per_frame = G * G;
   if ((rc = gemm_bf16_tn(EPI_PATCH, m->big, m->patch_dim, m->conv_w, m->patch_dim, p, s))) return rc;
   if ((rc = cls_rows(m->x, m->cls, m->vpos, F, L, W, s))) return rc;
-  if ((rc = layernorm_bf16(m->x, W, m->x, W, m->ln_pre_g, m->ln_pre_b, F * L, W, 1e-5f, m->stats_a, s))) return rc;
-  if ((rc = run_blocks(m->vblocks, m->x, m->y, m->big, m->stats_a, m->stats_b, F, L, W, W / 64, 0, s))) return rc;
-  return head_project(m->x, nullptr, m->ln_post_g, m->ln_post_b, m->vproj, feat, F, L, W, c.embed_dim, 1e-5f, s);
+  const bool timm = c.vision_tower == FC_TOWER_TIMM;
+  const float eps = timm ? 1e-6f : 1e-5f;
+  if (timm) {  // blocks start on the embedded tokens themselves: only their row statistics are needed
+    if ((rc = row_stats_bf16(m->x, W, F * L, W, m->stats_a, s))) return rc;
+  } else if ((rc = layernorm_bf16(m->x, W, m->x, W, m->ln_pre_g, m->ln_pre_b, F * L, W, eps, m->stats_a, s))) {
+    return rc;
+  }
+  if ((rc = run_blocks(m->vblocks, m->x, m->y, m->big, m->stats_a, m->stats_b, F, L, W, W / 64, 0,
+                       timm ? EPI_LN_BIAS_GELU : EPI_LN_BIAS_QGELU, eps, s)))
+    return rc;
+  return head_project(m->x, nullptr, m->ln_post_g, m->ln_post_b, m->vproj, feat, F, L, W, c.embed_dim, eps, s);
 }
 
 // CLIP.encode_text for C captions -> un-normalised features feat[C, E]   (slip.py:468-480)
@@ -316,7 +327,8 @@ static int text_pass(fc_model* m, const int32_t* ids, int64_t C, float* feat, cu
   const int W = c.transformer_width, L = c.context_length;
   int rc;
   if ((rc = text_embed(ids, m->tok, m->tpos, m->x, C, L, W, c.vocab_size, m->err_flag, m->stats_a, s))) return rc;
-  if ((rc = run_blocks(m->tblocks, m->x, m->y, m->big, m->stats_a, m->stats_b, C, L, W, c.transformer_heads, 1, s)))
+  if ((rc = run_blocks(m->tblocks, m->x, m->y, m->big, m->stats_a, m->stats_b, C, L, W, c.transformer_heads, 1,
+                       EPI_LN_BIAS_QGELU, 1e-5f, s)))
     return rc;
   return head_project(m->x, ids, m->ln_final_g, m->ln_final_b, m->tproj, feat, C, L, W, c.embed_dim, 1e-5f, s);
 }
@@ -328,7 +340,7 @@ using namespace fc;
 // =================================================================================================== C ABI
 extern "C" {
 
-int fc_version(void) { return 100; }
+int fc_version(void) { return 101; }
 
 size_t fc_last_error(char* buf, size_t cap) {
   const size_t n = strlen(g_err);
@@ -395,6 +407,8 @@ int fc_model_create(const fc_config* cfg, fc_model** out) {
              "fc_model_create: widths must be multiples of 64 and <= 1024 (got %d / %d)", c.vision_width,
              c.transformer_width);
   FC_REQUIRE(c.transformer_heads * 64 == c.transformer_width, "fc_model_create: text head dim must be 64");
+  FC_REQUIRE(c.vision_tower == FC_TOWER_OPENAI || c.vision_tower == FC_TOWER_TIMM,
+             "fc_model_create: unknown vision tower %d", c.vision_tower);
   FC_REQUIRE(c.image_resolution % c.vision_patch_size == 0,
              "fc_model_create: image resolution %d is not a multiple of the patch size %d", c.image_resolution,
              c.vision_patch_size);

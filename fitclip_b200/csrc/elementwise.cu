@@ -121,6 +121,32 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf1
   }
 }
 
+// Row statistics of x alone, in the [rows, D/64, 2] layout the folded-LayerNorm GEMM epilogue reads.  One warp per row.
+__global__ void __launch_bounds__(256) row_stats_kernel(const bf16* __restrict__ x, int64_t ldx, int64_t rows, int D,
+                                                        float* __restrict__ stats_out) {
+  const int lane = threadIdx.x & 31;
+  const int chunks = D >> 3, parts = D >> 6;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < rows; row += nwarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+    float o1 = 0.f, o2 = 0.f;
+    for (int c = lane; c < chunks; c += 32) {
+      const uint4 q4 = ld_stream_v4(xr + c);
+      const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_bf16x2(w[t]);
+        o1 += f.x + f.y;
+        o2 = fmaf(f.x, f.x, fmaf(f.y, f.y, o2));
+      }
+    }
+    o1 = warp_sum(o1);
+    o2 = warp_sum(o2);
+    float2* so = reinterpret_cast<float2*>(stats_out) + row * parts;
+    for (int pi = lane; pi < parts; pi += 32) so[pi] = pi == 0 ? make_float2(o1, o2) : make_float2(0.f, 0.f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- im2col (K1a)
 // frames (F,3,R,R) -> patches (F*G*G, 3*P*P) bf16, column order (c, ky, kx) = conv1.weight.reshape(width, -1).
 // One thread moves 8 consecutive kx: a 32-byte (fp32) read and a 16-byte write; consecutive threads walk the image row.
@@ -548,6 +574,16 @@ inline int grid_for(int64_t n, int block, int cap_mult = 32) {
 }
 
 }  // namespace
+
+int row_stats_bf16(const bf16* x, int64_t ldx, int64_t rows, int D, float* stats_out, cudaStream_t s) {
+  FC_REQUIRE(x && stats_out && rows > 0 && D % 64 == 0 && ldx % 8 == 0, "row_stats: bad arguments (D=%d)", D);
+  const int64_t blocks = (rows + 7) / 8;
+  const int grid = static_cast<int>(blocks < 16 * num_sms() ? blocks : 16 * num_sms());
+  note_launch();
+  row_stats_kernel<<<grid, 256, 0, s>>>(x, ldx, rows, D, stats_out);
+  FC_CUDA(cudaGetLastError());
+  return FC_OK;
+}
 
 int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float* gamma, const float* beta,
                    int64_t rows, int D, float eps, float* stats_out, cudaStream_t s) {

@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmParams p) {
-  constexpr bool kLn = (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_QGELU);
+  constexpr bool kLn = (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_QGELU || EPI == EPI_LN_BIAS_GELU);
+  constexpr bool kErfGelu = (EPI == EPI_LN_BIAS_GELU);
   constexpr bool kGelu = (EPI == EPI_BIAS_QGELU || EPI == EPI_LN_BIAS_QGELU);
   constexpr bool kStaged = (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || EPI == EPI_BIAS_RESID || kLn);
   constexpr bool kAmn = (MAJ & 1) != 0, kBmn = (MAJ & 2) != 0;
@@ -412,6 +413,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v2[e] = fma_f32x2(h2, pack_f32x2(tanh_approx(a0), tanh_approx(a1)), h2);
               }
             }
+            if (kErfGelu) {
+              // nn.GELU() of timm's Mlp: 0.5 x (1 + erf(x / sqrt(2))), CUDA's erff (<= 2 ulp)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a0, a1;
+                unpack_f32x2(v2[e], a0, a1);
+                a0 = 0.5f * a0 * (1.f + erff(a0 * 0.70710678118654752f));
+                a1 = 0.5f * a1 * (1.f + erff(a1 * 0.70710678118654752f));
+                v2[e] = pack_f32x2(a0, a1);
+              }
+            }
             const uint32_t addr = stg_row + ((c ^ sw) << 4);
             if (EPI == EPI_BIAS_RESID) {
               const uint4 u = ld_shared_v4(addr);
@@ -733,7 +745,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
              "gemm: lda/ldb (and K of a K-major operand) must be multiples of 8 (K=%d)", p.K);
   FC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
              "gemm: operands must be 16-byte aligned");
-  const bool ln = epilogue == EPI_LN_BIAS || epilogue == EPI_LN_BIAS_QGELU;
+  const bool ln = epilogue == EPI_LN_BIAS || epilogue == EPI_LN_BIAS_QGELU || epilogue == EPI_LN_BIAS_GELU;
   const bool staged = epilogue == EPI_BIAS || epilogue == EPI_BIAS_QGELU || epilogue == EPI_BIAS_RESID || ln;
   if (ln) {
     FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.bias,
@@ -807,6 +819,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
     case EPI_TARGET: return launch<EPI_TARGET>(ta, tb, tc, tr, p, stream);
     case EPI_LN_BIAS: return launch<EPI_LN_BIAS>(ta, tb, tc, tr, p, stream);
     case EPI_LN_BIAS_QGELU: return launch<EPI_LN_BIAS_QGELU>(ta, tb, tc, tr, p, stream);
+    case EPI_LN_BIAS_GELU: return launch<EPI_LN_BIAS_GELU>(ta, tb, tc, tr, p, stream);
     default: return launch<EPI_COUNT>(ta, tb, tc, tr, p, stream);
   }
 }

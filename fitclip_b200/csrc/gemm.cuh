@@ -16,7 +16,8 @@ enum Epilogue : int {
   EPI_LN_BIAS_QGELU = 8,  //   LayerNorm affine folded into B / colsum / bias (see fold_ln_weights); 8 adds QuickGELU
   EPI_F32_SPLITK = 9,     // C(fp32) += alpha * acc over `k_splits` K ranges (atomic adds; the caller zeroes C): weight
                           //   gradients, whose few output tiles would otherwise leave most SM pairs idle
-  EPI_NUM = 10,
+  EPI_LN_BIAS_GELU = 10,  // EPI_LN_BIAS + exact GELU 0.5 x (1 + erf(x / sqrt 2)): the timm vision tower of the SLIP layout
+  EPI_NUM = 11,
 };
 
 struct GemmParams {

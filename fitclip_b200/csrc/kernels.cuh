@@ -12,6 +12,9 @@ enum DType : int { FC_DTYPE_F32 = 0, FC_DTYPE_BF16 = 1, FC_DTYPE_F16 = 2 };
 // stats_out (optional): per-row (sum, sumsq) of the OUTPUT, layout [rows, D/64, 2]
 int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float* gamma, const float* beta,
                    int64_t rows, int D, float eps, float* stats_out, cudaStream_t s);
+// Row statistics alone: stats_out[rows, D/64, 2] = per-row (sum, sum of squares) of x (everything in part 0) -- what a
+// folded-LayerNorm GEMM needs when no LayerNorm kernel ran in front of it (timm's VisionTransformer has no ln_pre).
+int row_stats_bf16(const bf16* x, int64_t ldx, int64_t rows, int D, float* stats_out, cudaStream_t s);
 int fold_ln_weights(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* colsum,
                     float* bias_f, int N, int K, cudaStream_t s);
 int im2col_patches(const void* frames, int dtype, bf16* patches, int64_t F, int R, int P, cudaStream_t s);

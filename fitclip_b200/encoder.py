@@ -97,9 +97,8 @@ class B200Clip(nn.Module):
                  max_texts_per_pass: int = 1024) -> None:
         super().__init__()
         state_dict = source.state_dict() if isinstance(source, nn.Module) else source
-        state_dict = {k: v for k, v in state_dict.items()
-                      if k not in ("input_resolution", "context_length", "vocab_size")}
-        self.config = infer_config(state_dict)
+        state_dict = self._filter_state_dict(state_dict)
+        self.config = self._infer_config(state_dict)
         if max_frames_per_pass is None:
             # ~400k image tokens per pass (ViT-B/16: 2030 frames, ViT-L/14: 1556, ViT-L/14@336: 693): measured on the
             # bench shape, 1920-frame passes run 1 % faster than 500-frame ones (fewer launches and wave tails; L2
@@ -123,9 +122,22 @@ class B200Clip(nn.Module):
         self.vocab_size = self.config["vocab_size"]
         self._engine = _Engine()
 
+    # ---- layout hooks (overridden by the SLIP layout, slip_encoder.py) ----------------------------------------------
+    @staticmethod
+    def _filter_state_dict(state_dict: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return {k: v for k, v in state_dict.items() if k not in ("input_resolution", "context_length", "vocab_size")}
+
+    @staticmethod
+    def _infer_config(state_dict: Mapping[str, torch.Tensor]) -> Dict[str, int]:
+        return infer_config(state_dict)
+
+    def _engine_params(self):
+        """``(name the engine knows, fp32 tensor)`` for every weight the native model needs."""
+        return [(n, p) for n, p in self.named_parameters() if n != "logit_scale"]
+
     @property
     def dtype(self) -> torch.dtype:
-        return self.visual.conv1.weight.dtype
+        return self.text_projection.dtype
 
     # ---- native engine ------------------------------------------------------------------------------------------
     def _native(self, device: torch.device) -> C.c_void_p:
@@ -148,7 +160,7 @@ class B200Clip(nn.Module):
                 eng.handle, eng.device, eng.signature = handle, device, None
             if eng.signature != signature:
                 stream = _lib.stream_ptr(device)
-                for name, p in params:
+                for name, p in self._engine_params():
                     data = p.detach().contiguous()
                     _lib.check(lib.fc_model_set_param(eng.handle, name.encode(), data.data_ptr(), data.numel(), stream))
                 if not lib.fc_model_ready(eng.handle):

@@ -154,6 +154,14 @@ def random_init_clip(seed: int = 0, **kwargs: int):
     return B200Clip(init_clip_state_dict(seed=seed, **kwargs))
 
 
+def random_init_slip(seed: int = 0, **kwargs: int):
+    """``slip.CLIP_VITB16()``-style random init (config/encoder/slip_from_scratch_vit_b_16.yaml): a
+    :class:`fitclip_b200.B200SlipClip` with timm-ViT image tower parameters under the SLIP checkpoint names."""
+    from . import B200SlipClip
+    from ._init import init_slip_state_dict
+    return B200SlipClip(init_slip_state_dict(seed=seed, **kwargs))
+
+
 class SyntheticRetrievalData:
     """Batches shaped like ``VideoTextDataModule`` output: ``{"video": (B,T,3,R,R) fp32, "text": {"input_ids": (B,77)},
     "video_id": [...]}`` -- N(0,1) frames generated on the device, ``[SOT] + random ids + [EOT]`` captions."""

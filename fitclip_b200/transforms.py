@@ -32,11 +32,14 @@ class RandomResizedCropWithRandomInterpolation(RandomResizedCrop):
         return F.resized_crop(img, i, j, h, w, self.size, interpolation, antialias=False)
 
 
-def eval_transform(size: int, dtype: torch.dtype, mean: Sequence[float], std: Sequence[float]) -> T.Compose:
+def eval_transform(size: int, dtype: torch.dtype, mean: Sequence[float], std: Sequence[float],
+                   interpolation: InterpolationMode = InterpolationMode.BICUBIC) -> T.Compose:
+    # bicubic: clip_video_text_encoder.py:124-133; the SLIP wrapper keeps Resize's default, bilinear
+    # (slip_video_text_encoder.py:78-87)
     return T.Compose([
         ConvertBHWCtoBCHW(),
         T.ConvertImageDtype(dtype),
-        T.Resize(size, interpolation=InterpolationMode.BICUBIC, antialias=False),
+        T.Resize(size, interpolation=interpolation, antialias=False),
         T.CenterCrop(size),
         T.Normalize(mean=mean, std=std),
     ])

@@ -59,7 +59,14 @@ typedef struct fc_config {
   int32_t transformer_layers;
   int32_t max_frames_per_pass; /* max frames per internal pass (workspace is sized for it; passes are equal-sized); 0 = 512 */
   int32_t max_texts_per_pass;  /* max captions per internal pass; 0 = 1024 */
+  /* Vision tower architecture.  FC_TOWER_OPENAI (0): clip.model.VisionTransformer -- ln_pre, QuickGELU, LayerNorm eps 1e-5.
+   * FC_TOWER_TIMM (1): timm's VisionTransformer as the SLIP-layout models build it (aligner/encoder/slip.py:585-627,
+   * `timm.create_model('vit_*_patch16_224', num_classes=0)`): no ln_pre, exact (erf) GELU, LayerNorm eps 1e-6; the
+   * caller passes its weights under the OpenAI names (the patch-embedding bias folded into the positional rows 1..,
+   * `norm` as `ln_post`, `image_projection` as `visual.proj`) and `visual.ln_pre.*` is neither expected nor accepted. */
+  int32_t vision_tower;
 } fc_config;
+enum { FC_TOWER_OPENAI = 0, FC_TOWER_TIMM = 1 };
 
 typedef struct fc_model fc_model;
 

@@ -19,7 +19,10 @@ checks the oracle and the CUDA path against the frozen loss / gradients / update
 implementations in the image -- ``transformers.CLIPModel`` for both towers (tests/test_oracle_clip.py), torchvision for
 the eval transform (tests/test_oracle_preprocess.py) -- and (b) seeded golden vectors frozen under ``tests/golden/`` by
 ``tests/golden/make_golden.py``; **the vision tower and the torchmetrics definitions stay "parity unpinned"** in the
-sense of the task statement.
+sense of the task statement.  The SLIP-layout models (row f4; ``slip_ref.py``): timm's ``VisionTransformer`` is likewise
+third-party and absent -- restated, pinned against ``transformers.ViTModel`` (tests/test_oracle_slip.py); the reference's own
+``slip.CLIP`` + ``SlipVideoTextEncoder`` around it were run in the build container
+(``tests/golden/make_reference_slip_golden.py`` -> ``tests/golden/reference_slip.pt``).
 """
 from .clip_ref import CLIP, build_model, clip_vit_b_16, perturb_trained_like, tokenize_synthetic  # noqa: F401
 from .encoder_ref import RefClipVideoTextEncoder  # noqa: F401
@@ -30,3 +33,4 @@ from .preprocess_ref import ref_eval_transform, ref_resized_size  # noqa: F401
 from .loss_ref import ref_nce_loss, ref_teacher_student_nce_loss  # noqa: F401
 from .bf16_emulation import bf16_stream_model  # noqa: F401
 from .train_ref import ref_training_loss, ref_training_step  # noqa: F401
+from .slip_ref import (RefSlipVideoTextEncoder, SlipClip, TimmVisionTransformer, slip_clip_vit_b_16)  # noqa: F401

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from fitclip_b200 import runner
-from fitclip_b200._init import init_clip_state_dict
+from fitclip_b200._init import init_clip_state_dict, init_slip_state_dict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TINY = ["encoder.model.vision_layers=1", "encoder.model.transformer_layers=1"]
@@ -59,6 +59,32 @@ def test_random_init_statistics_match_the_published_init():
     # deterministic per seed, different across seeds
     assert torch.equal(sd["text_projection"], init_clip_state_dict(seed=0, vision_layers=1, transformer_layers=2)["text_projection"])
     assert not torch.equal(sd["text_projection"], init_clip_state_dict(seed=1, vision_layers=1, transformer_layers=2)["text_projection"])
+
+
+def test_compose_slip_encoder_chain_and_slip_init():
+    cfg = runner.compose(["command=evaluate", "encoder=slip_from_scratch_vit_b_16", "data=synthetic_msrvtt"])
+    assert cfg["encoder"]["_target_"] == "fitclip_b200.B200SlipVideoTextEncoder"  # from slip.yaml through the chain
+    assert cfg["encoder"]["model"]["_target_"] == "fitclip_b200.runner.random_init_slip"
+    with pytest.raises(ValueError, match="missing mandatory"):  # slip_from_pretrained needs a local checkpoint path
+        runner.instantiate(runner.compose(["command=evaluate", "encoder=slip_from_pretrained",
+                                           "data=synthetic_msrvtt"])["encoder"])
+    # timm's init (slip.py:595-600 builds timm.create_model('vit_base_patch16_224')): truncated normal 0.02, zero biases
+    sd = init_slip_state_dict(seed=0, vision_layers=1, transformer_layers=1)
+    assert sd["visual.pos_embed"].shape == (1, 197, 768) and sd["visual.cls_token"].shape == (1, 1, 768)
+    w = sd["visual.blocks.0.mlp.fc1.weight"]
+    assert abs(w.std().item() - 0.02) < 1e-3 and w.abs().max().item() <= 2.0  # trunc_normal_'s cut is +-2 ABSOLUTE
+    assert torch.count_nonzero(sd["visual.blocks.0.attn.qkv.bias"]) == 0
+    assert abs(sd["image_projection"].std().item() - 768 ** -0.5) < 1e-3
+    model = runner.random_init_slip(seed=0, vision_layers=1, transformer_layers=1)
+    assert model.config["vision_tower"] == 1 and model.visual.input_resolution == 224
+
+
+@pytest.mark.gpu
+def test_evaluate_command_on_a_slip_layout_encoder():
+    cfg = runner.compose(["command=evaluate", "encoder=slip_from_scratch_vit_b_16", "data=synthetic_msrvtt",
+                          "data.num_videos=48", *TINY])
+    result = runner.evaluate(cfg)
+    assert set(result) == {"r1", "r5", "r10", "mr", "loss/val"} and 1 <= int(result["mr"]) <= 48
 
 
 @pytest.mark.gpu

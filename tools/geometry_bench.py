@@ -14,7 +14,8 @@ from fitclip_b200 import _lib as _libmod  # noqa: E402
 if os.environ.get("FITCLIP_VARIANT"):  # A/B runs against a `make VARIANT=name` build of the library
     _libmod.LIB_PATH = _libmod.LIB_PATH.replace("libfitclip_b200.so", "libfitclip_b200_%s.so" % os.environ["FITCLIP_VARIANT"])
 import oracle  # noqa: E402
-from fitclip_b200 import B200ClipVideoTextEncoder, metrics_from_ranks, ops, retrieval_ranks  # noqa: E402
+from fitclip_b200 import (B200ClipVideoTextEncoder, B200SlipVideoTextEncoder, metrics_from_ranks, ops,  # noqa: E402
+                          retrieval_ranks)
 
 dev = torch.device("cuda:0")
 GEOM = {
@@ -24,6 +25,9 @@ GEOM = {
                           transformer_heads=12),
     "clip_vit_l_14_336px": dict(embed_dim=768, image_resolution=336, vision_patch_size=14, vision_width=1024,
                                 vision_layers=24, transformer_width=768, transformer_heads=12),
+    # SLIP layout (slip.py:595-600 / 618-623): timm ViT image tower (no ln_pre, exact GELU) + CLIP text tower
+    "slip_vit_b_16": dict(slip=True),
+    "slip_vit_l_16": dict(slip=True, vision_width=1024, vision_layers=24),
 }
 
 
@@ -47,8 +51,13 @@ def timed(fn, reps):
 
 names = sys.argv[1:] or list(GEOM)
 for name in names:
-    cfg = {**oracle.clip_ref.VIT_B_16, **GEOM[name]}
-    enc = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0, **GEOM[name]).state_dict(), num_frames=4).to(dev)
+    geom = dict(GEOM[name])
+    if geom.pop("slip", False):
+        cfg = {**oracle.clip_ref.VIT_B_16, **geom}
+        enc = B200SlipVideoTextEncoder(oracle.slip_clip_vit_b_16(seed=0, **geom).state_dict(), num_frames=4).to(dev)
+    else:
+        cfg = {**oracle.clip_ref.VIT_B_16, **geom}
+        enc = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0, **geom).state_dict(), num_frames=4).to(dev)
     res, patch = cfg["image_resolution"], cfg["vision_patch_size"]
     L = (res // patch) ** 2 + 1
     n = 256
