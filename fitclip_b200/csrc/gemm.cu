@@ -414,14 +414,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
             if (kErfGelu) {
-              // nn.GELU() of timm's Mlp: 0.5 x (1 + erf(x / sqrt(2))), CUDA's erff (<= 2 ulp)
+              // nn.GELU() of timm's Mlp: x Phi(x) = max(x, 0) - |x| erfc(|x| / sqrt 2) / 2, with erfc from Abramowitz & Stegun
+              // 7.1.26 (|error| <= 1.5e-7, relative accuracy kept in the negative tail): t = 1 / (1 + p |u|),
+              // erfc(|u|) = (a1 t + ... + a5 t^5) exp(-u^2).  Two MUFU ops (rcp, ex2) and packed Horner steps per element
+              // pair; CUDA's erff in this place made the epilogue longer than the K = 768 main loop (+16 % on the step).
+              const uint64_t ch2 = pack_f32x2(-0.72134752044448170f, -0.72134752044448170f);  // -log2(e) / 2
+              const uint64_t a5 = pack_f32x2(0.5307027145f, 0.5307027145f), a4 = pack_f32x2(-0.7265760135f, -0.7265760135f),
+                             a3 = pack_f32x2(0.7107068705f, 0.7107068705f), a2 = pack_f32x2(-0.142248368f, -0.142248368f),
+                             a1 = pack_f32x2(0.127414796f, 0.127414796f);  // the series' coefficients, halved
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float a0, a1;
-                unpack_f32x2(v2[e], a0, a1);
-                a0 = 0.5f * a0 * (1.f + erff(a0 * 0.70710678118654752f));
-                a1 = 0.5f * a1 * (1.f + erff(a1 * 0.70710678118654752f));
-                v2[e] = pack_f32x2(a0, a1);
+                float x0, x1, s0, s1;
+                unpack_f32x2(v2[e], x0, x1);
+                unpack_f32x2(mul_f32x2(mul_f32x2(v2[e], v2[e]), ch2), s0, s1);
+                const float ax0 = fabsf(x0), ax1 = fabsf(x1);
+                const uint64_t t2 = pack_f32x2(rcp_approx(fmaf(0.23164189f, ax0, 1.f)), rcp_approx(fmaf(0.23164189f, ax1, 1.f)));
+                uint64_t q2 = fma_f32x2(a5, t2, a4);
+                q2 = fma_f32x2(q2, t2, a3);
+                q2 = fma_f32x2(q2, t2, a2);
+                q2 = fma_f32x2(q2, t2, a1);
+                q2 = mul_f32x2(mul_f32x2(q2, t2), pack_f32x2(ex2_approx(s0), ex2_approx(s1)));  // erfc(|u|) / 2
+                v2[e] = fma_f32x2(pack_f32x2(-ax0, -ax1), q2, pack_f32x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
               }
             }
             const uint32_t addr = stg_row + ((c ^ sw) << 4);
