@@ -160,7 +160,7 @@ class B200SlipVideoTextEncoder(VideoTextEncoder):
         return self.model.encode_text_normalized(text["input_ids"])
 
     def get_tokenizer(self) -> TYPE_TOKENIZER:
-        return tokenizer.tokenize
+        return tokenizer.slip_tokenize
 
     def decode_text(self, text: TYPE_TEXT_INPUT) -> Iterator[str]:
         return tokenizer.decode(text["input_ids"] if isinstance(text, Mapping) else (t["input_ids"] for t in text))
