@@ -84,7 +84,7 @@ SIGNATURES = {
     "fc_quickgelu_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "fc_quickgelu_bwd_bf16": (C.c_int, [_p, _p, _p, _p, _i64, _p]),
     "fc_attention_bwd_bf16": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
-    "fc_loss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i32, _p, _f32, _p, _p, _i64, _p]),
+    "fc_loss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _f32, _p, _p, _i64, _p]),
     "fc_sgemm_f32": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _f32, _p, _i64, _p, _i64, _p, _i64, _p]),
     "fc_pool_normalize_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _f32, _p]),
     "fc_seq_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),

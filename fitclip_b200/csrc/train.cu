@@ -686,20 +686,24 @@ __device__ float block_sum_f(float v, float* red) {
   return r;
 }
 
+// S / T are (R, C): R video rows, C text columns (R == C unless the unlabelled texts were replaced by prompts,
+// teacher_student.py:104-120).  lse layout: rows(S) [R] | cols(S) [C] | rows(T) [R] | cols(T) [C].
 __global__ void __launch_bounds__(256) lse_lines_kernel(const float* __restrict__ S, const float* __restrict__ T,
-                                                        int64_t ld, int B, float* __restrict__ lse) {
+                                                        int64_t ld, int R, int C, float* __restrict__ lse) {
   __shared__ float red[8];
-  const int which = blockIdx.x / B, i = blockIdx.x - which * B;  // 0 rows(S) 1 cols(S) 2 rows(T) 3 cols(T)
-  const float* M = which < 2 ? S : T;
-  const bool is_col = which & 1;
+  const int b = blockIdx.x;
+  const int half = b / (R + C), in_half = b - half * (R + C);  // half 0: S, half 1: T
+  const bool is_col = in_half >= R;
+  const int i = is_col ? in_half - R : in_half, n = is_col ? R : C;
+  const float* M = half == 0 ? S : T;
   const int64_t off = is_col ? i : static_cast<int64_t>(i) * ld, stride = is_col ? ld : 1;
   float mx = -INFINITY;
-  for (int j = threadIdx.x; j < B; j += 256) mx = fmaxf(mx, M[off + j * stride]);
+  for (int j = threadIdx.x; j < n; j += 256) mx = fmaxf(mx, M[off + j * stride]);
   mx = block_max_f(mx, red);
   float sum = 0.f;
-  for (int j = threadIdx.x; j < B; j += 256) sum += expf(M[off + j * stride] - mx);
+  for (int j = threadIdx.x; j < n; j += 256) sum += expf(M[off + j * stride] - mx);
   sum = block_sum_f(sum, red);
-  if (threadIdx.x == 0) lse[blockIdx.x] = mx + logf(sum);
+  if (threadIdx.x == 0) lse[b] = mx + logf(sum);
 }
 
 __global__ void __launch_bounds__(256) nce_grad_kernel(const float* __restrict__ S, int64_t ld, int B,
@@ -713,36 +717,46 @@ __global__ void __launch_bounds__(256) nce_grad_kernel(const float* __restrict__
   }
 }
 
+// "batchmean" divides the row direction by R and the column direction (the loss of scores.T, loss.py:36-39) by C
 __global__ void __launch_bounds__(256) ts_nce_grad_kernel(const float* __restrict__ S, const float* __restrict__ T,
-                                                          int64_t ld, int B, const float* __restrict__ lse,
+                                                          int64_t ld, int R, int C, const float* __restrict__ lse,
                                                           float gscale, float* __restrict__ dS, int64_t ldd) {
   const int i = blockIdx.x;
-  const float k = gscale / static_cast<float>(B);
-  for (int j = threadIdx.x; j < B; j += 256) {
+  const float kr = gscale / static_cast<float>(R), kc = gscale / static_cast<float>(C);
+  const float* lse_sc = lse + R;
+  const float* lse_tr = lse + R + C;
+  const float* lse_tc = lse + 2 * R + C;
+  for (int j = threadIdx.x; j < C; j += 256) {
     const float s = S[static_cast<int64_t>(i) * ld + j], t = T[static_cast<int64_t>(i) * ld + j];
     dS[static_cast<int64_t>(i) * ldd + j] =
-        k * (expf(s - lse[i]) - expf(t - lse[2 * B + i]) + expf(s - lse[B + j]) - expf(t - lse[3 * B + j]));
+        kr * (expf(s - lse[i]) - expf(t - lse_tr[i])) + kc * (expf(s - lse_sc[j]) - expf(t - lse_tc[j]));
   }
 }
 
 // value from the log-sum-exps: terms per line, then one block sums them (double accumulation like reduce_terms_kernel)
 __global__ void __launch_bounds__(256) loss_value_kernel(const float* __restrict__ S, const float* __restrict__ T,
-                                                         int64_t ld, int B, const float* __restrict__ lse,
+                                                         int64_t ld, int R, int C, const float* __restrict__ lse,
                                                          float* __restrict__ out) {
   __shared__ double red[256];
   double a = 0.0;
-  if (!T) {
-    for (int i = threadIdx.x; i < B; i += 256)
-      a += static_cast<double>(lse[i] + lse[B + i] - 2.f * S[static_cast<int64_t>(i) * ld + i]);
+  if (!T) {  // R == C
+    for (int i = threadIdx.x; i < R; i += 256)
+      a += static_cast<double>(lse[i] + lse[R + i] - 2.f * S[static_cast<int64_t>(i) * ld + i]) / R;
   } else {
-    // sum_ij p_row(T)_ij (log p_row(T)_ij - log p_row(S)_ij) + the same over columns
-    for (int64_t e = threadIdx.x; e < static_cast<int64_t>(B) * B; e += 256) {
-      const int i = static_cast<int>(e / B), j = static_cast<int>(e - static_cast<int64_t>(i) * B);
+    // sum_ij p_row(T)_ij (log p_row(T)_ij - log p_row(S)_ij) / R + the same over columns / C
+    const float* lse_sc = lse + R;
+    const float* lse_tr = lse + R + C;
+    const float* lse_tc = lse + 2 * R + C;
+    double ar = 0.0, ac = 0.0;
+    for (int64_t e = threadIdx.x; e < static_cast<int64_t>(R) * C; e += 256) {
+      const int i = static_cast<int>(e / C), j = static_cast<int>(e - static_cast<int64_t>(i) * C);
       const float s = S[static_cast<int64_t>(i) * ld + j], t = T[static_cast<int64_t>(i) * ld + j];
-      const float ltr = t - lse[2 * B + i], lsr = s - lse[i], ltc = t - lse[3 * B + j], lsc = s - lse[B + j];
+      const float ltr = t - lse_tr[i], lsr = s - lse[i], ltc = t - lse_tc[j], lsc = s - lse_sc[j];
       const float pr = expf(ltr), pc = expf(ltc);
-      a += static_cast<double>((pr > 0.f ? pr * (ltr - lsr) : 0.f) + (pc > 0.f ? pc * (ltc - lsc) : 0.f));
+      ar += static_cast<double>(pr > 0.f ? pr * (ltr - lsr) : 0.f);
+      ac += static_cast<double>(pc > 0.f ? pc * (ltc - lsc) : 0.f);
     }
+    a = ar / R + ac / C;
   }
   red[threadIdx.x] = a;
   __syncthreads();
@@ -750,7 +764,7 @@ __global__ void __launch_bounds__(256) loss_value_kernel(const float* __restrict
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = static_cast<float>(red[0] / static_cast<double>(B));
+  if (threadIdx.x == 0) *out = static_cast<float>(red[0]);
 }
 
 // ------------------------------------------------------------------------------------------- small fp32 GEMM
@@ -1128,22 +1142,24 @@ int fc_attention_bwd_bf16(const void* qkv, const void* out, const void* dout, vo
   }
 }
 
-// lse: 4 B floats of workspace.  teacher == NULL: nce_loss;  else TeacherStudentNCELoss("batchmean").
-// loss_out (optional) = the loss value, dscores (optional, (B, ldd)) = gscale * d loss / d scores.
-int fc_loss_fwd_bwd(const float* scores, const float* teacher, int64_t ld, int32_t B, float* lse, float gscale,
-                    float* loss_out, float* dscores, int64_t ldd, void* stream) {
-  FC_REQUIRE(scores && lse && B >= 1 && ld >= B, "fc_loss_fwd_bwd: bad arguments");
-  FC_REQUIRE(!dscores || ldd >= B, "fc_loss_fwd_bwd: bad gradient pitch");
+// lse: 2 (rows + cols) floats of workspace.  teacher == NULL: nce_loss (rows == cols);  else
+// TeacherStudentNCELoss("batchmean") of (rows, cols) scores.  loss_out (optional) = the loss value, dscores (optional,
+// (rows, ldd)) = gscale * d loss / d scores.
+int fc_loss_fwd_bwd(const float* scores, const float* teacher, int64_t ld, int32_t rows, int32_t cols, float* lse,
+                    float gscale, float* loss_out, float* dscores, int64_t ldd, void* stream) {
+  FC_REQUIRE(scores && lse && rows >= 1 && cols >= 1 && ld >= cols, "fc_loss_fwd_bwd: bad arguments");
+  FC_REQUIRE(teacher || rows == cols, "fc_loss_fwd_bwd: nce_loss needs a square score matrix (%d x %d)", rows, cols);
+  FC_REQUIRE(!dscores || ldd >= cols, "fc_loss_fwd_bwd: bad gradient pitch");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  lse_lines_kernel<<<(teacher ? 4 : 2) * B, 256, 0, s>>>(scores, teacher, ld, B, lse);
+  lse_lines_kernel<<<(teacher ? 2 : 1) * (rows + cols), 256, 0, s>>>(scores, teacher, ld, rows, cols, lse);
   FC_CHECK_LAUNCH();
   if (loss_out) {
-    loss_value_kernel<<<1, 256, 0, s>>>(scores, teacher, ld, B, lse, loss_out);
+    loss_value_kernel<<<1, 256, 0, s>>>(scores, teacher, ld, rows, cols, lse, loss_out);
     FC_CHECK_LAUNCH();
   }
   if (dscores) {
-    if (teacher) ts_nce_grad_kernel<<<B, 256, 0, s>>>(scores, teacher, ld, B, lse, gscale, dscores, ldd);
-    else nce_grad_kernel<<<B, 256, 0, s>>>(scores, ld, B, lse, gscale, dscores, ldd);
+    if (teacher) ts_nce_grad_kernel<<<rows, 256, 0, s>>>(scores, teacher, ld, rows, cols, lse, gscale, dscores, ldd);
+    else nce_grad_kernel<<<rows, 256, 0, s>>>(scores, ld, rows, lse, gscale, dscores, ldd);
     FC_CHECK_LAUNCH();
   }
   return FC_OK;

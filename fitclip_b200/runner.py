@@ -309,8 +309,12 @@ def train(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> Dict
     encoders = {k: v.to(device) for k, v in instantiate(cfg["encoder"]).items()}
     data = instantiate(cfg["data"], encoder=encoders)
     opt = cfg.get("optimizer", {})
+    extra = {}
+    if cfg.get("prompts"):  # aligner/cli.py:117-121: a text file, one prompt per non-empty line
+        with open(cfg["prompts"]) as file:
+            extra["prompts"] = [line.strip() for line in file if line.strip()]
     model = instantiate(cfg["model"], encoder=encoders["student"], teacher=encoders["teacher"],
-                        lr=float(opt.get("lr", 3e-6)), weight_decay=float(opt.get("weight_decay", 1e-2)))
+                        lr=float(opt.get("lr", 3e-6)), weight_decay=float(opt.get("weight_decay", 1e-2)), **extra)
     steps = int(cfg.get("trainer", {}).get("max_steps", 10))
     losses = []
     for i, batch in enumerate(data.train_batches(device, steps)):

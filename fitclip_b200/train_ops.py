@@ -135,18 +135,21 @@ def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, seqs
 def loss_fwd_bwd(scores: torch.Tensor, teacher_scores: Optional[torch.Tensor] = None, gscale: float = 1.0,
                  want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """-> (loss (), ``gscale * dloss/dscores`` or None).  ``teacher_scores`` None: ``nce_loss``; else the
-    teacher-student KL form with ``batchmean`` reduction (``aligner/loss.py:13-39``)."""
+    teacher-student KL form with ``batchmean`` reduction (``aligner/loss.py:13-39``), which also takes rectangular
+    (videos x prompts) matrices."""
     dev = _dev(scores)
-    B = scores.shape[0]
-    assert scores.dtype == torch.float32 and scores.shape == (B, B) and scores.stride(1) == 1
+    R, C = scores.shape
+    assert scores.dtype == torch.float32 and scores.stride(1) == 1
     if teacher_scores is not None:
-        assert teacher_scores.dtype == torch.float32 and teacher_scores.shape == (B, B)
+        assert teacher_scores.dtype == torch.float32 and teacher_scores.shape == (R, C)
         assert teacher_scores.stride() == scores.stride()
-    lse = torch.empty(4 * B, device=dev, dtype=torch.float32)
+    else:
+        assert R == C, "nce_loss pairs row i with column i"
+    lse = torch.empty(2 * (R + C), device=dev, dtype=torch.float32)
     loss = torch.empty((), device=dev, dtype=torch.float32)
-    grad = torch.empty(B, B, device=dev, dtype=torch.float32) if want_grad else None
-    _call(dev, "fc_loss_fwd_bwd", ptr(scores), ptr(teacher_scores), scores.stride(0), B, ptr(lse), gscale, ptr(loss),
-          ptr(grad), B)
+    grad = torch.empty(R, C, device=dev, dtype=torch.float32) if want_grad else None
+    _call(dev, "fc_loss_fwd_bwd", ptr(scores), ptr(teacher_scores), scores.stride(0), R, C, ptr(lse), gscale, ptr(loss),
+          ptr(grad), C)
     return loss, grad
 
 

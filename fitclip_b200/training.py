@@ -315,7 +315,9 @@ class TeacherStudentTrainingModule:
 
     ``batch``: ``video_student`` / ``video_teacher`` ``(B,T,3,R,R)``, ``text_student`` / ``text_teacher``
     ``{"input_ids": (B, 77)}``, and ``dataset``: a sequence of dataset names, one per sample, grouped
-    (``teacher_student.py:101-103``); default: all samples belong to the unlabelled dataset.  ``group``: the process
+    (``teacher_student.py:101-103``); default: all samples belong to the unlabelled dataset.  ``prompts``: texts that
+    replace the unlabelled section's captions in every step (``:104-120``), giving (videos x prompts) score matrices
+    there.  ``group``: the process
     group to gather embeddings / reduce gradients over (None = the default group when one is initialised, False = never
     communicate)."""
 
@@ -323,7 +325,7 @@ class TeacherStudentTrainingModule:
                  labeled_dataset_loss_share: Optional[float] = None,
                  dataset_names: Sequence[str] = ("labeled", "unlabeled"), lr: float = 3e-6,
                  weight_decay: float = 1e-2, group=None, kernels: Any = None, fit_temperature: bool = False,
-                 min_temperature: float = 0.001) -> None:
+                 min_temperature: float = 0.001, prompts: Optional[Sequence[str]] = None) -> None:
         self.encoder, self.teacher = encoder, teacher
         self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels)
         self.K = self.trainer.K
@@ -351,6 +353,27 @@ class TeacherStudentTrainingModule:
             self.dataset_loss_share = {n: (1 - labeled_dataset_loss_share) / (len(names) - 1) for n in names}
             self.dataset_loss_share[labeled_dataset_name] = labeled_dataset_loss_share
         self.unlabeled_dataset_name = next(n for n in names if n != labeled_dataset_name)
+        # prompts (teacher_student.py:47,81-90): a fixed list of texts that stands in for the unlabelled dataset's own
+        # captions in every training step; tokenised once, by the student's and by the teacher's tokenizer
+        if prompts is None:
+            self.tokenized_prompts = self.teacher_tokenized_prompts = None
+        else:
+            prompts = list(prompts)
+            self.tokenized_prompts = dict(encoder.get_tokenizer()(prompts))
+            self.teacher_tokenized_prompts = dict(teacher.get_tokenizer()(prompts))
+
+    @staticmethod
+    def _splice(text: Mapping[str, torch.Tensor], prompts: Mapping[str, torch.Tensor], lo: int, hi: int):
+        """``_replace_in_tokenized_text`` (teacher_student.py:20-40): rows ``[lo, hi)`` of every tensor of ``text`` are
+        replaced by the prompt rows; the narrower of the two is right-padded with zeros first."""
+        out = {}
+        for k, v in text.items():
+            new = prompts[k].to(device=v.device, dtype=v.dtype)
+            width = max(v.shape[1], new.shape[1])
+            v = torch.nn.functional.pad(v, (0, width - v.shape[1]))
+            new = torch.nn.functional.pad(new, (0, width - new.shape[1]))
+            out[k] = torch.cat((v[:lo], new, v[hi:]))
+        return out
 
     def _sections(self, batch: Mapping[str, Any], n: int) -> List[Tuple[str, int, int]]:
         names = batch.get("dataset")
@@ -366,13 +389,25 @@ class TeacherStudentTrainingModule:
     def training_step(self, batch: Mapping[str, Any], _batch_idx: int = 0, optimize: bool = True) -> torch.Tensor:
         K, tr = self.K, self.trainer
         tr.zero_grad()
+        n_local = batch["video_student"].shape[0]
+        sections = self._sections(batch, n_local)
+        text_student, text_teacher = batch["text_student"], batch["text_teacher"]
+        text_ranges = [(lo, hi) for _, lo, hi in sections]  # rows of the text batch that belong to each section
+        if self.tokenized_prompts is not None:  # training_step, teacher_student.py:104-120 and :128-139
+            idx = next(i for i, (name, _, _) in enumerate(sections) if name == self.unlabeled_dataset_name)
+            _, lo, hi = sections[idx]
+            text_student = self._splice(text_student, self.tokenized_prompts, lo, hi)
+            text_teacher = self._splice(text_teacher, self.teacher_tokenized_prompts, lo, hi)
+            n_prompts = next(iter(self.tokenized_prompts.values())).shape[0]
+            shift = n_prompts - (hi - lo)
+            text_ranges = [(a, b) if i < idx else (lo, lo + n_prompts) if i == idx else (a + shift, b + shift)
+                           for i, (a, b) in enumerate(text_ranges)]
         # _step (teacher_student.py:93-96): student with saved activations, teacher on the evaluation path
         v_local = tr.encode_video(batch["video_student"])
-        t_local = tr.encode_text(batch["text_student"]["input_ids"])
+        t_local = tr.encode_text(text_student["input_ids"])
         with torch.no_grad():
             tv_local = self.teacher.encode_video(batch["video_teacher"])
-            tt_local = self.teacher.encode_text(batch["text_teacher"])
-        n_local = v_local.shape[0]
+            tt_local = self.teacher.encode_text(text_teacher)
         # _dataset_step_end (:142-173): gather across ranks (sections are per-rank contiguous, so gather per section)
         if self.fit_temperature:
             self.logit_scale, self.teacher_student_logit_scale = self.temps.tolist()
@@ -381,9 +416,9 @@ class TeacherStudentTrainingModule:
         dv = torch.zeros_like(v_local)
         dt = torch.zeros_like(t_local)
         total = None
-        for name, lo, hi in self._sections(batch, n_local):
+        for (name, lo, hi), (tlo, thi) in zip(sections, text_ranges):
             v, off = _all_gather_rows(v_local[lo:hi].contiguous(), self.group)
-            t, _ = _all_gather_rows(t_local[lo:hi].contiguous(), self.group)
+            t, toff = _all_gather_rows(t_local[tlo:thi].contiguous(), self.group)
             share = self.dataset_loss_share[name]
             scores = K.sgemm(v, t, trans_b=True, alpha=scale)
             if name == self.labeled_dataset_name:
@@ -391,7 +426,7 @@ class TeacherStudentTrainingModule:
                 loss = loss * share
             else:
                 tv, _ = _all_gather_rows(tv_local[lo:hi].contiguous(), self.group)
-                tt, _ = _all_gather_rows(tt_local[lo:hi].contiguous(), self.group)
+                tt, _ = _all_gather_rows(tt_local[tlo:thi].contiguous(), self.group)
                 teacher_scores = K.sgemm(tv, tt, trans_b=True, alpha=ts_scale)
                 loss, dscores = K.loss_fwd_bwd(scores, teacher_scores, gscale=share * ts_scale ** 2)
                 loss = loss * (share * ts_scale ** 2)
@@ -400,10 +435,12 @@ class TeacherStudentTrainingModule:
             if self.fit_temperature:  # scores = exp(logit_scale) * V T^T  =>  dL/d logit_scale = sum(dL/dscores * scores)
                 self.temps_grad[0] += (dscores * scores).sum()
             total = loss if total is None else total + loss
-            # scores = scale * V T^T:  dV = scale * dS T,  dT = scale * dS^T V; keep this rank's rows
-            n = hi - lo
+            # scores = scale * V T^T:  dV = scale * dS T,  dT = scale * dS^T V; keep this rank's rows (videos) / columns
+            # (texts: with prompts every rank holds the same list and the gathered matrix carries one copy per rank,
+            # exactly as the reference's all_gather of the encoded prompts does, teacher_student.py:144)
+            n, nt = hi - lo, thi - tlo
             dv[lo:hi] = K.sgemm(dscores[off:off + n], t, alpha=scale)
-            dt[lo:hi] = K.sgemm(dscores[:, off:off + n], v, trans_a=True, alpha=scale)
+            dt[tlo:thi] = K.sgemm(dscores[:, toff:toff + nt], v, trans_a=True, alpha=scale)
         tr.backward_text(dt)
         tr.backward_video(dv)
         if optimize:
@@ -419,9 +456,9 @@ class TeacherStudentTrainingModule:
         ``weight = share * exp(ts)^2`` (teacher_student.py:156-158): the product rule gives ``2 * weighted_loss`` plus the
         path through the teacher's soft targets, ``weight * sum(dKL/dT * T)`` with, per softmax direction,
         ``dKL/dT = p * (a - sum_line(p * a)) / B``, ``p = softmax(T)``, ``a = log p - log softmax(scores)``."""
-        B = scores.shape[0]
         through_targets = scores.new_zeros(())
         for dim in (1, 0):
+            B = scores.shape[1 - dim]  # "batchmean": the number of lines of that direction (rows, then columns)
             logp, logq = torch.log_softmax(teacher_scores, dim), torch.log_softmax(scores, dim)
             p, a = logp.exp(), logp - logq
             d = p * (a - (p * a).sum(dim, keepdim=True)) / B

@@ -221,11 +221,13 @@ FC_API int fc_quickgelu_bwd_bf16(const void* u, const void* dg, void* du, void* 
 /* Backward of fc_attention_bf16: qkv / dqkv (seqs*L, 3*heads*64), out / dout (seqs*L, heads*64); L <= 432. */
 FC_API int fc_attention_bwd_bf16(const void* qkv, const void* out, const void* dout, void* dqkv, int64_t seqs,
                                  int32_t L, int32_t heads, int32_t causal, void* stream);
-/* nce_loss (teacher == NULL; aligner/loss.py:13-26) or TeacherStudentNCELoss("batchmean") (loss.py:29-39,
- * teacher_student.py:73) of (B, ld) fp32 scores: value (optional) and gscale * d loss / d scores (optional).
- * lse: 4*B floats of workspace. */
-FC_API int fc_loss_fwd_bwd(const float* scores, const float* teacher, int64_t ld, int32_t B, float* lse, float gscale,
-                           float* loss_out, float* dscores, int64_t ldd, void* stream);
+/* nce_loss (teacher == NULL, rows == cols; aligner/loss.py:13-26) or TeacherStudentNCELoss("batchmean") (loss.py:29-39,
+ * teacher_student.py:73) of (rows, ld) fp32 scores -- rows = videos, cols = texts; they differ when the unlabelled texts
+ * were replaced by a prompt list (teacher_student.py:104-120): the row direction is then averaged over `rows`, the
+ * column direction over `cols`.  value (optional) and gscale * d loss / d scores (optional).
+ * lse: 2 * (rows + cols) floats of workspace. */
+FC_API int fc_loss_fwd_bwd(const float* scores, const float* teacher, int64_t ld, int32_t rows, int32_t cols, float* lse,
+                           float gscale, float* loss_out, float* dscores, int64_t ldd, void* stream);
 /* C = alpha * op(A) . op(B) in fp32 (score-matrix gradients dV = dS . T, dT = dS^T . V); trans_x: operand stored transposed. */
 FC_API int fc_sgemm_f32(int32_t trans_a, int32_t trans_b, int32_t M, int32_t N, int32_t K, float alpha, const float* A,
                         int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, void* stream);

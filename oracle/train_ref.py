@@ -21,20 +21,33 @@ from .loss_ref import ref_nce_loss, ref_teacher_student_nce_loss
 
 def ref_training_loss(student, teacher, batch: Mapping, sections: Sequence[Tuple[str, int, int]],
                       init_temperature: float = 0.05, labeled_dataset_name: str = "labeled",
-                      shares: Optional[Mapping[str, float]] = None) -> torch.Tensor:
+                      shares: Optional[Mapping[str, float]] = None,
+                      prompts: Optional[Tuple[Mapping[str, torch.Tensor], Mapping[str, torch.Tensor]]] = None) -> torch.Tensor:
+    """``prompts``: (student-tokenised, teacher-tokenised) prompt lists that replace the texts of the unlabelled section
+    (``teacher_student.py:104-120``; same token width as the batch here)."""
     scale = math.exp(-math.log(init_temperature))  # video_text_module.py:32; ts scale is a clone (teacher_student.py:70)
-    v, t = student(batch["video_student"], batch["text_student"])
+    text_student, text_teacher = batch["text_student"], batch["text_teacher"]
+    text_sections = [(lo, hi) for _, lo, hi in sections]
+    if prompts is not None:
+        idx = next(i for i, (n, _, _) in enumerate(sections) if n != labeled_dataset_name)
+        _, lo, hi = sections[idx]
+        text_student = {k: torch.cat((v[:lo], prompts[0][k].to(v.dtype), v[hi:])) for k, v in text_student.items()}
+        text_teacher = {k: torch.cat((v[:lo], prompts[1][k].to(v.dtype), v[hi:])) for k, v in text_teacher.items()}
+        p = len(prompts[0]["input_ids"])
+        text_sections = [(a, b) if i < idx else (lo, lo + p) if i == idx else (a + p - (hi - lo), b + p - (hi - lo))
+                         for i, (a, b) in enumerate(text_sections)]
+    v, t = student(batch["video_student"], text_student)
     with torch.no_grad():
-        tv, tt = teacher(batch["video_teacher"], batch["text_teacher"])
+        tv, tt = teacher(batch["video_teacher"], text_teacher)
     names = {n for n, _, _ in sections}
     shares = shares or {n: 1 / max(len(names), 2) for n in names}
     total = 0.0
-    for name, lo, hi in sections:
-        scores = scale * v[lo:hi] @ t[lo:hi].T
+    for (name, lo, hi), (tlo, thi) in zip(sections, text_sections):
+        scores = scale * v[lo:hi] @ t[tlo:thi].T
         if name == labeled_dataset_name:
             loss = ref_nce_loss(scores)
         else:
-            teacher_scores = scale * tv[lo:hi] @ tt[lo:hi].T
+            teacher_scores = scale * tv[lo:hi] @ tt[tlo:thi].T
             loss = ref_teacher_student_nce_loss(scores, teacher_scores, reduction="batchmean") * scale ** 2
         total = total + loss * shares[name]
     return total

@@ -78,6 +78,35 @@ def main() -> None:
     out["student_after_step"] = {k: after[k].detach().clone() for k in keep}
     path = os.path.join(base.ROOT, "tests", "golden", "reference_training.pt")
     torch.save(out, path)
+
+    # ---- the same step with `prompts` (teacher_student.py:47,81-90,104-120,128-139): the unlabelled section's captions are
+    # replaced by a fixed prompt list, its score matrices become (6 videos x 5 prompts).  Same weights and inputs as above
+    # (reloaded: the optimizer step above moved the student), so the second fixture stores only what differs.
+    student.load_state_dict({k: v for k, v in out["student_state_dict"].items() if k != "logit_scale"})  # dropped by the wrapper
+    for p in student.parameters():
+        p.grad = None  # the first step's gradients are still attached to the same parameter objects
+    prompts = ["a video of a person cooking", "a video of a dog", "someone playing guitar", "a cartoon", "news"]
+    enc_s = ClipVideoTextEncoder(student, num_frames=2).train()
+    module = TeacherStudentLightningModule(encoder=enc_s, teacher=enc_t, init_temperature=0.05, fit_temperature=False,
+                                           prompts=prompts)
+    module.trainer = types.SimpleNamespace(optimizers=[torch.optim.AdamW(
+        [p for p in module.parameters() if p.requires_grad], lr=3e-6)])
+    batch = {"video_student": video, "video_teacher": video, "text_student": {"input_ids": ids.clone()},
+             "text_teacher": {"input_ids": ids.clone()}, "dataset": list(names)}
+    loss_p = module.training_step_end(module.training_step(batch, 0))
+    loss_p.backward()
+    grads = {k: p.grad.detach().clone() for k, p in enc_s.model.named_parameters() if p.grad is not None}
+    keep_g = keep + ("visual.conv1.weight", "token_embedding.weight", "transformer.resblocks.0.attn.in_proj_weight",
+                     "visual.transformer.resblocks.0.ln_1.weight", "visual.positional_embedding", "ln_final.bias")
+    out_p = {"prompts": prompts, "tokenized_prompts": {k: v.detach().clone() for k, v in module.tokenized_prompts.items()},
+             "loss": loss_p.detach().clone(), "num_grads": len(grads),
+             "logged": {name: (v.clone() if isinstance(v, torch.Tensor) else v) for name, v, _ in module.logged
+                        if name.startswith("loss/")},
+             "grads": {k: grads[k] for k in keep_g},
+             "reference_files": ["aligner/teacher_student.py", "aligner/loss.py", "util/tensor_utils.py"]}
+    path_p = os.path.join(base.ROOT, "tests", "golden", "reference_training_prompts.pt")
+    torch.save(out_p, path_p)
+    print(f"wrote {path_p} ({os.path.getsize(path_p) / 1e6:.2f} MB); loss with prompts {float(loss_p):.6f}")
     print(f"wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB); loss {float(loss):.6f}; {len(out['grads'])} gradient "
           f"tensors; torch {torch.__version__}")
 

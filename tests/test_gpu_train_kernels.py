@@ -142,6 +142,24 @@ def test_loss_fwd_bwd(dev, B):
     _close(grad, 2.0 * s.grad, 2e-5, "ts grad")
 
 
+@pytest.mark.parametrize("R,C", [(6, 5), (1, 9), (300, 17), (33, 600)])
+def test_teacher_student_loss_on_rectangular_scores(dev, R, C):
+    """(videos x prompts) matrices (teacher_student.py:104-120): ``batchmean`` divides the row direction by R and the
+    column direction -- the loss of the transposed matrices, loss.py:36-39 -- by C."""
+    from fitclip_b200 import train_ops as T
+    from oracle.loss_ref import ref_teacher_student_nce_loss
+    torch.manual_seed(R * 1000 + C)
+    s = (torch.randn(R, C, device=dev) * 3).requires_grad_(True)
+    t = torch.randn(R, C, device=dev) * 3
+    ref = ref_teacher_student_nce_loss(s, t, reduction="batchmean")
+    ref.backward()
+    loss, grad = T.loss_fwd_bwd(s.detach(), t, gscale=1.5)
+    assert torch.allclose(loss, ref.detach(), rtol=2e-5, atol=2e-5)
+    _close(grad, 1.5 * s.grad, 2e-5, "ts grad (rectangular)")
+    with pytest.raises(AssertionError):
+        T.loss_fwd_bwd(s.detach(), None)  # nce_loss pairs row i with column i
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 def test_sgemm(dev, ta, tb):
     from fitclip_b200 import train_ops as T

@@ -98,3 +98,76 @@ def test_cuda_training_step_matches_reference_training_code(gold, dev):
         checked += 1
     assert not bad, bad
     assert checked >= 40
+
+
+# ------------------------------------------------------------------------------------------------ prompts (teacher_student.py:104-120)
+PROMPTS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_training_prompts.pt")
+
+
+@pytest.fixture(scope="module")
+def gold_p():
+    return torch.load(PROMPTS)
+
+
+def _with_prompt_tokenizer(encoder, gold_p):
+    """The reference tokenised the prompts with a synthetic stand-in for clip.tokenize (make_reference_golden.py); the ids
+    are in the fixture, so the encoders' tokenizer hook simply returns them."""
+    ids = gold_p["tokenized_prompts"]["input_ids"]
+    encoder.get_tokenizer = lambda: (lambda texts: {"input_ids": ids.clone()} if list(texts) == gold_p["prompts"] else None)
+    return encoder
+
+
+def test_reference_prompt_step_has_rectangular_unlabelled_scores(gold, gold_p):
+    assert gold_p["tokenized_prompts"]["input_ids"].shape == (5, 16) and gold_p["num_grads"] == 61
+    # the labelled section is untouched by the prompts, the unlabelled one is not
+    assert abs(float(gold_p["logged"]["loss/train_labeled"]) - float(gold["logged"]["loss/train_labeled"])) < 1e-4
+    assert abs(float(gold_p["logged"]["loss/train_unlabeled"]) - float(gold["logged"]["loss/train_unlabeled"])) > 1.0
+
+
+def test_oracle_matches_reference_training_code_with_prompts(gold, gold_p):
+    student, teacher = _models(gold)
+    ref_student, ref_teacher = oracle.RefClipVideoTextEncoder(student, 2), oracle.RefClipVideoTextEncoder(teacher, 2)
+    opt = torch.optim.AdamW(ref_student.model.parameters(), lr=3e-6)
+    tok = {"input_ids": gold_p["tokenized_prompts"]["input_ids"]}
+    loss, grads = oracle.ref_training_step(ref_student, ref_teacher, _batch(gold), SECTIONS, opt,
+                                           init_temperature=gold["init_temperature"], prompts=(tok, tok))
+    assert abs(float(loss) - float(gold_p["loss"])) <= 1e-5 * abs(float(gold_p["loss"]))
+    for name, ref in gold_p["grads"].items():
+        err, scale = (grads[name] - ref).abs().max().item(), ref.abs().max().item()
+        assert err <= 1e-4 * scale + 1e-7, f"{name}: {err:.3e} vs {scale:.3e}"
+
+
+def test_trainer_orchestration_matches_reference_training_code_with_prompts(gold, gold_p):
+    from torch_kernels import TorchKernels
+    student, teacher = _models(gold)
+    enc = _with_prompt_tokenizer(B200ClipVideoTextEncoder(student.state_dict(), num_frames=2), gold_p)
+    teach = _with_prompt_tokenizer(oracle.RefClipVideoTextEncoder(teacher, 2), gold_p)
+    module = TeacherStudentTrainingModule(enc, teach, init_temperature=gold["init_temperature"], kernels=TorchKernels(),
+                                          prompts=gold_p["prompts"])
+    loss = module.training_step(_batch(gold), 0, optimize=False)
+    assert abs(float(loss) - float(gold_p["loss"])) <= 1e-4 * abs(float(gold_p["loss"]))
+    for name, ref in gold_p["grads"].items():
+        err, scale = (module.trainer.g[name] - ref).abs().max().item(), ref.abs().max().item()
+        assert err <= 3e-4 * scale + 1e-6, f"{name}: {err:.3e} vs {scale:.3e}"
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_matches_reference_training_code_with_prompts(gold, gold_p, dev):
+    student, teacher = _models(gold)
+    enc = _with_prompt_tokenizer(B200ClipVideoTextEncoder(student.state_dict(), num_frames=2).to(dev), gold_p)
+    teach = _with_prompt_tokenizer(B200ClipVideoTextEncoder(teacher.state_dict(), num_frames=2).to(dev), gold_p)
+    module = TeacherStudentTrainingModule(enc, teach, init_temperature=gold["init_temperature"], prompts=gold_p["prompts"])
+    loss = module.training_step(_batch(gold, dev), 0, optimize=False)
+    assert abs(float(loss) - float(gold_p["loss"])) <= 0.02 * abs(float(gold_p["loss"])), (float(loss), float(gold_p["loss"]))
+    top = max(float(v.norm()) for v in gold_p["grads"].values())
+    checked = 0
+    for name, ref in gold_p["grads"].items():
+        if float(ref.norm()) < 1e-3 * top:
+            continue
+        got = module.trainer.g[name].cpu()
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+        ratio = float(got.norm()) / float(ref.norm())
+        print(f"grad (prompts) {name}: cos {cos:.5f} norm ratio {ratio:.4f}")
+        assert cos >= 0.995 and abs(ratio - 1) <= 0.08, name
+        checked += 1
+    assert checked >= 10

@@ -143,3 +143,22 @@ def test_train_command():
     assert out.returncode == 0, out.stderr[-2000:]
     result = json.loads(out.stdout.strip().splitlines()[-1])
     assert result["step"] == 4 and result["loss/train"] == result["loss/train"]  # finite
+
+
+@pytest.mark.gpu
+def test_train_command_with_a_prompts_file(tmp_path):
+    """``prompts=<file>`` (aligner/cli.py:117-121 -> teacher_student.py:47,104-120): the unlabelled captions are replaced by
+    the file's lines, tokenised by the in-tree byte-pair tokenizer on the (synthetic, tests-only) merges file."""
+    prompts = tmp_path / "prompts.txt"
+    prompts.write_text("a video of a man playing guitar\n\n a woman is cooking pasta \npeople are dancing\n")
+    env = dict(os.environ, PYTHONPATH=ROOT,
+               FITCLIP_BPE_VOCAB=os.path.join(ROOT, "tests", "golden", "bpe_synthetic_vocab.txt.gz"))
+    tiny = [f"encoder.{who}.model.{k}=1" for who in ("student", "teacher") for k in ("vision_layers", "transformer_layers")]
+    out = subprocess.run([sys.executable, "-m", "aligner", "--config-name", "teacher_student_trainer", "command=train",
+                          "+encoder@encoder.student=clip_vit_b_16", "+encoder@encoder.teacher=clip_vit_b_16",
+                          "encoder.teacher.model.seed=1", "data=synthetic_teacher_student", "data.batch_size=16",
+                          "trainer.max_steps=3", "optimizer.lr=1e-4", f"+prompts={prompts}", *tiny], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    result = json.loads(out.stdout.strip().splitlines()[-1])
+    assert result["step"] == 3 and result["loss/train"] == result["loss/train"]

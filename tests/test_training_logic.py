@@ -227,3 +227,40 @@ def test_fit_temperature_matches_autograd_and_clamps():
     module.temps.fill_(module.max_logit_scale + 1.0)
     module.training_step(batch, 2)
     assert float(module.temps.max()) <= module.max_logit_scale + 1e-6
+
+
+def test_fit_temperature_gradients_with_prompts_match_autograd():
+    """Prompts make the unlabelled score matrices rectangular (5 videos x 3 prompts): ``batchmean`` then divides the row
+    direction by 5 and the column direction by 3, which the scale gradients (sum dL/dS * S and the product rule through the
+    teacher's soft targets) must follow -- against autograd on the reference's expression (teacher_student.py:104-173)."""
+    import math
+    student, teacher = make_models()
+    ref_student = oracle.RefClipVideoTextEncoder(copy.deepcopy(student))
+    ref_teacher = oracle.RefClipVideoTextEncoder(teacher)
+    names = ["labeled"] * 3 + ["unlabeled"] * 5
+    batch = make_batch(8, seed=9, names=names)
+    prompt_ids = make_batch(3, seed=10)["text_student"]["input_ids"]
+    ls = torch.nn.Parameter(torch.tensor([-math.log(0.05)]))
+    ts = torch.nn.Parameter(ls.detach().clone())
+    text = {"input_ids": torch.cat((batch["text_student"]["input_ids"][:3], prompt_ids))}
+    v, t = ref_student(batch["video_student"], text)
+    with torch.no_grad():
+        tv, tt = ref_teacher(batch["video_teacher"], text)
+    labeled = oracle.ref_nce_loss(ls.exp() * v[:3] @ t[:3].T)
+    scores, teacher_scores = ls.exp() * v[3:] @ t[3:].T, ts.exp() * tv[3:] @ tt[3:].T
+    assert scores.shape == (5, 3)
+    total = 0.5 * labeled + 0.5 * oracle.ref_teacher_student_nce_loss(scores, teacher_scores, reduction="batchmean") * ts.exp() ** 2
+    total.backward()
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    for e in (enc, ref_teacher):
+        e.get_tokenizer = lambda: (lambda texts: {"input_ids": prompt_ids.clone()})
+    module = TeacherStudentTrainingModule(enc, ref_teacher, lr=1e-3, kernels=TorchKernels(), fit_temperature=True,
+                                          prompts=["p0", "p1", "p2"])
+    loss = module.training_step(batch, 0, optimize=False)
+    assert torch.allclose(loss, total.detach(), rtol=1e-4, atol=1e-5)
+    assert abs(float(module.temps_grad[0]) - float(ls.grad)) <= 2e-4 * abs(float(ls.grad)) + 1e-6
+    assert abs(float(module.temps_grad[1]) - float(ts.grad)) <= 2e-4 * abs(float(ts.grad)) + 1e-6
+    for name, p in ref_student.model.named_parameters():
+        if p.grad is not None and name in module.trainer.g:
+            err, scale = (module.trainer.g[name] - p.grad).abs().max().item(), p.grad.abs().max().item()
+            assert err <= 3e-4 * scale + 1e-6, name

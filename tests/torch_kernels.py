@@ -195,16 +195,16 @@ class TorchKernels:
 
     @staticmethod
     def loss_fwd_bwd(scores, teacher_scores=None, gscale=1.0, want_grad=True):
-        B = scores.shape[0]
+        B, C = scores.shape  # rows = videos, columns = texts (C != B only with prompts, teacher-student form)
         pr, pc = torch.softmax(scores, 1), torch.softmax(scores, 0)
         if teacher_scores is None:
             loss = (-F.log_softmax(scores, 1).diag()).mean() + (-F.log_softmax(scores, 0).diag()).mean()
             grad = (pr + pc - 2 * torch.eye(B)) / B
         else:
             tr, tc = torch.softmax(teacher_scores, 1), torch.softmax(teacher_scores, 0)
-            loss = ((tr * (F.log_softmax(teacher_scores, 1) - F.log_softmax(scores, 1))).sum()
-                    + (tc * (F.log_softmax(teacher_scores, 0) - F.log_softmax(scores, 0))).sum()) / B
-            grad = (pr - tr + pc - tc) / B
+            loss = (tr * (F.log_softmax(teacher_scores, 1) - F.log_softmax(scores, 1))).sum() / B \
+                + (tc * (F.log_softmax(teacher_scores, 0) - F.log_softmax(scores, 0))).sum() / C
+            grad = (pr - tr) / B + (pc - tc) / C
         return loss, gscale * grad
 
     @staticmethod
