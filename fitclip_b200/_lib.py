@@ -96,7 +96,7 @@ SIGNATURES = {
     "fc_text_embed": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
 }
 
-EPI_BIAS, EPI_BIAS_QGELU, EPI_BIAS_RESID, EPI_F32, EPI_F32_SPLITK = 0, 1, 2, 4, 9
+EPI_BIAS, EPI_BIAS_QGELU, EPI_BIAS_RESID, EPI_F32, EPI_F32_SPLITK, EPI_QGELU_BWD = 0, 1, 2, 4, 9, 11
 DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 _lib: Optional[C.CDLL] = None

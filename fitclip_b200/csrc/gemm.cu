@@ -91,7 +91,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr bool kLn = (EPI == EPI_LN_BIAS || EPI == EPI_LN_BIAS_QGELU || EPI == EPI_LN_BIAS_GELU);
   constexpr bool kErfGelu = (EPI == EPI_LN_BIAS_GELU);
   constexpr bool kGelu = (EPI == EPI_BIAS_QGELU || EPI == EPI_LN_BIAS_QGELU);
-  constexpr bool kStaged = (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || EPI == EPI_BIAS_RESID || kLn);
+  constexpr bool kResid = (EPI == EPI_BIAS_RESID || EPI == EPI_QGELU_BWD);  // a second bf16 input tile, TMA-loaded into staging
+  constexpr bool kStaged = (EPI == EPI_BIAS || EPI == EPI_BIAS_QGELU || kResid || kLn);
   constexpr bool kAmn = (MAJ & 1) != 0, kBmn = (MAJ & 2) != 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
@@ -131,7 +132,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (kStaged) tma_prefetch_desc(&tmC);
-    if (EPI == EPI_BIAS_RESID) tma_prefetch_desc(&tmR);
+    if (kResid) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -261,7 +262,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // (issuer) TMA-load the residual sub-tiles of pair-tile t into this group's staging tiles.  `drained`: the caller
     // has made sure no earlier TMA store still reads them.
     auto prefetch_resid = [&](int t, bool two_pending) {
-      if (EPI != EPI_BIAS_RESID || t >= num_tiles) return;
+      if (!kResid || t >= num_tiles) return;
       const int mb = 2 * (t / num_n_tiles) + cta_rank, nb = t % num_n_tiles;
 #pragma unroll
       for (int si = 0; si < 2; ++si) {
@@ -285,7 +286,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (!kStaged || t >= num_tiles) return;
       const int mb = 2 * (t / num_n_tiles) + cta_rank, nb = t % num_n_tiles;
       const int n = nb * BN + etid;
-      nxt_bias = n < p.N ? __ldg(p.bias + n) : 0.f;
+      nxt_bias = (EPI != EPI_QGELU_BWD && n < p.N) ? __ldg(p.bias + n) : 0.f;
       if (kLn) {
         nxt_cs = n < p.N ? __ldg(p.colsum + n) : 0.f;
         nxt_s1 = 0.f;
@@ -352,7 +353,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t stg_row = smem_u32(stg_ptr) + row_in_tile * 128;
           // (a) staging tile si is free once the store issued from it one tile ago has finished reading it (the
           //     residual path learns that -- and that the residual has landed -- from resid_bar below)
-          if (EPI != EPI_BIAS_RESID) {
+          if (!kResid) {
             if (issuer) {
               if (prev_two) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
             }
@@ -370,7 +371,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_arrive_cluster(leader_tmem_empty[acc]);
             released = true;
           }
-          if (EPI == EPI_BIAS_RESID) {
+          if (kResid) {
             mbar_wait(&resid_bar[2 * grp + si], (resid_phase >> si) & 1u);
             resid_phase ^= 1u << si;
           }
@@ -445,6 +446,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int e = 0; e < 4; ++e) {
                 const float2 f = unpack_bf16x2(w[e]);
                 v2[e] = add_f32x2(v2[e], pack_f32x2(f.x, f.y));
+              }
+            }
+            if (EPI == EPI_QGELU_BWD) {
+              // d/du [u s(u)] = s + 1.702 u s (1 - s) with s = sigmoid(1.702 u) = 0.5 + 0.5 tanh(0.851 u); the staging tile
+              // holds u (the same formula as quickgelu_bwd_kernel, applied to the fp32 accumulator instead of a bf16 dg)
+              const uint4 u = ld_shared_v4(addr);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              const uint64_t one2 = pack_f32x2(1.f, 1.f), k1702 = pack_f32x2(1.702f, 1.702f);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w[e]);
+                const uint64_t u2 = pack_f32x2(f.x, f.y);
+                const uint64_t s2 = fma_f32x2(half2, pack_f32x2(tanh_approx(0.851f * f.x), tanh_approx(0.851f * f.y)), half2);
+                // s * (1 + 1.702 u (1 - s))
+                const uint64_t oms2 = fma_f32x2(s2, pack_f32x2(-1.f, -1.f), one2);
+                const uint64_t d2 = mul_f32x2(s2, fma_f32x2(mul_f32x2(k1702, u2), oms2, one2));
+                v2[e] = mul_f32x2(v2[e], d2);
               }
             }
             float v[8];
@@ -759,7 +777,8 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   FC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
              "gemm: operands must be 16-byte aligned");
   const bool ln = epilogue == EPI_LN_BIAS || epilogue == EPI_LN_BIAS_QGELU || epilogue == EPI_LN_BIAS_GELU;
-  const bool staged = epilogue == EPI_BIAS || epilogue == EPI_BIAS_QGELU || epilogue == EPI_BIAS_RESID || ln;
+  const bool resid_in = epilogue == EPI_BIAS_RESID || epilogue == EPI_QGELU_BWD;
+  const bool staged = epilogue == EPI_BIAS || epilogue == EPI_BIAS_QGELU || resid_in || ln;
   if (ln) {
     FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.bias,
                "gemm: folded-LayerNorm epilogue needs bf16 C (N %% 32 == 0, ldc %% 8 == 0) and a bias");
@@ -777,6 +796,11 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
                  "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
       FC_REQUIRE(p.stats_out == nullptr || p.N % SUB_N == 0, "gemm: stats_out needs N %% 64 == 0");
     }
+  } else if (epilogue == EPI_QGELU_BWD) {
+    FC_REQUIRE(p.C && p.N % 32 == 0 && p.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0,
+               "gemm: bf16 epilogues need N %% 32 == 0, ldc %% 8 == 0 and a 16-byte aligned C");
+    FC_REQUIRE(p.resid && p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 15) == 0,
+               "gemm: the pre-activation input must be 16-byte aligned with ldr %% 8 == 0");
   } else if (epilogue == EPI_F32) {
     FC_REQUIRE(p.C, "gemm: null C");
   } else if (epilogue == EPI_F32_SPLITK) {
@@ -793,11 +817,11 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   const double mn = static_cast<double>(p.M) * p.N;
   ProfScope prof(stream, PROF_GEMM, epilogue, p.M, p.N, p.K, 2.0 * mn * p.K,
                  2.0 * (static_cast<double>(p.M) + p.N) * p.K +
-                     (epilogue <= EPI_PATCH || ln ? 2.0 * mn : 0.0) * (epilogue == EPI_BIAS_RESID ? 2.0 : 1.0) +
+                     (epilogue <= EPI_PATCH || ln || resid_in ? 2.0 * mn : 0.0) * (resid_in ? 2.0 : 1.0) +
                      (epilogue == EPI_F32 || epilogue == EPI_F32_SPLITK ? 4.0 * mn : 0.0));
   CUtensorMap ta, tb, tc, tr;
   const int maj = (p.a_mn ? 1 : 0) | (p.b_mn ? 2 : 0);
-  FC_REQUIRE(maj == 0 || (maj == 2 && (epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESID || epilogue == EPI_F32)) ||
+  FC_REQUIRE(maj == 0 || (maj == 2 && (epilogue == EPI_BIAS || resid_in || epilogue == EPI_F32)) ||
                  (maj == 3 && epilogue == EPI_F32_SPLITK),
              "gemm: operand layout a_mn=%d b_mn=%d is not built for epilogue %d", p.a_mn, p.b_mn, epilogue);
   int rc = p.a_mn ? make_tmap_mn(&ta, A, p.K, p.M, lda) : make_tmap(&ta, A, p.M, p.K, lda, BM);
@@ -811,7 +835,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
     rc = make_tmap(&tc, static_cast<const bf16*>(p.C), p.M, p.N, p.ldc, BM);
     if (rc) return rc;
     tr = tc;
-    if (epilogue == EPI_BIAS_RESID) {
+    if (resid_in) {
       rc = make_tmap(&tr, p.resid, p.M, p.N, p.ldr, BM);
       if (rc) return rc;
     }
@@ -819,6 +843,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
   if (maj == 2) {
     if (epilogue == EPI_BIAS) return launch<EPI_BIAS, 2>(ta, tb, tc, tr, p, stream);
     if (epilogue == EPI_BIAS_RESID) return launch<EPI_BIAS_RESID, 2>(ta, tb, tc, tr, p, stream);
+    if (epilogue == EPI_QGELU_BWD) return launch<EPI_QGELU_BWD, 2>(ta, tb, tc, tr, p, stream);
     return launch<EPI_F32, 2>(ta, tb, tc, tr, p, stream);
   }
   if (maj == 3) return launch<EPI_F32_SPLITK, 3>(ta, tb, tc, tr, p, stream);
@@ -833,6 +858,7 @@ int gemm_bf16_tn(int epilogue, const bf16* A, int64_t lda, const bf16* B, int64_
     case EPI_LN_BIAS: return launch<EPI_LN_BIAS>(ta, tb, tc, tr, p, stream);
     case EPI_LN_BIAS_QGELU: return launch<EPI_LN_BIAS_QGELU>(ta, tb, tc, tr, p, stream);
     case EPI_LN_BIAS_GELU: return launch<EPI_LN_BIAS_GELU>(ta, tb, tc, tr, p, stream);
+    case EPI_QGELU_BWD: return launch<EPI_QGELU_BWD>(ta, tb, tc, tr, p, stream);
     default: return launch<EPI_COUNT>(ta, tb, tc, tr, p, stream);
   }
 }

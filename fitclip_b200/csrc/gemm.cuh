@@ -17,7 +17,9 @@ enum Epilogue : int {
   EPI_F32_SPLITK = 9,     // C(fp32) += alpha * acc over `k_splits` K ranges (atomic adds; the caller zeroes C): weight
                           //   gradients, whose few output tiles would otherwise leave most SM pairs idle
   EPI_LN_BIAS_GELU = 10,  // EPI_LN_BIAS + exact GELU 0.5 x (1 + erf(x / sqrt 2)): the timm vision tower of the SLIP layout
-  EPI_NUM = 11,
+  EPI_QGELU_BWD = 11,     // C(bf16) = acc * quickgelu'(resid): the dgrad of c_proj fused with QuickGELU's backward (resid = the
+                          //   pre-activation u the forward kept); no bias
+  EPI_NUM = 12,
 };
 
 struct GemmParams {

@@ -1012,7 +1012,7 @@ int fc_gemm_bf16_layout(int epilogue, int a_mn, int b_mn, const void* A, int64_t
     if (k_splits <= 0) k_splits = pick_k_splits(M, N, K);
     p.k_splits = k_splits > num_k ? num_k : k_splits;
   } else {
-    FC_REQUIRE(epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESID || epilogue == EPI_F32,
+    FC_REQUIRE(epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESID || epilogue == EPI_F32 || epilogue == EPI_QGELU_BWD,
                "fc_gemm_bf16_layout: epilogue %d is not exposed", epilogue);
   }
   return gemm_bf16_tn(epilogue, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb, p,

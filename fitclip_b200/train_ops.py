@@ -35,16 +35,22 @@ def gemm_splitk(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, alpha: floa
     return out
 
 
-def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, resid: Optional[torch.Tensor] = None,
-            f32: bool = False) -> torch.Tensor:
+def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: Optional[torch.Tensor] = None,
+            f32: bool = False, qgelu_bwd_of: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``a (M,K) @ w (K,N)`` with ``w`` read in place as an MN-major B operand: the dgrad ``dX = dY @ W`` with ``W`` stored
-    ``(N_w, K_w)`` as the forward pass has it (``K`` here = ``N_w``).  bf16 out (+ bias [+ resid]) or fp32 out."""
+    ``(N_w, K_w)`` as the forward pass has it (``K`` here = ``N_w``).  bf16 out (+ bias [+ resid]) or fp32 out.
+    ``qgelu_bwd_of=u``: bf16 out = ``(a @ w) * quickgelu'(u)`` -- the dgrad of ``c_proj`` and QuickGELU's backward in one
+    kernel (``u (M, N)``: the pre-activation the forward kept)."""
     dev = _dev(a)
     assert a.dtype == BF16 and w.dtype == BF16 and a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[0]
     M, K = a.shape
     N = w.shape[1]
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else BF16)
     epi = _lib.EPI_F32 if f32 else (_lib.EPI_BIAS if resid is None else _lib.EPI_BIAS_RESID)
+    if qgelu_bwd_of is not None:
+        assert not f32 and resid is None and qgelu_bwd_of.dtype == BF16 and qgelu_bwd_of.shape == (M, N)
+        assert qgelu_bwd_of.stride(1) == 1
+        epi, resid, bias = _lib.EPI_QGELU_BWD, qgelu_bwd_of, None
     _call(dev, "fc_gemm_bf16_layout", epi, 0, 1, ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0),
           ptr(bias), ptr(resid), 0 if resid is None else resid.stride(0), 1.0, M, N, K, 1)
     return out

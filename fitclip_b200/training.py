@@ -65,6 +65,10 @@ class NativeKernels:
     def matmul_nt_f32(self, a, w):
         return T.gemm_nt(a, w, None, f32=True)
 
+    def linear_nt_qgelu_bwd(self, a, w, u):
+        """``(a @ w) * quickgelu'(u)``: c_proj's dgrad with QuickGELU's backward in its epilogue."""
+        return T.gemm_nt(a, w, None, qgelu_bwd_of=u)
+
     wgrad_tn = staticmethod(T.wgrad_tn)
     colsum = staticmethod(T.colsum)
 
@@ -195,12 +199,12 @@ class ClipTrainer:
             # x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
             # dact first (it does not need quickgelu(u)); then ONE pass over u gives du -- and, unless the forward kept it,
             # quickgelu(u), which the c_proj weight gradient reads
-            dact = K.linear_nt(dx, self.wb[p + "mlp.c_proj.weight"])
             if act is None:
+                dact = K.linear_nt(dx, self.wb[p + "mlp.c_proj.weight"])
                 act = K.empty_like(u)
                 du = K.quickgelu_bwd(u, dact, out=dact, g_out=act)
-            else:
-                du = K.quickgelu_bwd(u, dact, out=dact)
+            else:  # the forward kept quickgelu(u): du = (dx W) o quickgelu'(u) leaves the dgrad GEMM's epilogue directly
+                dact = du = K.linear_nt_qgelu_bwd(dx, self.wb[p + "mlp.c_proj.weight"], u)
             K.colsum(dx, g[p + "mlp.c_proj.bias"])
             K.wgrad_tn(dx, act, g[p + "mlp.c_proj.weight"])
             del act

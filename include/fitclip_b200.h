@@ -199,6 +199,8 @@ FC_API int fc_gemm_bf16_splitk(const void* A, int64_t lda, const void* B, int64_
 /* The tcgen05 GEMM with operands read in place as the TRANSPOSE of a row-major matrix ("MN-major"): a_mn: A is stored
  * (K, M) with row stride lda; b_mn: B is stored (K, N) with row stride ldb.  Built combinations:
  *   FC_EPI_BIAS / FC_EPI_BIAS_RESID / FC_EPI_F32 with b_mn   dgrad  dX = dY . W     (B = W as stored, (N_w, K_w))
+ *   epilogue 11 with b_mn: C = (dY . W) o quickgelu'(resid)  the same dgrad fused with QuickGELU's backward (resid = the
+ *                                                            pre-activation kept by the forward; bias unused)
  *   epilogue 9 (split-K, C fp32 +=) with a_mn and b_mn       wgrad  dW = dY^T . X   (A = dY, B = X as stored)
  * so the backward pass needs no transposed copies of weights or activations. */
 FC_API int fc_gemm_bf16_layout(int epilogue, int a_mn, int b_mn, const void* A, int64_t lda, const void* B,

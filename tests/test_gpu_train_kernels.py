@@ -142,6 +142,23 @@ def test_loss_fwd_bwd(dev, B):
     _close(grad, 2.0 * s.grad, 2e-5, "ts grad")
 
 
+@pytest.mark.parametrize("M,N,K", [(197 * 9, 3072, 768), (300, 256, 128), (77 * 5 + 3, 2048, 512)])
+def test_dgrad_fused_with_quickgelu_backward(dev, M, N, K):
+    """``(dy @ W) * quickgelu'(u)`` from the dgrad GEMM's epilogue (EPI_QGELU_BWD, B read MN-major) against autograd of
+    ``quickgelu(u) @ W.T`` w.r.t. u, and against the two-kernel path it replaces."""
+    from fitclip_b200 import train_ops as T
+    torch.manual_seed(M + N)
+    dy = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(K, N, device=dev) * K ** -0.5).bfloat16()   # c_proj.weight as stored: (out = K, in = N)
+    u = (torch.randn(M, N, device=dev) * 2).bfloat16()
+    uf = u.float().requires_grad_(True)
+    (uf * torch.sigmoid(1.702 * uf) @ w.float().T * dy.float()).sum().backward()
+    got = T.gemm_nt(dy, w, None, qgelu_bwd_of=u)
+    _close(got, uf.grad, 2e-2, "fused du")
+    two_step = T.quickgelu_bwd(u, T.gemm_nt(dy, w, torch.zeros(N, device=dev)))
+    assert (got.float() - two_step.float()).abs().max().item() <= 2e-2 * uf.grad.abs().max().item()
+
+
 @pytest.mark.parametrize("R,C", [(6, 5), (1, 9), (300, 17), (33, 600)])
 def test_teacher_student_loss_on_rectangular_scores(dev, R, C):
     """(videos x prompts) matrices (teacher_student.py:104-120): ``batchmean`` divides the row direction by R and the

@@ -41,6 +41,11 @@ class TorchKernels:
         return a @ w
 
     @staticmethod
+    def linear_nt_qgelu_bwd(a, w, u):
+        s = torch.sigmoid(1.702 * u)
+        return (a @ w) * (s * (1 + 1.702 * u * (1 - s)))
+
+    @staticmethod
     def wgrad_tn(dy, x, out, alpha=1.0, k_splits=0, rows=None):
         rows = dy.shape[0] if rows is None else rows
         out += alpha * (dy[:rows].T @ x[:rows])
