@@ -30,6 +30,7 @@ class fc_config(C.Structure):
 
 
 TOWER_OPENAI, TOWER_TIMM = 0, 1
+INTERPOLATION = {"bicubic": 0, "bilinear": 1}
 
 
 class fc_profile_record(C.Structure):
@@ -53,11 +54,11 @@ SIGNATURES = {
     "fc_model_ready": (C.c_int, [_p]),
     "fc_model_workspace_bytes": (_i64, [_p]),
     "fc_encode_video": (C.c_int, [_p, _p, C.c_int, _i64, _i32, _p, _p, _p]),
-    "fc_encode_video_uint8": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "fc_encode_video_uint8": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p]),
     "fc_encode_text": (C.c_int, [_p, _p, _i64, _p, _p]),
     "fc_model_check": (C.c_int, [_p, _p]),
-    "fc_preprocess_frames": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, C.c_int, _p]),
-    "fc_preprocess_to_patches": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
+    "fc_preprocess_frames": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, C.c_int, _i32, _p]),
+    "fc_preprocess_to_patches": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _i64, _i32, _p]),
     "fc_pool_normalize": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _f32, _p]),
     "fc_wise_lerp": (C.c_int, [_p, _p, _p, _p, _i64, _f64, _p]),
     "fc_sim_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32]),

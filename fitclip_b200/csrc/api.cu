@@ -519,14 +519,16 @@ int fc_encode_video(fc_model* m, const void* frames, int dtype, int64_t videos, 
 }
 
 int fc_preprocess_to_patches(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size, int32_t patch,
-                             const float* mean, const float* std, void* patches, int64_t ldp, void* stream) {
+                             const float* mean, const float* std, void* patches, int64_t ldp, int32_t interpolation,
+                             void* stream) {
   FC_REQUIRE(ldp > 0 && ldp < (int64_t(1) << 31), "fc_preprocess_to_patches: bad row stride");
   return preprocess_to_patches(frames, n, H, W, size, patch, mean, std, static_cast<bf16*>(patches),
-                               static_cast<int>(ldp), static_cast<cudaStream_t>(stream));
+                               static_cast<int>(ldp), interpolation, static_cast<cudaStream_t>(stream));
 }
 
 int fc_encode_video_uint8(fc_model* m, const uint8_t* frames, int64_t videos, int32_t T, int32_t H, int32_t W,
-                          const float* mean, const float* std, float* out_video, float* out_frames, void* stream) {
+                          const float* mean, const float* std, int32_t interpolation, float* out_video, float* out_frames,
+                          void* stream) {
   FC_REQUIRE(m && ((out_video && frames) || videos == 0) && mean && std, "fc_encode_video_uint8: null argument");
   FC_REQUIRE(videos >= 0 && T >= 1 && H > 0 && W > 0, "fc_encode_video_uint8: bad shape videos=%lld T=%d H=%d W=%d",
              static_cast<long long>(videos), T, H, W);
@@ -546,7 +548,7 @@ int fc_encode_video_uint8(fc_model* m, const uint8_t* frames, int64_t videos, in
     if (m->patch_dim != m->patch_cols)  // padded patch rows (ViT-L/14: 588 -> 592): the pad columns must be zero
       FC_CUDA(cudaMemsetAsync(m->big, 0, static_cast<size_t>(F) * m->grid * m->grid * m->patch_dim * sizeof(bf16), s));
     int rc = preprocess_to_patches(frames + v0 * T * frame_bytes, F, H, W, c.image_resolution, c.vision_patch_size, mean,
-                                   std, m->big, m->patch_dim, s);
+                                   std, m->big, m->patch_dim, interpolation, s);
     if (rc) return rc;
     if ((rc = vision_pass(m, nullptr, FC_BF16, F, m->feat, s))) return rc;
     if (out_frames)
@@ -589,10 +591,11 @@ int fc_model_check(fc_model* m, void* stream) {
 }
 
 int fc_preprocess_frames(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size, const float* mean,
-                         const float* std, void* out, int out_dtype, void* stream) {
+                         const float* std, void* out, int out_dtype, int32_t interpolation, void* stream) {
   int rc = check_arch();
   if (rc) return rc;
-  return preprocess_frames(frames, n, H, W, size, mean, std, out, out_dtype, static_cast<cudaStream_t>(stream));
+  return preprocess_frames(frames, n, H, W, size, mean, std, out, out_dtype, interpolation,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int fc_pool_normalize(const float* x, float* out, void* out_bf16, int64_t rows_out, int32_t T, int32_t D, float scale,

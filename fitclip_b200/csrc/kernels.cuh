@@ -31,11 +31,12 @@ int f32_to_bf16_padded(const float* in, bf16* out, int64_t rows, int cols, int l
 int split_bf16(const float* in, bf16* out, int64_t rows, int D, int mode, int terms, cudaStream_t s);
 
 // preprocess.cu : uint8 (F,H,W,3) -> [x/255 -> bicubic resize (shorter side = size) -> centre crop -> normalise] -> (F,3,size,size)
+// interpolation: 0 = bicubic (A = -0.75), 1 = bilinear
 int preprocess_frames(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
-                      void* out, int out_dtype, cudaStream_t s);
+                      void* out, int out_dtype, int interpolation, cudaStream_t s);
 // uint8 frames -> the bf16 patch matrix [F * (size/patch)^2, ldp] the patch-embedding GEMM reads (no NCHW intermediate)
 int preprocess_to_patches(const uint8_t* frames, int64_t F, int H, int W, int size, int patch, const float* mean,
-                          const float* stdv, bf16* patches, int ldp, cudaStream_t s);
+                          const float* stdv, bf16* patches, int ldp, int interpolation, cudaStream_t s);
 
 // attention.cu : out[s*L + l, h*64 + d] = softmax(q k^T / 8 [+ causal mask]) v, qkv rows are [q | k | v] of width 3*D
 int attention_bf16(const bf16* qkv, bf16* out, int64_t seqs, int L, int heads, int causal, cudaStream_t s);

@@ -23,7 +23,18 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
   c[3] = cubic2(u + 1.f, A);
 }
 
+// Bilinear resize (Resize's default for the SLIP wrapper, slip_video_text_encoder.py:78-87) runs through the same four taps
+// with weights (0, 1 - t, t, 0): ATen's upsample_bilinear2d clamps the source coordinate at 0 and the second tap at the
+// last row / column, which is what the border-replicated taps give (0.3 a + 0.7 a = a up to one rounding).
+__device__ __forceinline__ void linear_coeffs(float t, float (&c)[4]) {
+  c[0] = 0.f;
+  c[1] = 1.f - t;
+  c[2] = t;
+  c[3] = 0.f;
+}
+
 struct PreParams {
+  int bilinear;    // 0: bicubic (CLIP's transform), 1: bilinear (SLIP's)
   int H, W;        // source frame
   int RH, RW;      // resized frame (shorter side == size)
   int top, left;   // crop offset inside the resized frame
@@ -62,8 +73,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   const float fy = floorf(ry), fx = floorf(rx);
   const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
   float cy[4], cx[4];
-  cubic_coeffs(ry - fy, cy);
-  cubic_coeffs(rx - fx, cx);
+  if (p.bilinear) {
+    linear_coeffs(ry - fy, cy);
+    linear_coeffs(rx - fx, cx);
+  } else {
+    cubic_coeffs(ry - fy, cy);
+    cubic_coeffs(rx - fx, cx);
+  }
   const float inv255 = 1.f / 255.f;  // x * (1/255) is within 1 ulp of torch's x / 255 (tolerance: tests/test_gpu_preprocess.py)
   const uint8_t* src = in + f * static_cast<int64_t>(p.H) * p.W * 3;
   const bool interior = ix >= 1 && ix + 2 <= p.W - 2;  // no clamping, and the aligned reads stay inside the row
@@ -114,13 +130,16 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
 
 // patch > 0: `out` is the bf16 patch matrix [F * (size/patch)^2, ldp] (see preprocess_kernel<.., true>)
 static int preprocess_impl(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
-                           void* out, int out_dtype, int patch, int ldp, cudaStream_t s) {
+                           void* out, int out_dtype, int patch, int ldp, int interpolation, cudaStream_t s) {
   FC_REQUIRE(frames && out && mean && stdv, "preprocess: null pointer");
+  FC_REQUIRE(interpolation == 0 || interpolation == 1, "preprocess: interpolation must be 0 (bicubic) or 1 (bilinear), got %d",
+             interpolation);
   FC_REQUIRE(F >= 0 && H > 0 && W > 0 && size > 0, "preprocess: bad shape F=%lld H=%d W=%d size=%d",
              static_cast<long long>(F), H, W, size);
   FC_REQUIRE(F <= 65535, "preprocess: at most 65535 frames per call (got %lld)", static_cast<long long>(F));
   if (F == 0) return FC_OK;
   PreParams p;
+  p.bilinear = interpolation;
   p.H = H;
   p.W = W;
   p.size = size;
@@ -164,13 +183,13 @@ static int preprocess_impl(const uint8_t* frames, int64_t F, int H, int W, int s
 }
 
 int preprocess_frames(const uint8_t* frames, int64_t F, int H, int W, int size, const float* mean, const float* stdv,
-                      void* out, int out_dtype, cudaStream_t s) {
-  return preprocess_impl(frames, F, H, W, size, mean, stdv, out, out_dtype, 0, 0, s);
+                      void* out, int out_dtype, int interpolation, cudaStream_t s) {
+  return preprocess_impl(frames, F, H, W, size, mean, stdv, out, out_dtype, 0, 0, interpolation, s);
 }
 
 int preprocess_to_patches(const uint8_t* frames, int64_t F, int H, int W, int size, int patch, const float* mean,
-                          const float* stdv, bf16* patches, int ldp, cudaStream_t s) {
-  return preprocess_impl(frames, F, H, W, size, mean, stdv, patches, FC_DTYPE_BF16, patch, ldp, s);
+                          const float* stdv, bf16* patches, int ldp, int interpolation, cudaStream_t s) {
+  return preprocess_impl(frames, F, H, W, size, mean, stdv, patches, FC_DTYPE_BF16, patch, ldp, interpolation, s);
 }
 
 }  // namespace fc

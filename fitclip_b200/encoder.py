@@ -186,7 +186,7 @@ class B200Clip(nn.Module):
                                                    _lib.ptr(out), None, _lib.stream_ptr(video.device)))
         return out
 
-    def encode_video_uint8_pooled(self, video: torch.Tensor, mean, std) -> torch.Tensor:
+    def encode_video_uint8_pooled(self, video: torch.Tensor, mean, std, interpolation: str = "bicubic") -> torch.Tensor:
         """raw frames (B, T, H, W, 3) uint8 -> (B, E): eval transform fused into the patch gather + the encoder, one
         native call (``fc_encode_video_uint8``)."""
         if not video.is_cuda:
@@ -200,7 +200,8 @@ class B200Clip(nn.Module):
         m3 = (C.c_float * 3)(*[float(v) for v in mean])
         s3 = (C.c_float * 3)(*[float(v) for v in std])
         with torch.cuda.device(video.device):
-            _lib.check(_lib.load().fc_encode_video_uint8(handle, _lib.ptr(video), B, T, H, W, m3, s3, _lib.ptr(out), None,
+            _lib.check(_lib.load().fc_encode_video_uint8(handle, _lib.ptr(video), B, T, H, W, m3, s3,
+                                                         _lib.INTERPOLATION[interpolation], _lib.ptr(out), None,
                                                          _lib.stream_ptr(video.device)))
         return out
 

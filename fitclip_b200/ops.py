@@ -54,10 +54,12 @@ def attention_bf16(qkv: torch.Tensor, seqs: int, L: int, heads: int, causal: boo
     return out
 
 
-def preprocess_frames(frames: torch.Tensor, size: int, mean, std, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+def preprocess_frames(frames: torch.Tensor, size: int, mean, std, dtype: torch.dtype = torch.float32,
+                      interpolation: str = "bicubic") -> torch.Tensor:
     """uint8 ``(..., H, W, 3)`` frames -> ``(..., 3, size, size)`` of ``dtype`` (fp32 / bf16): the reference's eval
     transform (``aligner/encoder/clip_video_text_encoder.py:124-133``: /255, bicubic resize of the shorter side to
-    ``size``, centre crop, normalise) as one kernel on the GPU."""
+    ``size``, centre crop, normalise) as one kernel on the GPU.  ``interpolation="bilinear"``: the SLIP wrapper's transform
+    (``slip_video_text_encoder.py:78-87``)."""
     import ctypes as C
     dev = _dev(frames)
     if frames.dtype != torch.uint8 or frames.dim() < 3 or frames.shape[-1] != 3:
@@ -73,11 +75,13 @@ def preprocess_frames(frames: torch.Tensor, size: int, mean, std, dtype: torch.d
         for lo in range(0, flat.shape[0], 65535):  # the kernel takes at most 65535 frames per launch
             chunk = flat[lo:lo + 65535]
             check(_lib.load().fc_preprocess_frames(ptr(chunk), chunk.shape[0], H, W, size, m3, s3, ptr(out[lo:]),
-                                                   _lib.DTYPE_CODE[dtype], stream_ptr(dev)))
+                                                   _lib.DTYPE_CODE[dtype], _lib.INTERPOLATION[interpolation],
+                                                   stream_ptr(dev)))
     return out.reshape(*lead, 3, size, size)
 
 
-def preprocess_to_patches(frames: torch.Tensor, size: int, patch: int, mean, std) -> torch.Tensor:
+def preprocess_to_patches(frames: torch.Tensor, size: int, patch: int, mean, std,
+                          interpolation: str = "bicubic") -> torch.Tensor:
     """uint8 ``(n, H, W, 3)`` frames -> the bf16 patch matrix ``(n * (size/patch)**2, 3 * patch * patch)`` of the ViT patch
     embedding (column order ``(c, ky, kx)`` = ``conv1.weight.reshape(width, -1)``): the eval transform of
     :func:`preprocess_frames` fused with the patch gather."""
@@ -92,7 +96,7 @@ def preprocess_to_patches(frames: torch.Tensor, size: int, patch: int, mean, std
     s3 = (C.c_float * 3)(*[float(v) for v in std])
     with torch.cuda.device(dev):
         check(_lib.load().fc_preprocess_to_patches(ptr(frames.contiguous()), n, H, W, size, patch, m3, s3, ptr(out),
-                                                   out.stride(0), stream_ptr(dev)))
+                                                   out.stride(0), _lib.INTERPOLATION[interpolation], stream_ptr(dev)))
     return out
 
 

@@ -155,6 +155,17 @@ class B200SlipVideoTextEncoder(VideoTextEncoder):
         # slip_video_text_encoder.py:37-47 -- fused natively: encode_image, x/||x|| per frame, mean over frames
         return self.model.encode_video_pooled(video)
 
+    def encode_video_uint8(self, video: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """Raw decoded frames ``(B, T, H, W, 3)`` uint8 on the GPU -> ``(B, E)``: ``get_eval_transform`` (bilinear resize,
+        centre crop, ImageNet statistics; slip_video_text_encoder.py:78-87) on the GPU, fused into the patch gather by
+        default (``dtype=None``) or through an NCHW intermediate of ``dtype``."""
+        if dtype is None:
+            return self.model.encode_video_uint8_pooled(video, IMAGENET_MEAN, IMAGENET_STD, "bilinear")
+        from . import ops
+        frames = ops.preprocess_frames(video, self.model.visual.input_resolution, IMAGENET_MEAN, IMAGENET_STD, dtype,
+                                       "bilinear")
+        return self.model.encode_video_pooled(frames)
+
     def encode_text(self, text: TYPE_TEXT_INPUT) -> torch.Tensor:
         # slip_video_text_encoder.py:49-51
         return self.model.encode_text_normalized(text["input_ids"])

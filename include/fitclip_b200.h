@@ -121,25 +121,30 @@ FC_API int fc_model_check(fc_model* m, void* stream);
 
 /* ---- evaluation pre-processing (the step before the path; the reference runs it on CPU DataLoader workers) ------
  * ClipVideoTextEncoder.get_eval_transform (clip_video_text_encoder.py:124-133): uint8 frames (n, H, W, 3) ->
- * x/255 -> bicubic resize, shorter side = `size` (align_corners = false, no antialias, A = -0.75) -> centre crop
- * `size` x `size` -> (x - mean[c]) / std[c] -> (n, 3, size, size) of out_dtype (FC_F32 or FC_BF16), which is what
- * fc_encode_video takes.  mean / std: 3 HOST floats each.  n <= 65535 per call. */
+ * x/255 -> resize, shorter side = `size` (align_corners = false, no antialias) -> centre crop `size` x `size` ->
+ * (x - mean[c]) / std[c] -> (n, 3, size, size) of out_dtype (FC_F32 or FC_BF16), which is what fc_encode_video takes.
+ * interpolation: FC_INTERP_BICUBIC (A = -0.75; CLIP's transform) or FC_INTERP_BILINEAR (Resize's default, which
+ * SlipVideoTextEncoder.get_eval_transform keeps, slip_video_text_encoder.py:78-87).  mean / std: 3 HOST floats each.
+ * n <= 65535 per call. */
+enum { FC_INTERP_BICUBIC = 0, FC_INTERP_BILINEAR = 1 };
 FC_API int fc_preprocess_frames(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size,
-                                const float* mean, const float* std, void* out, int out_dtype, void* stream);
+                                const float* mean, const float* std, void* out, int out_dtype, int32_t interpolation,
+                                void* stream);
 
 /* Same transform, written as the bf16 patch matrix of the ViT patch embedding instead of an NCHW image: pixel (c, y, x)
  * of frame f -> row f*G*G + (y/patch)*G + x/patch, column c*patch*patch + (y%patch)*patch + x%patch, G = size/patch,
  * row stride ldp elements (>= 3*patch*patch; pad columns are NOT written) -- conv1.weight.reshape(width, -1)'s column
  * order, i.e. the A operand of the patch-embedding GEMM (VisionTransformer.forward's conv1 as a GEMM). */
 FC_API int fc_preprocess_to_patches(const uint8_t* frames, int64_t n, int32_t H, int32_t W, int32_t size, int32_t patch,
-                                    const float* mean, const float* std, void* patches, int64_t ldp, void* stream);
+                                    const float* mean, const float* std, void* patches, int64_t ldp,
+                                    int32_t interpolation, void* stream);
 /* The two steps above in one call, for raw decoded frames: uint8 (videos*frames_per_video, H, W, 3) -> eval transform
  * (same arithmetic as fc_preprocess_frames) written STRAIGHT into the bf16 patch matrix of the patch-embedding GEMM
  * (the normalised NCHW frame never exists in memory) -> fc_encode_video's path.  Replaces the CPU DataLoader transform
  * of clip_video_text_encoder.py:124-133 + encode_video (:80-89); 4x fewer host->device bytes than fp32 frames. */
 FC_API int fc_encode_video_uint8(fc_model* m, const uint8_t* frames, int64_t videos, int32_t frames_per_video, int32_t H,
-                                 int32_t W, const float* mean, const float* std, float* out_video, float* out_frames,
-                                 void* stream);
+                                 int32_t W, const float* mean, const float* std, int32_t interpolation, float* out_video,
+                                 float* out_frames, void* stream);
 
 /* ---- pooling / WiSE ---------------------------------------------------------------------------------------------
  * out[b] = scale * mean_t( x[b*T+t] / ||x[b*T+t]||_2 ), fp32 (clip_video_text_encoder.py:85-89; T = 1 is the text

@@ -23,15 +23,16 @@ def ref_resized_size(h: int, w: int, size: int):
 
 
 def ref_eval_transform(video: torch.Tensor, size: int, mean: Sequence[float], std: Sequence[float],
-                       dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """uint8 ``(T, H, W, 3)`` -> ``dtype`` ``(T, 3, size, size)``."""
+                       dtype: torch.dtype = torch.float32, interpolation: str = "bicubic") -> torch.Tensor:
+    """uint8 ``(T, H, W, 3)`` -> ``dtype`` ``(T, 3, size, size)``.  ``interpolation="bilinear"``: the SLIP wrapper's
+    transform, which keeps ``Resize``'s default (``slip_video_text_encoder.py:78-87``)."""
     assert video.dtype == torch.uint8 and video.shape[-1] == 3
     x = video.permute(0, 3, 1, 2)                       # ConvertBHWCtoBCHW (aligner/transforms.py:13-17)
     x = x.to(dtype) / 255                               # ConvertImageDtype(uint8 -> float)
     h, w = x.shape[-2:]
     new_h, new_w = ref_resized_size(h, w, size)
     if (h, w) != (new_h, new_w):                        # Resize(size, BICUBIC): shorter side -> size, no antialias
-        x = F.interpolate(x, size=(new_h, new_w), mode="bicubic", align_corners=False, antialias=False)
+        x = F.interpolate(x, size=(new_h, new_w), mode=interpolation, align_corners=False, antialias=False)
     top = int(round((new_h - size) / 2.0))              # CenterCrop(size)
     left = int(round((new_w - size) / 2.0))
     x = x[..., top:top + size, left:left + size]

@@ -28,6 +28,42 @@ def test_preprocess_matches_oracle(dev, h, w):
     assert torch.allclose(got16.float().cpu(), ref, atol=1e-5, rtol=2 ** -8)
 
 
+@pytest.mark.parametrize("h,w", [(240, 320), (360, 202), (224, 224), (113, 400), (1080, 1920), (100, 90)])
+def test_bilinear_preprocess_matches_oracle(dev, h, w):
+    """The SLIP wrapper's transform (slip_video_text_encoder.py:78-87): bilinear resize (up- and down-scaling, borders),
+    ImageNet statistics; NCHW output and the patch-matrix output of the fused path."""
+    import oracle
+    from fitclip_b200 import ops
+    from fitclip_b200.slip_encoder import IMAGENET_MEAN, IMAGENET_STD
+    g = torch.Generator().manual_seed(h * 1000 + w + 1)
+    video = torch.randint(0, 256, (2, h, w, 3), dtype=torch.uint8, generator=g)
+    ref = oracle.ref_eval_transform(video, 224, IMAGENET_MEAN, IMAGENET_STD, interpolation="bilinear")
+    got = ops.preprocess_frames(video.to(dev), 224, IMAGENET_MEAN, IMAGENET_STD, interpolation="bilinear")
+    err = (got.cpu() - ref).abs().max().item()
+    assert err <= 2e-5, err
+    patches = ops.preprocess_to_patches(video.to(dev), 224, 16, IMAGENET_MEAN, IMAGENET_STD, interpolation="bilinear")
+    unfold = torch.nn.functional.unfold(ref, kernel_size=16, stride=16).transpose(1, 2).reshape(-1, 768)
+    assert torch.allclose(patches.float().cpu(), unfold, atol=1e-5, rtol=2 ** -8)
+    with pytest.raises(KeyError):
+        ops.preprocess_frames(video.to(dev), 224, IMAGENET_MEAN, IMAGENET_STD, interpolation="nearest")
+
+
+def test_slip_encode_video_uint8_equals_transform_then_encode(dev):
+    import oracle
+    from fitclip_b200 import B200SlipVideoTextEncoder
+    enc = B200SlipVideoTextEncoder(oracle.slip_clip_vit_b_16(seed=2, vision_layers=1, transformer_layers=1).state_dict(),
+                                   num_frames=2).to(dev)
+    raw = torch.randint(0, 256, (3, 2, 180, 250, 3), dtype=torch.uint8, device=dev,
+                        generator=torch.Generator(device=dev).manual_seed(4))
+    with torch.inference_mode():
+        fused = enc.encode_video_uint8(raw)
+        two_step = enc.encode_video_uint8(raw, dtype=torch.bfloat16)
+        hook = enc.get_eval_transform(torch.float32)
+        host = enc.encode_video(torch.stack([hook(v.cpu()) for v in raw]).to(dev))
+    assert torch.equal(fused, two_step)  # same bf16 pixels reach the patch GEMM either way
+    assert torch.nn.functional.cosine_similarity(fused, host).min().item() >= 0.9999
+
+
 def test_preprocess_batched_leading_dims_and_flat_colour(dev):
     from fitclip_b200 import ops
     # a constant image must stay constant through the cubic kernel (weights sum to one)

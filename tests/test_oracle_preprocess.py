@@ -36,3 +36,17 @@ def test_eval_hook_does_not_antialias():
     m = torch.tensor(MEAN).view(1, 3, 1, 1)
     s = torch.tensor(STD).view(1, 3, 1, 1)
     assert torch.allclose(hook, (plain - m) / s, atol=1e-6)
+
+
+@pytest.mark.parametrize("h,w", [(240, 320), (360, 202), (113, 400)])
+def test_bilinear_oracle_matches_the_slip_wrapper_transform(h, w):
+    """``SlipVideoTextEncoder.get_eval_transform`` (slip_video_text_encoder.py:78-87): ``T.Resize(size)`` with its default
+    interpolation (bilinear, no antialias for tensors in the pinned torchvision), ImageNet statistics."""
+    from torchvision.transforms import InterpolationMode
+    from fitclip_b200.slip_encoder import IMAGENET_MEAN, IMAGENET_STD
+    g = torch.Generator().manual_seed(h + w)
+    video = torch.randint(0, 256, (2, h, w, 3), dtype=torch.uint8, generator=g)
+    ours = oracle.ref_eval_transform(video, 224, IMAGENET_MEAN, IMAGENET_STD, interpolation="bilinear")
+    hook = eval_transform(224, torch.float32, IMAGENET_MEAN, IMAGENET_STD, interpolation=InterpolationMode.BILINEAR)(video)
+    assert torch.allclose(ours, hook, atol=1e-6, rtol=0), (ours - hook).abs().max().item()
+    assert not torch.allclose(ours, oracle.ref_eval_transform(video, 224, IMAGENET_MEAN, IMAGENET_STD), atol=1e-3)
