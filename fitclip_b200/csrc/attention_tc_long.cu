@@ -33,6 +33,9 @@ constexpr int HD = 64;
 constexpr int QT = 128;   // query rows per tile
 constexpr int Q_BYTES = 128 * 128;     // a [128 x 64] bf16 tile, 128-byte rows
 constexpr int LONG_THREADS = 160;      // warps 0-3 softmax / epilogue, warp 4 TMA + MMA + TMEM alloc
+#ifndef ATT_LONG_POLY
+#define ATT_LONG_POLY 4  // of every 16 column pairs of a x32 chunk, this many take exp2 on the FMA pipe (ex2_poly_x2)
+#endif
 
 // KB keys per block: S in TMEM columns [0, KB), P (bf16) over [0, KB / 2), O in [KB, KB + 64).
 //   KB = 128: 256 TMEM columns (192 used), K / V double-buffered, 2 CTAs per SM
@@ -106,10 +109,17 @@ __device__ __forceinline__ void softmax_block(uint32_t trow, int valid, bool fir
     const bool full = FULL || (c4 + 1) * 32 <= valid;
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-      float x0, x1;
-      unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[c4 & 1][2 * c]), __uint_as_float(r[c4 & 1][2 * c + 1])), sc2, nmc2),
-                   x0, x1);
-      float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+      const uint64_t x2 =
+          fma_f32x2(pack_f32x2(__uint_as_float(r[c4 & 1][2 * c]), __uint_as_float(r[c4 & 1][2 * c + 1])), sc2, nmc2);
+      float p0, p1;
+      if (ATT_LONG_POLY > 0 && (c * ATT_LONG_POLY) % 16 < ATT_LONG_POLY) {
+        ex2_poly_x2(x2, p0, p1);
+      } else {
+        float x0, x1;
+        unpack_f32x2(x2, x0, x1);
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+      }
       if (!full) {
         if (c4 * 32 + 2 * c >= valid) p0 = 0.f;
         if (c4 * 32 + 2 * c + 1 >= valid) p1 = 0.f;

@@ -346,6 +346,31 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 
+// exp2 of two non-positive arguments on the FMA pipe (no MUFU): Cody-Waite split x = n + f with n = round(x) taken from
+// the low mantissa bits of x + 1.5 * 2^23, degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max relative error
+// 7.7e-5, far below the bf16 rounding of P), and 2^n applied by adding n << 23 to the exponent field.  Arguments are
+// clamped at -126 (the result would be a denormal; everything that small is irrelevant to a row whose maximum is 1).
+__device__ __forceinline__ void ex2_poly_x2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  x2 = pack_f32x2(x0, x1);
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f), nmagic = pack_f32x2(-12582912.f, -12582912.f);
+  const uint64_t r2 = add_f32x2(x2, magic);                 // bits: 0x4B400000 + n
+  const uint64_t n2 = add_f32x2(r2, nmagic);                // n as a float
+  const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.f, -1.f), x2);
+  uint64_t q2 = fma_f32x2(pack_f32x2(0.05508868f, 0.05508868f), f2, pack_f32x2(0.24260405f, 0.24260405f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.69327623f, 0.69327623f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.99992895f, 0.99992895f));
+  float r0, r1, q0, q1;
+  unpack_f32x2(r2, r0, r1);
+  unpack_f32x2(q2, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));  // (0x4B400000 + n) << 23 == n << 23 (mod 2^32)
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
+
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of exactly 128 bytes (64 bf16) with the
 // 128-byte swizzle TMA applies (CU_TENSOR_MAP_SWIZZLE_128B); the tile base must be 1024-byte aligned.
