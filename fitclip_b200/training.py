@@ -107,6 +107,9 @@ class ClipTrainer:
         # instead of re-emitting it from the backward's pass over u: that pass then writes 2 B per element less
         self.keep_activation = keep_activation
         self.cfg = dict(model.config)
+        if self.cfg.get("vision_tower", 0) != 0:
+            raise NotImplementedError("the training step is built for OpenAI-layout students (ln_pre, QuickGELU); a "
+                                      "SLIP-layout model (timm tower) can be the frozen TEACHER, not the student")
         if (3 * self.cfg["vision_patch_size"] ** 2) % 8:
             raise ValueError("training needs 3 * patch_size^2 to be a multiple of 8 (ViT-B/16, ViT-B/32)")
         named = [(n, p) for n, p in model.named_parameters() if n != "logit_scale"]

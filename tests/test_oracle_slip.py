@@ -128,3 +128,11 @@ def test_slip_vit_small_variant_is_rejected_clearly():
     with pytest.raises(_lib.FitclipError, match="head dimension 64"):
         B200SlipClip(sd, vision_heads=12)
     assert B200SlipClip(sd, vision_heads=6).config["vision_width"] == 384
+
+
+def test_slip_layout_student_is_refused_by_the_trainer_but_fine_as_teacher(ref):
+    from fitclip_b200 import B200SlipVideoTextEncoder
+    from fitclip_b200.training import ClipTrainer
+    enc = B200SlipVideoTextEncoder(ref["checkpoint_1"], num_frames=3)
+    with pytest.raises(NotImplementedError, match="SLIP-layout"):
+        ClipTrainer(enc.model, kernels=object())
