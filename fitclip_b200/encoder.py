@@ -30,6 +30,13 @@ CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 def infer_config(state_dict: Mapping[str, torch.Tensor]) -> Dict[str, int]:
     """Geometry from tensor shapes, the way ``clip.model.build_model`` does it."""
+    if any(k.startswith("visual.layer1.") for k in state_dict):
+        # config/encoder/clip_rn50.yaml ... clip_rn50x64.yaml, open_clip_rn*.yaml: CLIP's ModifiedResNet image tower
+        raise _lib.FitclipError(-1, "this state dict holds a ModifiedResNet image tower (CLIP RN50 / RN101 / RN50x*): only "
+                                    "the VisionTransformer towers are built (ViT-B/32, B/16, L/14, L/14@336, SLIP layout)")
+    if "visual.pos_embed" in state_dict or "module.visual.pos_embed" in state_dict:
+        raise _lib.FitclipError(-1, "this is a SLIP-layout state dict (timm image tower): use B200SlipClip / "
+                                    "B200SlipVideoTextEncoder / load_slip_model")
     conv = state_dict["visual.conv1.weight"]
     vision_width, patch = conv.shape[0], conv.shape[-1]
     grid = round((state_dict["visual.positional_embedding"].shape[0] - 1) ** 0.5)

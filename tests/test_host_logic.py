@@ -131,3 +131,20 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libfitclip_b200.so")
     with pytest.raises(_lib.FitclipError, match="no fallback"):
         _lib.load()
+
+
+def test_unsupported_layouts_are_named_in_the_error():
+    import oracle
+    from fitclip_b200 import B200Clip, _lib
+    sd = oracle.clip_vit_b_16(seed=0, vision_layers=1, transformer_layers=1, vision_width=64, transformer_width=64,
+                              transformer_heads=1, embed_dim=64, image_resolution=32, context_length=8,
+                              vocab_size=64).state_dict()
+    resnet = dict(sd)
+    resnet["visual.layer1.0.conv1.weight"] = torch.zeros(64, 64, 1, 1)  # clip_rn50.yaml and friends
+    with pytest.raises(_lib.FitclipError, match="ModifiedResNet"):
+        B200Clip(resnet)
+    slip = oracle.slip_clip_vit_b_16(seed=0, img_size=32, vision_width=64, vision_layers=1, vision_heads=1, embed_dim=64,
+                                     context_length=8, vocab_size=64, transformer_width=64, transformer_heads=1,
+                                     transformer_layers=1).state_dict()
+    with pytest.raises(_lib.FitclipError, match="SLIP-layout"):
+        B200Clip(slip)
