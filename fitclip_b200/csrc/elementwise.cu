@@ -14,11 +14,20 @@ namespace {
 // ------------------------------------------------------------------------------------------- LayerNorm (K2)
 // One warp per row; the row lives in registers (D <= 1024): one HBM read, one HBM write. fp32 statistics, eps inside
 // the sqrt, two-pass (mean, then centred variance) like ATen's CPU kernel within rounding.
-// Round 2: warps walk rows with a grid stride, gamma / beta come from shared memory (the one-row-per-warp version re-read
-// 6 KB of gamma / beta from L1 for every 1.5 KB row) and the rows TWO strides ahead are requested before the current row's
-// shuffle reductions start, so every warp always has two rows of loads in flight.
+// Warps walk rows with a grid stride; gamma / beta come from shared memory.  Rows reach a warp through a three-slot
+// shared-memory ring filled by cp.async (L2 -> shared, no registers): while row r is normalised, rows r + 1 and r + 2 are
+// in flight.  (Round 1: one row per warp, 0.71 of the copy peak; early round 2: two rows prefetched into registers, which
+// cost an SM a block: 0.71 / 0.79 at 512 / 2000 frames.)
 constexpr int LN_MAX_CHUNKS = 4;  // 4 x 32 lanes x 8 bf16 = 1024
 constexpr int LN_WARPS = 8;
+constexpr int LN_SLOTS = 3;
+constexpr int ln_ring_bytes(int ch) { return LN_WARPS * LN_SLOTS * ch * 32 * 16; }
+
+__device__ __forceinline__ void ln_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
 
 template <int CH>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf16* x, bf16* y,  // may alias (ln_pre runs in place)
@@ -26,11 +35,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf1
                                                                      const float* __restrict__ beta, int64_t rows, int D,
                                                                      int64_t ldx, int64_t ldy, float eps,
                                                                      float* __restrict__ stats_out) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunks = D >> 3;
   const float inv_d = 1.f / static_cast<float>(D);
-  // gamma / beta: staged once per (persistent) block in shared memory -- in registers they cost 48 of them at D = 768 and a
-  // block per SM; re-read from L1 for every row (round 1) they were 6 KB of traffic per 1.5 KB row
+  extern __shared__ __align__(16) uint4 ln_dyn[];  // [warp][slot][16-byte chunk]
+  uint4(*ring)[LN_SLOTS][CH * 32] = reinterpret_cast<uint4(*)[LN_SLOTS][CH * 32]>(ln_dyn);
   __shared__ __align__(16) float s_gamma[CH * 256], s_beta[CH * 256];
   for (int k = threadIdx.x; k < CH * 256; k += LN_WARPS * 32) {
     s_gamma[k] = k < D ? gamma[k] : 0.f;
@@ -38,27 +47,29 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf1
   }
   __syncthreads();
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * LN_WARPS;
-  int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
-  // two rows ahead: 2 blocks x 8 warps per SM (125 registers at D = 768) with ONE row in flight each are 24 KB per SM, which
-  // caps the kernel near 4.6 TB/s at ~700 ns of HBM latency; two rows in flight lift the cap
-  uint4 nx[2][CH];
-  auto fetch = [&](int64_t r, int slot) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
+  int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp;
+  // every lane copies, and later reads, only its own chunks; rows ahead are only read (y may alias x: this warp is the one
+  // that writes them, later)
+  auto issue = [&](int64_t r, int slot) {
+    if (r < rows) {
+      const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
 #pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (lane + 32 * i < chunks) nx[slot][i] = ld_stream_v4(xr + lane + 32 * i);  // plain (coherent) loads: y may alias x
+      for (int i = 0; i < CH; ++i)
+        if (lane + 32 * i < chunks) ln_cp_async16(&ring[warp][slot][lane + 32 * i], xr + lane + 32 * i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // an (empty) group per call keeps the wait arithmetic uniform
   };
-  if (row < rows) fetch(row, 0);
-  if (row + nwarps < rows) fetch(row + nwarps, 1);
-  int slot = 0;
-#pragma unroll 2
-  for (; row < rows; row += nwarps, slot ^= 1) {
+  issue(row, 0);
+  issue(row + nwarps, 1);
+  for (int slot = 0; row < rows; row += nwarps, slot = slot == LN_SLOTS - 1 ? 0 : slot + 1) {
+    issue(row + 2 * nwarps, slot >= 1 ? slot - 1 : LN_SLOTS - 1);  // the slot freed one iteration ago
+    asm volatile("cp.async.wait_group 2;" ::: "memory");           // all but the two newest groups: this row has landed
     float v[CH][8];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       if (lane + 32 * i < chunks) {
-        const uint4 q4 = slot ? nx[1][i] : nx[0][i];
+        const uint4 q4 = ring[warp][slot][lane + 32 * i];
         const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -68,10 +79,6 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf1
           sum += f.x + f.y;
         }
       }
-    }
-    if (row + 2 * nwarps < rows) {  // refill the slot just consumed: in flight during the next TWO rows' work
-      if (slot) fetch(row + 2 * nwarps, 1);
-      else fetch(row + 2 * nwarps, 0);
     }
     const float mean = warp_sum(sum) * inv_d;
     float sq = 0.f;
@@ -119,6 +126,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bf16_kernel(const bf1
       for (int pi = lane; pi < parts; pi += 32) so[pi] = pi == 0 ? make_float2(o1, o2) : make_float2(0.f, 0.f);
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Row statistics of x alone, in the [rows, D/64, 2] layout the folded-LayerNorm GEMM epilogue reads.  One warp per row.
@@ -597,10 +605,15 @@ int layernorm_bf16(const bf16* x, int64_t ldx, bf16* y, int64_t ldy, const float
   const int64_t want = (rows + LN_WARPS - 1) / LN_WARPS;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, int64_t(4) * num_sms()));
   const int ch = (D + 255) / 256;
-  if (ch == 1) layernorm_bf16_kernel<1><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
-  else if (ch == 2) layernorm_bf16_kernel<2><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
-  else if (ch == 3) layernorm_bf16_kernel<3><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
-  else layernorm_bf16_kernel<4><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
+  static bool configured = false;
+  if (!configured) {  // D = 1024: 48 KB of ring + 8 KB of gamma / beta exceed the default 48 KB limit
+    FC_CUDA(cudaFuncSetAttribute(layernorm_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_ring_bytes(4)));
+    configured = true;
+  }
+  if (ch == 1) layernorm_bf16_kernel<1><<<grid, LN_WARPS * 32, ln_ring_bytes(1), s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
+  else if (ch == 2) layernorm_bf16_kernel<2><<<grid, LN_WARPS * 32, ln_ring_bytes(2), s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
+  else if (ch == 3) layernorm_bf16_kernel<3><<<grid, LN_WARPS * 32, ln_ring_bytes(3), s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
+  else layernorm_bf16_kernel<4><<<grid, LN_WARPS * 32, ln_ring_bytes(4), s>>>(x, y, gamma, beta, rows, D, ldx, ldy, eps, stats_out);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }

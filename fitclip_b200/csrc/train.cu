@@ -18,6 +18,7 @@
 #include "../../include/fitclip_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace fc {
 
@@ -137,141 +138,164 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 // One warp per row (same register layout as layernorm_bf16_kernel: lane owns 16-byte chunks lane + 32 i), warps walk
 // rows with a grid stride and keep their dgamma/dbeta partials in registers; one block reduction + atomics at the end.
 constexpr int LNB_WARPS = 4;
-#ifndef LNB_PREFETCH_ADD
-#define LNB_PREFETCH_ADD 0  // 1: prefetch the residual-gradient row with x / dy as well (185 registers: 2 blocks per SM) --
-                           // measured SLOWER (2965 vs 3613 GB/s standalone, 24.0 vs 19.5 ms in the step): occupancy wins
-#endif
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Rows reach the warp through a two-slot shared-memory ring filled by cp.async (L2 -> shared, no registers): while row r is
+// processed, rows r + 1 and r + 2 (x, dy and the residual gradient: 4.6 KB each at D = 768) are in flight.  Round 1 / early
+// round 2 prefetched ONE row of x / dy into registers (and none of `add`: the registers cost a block per SM): 0.55 of the
+// copy peak with ~1 us of HBM latency exposed per row.  Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) halves the issue
+// slots of the four passes over the row.
+constexpr int ln_bwd_ring_bytes(int chunks) { return LNB_WARPS * 2 * 3 * chunks * 32 * 16; }
 
 template <int LNB_CHUNKS>
-__global__ void __launch_bounds__(LNB_WARPS * 32, (LNB_PREFETCH_ADD || LNB_CHUNKS == 4) ? 2 : 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* dy,
+__global__ void __launch_bounds__(LNB_WARPS * 32, LNB_CHUNKS == 4 ? 2 : 3) ln_bwd_kernel(const bf16* __restrict__ x, const bf16* dy,
                                                      const float* __restrict__ gamma, const bf16* add, bf16* dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      int64_t rows, int D, float eps) {
-  __shared__ float red[LNB_WARPS][LNB_CHUNKS * 256];
+  extern __shared__ __align__(16) uint4 lnb_dyn[];  // ln_bwd_ring_bytes(LNB_CHUNKS): 48 KB at D = 1024, above the static limit
+  uint4(*ring)[2][3][LNB_CHUNKS * 32] = reinterpret_cast<uint4(*)[2][3][LNB_CHUNKS * 32]>(lnb_dyn);  // [warp][slot][x | dy | add][chunk]
   __shared__ float sgamma[LNB_CHUNKS * 256];
+  static_assert(2 * 3 * 32 * 16 >= 256 * 4, "the block reduction re-uses the ring");
+  float(*red)[LNB_CHUNKS * 256] = reinterpret_cast<float(*)[LNB_CHUNKS * 256]>(lnb_dyn);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunks = D >> 3;
   const float inv_d = 1.f / static_cast<float>(D);
   for (int k = threadIdx.x; k < LNB_CHUNKS * 256; k += LNB_WARPS * 32) sgamma[k] = k < D ? gamma[k] : 0.f;
   __syncthreads();
-  float ag[LNB_CHUNKS][8], ab[LNB_CHUNKS][8];
+  uint64_t ag[LNB_CHUNKS][4], ab[LNB_CHUNKS][4];
 #pragma unroll
   for (int i = 0; i < LNB_CHUNKS; ++i)
 #pragma unroll
-    for (int t = 0; t < 8; ++t) ag[i][t] = ab[i][t] = 0.f;
-  // The next row's x / dy are requested before this row's reductions start, so a warp always has loads in flight
-  // (without the prefetch its loads and its shuffle reductions serialise: 0.36 of the copy peak).
-  // (the residual-gradient row `add` is requested at the top of the row's own iteration and consumed after the four
-  // reductions; prefetching it too costs a block per SM and loses -- see LNB_PREFETCH_ADD)
-  uint4 nx[LNB_CHUNKS], nd[LNB_CHUNKS], na[LNB_CHUNKS];
-  auto fetch = [&](int64_t r) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + r * D);
-    const uint4* dr = reinterpret_cast<const uint4*>(dy + r * D);
-    const uint4* ar = reinterpret_cast<const uint4*>(add + r * D);
+    for (int t = 0; t < 4; ++t) ag[i][t] = ab[i][t] = pack_f32x2(0.f, 0.f);
+  // every lane copies, and later reads, only its own 16-byte chunks: no cross-lane hazard on the ring.  dx may alias dy or
+  // add (training.py backward_video): rows ahead are only READ here, and this warp is the one that later writes them.
+  auto issue = [&](int64_t r, int slot) {
+    if (r < rows) {
 #pragma unroll
-    for (int i = 0; i < LNB_CHUNKS; ++i) {
-      const int c = lane + 32 * i;
-      if (c < chunks) {
-        nx[i] = ld_nc_v4(xr + c);
-        nd[i] = ld_stream_v4(dr + c);  // dx may alias dy (training.py backward_video): no non-coherent load
-        if (LNB_PREFETCH_ADD && add) na[i] = ld_stream_v4(ar + c);  // (dx may alias add as well)
+      for (int i = 0; i < LNB_CHUNKS; ++i) {
+        const int c = lane + 32 * i;
+        if (c < chunks) {
+          cp_async16(&ring[warp][slot][0][c], reinterpret_cast<const uint4*>(x + r * D) + c);
+          cp_async16(&ring[warp][slot][1][c], reinterpret_cast<const uint4*>(dy + r * D) + c);
+          if (add) cp_async16(&ring[warp][slot][2][c], reinterpret_cast<const uint4*>(add + r * D) + c);
+        }
       }
     }
+    cp_async_commit();  // an (empty) group per call keeps the wait_group arithmetic uniform
   };
+  // bf16 pair -> two fp32 in one 64-bit register pair: low element = bits << 16, high element = bits & 0xffff0000
+  auto widen = [](uint32_t w) { return (static_cast<uint64_t>(w & 0xffff0000u) << 32) | static_cast<uint64_t>(w << 16); };
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * LNB_WARPS;
   int64_t row = static_cast<int64_t>(blockIdx.x) * LNB_WARPS + warp;
-  if (row < rows) fetch(row);
-  for (; row < rows; row += nwarps) {
-    float xv[LNB_CHUNKS][8], dv[LNB_CHUNKS][8];
+  issue(row, 0);
+  issue(row + nwarps, 1);
+  for (int slot = 0; row < rows; row += nwarps, slot ^= 1) {
+    cp_async_wait<1>();  // everything but the newest group (row + nwarps) has landed
+    uint64_t xv[LNB_CHUNKS][4], dv[LNB_CHUNKS][4];
     uint4 av[LNB_CHUNKS];
-    float sum = 0.f;
+    uint64_t sum2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < LNB_CHUNKS; ++i) {
       const int c = lane + 32 * i;
       if (c < chunks) {
-        const uint32_t uw[4] = {nx[i].x, nx[i].y, nx[i].z, nx[i].w}, dw[4] = {nd[i].x, nd[i].y, nd[i].z, nd[i].w};
+        const uint4 qx = ring[warp][slot][0][c], qd = ring[warp][slot][1][c];
+        if (add) av[i] = ring[warp][slot][2][c];
+        const uint32_t uw[4] = {qx.x, qx.y, qx.z, qx.w}, dw[4] = {qd.x, qd.y, qd.z, qd.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float2 a = unpack_bf16x2(uw[t]), b = unpack_bf16x2(dw[t]);
-          xv[i][2 * t] = a.x;
-          xv[i][2 * t + 1] = a.y;
-          dv[i][2 * t] = b.x;
-          dv[i][2 * t + 1] = b.y;
-          sum += a.x + a.y;
+          xv[i][t] = widen(uw[t]);
+          dv[i][t] = widen(dw[t]);
+          sum2 = add_f32x2(sum2, xv[i][t]);
         }
-        if (add) av[i] = LNB_PREFETCH_ADD ? na[i] : ld_stream_v4(reinterpret_cast<const uint4*>(add + row * D) + c);
       }
     }
-    if (row + nwarps < rows) fetch(row + nwarps);
-    const float mean = warp_sum(sum) * inv_d;
-    float sq = 0.f;
+    issue(row + 2 * nwarps, slot);  // the slot just emptied: in flight during this row's and the next row's work
+    float s0, s1;
+    unpack_f32x2(sum2, s0, s1);
+    const float mean = warp_sum(s0 + s1) * inv_d;
+    const uint64_t nmean2 = pack_f32x2(-mean, -mean);
+    uint64_t sq2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < LNB_CHUNKS; ++i)
       if (lane + 32 * i < chunks) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float d = xv[i][t] - mean;
-          sq += d * d;
+        for (int t = 0; t < 4; ++t) {
+          const uint64_t d = add_f32x2(xv[i][t], nmean2);
+          sq2 = fma_f32x2(d, d, sq2);
         }
       }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
-    float c1 = 0.f, c2 = 0.f;
+    unpack_f32x2(sq2, s0, s1);
+    const float rstd = rsqrtf(warp_sum(s0 + s1) * inv_d + eps);
+    const uint64_t rstd2 = pack_f32x2(rstd, rstd), shift2 = pack_f32x2(-mean * rstd, -mean * rstd);
+    uint64_t c1_2 = pack_f32x2(0.f, 0.f), c2_2 = c1_2;
 #pragma unroll
     for (int i = 0; i < LNB_CHUNKS; ++i) {
       const int c = lane + 32 * i;
       if (c < chunks) {
         const float4 g0 = *reinterpret_cast<const float4*>(sgamma + c * 8);
         const float4 g1 = *reinterpret_cast<const float4*>(sgamma + c * 8 + 4);
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const uint64_t gm[4] = {pack_f32x2(g0.x, g0.y), pack_f32x2(g0.z, g0.w), pack_f32x2(g1.x, g1.y), pack_f32x2(g1.z, g1.w)};
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float xh = (xv[i][t] - mean) * rstd;
-          ag[i][t] += dv[i][t] * xh;
-          ab[i][t] += dv[i][t];
-          const float g = dv[i][t] * gm[t];
+        for (int t = 0; t < 4; ++t) {
+          const uint64_t xh = fma_f32x2(xv[i][t], rstd2, shift2);  // (x - mean) * rstd
+          ag[i][t] = fma_f32x2(dv[i][t], xh, ag[i][t]);
+          ab[i][t] = add_f32x2(ab[i][t], dv[i][t]);
+          const uint64_t g = mul_f32x2(dv[i][t], gm[t]);
           xv[i][t] = xh;
           dv[i][t] = g;  // from here on dv holds dy * gamma
-          c1 += g;
-          c2 += g * xh;
+          c1_2 = add_f32x2(c1_2, g);
+          c2_2 = fma_f32x2(g, xh, c2_2);
         }
       }
     }
-    c1 = warp_sum(c1) * inv_d;
-    c2 = warp_sum(c2) * inv_d;
+    unpack_f32x2(c1_2, s0, s1);
+    const float c1 = warp_sum(s0 + s1) * inv_d;
+    unpack_f32x2(c2_2, s0, s1);
+    const float c2 = warp_sum(s0 + s1) * inv_d;
+    // dx = rstd * (g - c1 - xh * c2) [+ add]
+    const uint64_t nc2r = pack_f32x2(-c2 * rstd, -c2 * rstd), nc1r = pack_f32x2(-c1 * rstd, -c1 * rstd);
 #pragma unroll
     for (int i = 0; i < LNB_CHUNKS; ++i) {
       const int c = lane + 32 * i;
       if (c < chunks) {
-        float o[8];
+        const uint32_t aw[4] = {av[i].x, av[i].y, av[i].z, av[i].w};
+        uint32_t ow[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = rstd * (dv[i][t] - c1 - xv[i][t] * c2);
-        if (add) {
-          const uint32_t aw[4] = {av[i].x, av[i].y, av[i].z, av[i].w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_bf16x2(aw[t]);
-            o[2 * t] += f.x;
-            o[2 * t + 1] += f.y;
-          }
+        for (int t = 0; t < 4; ++t) {
+          uint64_t o = fma_f32x2(dv[i][t], rstd2, fma_f32x2(xv[i][t], nc2r, nc1r));
+          if (add) o = add_f32x2(o, widen(aw[t]));
+          float o0, o1;
+          unpack_f32x2(o, o0, o1);
+          ow[t] = pack_bf16x2(o0, o1);
         }
-        uint4 u;
-        u.x = pack_bf16x2(o[0], o[1]);
-        u.y = pack_bf16x2(o[2], o[3]);
-        u.z = pack_bf16x2(o[4], o[5]);
-        u.w = pack_bf16x2(o[6], o[7]);
-        *(reinterpret_cast<uint4*>(dx + row * D) + c) = u;
+        *(reinterpret_cast<uint4*>(dx + row * D) + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
   }
-  // block reduction of the per-warp partial sums, gamma then beta through the same buffer
+  cp_async_wait<0>();
+  // block reduction of the per-warp partial sums through the (now idle) ring, gamma then beta
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < LNB_CHUNKS; ++i) {
       const int c = lane + 32 * i;
       if (c < chunks) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) red[warp][c * 8 + t] = pass ? ab[i][t] : ag[i][t];
+        for (int t = 0; t < 4; ++t) {
+          float lo, hi;
+          unpack_f32x2(pass ? ab[i][t] : ag[i][t], lo, hi);
+          red[warp][c * 8 + 2 * t] = lo;
+          red[warp][c * 8 + 2 * t + 1] = hi;
+        }
       }
     }
     __syncthreads();
@@ -282,7 +306,6 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, (LNB_PREFETCH_ADD || LNB_CHUNK
       for (int w = 0; w < LNB_WARPS; ++w) a += red[w][k];
       atomicAdd(dst + k, a);
     }
-    __syncthreads();
   }
 }
 
@@ -1069,10 +1092,15 @@ int fc_layernorm_bwd_bf16(const void* x, const void* dy, const float* gamma, con
   ProfScope prof(s, PROF_OTHER, 12, rows, D, 0, 0.0, (add ? 8.0 : 6.0) * rows * D);
   const bf16 *xb = static_cast<const bf16*>(x), *dyb = static_cast<const bf16*>(dy), *ab = static_cast<const bf16*>(add);
   bf16* dxb = static_cast<bf16*>(dx);
-  if (D <= 256) ln_bwd_kernel<1><<<blocks, LNB_WARPS * 32, 0, s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
-  else if (D <= 512) ln_bwd_kernel<2><<<blocks, LNB_WARPS * 32, 0, s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
-  else if (D <= 768) ln_bwd_kernel<3><<<blocks, LNB_WARPS * 32, 0, s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
-  else ln_bwd_kernel<4><<<blocks, LNB_WARPS * 32, 0, s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
+  static bool configured = false;
+  if (!configured) {  // D = 1024: 48 KB of ring + the static gamma copy exceed the default 48 KB limit
+    FC_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_bwd_ring_bytes(4)));
+    configured = true;
+  }
+  if (D <= 256) ln_bwd_kernel<1><<<blocks, LNB_WARPS * 32, ln_bwd_ring_bytes(1), s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
+  else if (D <= 512) ln_bwd_kernel<2><<<blocks, LNB_WARPS * 32, ln_bwd_ring_bytes(2), s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
+  else if (D <= 768) ln_bwd_kernel<3><<<blocks, LNB_WARPS * 32, ln_bwd_ring_bytes(3), s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
+  else ln_bwd_kernel<4><<<blocks, LNB_WARPS * 32, ln_bwd_ring_bytes(4), s>>>(xb, dyb, gamma, ab, dxb, dgamma, dbeta, rows, D, eps);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
