@@ -26,7 +26,7 @@ class fc_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "embed_dim", "image_resolution", "vision_layers", "vision_width", "vision_patch_size", "context_length",
         "vocab_size", "transformer_width", "transformer_heads", "transformer_layers", "max_frames_per_pass",
-        "max_texts_per_pass", "vision_tower")]
+        "max_texts_per_pass", "vision_tower", "vision_attn_width")]
 
 
 TOWER_OPENAI, TOWER_TIMM = 0, 1

@@ -139,8 +139,9 @@ struct ArenaPlan {
   }
 };
 
+// Wa: width of the attention (3 Wa rows of in_proj, Wa columns of out_proj); == W except for padded narrow heads
 static void plan_blocks(fc_model* m, ArenaPlan& plan, std::vector<Block>& blocks, const std::string& prefix, int layers,
-                        int W, bool assign) {
+                        int W, int Wa, bool assign) {
   blocks.resize(layers);
   for (int i = 0; i < layers; ++i) {
     Block& b = blocks[i];
@@ -151,9 +152,9 @@ static void plan_blocks(fc_model* m, ArenaPlan& plan, std::vector<Block>& blocks
       int64_t numel;
       bool bf;
     } items[] = {
-        {"attn.in_proj_weight", reinterpret_cast<void**>(&b.qkv_w32), int64_t(3) * W * W, false},
-        {"attn.in_proj_bias", reinterpret_cast<void**>(&b.qkv_b), int64_t(3) * W, false},
-        {"attn.out_proj.weight", reinterpret_cast<void**>(&b.out_w), int64_t(W) * W, true},
+        {"attn.in_proj_weight", reinterpret_cast<void**>(&b.qkv_w32), int64_t(3) * Wa * W, false},
+        {"attn.in_proj_bias", reinterpret_cast<void**>(&b.qkv_b), int64_t(3) * Wa, false},
+        {"attn.out_proj.weight", reinterpret_cast<void**>(&b.out_w), int64_t(W) * Wa, true},
         {"attn.out_proj.bias", reinterpret_cast<void**>(&b.out_b), W, false},
         {"ln_1.weight", reinterpret_cast<void**>(&b.ln1_g), W, false},
         {"ln_1.bias", reinterpret_cast<void**>(&b.ln1_b), W, false},
@@ -175,8 +176,8 @@ static void plan_blocks(fc_model* m, ArenaPlan& plan, std::vector<Block>& blocks
       void** dst;
       int64_t bytes;
     } derived[] = {
-        {reinterpret_cast<void**>(&b.qkv_w), int64_t(3) * W * W * 2}, {reinterpret_cast<void**>(&b.qkv_cs), int64_t(3) * W * 4},
-        {reinterpret_cast<void**>(&b.qkv_bf), int64_t(3) * W * 4},    {reinterpret_cast<void**>(&b.fc_w), int64_t(4) * W * W * 2},
+        {reinterpret_cast<void**>(&b.qkv_w), int64_t(3) * Wa * W * 2}, {reinterpret_cast<void**>(&b.qkv_cs), int64_t(3) * Wa * 4},
+        {reinterpret_cast<void**>(&b.qkv_bf), int64_t(3) * Wa * 4},    {reinterpret_cast<void**>(&b.fc_w), int64_t(4) * W * W * 2},
         {reinterpret_cast<void**>(&b.fc_cs), int64_t(4) * W * 4},     {reinterpret_cast<void**>(&b.fc_bf), int64_t(4) * W * 4},
     };
     for (auto& d : derived) {
@@ -187,10 +188,10 @@ static void plan_blocks(fc_model* m, ArenaPlan& plan, std::vector<Block>& blocks
 }
 
 // (Re)build the LayerNorm-folded weights of every block; called lazily by the encoders after parameters changed.
-static int finalize_blocks(const std::vector<Block>& blocks, int W, cudaStream_t s) {
+static int finalize_blocks(const std::vector<Block>& blocks, int W, int Wa, cudaStream_t s) {
   int rc;
   for (const Block& b : blocks) {
-    if ((rc = fold_ln_weights(b.qkv_w32, b.ln1_g, b.ln1_b, b.qkv_b, b.qkv_w, b.qkv_cs, b.qkv_bf, 3 * W, W, s))) return rc;
+    if ((rc = fold_ln_weights(b.qkv_w32, b.ln1_g, b.ln1_b, b.qkv_b, b.qkv_w, b.qkv_cs, b.qkv_bf, 3 * Wa, W, s))) return rc;
     if ((rc = fold_ln_weights(b.fc_w32, b.ln2_g, b.ln2_b, b.fc_b, b.fc_w, b.fc_cs, b.fc_bf, 4 * W, W, s))) return rc;
   }
   return FC_OK;
@@ -200,6 +201,7 @@ static int finalize_blocks(const std::vector<Block>& blocks, int W, cudaStream_t
 static void plan_model(fc_model* m, ArenaPlan& plan, bool assign) {
   const fc_config& c = m->cfg;
   const int W = c.vision_width, Wt = c.transformer_width, E = c.embed_dim;
+  const int Wa = c.vision_attn_width > 0 ? c.vision_attn_width : W;
   auto one = [&](const std::string& name, void** dst, int64_t numel, bool bf) {
     const int64_t o = plan.take(numel * (bf ? 2 : 4));
     if (assign) {
@@ -228,18 +230,19 @@ static void plan_model(fc_model* m, ArenaPlan& plan, bool assign) {
   one("visual.ln_post.weight", reinterpret_cast<void**>(&m->ln_post_g), W, false);
   one("visual.ln_post.bias", reinterpret_cast<void**>(&m->ln_post_b), W, false);
   one("visual.proj", reinterpret_cast<void**>(&m->vproj), int64_t(W) * E, false);
-  plan_blocks(m, plan, m->vblocks, "visual.transformer.", c.vision_layers, W, assign);
+  plan_blocks(m, plan, m->vblocks, "visual.transformer.", c.vision_layers, W, Wa, assign);
   one("token_embedding.weight", reinterpret_cast<void**>(&m->tok), int64_t(c.vocab_size) * Wt, false);
   one("positional_embedding", reinterpret_cast<void**>(&m->tpos), int64_t(c.context_length) * Wt, false);
   one("ln_final.weight", reinterpret_cast<void**>(&m->ln_final_g), Wt, false);
   one("ln_final.bias", reinterpret_cast<void**>(&m->ln_final_b), Wt, false);
   one("text_projection", reinterpret_cast<void**>(&m->tproj), int64_t(Wt) * E, false);
-  plan_blocks(m, plan, m->tblocks, "transformer.", c.transformer_layers, Wt, assign);
+  plan_blocks(m, plan, m->tblocks, "transformer.", c.transformer_layers, Wt, Wt, assign);
 
   // workspace: x (residual stream), y (LayerNorm out / attention out), big (patches | qkv | MLP hidden), features
   const int64_t vtok = int64_t(m->maxF) * m->L_img, ttok = int64_t(m->maxC) * c.context_length;
-  const int64_t x_el = std::max(vtok * W, ttok * Wt);
-  const int64_t big_el = std::max(std::max(vtok * 4 * W, ttok * 4 * Wt), int64_t(m->maxF) * m->grid * m->grid * m->patch_dim);
+  const int64_t x_el = std::max(vtok * std::max(W, Wa), ttok * Wt);  // y also holds the attention output (width Wa)
+  const int64_t big_el = std::max(std::max(vtok * std::max(4 * W, 3 * Wa), ttok * 4 * Wt),
+                                  int64_t(m->maxF) * m->grid * m->grid * m->patch_dim);
   const int64_t ws0 = plan.off;
   auto ws = [&](void** dst, int64_t bytes) {
     const int64_t o = plan.take(bytes);
@@ -260,6 +263,7 @@ static void plan_model(fc_model* m, ArenaPlan& plan, bool assign) {
 // act / eps: EPI_LN_BIAS_QGELU and 1e-5 for the OpenAI towers, EPI_LN_BIAS_GELU and 1e-6 for timm's VisionTransformer.
 static int run_blocks(const std::vector<Block>& blocks, bf16* x, bf16* y, bf16* big, float* stats_a, float* stats_b,
                       int64_t seqs, int L, int W, int heads, int causal, int act, float eps, cudaStream_t s) {
+  const int Wa = heads * 64;  // attention width (== W unless narrow heads were padded to 64-wide slots)
   const int64_t rows64 = seqs * L;
   FC_REQUIRE(rows64 < (int64_t(1) << 31), "too many tokens in one pass");
   const int rows = static_cast<int>(rows64);
@@ -268,13 +272,13 @@ static int run_blocks(const std::vector<Block>& blocks, bf16* x, bf16* y, bf16* 
   for (const Block& b : blocks) {
     // x = x + out_proj(attention(ln_1(x)))                      (slip.py:383); ln_1 folded into the QKV GEMM
     GemmParams p;
-    p.M = rows; p.N = 3 * W; p.K = W; p.C = big; p.ldc = 3 * W; p.bias = b.qkv_bf;
+    p.M = rows; p.N = 3 * Wa; p.K = W; p.C = big; p.ldc = 3 * Wa; p.bias = b.qkv_bf;
     p.ln_stats = stats_a; p.ln_parts = parts; p.colsum = b.qkv_cs; p.ln_eps = eps;
     if ((rc = gemm_bf16_tn(EPI_LN_BIAS, x, W, b.qkv_w, W, p, s))) return rc;
     if ((rc = attention_bf16(big, y, seqs, L, heads, causal, s))) return rc;
     p = GemmParams();
-    p.M = rows; p.N = W; p.K = W; p.C = x; p.ldc = W; p.bias = b.out_b; p.resid = x; p.ldr = W; p.stats_out = stats_b;
-    if ((rc = gemm_bf16_tn(EPI_BIAS_RESID, y, W, b.out_w, W, p, s))) return rc;
+    p.M = rows; p.N = W; p.K = Wa; p.C = x; p.ldc = W; p.bias = b.out_b; p.resid = x; p.ldr = W; p.stats_out = stats_b;
+    if ((rc = gemm_bf16_tn(EPI_BIAS_RESID, y, Wa, b.out_w, Wa, p, s))) return rc;
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                  (slip.py:384); ln_2 folded into the fc1 GEMM
     p = GemmParams();
     p.M = rows; p.N = 4 * W; p.K = W; p.C = big; p.ldc = 4 * W; p.bias = b.fc_bf;
@@ -290,8 +294,9 @@ static int run_blocks(const std::vector<Block>& blocks, bf16* x, bf16* y, bf16* 
 static int finalize(fc_model* m, cudaStream_t s) {
   if (!m->dirty) return FC_OK;
   int rc;
-  if ((rc = finalize_blocks(m->vblocks, m->cfg.vision_width, s))) return rc;
-  if ((rc = finalize_blocks(m->tblocks, m->cfg.transformer_width, s))) return rc;
+  const int Wa = m->cfg.vision_attn_width > 0 ? m->cfg.vision_attn_width : m->cfg.vision_width;
+  if ((rc = finalize_blocks(m->vblocks, m->cfg.vision_width, Wa, s))) return rc;
+  if ((rc = finalize_blocks(m->tblocks, m->cfg.transformer_width, m->cfg.transformer_width, s))) return rc;
   m->dirty = false;
   return FC_OK;
 }
@@ -315,7 +320,8 @@ static int vision_pass(fc_model* m, const void* frames, int dtype, int64_t F, fl
   } else if ((rc = layernorm_bf16(m->x, W, m->x, W, m->ln_pre_g, m->ln_pre_b, F * L, W, eps, m->stats_a, s))) {
     return rc;
   }
-  if ((rc = run_blocks(m->vblocks, m->x, m->y, m->big, m->stats_a, m->stats_b, F, L, W, W / 64, 0,
+  const int Wa = c.vision_attn_width > 0 ? c.vision_attn_width : W;
+  if ((rc = run_blocks(m->vblocks, m->x, m->y, m->big, m->stats_a, m->stats_b, F, L, W, Wa / 64, 0,
                        timm ? EPI_LN_BIAS_GELU : EPI_LN_BIAS_QGELU, eps, s)))
     return rc;
   return head_project(m->x, nullptr, m->ln_post_g, m->ln_post_b, m->vproj, feat, F, L, W, c.embed_dim, eps, s);
@@ -407,6 +413,9 @@ int fc_model_create(const fc_config* cfg, fc_model** out) {
              "fc_model_create: widths must be multiples of 64 and <= 1024 (got %d / %d)", c.vision_width,
              c.transformer_width);
   FC_REQUIRE(c.transformer_heads * 64 == c.transformer_width, "fc_model_create: text head dim must be 64");
+  FC_REQUIRE(c.vision_attn_width == 0 || (c.vision_attn_width % 64 == 0 && c.vision_attn_width >= c.vision_width &&
+                                          c.vision_attn_width <= 1024),
+             "fc_model_create: vision_attn_width %d must be a multiple of 64 in [vision_width, 1024]", c.vision_attn_width);
   FC_REQUIRE(c.vision_tower == FC_TOWER_OPENAI || c.vision_tower == FC_TOWER_TIMM,
              "fc_model_create: unknown vision tower %d", c.vision_tower);
   FC_REQUIRE(c.image_resolution % c.vision_patch_size == 0,

@@ -13,8 +13,8 @@ wrapper's (``:37-51``): per-frame L2 normalisation, mean over the frames, no re-
 * :class:`B200SlipVideoTextEncoder` mirrors ``SlipVideoTextEncoder``: same hooks, ImageNet statistics, bilinear resize.
 * :func:`load_slip_model` mirrors ``load_model`` (``:19-23``) for local checkpoint files.
 
-Head dimension 64 only: the ViT-S/16 variants (``vit_small_mocov3_patch16_224``: 384 wide, 12 heads of 32, ``slip.py:566-569``)
-are rejected with a clear error.
+Heads narrower than 64 (the ViT-S/16 variants: ``vit_small_mocov3_patch16_224``, 384 wide, 12 heads of 32, ``slip.py:566-569``)
+run with every head in a 64-wide slot of zero-padded q / k / v rows and out_proj columns (``fc_config.vision_attn_width``).
 """
 from __future__ import annotations
 
@@ -76,11 +76,33 @@ class B200SlipClip(B200Clip):
         if vision_heads is None and width == 384:
             # the SLIP repository's ViT-S/16 is the MoCo-v3 variant with 12 heads of 32 (slip.py:566-569), timm's stock
             # vit_small_patch16_224 has 6 heads of 64: the state dict cannot tell them apart
-            raise _lib.FitclipError(-1, "384-wide SLIP-layout vision tower: pass vision_heads (6 runs; 12, the SLIP "
-                                        "ViT-S/16 checkpoints, needs head dimension 32, which is not built)")
-        if vision_heads is not None and vision_heads * 64 != width:
-            raise _lib.FitclipError(-1, f"SLIP-layout vision tower with {vision_heads} heads of {width // vision_heads}: "
-                                        f"the attention kernels are built for head dimension 64")
+            raise _lib.FitclipError(-1, "384-wide SLIP-layout vision tower: pass vision_heads (12 for the SLIP repository's "
+                                        "ViT-S/16 checkpoints, 6 for timm's stock vit_small_patch16_224)")
+        self.vision_heads = vision_heads or width // 64
+        head_dim, rem = divmod(width, self.vision_heads)
+        if rem or head_dim > 64 or 64 % head_dim:
+            raise _lib.FitclipError(-1, f"SLIP-layout vision tower with {self.vision_heads} heads over width {width}: the "
+                                        f"attention kernels take head dimensions that divide 64")
+        self.vision_head_dim = head_dim
+        if head_dim < 64:
+            # every head gets a 64-wide slot (zero rows / columns): include/fitclip_b200.h, fc_config.vision_attn_width
+            if self.vision_heads * 64 > 1024:
+                raise _lib.FitclipError(-1, f"{self.vision_heads} heads padded to 64 exceed the 1024-wide attention limit")
+            self.config["vision_attn_width"] = self.vision_heads * 64
+
+    def _pad_heads(self, t: torch.Tensor, groups: int, dim: int) -> torch.Tensor:
+        """``t`` holds ``groups * heads * head_dim`` entries along ``dim`` (q | k | v blocks of in_proj, or the input
+        columns of out_proj): spread every head over a 64-wide slot, zeros in the upper part."""
+        hd, heads = self.vision_head_dim, self.vision_heads
+        shape = list(t.shape)
+        shape[dim:dim + 1] = [groups, heads, hd]
+        t = t.reshape(shape)
+        pad = [0, 0] * (t.dim() - (dim + 3)) + [0, 64 - hd]  # F.pad counts dimensions from the last
+        t = torch.nn.functional.pad(t, pad)
+        shape[dim + 2] = 64
+        out = list(t.shape)
+        out[dim:dim + 3] = [groups * heads * 64]
+        return t.reshape(out)
 
     @staticmethod
     def _filter_state_dict(state_dict: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -104,7 +126,16 @@ class B200SlipClip(B200Clip):
                 continue
             m = _BLOCK.match(name)
             if m:
-                out.append((f"visual.transformer.resblocks.{m.group(1)}.{_BLOCK_LEAF[m.group(2)]}", p))
+                leaf = m.group(2)
+                if self.vision_head_dim < 64 and leaf.startswith("attn."):
+                    if leaf.startswith("attn.qkv."):
+                        # the kernels' softmax scale is 64^-0.5: the q rows carry the rest of head_dim^-0.5
+                        p = p.detach().clone()
+                        p[:self.config["vision_width"]] *= (64 / self.vision_head_dim) ** 0.5
+                        p = self._pad_heads(p, 3, 0)
+                    elif leaf == "attn.proj.weight":
+                        p = self._pad_heads(p.detach(), 1, 1)
+                out.append((f"visual.transformer.resblocks.{m.group(1)}.{_BLOCK_LEAF[leaf]}", p))
             elif name in _TOP:
                 out.append((_TOP[name], p))
             elif name == "visual.cls_token":
@@ -131,7 +162,7 @@ def load_slip_model(path: Union[str, os.PathLike, Mapping], **kwargs) -> B200Sli
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path!r}: SLIP checkpoints cannot be downloaded offline; pass a local file")
         path = torch.load(path, map_location="cpu", weights_only=False)
-    vision_heads = None
+    vision_heads = kwargs.pop("vision_heads", None)
     if isinstance(path, Mapping) and "state_dict" in path:
         arch = getattr(path.get("args"), "model", None)
         if arch is not None and arch.upper().endswith("VITS16"):

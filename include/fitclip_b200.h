@@ -65,6 +65,12 @@ typedef struct fc_config {
    * caller passes its weights under the OpenAI names (the patch-embedding bias folded into the positional rows 1..,
    * `norm` as `ln_post`, `image_projection` as `visual.proj`) and `visual.ln_pre.*` is neither expected nor accepted. */
   int32_t vision_tower;
+  /* Width of the image tower's attention (q / k / v rows of in_proj, columns of out_proj): heads * 64.  0 = vision_width.
+   * A tower whose heads are narrower than 64 (the SLIP ViT-S/16: 384 wide, 12 heads of 32, slip.py:566-569) is run by giving
+   * every head a 64-wide slot: the caller passes in_proj_weight (3 * attn_width, vision_width) / in_proj_bias with the extra
+   * rows zero and the q rows scaled by sqrt(64 / head_dim) (the kernels' softmax scale is 1/8), and out_proj.weight
+   * (vision_width, attn_width) with the extra columns zero -- the zero dimensions add nothing to q.k and carry no value. */
+  int32_t vision_attn_width;
 } fc_config;
 enum { FC_TOWER_OPENAI = 0, FC_TOWER_TIMM = 1 };
 

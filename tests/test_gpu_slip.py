@@ -118,6 +118,26 @@ def test_slip_vit_l_16_geometry_runs_and_matches(dev):
     assert cos >= 0.9995 and max_abs <= 5e-3 and centred <= 0.1
 
 
+@pytest.mark.parametrize("layers", [2, 12])
+def test_slip_vit_s_16_narrow_heads_match_oracle(layers, dev):
+    """``CLIP_VITS16`` / ``SLIP_VITS16`` (slip.py:566-590): 384 wide, 12 heads of 32 -- run as 12 zero-padded 64-wide heads
+    (``fc_config.vision_attn_width = 768``); 12 layers is the full depth of the reference's model."""
+    import oracle
+    from fitclip_b200 import B200SlipVideoTextEncoder, load_slip_model
+    model = oracle.slip_clip_vit_b_16(seed=6, vision_width=384, vision_heads=12, vision_layers=layers, transformer_layers=2)
+    ref_enc = oracle.RefSlipVideoTextEncoder(copy.deepcopy(model))
+    import argparse
+    ckpt = {"args": argparse.Namespace(model="SLIP_VITS16"), "state_dict": {"module." + k: v for k, v in model.state_dict().items()}}
+    enc = B200SlipVideoTextEncoder(load_slip_model(ckpt), num_frames=2).to(dev)
+    assert enc.model.vision_heads == 12 and enc.model.config["vision_attn_width"] == 768
+    video = torch.randn(4, 2, 3, 224, 224, generator=torch.Generator().manual_seed(layers))
+    with torch.inference_mode():
+        expect = ref_enc.encode_video(video)
+        got = enc.encode_video(video.to(dev)).cpu()
+    cos, max_abs, centred = _report(f"slip vit-s/16 x{layers}", got, expect)
+    assert cos >= 0.9995 and max_abs <= 5e-3 and centred <= 0.1
+
+
 def test_engine_rejects_ln_pre_for_the_timm_tower(ref, dev):
     """FC_TOWER_TIMM has no ln_pre slot: handing it one is an error, not a silently ignored tensor."""
     from fitclip_b200 import B200SlipClip, _lib

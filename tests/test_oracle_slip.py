@@ -118,16 +118,33 @@ def test_slip_layout_keeps_checkpoint_names_and_maps_them_for_the_engine(ref):
     assert torch.equal(handed["visual.proj"], sd["image_projection"])
 
 
-def test_slip_vit_small_variant_is_rejected_clearly():
+def test_slip_vit_small_heads_are_padded_to_64_wide_slots():
+    """``vit_small_mocov3_patch16_224`` (slip.py:566-569): 384 wide, 12 heads of 32.  The engine's attention kernels take
+    64-wide heads, so every head gets a 64-wide slot of zero-padded q / k / v rows (q scaled by sqrt 2: the kernels' softmax
+    scale is 1/8) and zero out_proj columns -- checked here in fp32 on the tensors handed to the engine."""
     from fitclip_b200 import B200SlipClip, _lib
     sd = oracle.slip_clip_vit_b_16(seed=0, img_size=32, patch_size=16, vision_width=384, vision_layers=1, vision_heads=12,
                                    embed_dim=64, context_length=16, vocab_size=512, transformer_width=64,
                                    transformer_heads=1, transformer_layers=1).state_dict()
     with pytest.raises(_lib.FitclipError, match="vision_heads"):
-        B200SlipClip(sd)
-    with pytest.raises(_lib.FitclipError, match="head dimension 64"):
-        B200SlipClip(sd, vision_heads=12)
-    assert B200SlipClip(sd, vision_heads=6).config["vision_width"] == 384
+        B200SlipClip(sd)  # 6 heads of 64 (timm's stock ViT-S) or 12 of 32 (SLIP's): the state dict cannot tell
+    with pytest.raises(_lib.FitclipError, match="divide 64"):
+        B200SlipClip(sd, vision_heads=8)  # head dimension 48
+    assert "vision_attn_width" not in B200SlipClip(sd, vision_heads=6).config
+    model = B200SlipClip(sd, vision_heads=12)
+    assert model.config["vision_attn_width"] == 768 and model.config["vision_width"] == 384
+    handed = dict(model._engine_params())
+    w2, b2 = handed["visual.transformer.resblocks.0.attn.in_proj_weight"], handed["visual.transformer.resblocks.0.attn.in_proj_bias"]
+    p2 = handed["visual.transformer.resblocks.0.attn.out_proj.weight"]
+    assert w2.shape == (3 * 768, 384) and b2.shape == (3 * 768,) and p2.shape == (384, 768)
+    x = torch.randn(7, 384, generator=torch.Generator().manual_seed(1))
+    qkv = (x @ sd["visual.blocks.0.attn.qkv.weight"].T + sd["visual.blocks.0.attn.qkv.bias"]).view(7, 3, 12, 32)
+    att = torch.softmax(torch.einsum("ihd,jhd->hij", qkv[:, 0], qkv[:, 1]) * 32 ** -0.5, -1)
+    expect = torch.einsum("hij,jhd->ihd", att, qkv[:, 2]).reshape(7, 384) @ sd["visual.blocks.0.attn.proj.weight"].T
+    qkv2 = (x @ w2.T + b2).view(7, 3, 12, 64)
+    att2 = torch.softmax(torch.einsum("ihd,jhd->hij", qkv2[:, 0], qkv2[:, 1]) * 0.125, -1)  # what the kernels compute
+    got = torch.einsum("hij,jhd->ihd", att2, qkv2[:, 2]).reshape(7, 768) @ p2.T
+    assert torch.allclose(got, expect, atol=1e-6, rtol=1e-5)
 
 
 def test_slip_layout_student_is_refused_by_the_trainer_but_fine_as_teacher(ref):

@@ -26,13 +26,14 @@ GEOM = {
     "clip_vit_l_14_336px": dict(embed_dim=768, image_resolution=336, vision_patch_size=14, vision_width=1024,
                                 vision_layers=24, transformer_width=768, transformer_heads=12),
     # SLIP layout (slip.py:595-600 / 618-623): timm ViT image tower (no ln_pre, exact GELU) + CLIP text tower
+    "slip_vit_s_16": dict(slip=True, vision_width=384, vision_heads=12),
     "slip_vit_b_16": dict(slip=True),
     "slip_vit_l_16": dict(slip=True, vision_width=1024, vision_layers=24),
 }
 
 
 def tower_flops(tokens, width, layers, heads):
-    per_layer = 2 * tokens * 12 * width * width + 4 * tokens * tokens * 64 * heads
+    per_layer = 2 * tokens * 12 * width * width + 4 * tokens * tokens * width  # heads * head_dim = width
     return layers * per_layer
 
 
@@ -54,7 +55,9 @@ for name in names:
     geom = dict(GEOM[name])
     if geom.pop("slip", False):
         cfg = {**oracle.clip_ref.VIT_B_16, **geom}
-        enc = B200SlipVideoTextEncoder(oracle.slip_clip_vit_b_16(seed=0, **geom).state_dict(), num_frames=4).to(dev)
+        from fitclip_b200 import B200SlipClip
+        enc = B200SlipVideoTextEncoder(B200SlipClip(oracle.slip_clip_vit_b_16(seed=0, **geom).state_dict(),
+                                                    vision_heads=geom.get("vision_heads")), num_frames=4).to(dev)
     else:
         cfg = {**oracle.clip_ref.VIT_B_16, **geom}
         enc = B200ClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0, **geom).state_dict(), num_frames=4).to(dev)
@@ -72,13 +75,13 @@ for name in names:
 
     with torch.inference_mode():
         ms, _ = timed(step, 3)
-        vw, heads = cfg["vision_width"], cfg["vision_width"] // 64
+        vw, heads = cfg["vision_width"], geom.get("vision_heads") or cfg["vision_width"] // 64
         frame = tower_flops(L, vw, cfg["vision_layers"], heads) + 2 * (L - 1) * vw * 3 * patch * patch + 2 * vw * cfg["embed_dim"]
         cap = tower_flops(77, cfg["transformer_width"], cfg["transformer_layers"], cfg["transformer_heads"]) \
             + 2 * cfg["transformer_width"] * cfg["embed_dim"]
         flops = n * 4 * frame + n * cap
         seqs = 512
-        qkv = torch.randn(seqs * L, 3 * vw, device=dev).bfloat16()
+        qkv = torch.randn(seqs * L, 3 * heads * 64, device=dev).bfloat16()  # narrow heads run in 64-wide slots
         att_ms, _ = timed(lambda: ops.attention_bf16(qkv, seqs, L, heads, False), 20)
         print(json.dumps({"geometry": name, "image_tokens": L, "videos": n, "frames_per_video": 4, "ms_per_step": round(ms, 2),
                           "videos_per_s": round(n / ms * 1e3, 1), "tflops": round(flops / ms / 1e9, 1),
