@@ -244,6 +244,61 @@ def train_leg(teacher, device, videos: int, steps: int = 3) -> dict:
             "peak_memory_gb": torch.cuda.max_memory_allocated(device) / 1e9, "losses_first_last": losses}
 
 
+def geometry_leg(device, videos: int, steps: int = 3) -> list:
+    """SURVEY.md 8f row f4 on the driver's box: the other tower geometries the reference ships configs for, random-init,
+    `videos` videos x 4 frames + as many captions -> similarity + ranks per step (the cfg2 step at another shape):
+    `clip_vit_l_14` (config/encoder/clip_vit_l_14.yaml: 257 image tokens -> attention_tc_long_kernel) and the SLIP layout
+    (config/encoder/slip_vit_b_16.yaml: timm image tower -- no ln_pre, erf-GELU epilogue).  FLOPs: dense algorithmic count."""
+    import torch
+
+    from fitclip_b200 import B200ClipVideoTextEncoder, B200SlipVideoTextEncoder, metrics_from_ranks, retrieval_ranks
+    from fitclip_b200._init import init_clip_state_dict, init_slip_state_dict
+
+    def tower(tokens, width, layers):
+        return layers * (2 * tokens * 12 * width * width + 4 * tokens * tokens * width)
+
+    out = []
+    for name, build, kw in (
+            ("clip_vit_l_14", lambda sd: B200ClipVideoTextEncoder(sd, num_frames=FRAMES), dict(
+                init=init_clip_state_dict, embed_dim=768, vision_patch_size=14, vision_width=1024, vision_layers=24,
+                transformer_width=768, transformer_heads=12)),
+            ("slip_vit_b_16", lambda sd: B200SlipVideoTextEncoder(sd, num_frames=FRAMES), dict(init=init_slip_state_dict))):
+        init = kw.pop("init")
+        enc = build(init(seed=11, **kw)).to(device)
+        cfg = enc.model.config
+        L = (cfg["image_resolution"] // cfg["vision_patch_size"]) ** 2 + 1
+        g = torch.Generator(device=device).manual_seed(5)
+        video = torch.randn(videos, FRAMES, 3, 224, 224, device=device, generator=g)
+        ids = torch.randint(1, 49405, (videos, CTX), device=device, generator=g, dtype=torch.int32)
+        ids[:, 0], ids[:, -1] = 49406, 49407
+
+        def step():
+            v = enc.encode_video(video)
+            t = enc.encode_text({"input_ids": ids})
+            return metrics_from_ranks(retrieval_ranks(t, v, group=False), videos)
+
+        with torch.inference_mode():
+            step()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / steps
+        frame = tower(L, cfg["vision_width"], cfg["vision_layers"]) \
+            + 2 * (L - 1) * cfg["vision_width"] * 3 * cfg["vision_patch_size"] ** 2 + 2 * cfg["vision_width"] * cfg["embed_dim"]
+        cap = tower(CTX, cfg["transformer_width"], cfg["transformer_layers"]) + 2 * cfg["transformer_width"] * cfg["embed_dim"]
+        flops = videos * (FRAMES * frame + cap)
+        out.append({"geometry": name, "image_tokens": L, "videos": videos, "frames_per_video": FRAMES, "steps": steps,
+                    "ms_per_step": ms, "videos_per_s": videos / ms * 1e3, "achieved_tflops": flops / ms / 1e9,
+                    "gflop_per_frame": frame / 1e9})
+        del enc, video
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -406,6 +461,7 @@ def run_ours(args) -> None:
     train = None
     if world == 1 and args.train_videos > 0:  # row f3 (outside inference_mode: the trainer writes parameters in place)
         train = train_leg(encoder, device, args.train_videos)
+    geometries = geometry_leg(device, args.geometry_videos) if world == 1 and args.geometry_videos > 0 else None
 
     if rank == 0:
         peak, sustained, hbm, src = measured_peaks()
@@ -490,6 +546,10 @@ def run_ours(args) -> None:
         if train is not None:
             train["roofline_frac"] = train["achieved_tflops"] / peak
             line.setdefault("extra", {})["train_step"] = train
+        if geometries is not None:
+            for rec in geometries:
+                rec["roofline_frac"] = rec["achieved_tflops"] / peak
+            line.setdefault("extra", {})["geometries"] = geometries
         line["cpu_baseline"] = cpu_baseline(sample_videos=args.cpu_sample)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -589,6 +649,8 @@ def main() -> None:
                     help="frames per internal encoder pass (default: the library's token budget, ~2000 frames of ViT-B/16)")
     ap.add_argument("--train-videos", type=int, default=512,
                     help="videos per step of the teacher-student TRAINING leg (row f3; extra.train_step, N = 1 only); 0 skips it")
+    ap.add_argument("--geometry-videos", type=int, default=128,
+                    help="N=1 only: videos per step of the other-geometry legs (ViT-L/14, SLIP-layout ViT-B/16); 0 skips them")
     ap.add_argument("--cpu-sample", type=int, default=128,
                     help="videos in the bounded CPU-baseline sample (128 videos x 4 frames + 128 captions: 10-30 s of CPU work)")
     args = ap.parse_args()
