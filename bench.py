@@ -461,6 +461,7 @@ def run_ours(args) -> None:
     train = None
     if world == 1 and args.train_videos > 0:  # row f3 (outside inference_mode: the trainer writes parameters in place)
         train = train_leg(encoder, device, args.train_videos)
+    torch.cuda.empty_cache()  # the engines cudaMalloc their arenas: hand torch's cached blocks (training leg) back first
     geometries = geometry_leg(device, args.geometry_videos) if world == 1 and args.geometry_videos > 0 else None
 
     if rank == 0:
