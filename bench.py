@@ -14,6 +14,10 @@ all-gather of text embeddings, column-sharded fused similarity+rank count, all-r
           D2H read of the metrics are inside the timed region).
 `roofline` the tcgen05 GEMM kernel, timed per launch with CUDA events on its stream during the timed steps.
 `cpu_baseline` the oracle (restated reference path, fp32 torch CPU) on a bounded sample, on this box's host cores.
+
+`oracle/` is imported in exactly two places: the CPU legs (`cpu_baseline`, `--impl reference`) and, as a checker outside every
+timed region, the sampled-row comparison of the 100k-video leg.  Weights and inputs of the CUDA arm come from the package's
+own initialiser and from this file (`synthetic_weights`, `synthetic_tokens`, `synthetic_inputs`); the CPU legs load the same.
 """
 from __future__ import annotations
 
@@ -90,13 +94,43 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def synthetic_weights(seed: int = 0):
+    """The benchmark's weights (no network, no checkpoints): the package's own seeded CLIP initialiser
+    (config/encoder/clip_from_scratch_vit_b_16.yaml) with trained-like values wherever an init leaves identities --
+    LayerNorm gamma ~ U(0.2, 3), beta ~ N(0, 0.5), attention biases ~ N(0, 0.1) -- so that the folded-LayerNorm arithmetic
+    runs on real numbers.  Both arms (ours, and the CPU oracle of `cpu_baseline` / `--impl reference`) load this state dict."""
+    import torch
+
+    from fitclip_b200._init import init_clip_state_dict
+    sd = init_clip_state_dict(seed=seed)
+    g = torch.Generator().manual_seed(1_000_003 + seed)
+    for name, p in sd.items():
+        parent, _, leaf = name.rpartition(".")
+        is_ln = parent.rsplit(".", 1)[-1] in ("ln_1", "ln_2", "ln_pre", "ln_post", "ln_final")
+        if is_ln and leaf == "weight":
+            p.copy_(0.2 + 2.8 * torch.rand(p.shape, generator=g))
+        elif is_ln and leaf == "bias":
+            p.copy_(0.5 * torch.randn(p.shape, generator=g))
+        elif name.endswith("attn.in_proj_bias") or name.endswith("attn.out_proj.bias"):
+            p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    return sd
+
+
+def synthetic_tokens(count: int, seed: int):
+    """SURVEY.md 8d captions: ``[SOT] + random ids + [EOT]``, dense (all CTX positions used), int32."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1, 49406, (count, CTX), generator=g, dtype=torch.int32)
+    ids[:, 0], ids[:, -1] = 49406, 49407
+    return ids
+
+
 def synthetic_inputs(rank: int, device, pinned: bool):
     """frames ~ N(0,1) (post-Normalize statistics), captions = [SOT] + random ids + [EOT], dense 77."""
     import torch
 
-    import oracle
     g = torch.Generator().manual_seed(1234 + rank)
-    ids = oracle.tokenize_synthetic(CAPTIONS_PER_GPU, CTX, seed=4321 + rank)
+    ids = synthetic_tokens(CAPTIONS_PER_GPU, 4321 + rank)
     if pinned:
         frames = torch.empty(VIDEOS_PER_GPU, FRAMES, 3, 224, 224, dtype=torch.float32, pin_memory=True)
         frames.normal_(generator=g)
@@ -157,7 +191,7 @@ def webvid_leg(encoder, device, rank, world, group, n_total, barrier) -> dict:
     gd = torch.Generator(device=device).manual_seed(777)
     pool = torch.randn(chunk, WEBVID_FRAMES, 3, 224, 224, device=device, generator=gd)
     buf = torch.empty_like(pool)
-    ids = oracle.tokenize_synthetic(1000, CTX, seed=555).to(device)  # 1000 captions, varied per block below
+    ids = synthetic_tokens(1000, 555).to(device)  # 1000 captions, varied per block below
     v_emb = torch.empty(n_local, 512, device=device)
     t_emb = torch.empty(n_local, 512, device=device)
     e0, e1, e_enc = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -303,7 +337,6 @@ def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
-    import oracle
     from fitclip_b200 import B200ClipVideoTextEncoder, _lib, metrics_from_ranks, retrieval_ranks
 
     # Libraries (NCCL's version banner, ...) may write to fd 1; the contract is ONE JSON line on stdout, so everything
@@ -323,11 +356,9 @@ def run_ours(args) -> None:
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
 
     # random-init ViT-B/16, identical on every rank (config/encoder/clip_from_scratch_vit_b_16.yaml)
-    model = oracle.clip_vit_b_16(seed=0)
     from fitclip_b200 import B200Clip
-    encoder = B200ClipVideoTextEncoder(B200Clip(model.state_dict(), max_frames_per_pass=args.frames_per_pass),
+    encoder = B200ClipVideoTextEncoder(B200Clip(synthetic_weights(0), max_frames_per_pass=args.frames_per_pass),
                                        num_frames=FRAMES).to(device)
-    del model
     frames, ids = synthetic_inputs(rank, device, pinned=False)
     n_total = VIDEOS_PER_GPU * world
 
@@ -579,10 +610,12 @@ def cpu_baseline(sample_videos: int = 128, steps: int = 1) -> dict:
     import oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    ref = oracle.RefClipVideoTextEncoder(oracle.clip_vit_b_16(seed=0))
+    model = oracle.CLIP(**oracle.clip_ref.VIT_B_16).float().eval()
+    model.load_state_dict(synthetic_weights(0))  # the same weights as the CUDA arm
+    ref = oracle.RefClipVideoTextEncoder(model)
     g = torch.Generator().manual_seed(1234)
     video = torch.randn(sample_videos, FRAMES, 3, 224, 224, generator=g)
-    ids = oracle.tokenize_synthetic(sample_videos, CTX, seed=4321)
+    ids = synthetic_tokens(sample_videos, 4321)
     with torch.inference_mode():
         ref(video[:2], {"input_ids": ids[:2]})  # warm-up
         t0 = time.perf_counter()
