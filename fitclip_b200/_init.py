@@ -80,7 +80,7 @@ def init_slip_state_dict(seed: int = 0, embed_dim: int = 512, image_resolution: 
     practice -- for ``pos_embed`` and every Linear weight,
     zero biases, unit LayerNorms, ``cls_token`` ~ N(0, 1e-6); the patch convolution keeps PyTorch's default), the normal
     inits of ``slip.py:438-452`` for the text tower and the two projections."""
-    assert transformer_heads * 64 == transformer_width and vision_width % 64 == 0, "the native kernels use head dim 64"
+    assert transformer_heads * 64 == transformer_width and vision_width % 64 == 0, "widths are multiples of 64"
     g = torch.Generator().manual_seed(seed)
 
     def trunc(*shape):

@@ -154,12 +154,13 @@ def random_init_clip(seed: int = 0, **kwargs: int):
     return B200Clip(init_clip_state_dict(seed=seed, **kwargs))
 
 
-def random_init_slip(seed: int = 0, **kwargs: int):
+def random_init_slip(seed: int = 0, vision_heads: Optional[int] = None, **kwargs: int):
     """``slip.CLIP_VITB16()``-style random init (config/encoder/slip_from_scratch_vit_b_16.yaml): a
-    :class:`fitclip_b200.B200SlipClip` with timm-ViT image tower parameters under the SLIP checkpoint names."""
+    :class:`fitclip_b200.B200SlipClip` with timm-ViT image tower parameters under the SLIP checkpoint names.
+    ``vision_heads``: 12 for the ViT-S/16 variant (heads of 32, config/encoder/slip_vit_s_16.yaml)."""
     from . import B200SlipClip
     from ._init import init_slip_state_dict
-    return B200SlipClip(init_slip_state_dict(seed=seed, **kwargs))
+    return B200SlipClip(init_slip_state_dict(seed=seed, **kwargs), vision_heads=vision_heads)
 
 
 class SyntheticRetrievalData:

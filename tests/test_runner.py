@@ -79,6 +79,29 @@ def test_compose_slip_encoder_chain_and_slip_init():
     assert model.config["vision_tower"] == 1 and model.visual.input_resolution == 224
 
 
+@pytest.mark.parametrize("name,expect", [
+    ("clip_vit_b_32", dict(vision_patch_size=32, vision_width=768)),
+    ("clip_vit_l_14", dict(vision_patch_size=14, vision_width=1024, vision_layers=24, embed_dim=768, transformer_width=768)),
+    ("clip_vit_l_14_336px", dict(image_resolution=336, vision_patch_size=14, vision_width=1024)),
+    ("slip_vit_b_16", dict(vision_width=768, vision_layers=12)),
+    ("slip_vit_l_16", dict(vision_width=1024, vision_layers=24)),
+    ("slip_vit_s_16", dict(vision_width=384, vision_heads=12))])
+def test_named_geometry_configs_resolve(name, expect):
+    """The reference's per-checkpoint encoder configs (config/encoder/<name>.yaml) resolve here to the same geometry,
+    random-initialised offline."""
+    cfg = runner.compose(["command=evaluate", f"encoder={name}", "data=synthetic_msrvtt"])["encoder"]
+    assert cfg["_target_"].endswith("B200SlipVideoTextEncoder" if name.startswith("slip") else "B200ClipVideoTextEncoder")
+    for k, v in expect.items():
+        assert cfg["model"][k] == v, (name, k, cfg["model"].get(k))
+
+
+def test_slip_vit_s_16_config_builds_padded_heads():
+    cfg = runner.compose(["command=evaluate", "encoder=slip_vit_s_16", "data=synthetic_msrvtt",
+                          "encoder.model.vision_layers=1", "encoder.model.transformer_layers=1"])
+    enc = runner.instantiate(cfg["encoder"])
+    assert enc.model.vision_heads == 12 and enc.model.config["vision_attn_width"] == 768
+
+
 @pytest.mark.gpu
 def test_evaluate_command_on_a_slip_layout_encoder():
     cfg = runner.compose(["command=evaluate", "encoder=slip_from_scratch_vit_b_16", "data=synthetic_msrvtt",
