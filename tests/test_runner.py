@@ -111,6 +111,14 @@ def test_evaluate_command_on_a_slip_layout_encoder():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["clip_vit_b_32", "slip_vit_s_16"])
+def test_evaluate_command_on_named_geometries(name):
+    cfg = runner.compose(["command=evaluate", f"encoder={name}", "data=synthetic_msrvtt", "data.num_videos=40", *TINY])
+    result = runner.evaluate(cfg)
+    assert set(result) == {"r1", "r5", "r10", "mr", "loss/val"} and 1 <= int(result["mr"]) <= 40
+
+
+@pytest.mark.gpu
 def test_evaluate_and_predict_commands(tmp_path):
     env = dict(os.environ, PYTHONPATH=ROOT)
     out = subprocess.run([sys.executable, "-m", "aligner", "command=evaluate", "encoder=clip_vit_b_16",
