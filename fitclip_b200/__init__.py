@@ -8,7 +8,7 @@ from .retrieval import (TextVideoRetrievalModule, metrics_from_ranks, retrieval_
                         shard_bounds)
 from .slip_encoder import B200SlipClip, B200SlipVideoTextEncoder, load_slip_model  # noqa: F401
 from .teacher_student import TeacherStudentScoringModule  # noqa: F401
-from .training import ClipTrainer, TeacherStudentTrainingModule  # noqa: F401
+from .training import ClipTrainer, TeacherStudentTrainingModule, VideoTextTrainingModule  # noqa: F401
 from .wise import wise, wise_state_dict  # noqa: F401
 
 __version__ = "0.1.0"

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import copy
 import importlib
+import math
 import json
 import os
 import re
@@ -192,6 +193,16 @@ class SyntheticRetrievalData:
             yield {"video": video, "text": {"input_ids": ids.to(device)},
                    "video_id": [f"video{lo + j}" for j in range(b)]}
 
+    def train_batches(self, device: torch.device, steps: int) -> Iterator[Dict[str, Any]]:
+        """``steps`` training batches of ``batch_size`` (video, caption) pairs (a fresh seed per step)."""
+        saved = self.num_videos, self.seed
+        try:
+            for i in range(steps):
+                self.num_videos, self.seed = self.batch_size, saved[1] + 104_729 * (i + 1)
+                yield next(iter(self.val_batches(device)))
+        finally:
+            self.num_videos, self.seed = saved
+
 
 class SyntheticClassificationData(SyntheticRetrievalData):
     """Batches shaped like ``VideoClassificationDataModule`` output (``target = (name, id)``) plus the label prompts."""
@@ -301,10 +312,11 @@ def train(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> Dict
     """``command=train`` with an encoder map (``aligner/__main__.py:49-62``: ``trainer.fit``): the teacher-student
     training loop, ``trainer.max_steps`` steps, logging ``loss/train`` per step like ``training_step_end``
     (``aligner/teacher_student.py:176-183``)."""
+    if "_target_" in cfg["encoder"]:  # a single encoder: VideoTextLightningModule's NCE training (video_text_module.py:25-97)
+        return _train_single(cfg, device)
     if not isinstance(cfg["encoder"], Mapping) or set(cfg["encoder"]) != {"student", "teacher"}:
-        raise ValueError("command=train needs an encoder map: --config-name teacher_student_trainer with "
-                         "+encoder@encoder.student=... +encoder@encoder.teacher=... (single-encoder fine-tuning is "
-                         "not implemented)")
+        raise ValueError("command=train needs one encoder (NCE fine-tuning) or an encoder map: --config-name "
+                         "teacher_student_trainer with +encoder@encoder.student=... +encoder@encoder.teacher=...")
     device = device or torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(cfg.get("seed", 42))
     encoders = {k: v.to(device) for k, v in instantiate(cfg["encoder"]).items()}
@@ -325,6 +337,27 @@ def train(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> Dict
     if hasattr(encoders["teacher"].model, "check_inputs"):
         encoders["teacher"].model.check_inputs()
     return {"loss/train": losses[-1], "step": len(losses), "losses": losses}
+
+
+def _train_single(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> Dict[str, Any]:
+    """``command=train`` with one encoder: the reference fits its ``TextVideoRetrievalLightningModule`` -- i.e.
+    ``VideoTextLightningModule.training_step`` / ``training_step_end`` (NCE on the gathered batch, logit scale trained when
+    ``model.fit_temperature``) -- for ``trainer.max_steps`` steps."""
+    from .training import VideoTextTrainingModule
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(cfg.get("seed", 42))
+    encoder = instantiate(cfg["encoder"]).to(device)
+    data = instantiate(cfg["data"], encoder=encoder)
+    opt, mcfg = cfg.get("optimizer", {}), cfg.get("model", {})
+    model = VideoTextTrainingModule(encoder, init_temperature=float(mcfg.get("init_temperature", 0.05)),
+                                    min_temperature=float(mcfg.get("min_temperature", 0.001)),
+                                    fit_temperature=bool(mcfg.get("fit_temperature", True)),
+                                    lr=float(opt.get("lr", 3e-6)), weight_decay=float(opt.get("weight_decay", 1e-2)))
+    steps = int(cfg.get("trainer", {}).get("max_steps", 10))
+    losses = [model.training_step(batch, i) for i, batch in enumerate(data.train_batches(device, steps))]
+    losses = [float(x) for x in losses]  # one device read-back at the end
+    model.trainer.check_inputs()
+    return {"loss/train": losses[-1], "step": len(losses), "losses": losses, "temperature": math.exp(-model.logit_scale)}
 
 
 def main(argv: Sequence[str]) -> int:

@@ -316,6 +316,69 @@ def _all_gather_rows(t: torch.Tensor, group) -> Tuple[torch.Tensor, int]:
     return out, dist.get_rank(group) * t.shape[0]
 
 
+def _adamw_scales_step(tr: "ClipTrainer", temps: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor,
+                       max_logit_scale: float) -> None:
+    """AdamW on the log-space logit scale(s) with the trainer's hyper-parameters (one parameter group in the reference,
+    ``aligner/cli.py:126-134``), then the clamp of ``optimizer_step`` (video_text_module.py:93-97)."""
+    b1, b2 = tr.betas
+    step = tr.step_count  # already advanced by ClipTrainer.optimizer_step
+    temps.mul_(1 - tr.lr * tr.weight_decay)
+    m.mul_(b1).add_(grad, alpha=1 - b1)
+    v.mul_(b2).addcmul_(grad, grad, value=1 - b2)
+    denom = v.sqrt() / (1 - b2 ** step) ** 0.5 + tr.eps
+    temps.addcdiv_(m, denom, value=-tr.lr / (1 - b1 ** step))
+    temps.clamp_(max=max_logit_scale)
+
+
+class VideoTextTrainingModule:
+    """``VideoTextLightningModule`` training path without Lightning (``aligner/video_text_module.py:25-97``; what
+    ``command=train`` runs for a single encoder with the default ``TextVideoRetrievalLightningModule``): one encoder, the
+    embeddings of the step gathered across ranks, ``scores = exp(logit_scale) * V @ T.T``, ``NCELoss`` (``loss.py:13-26``),
+    backward, AdamW; the logit scale is a trained parameter by default (``fit_temperature=True``, ``:26-34``) and is clamped
+    at ``-log(min_temperature)`` after every optimizer step (``:93-97``).
+
+    ``batch``: ``video (B,T,3,R,R)``, ``text {"input_ids": (B, 77)}`` (``video_id`` is ignored, ``:41``)."""
+
+    def __init__(self, encoder, init_temperature: float = 0.05, min_temperature: float = 0.001,
+                 fit_temperature: bool = True, lr: float = 3e-6, weight_decay: float = 1e-2, group=None,
+                 kernels: Any = None) -> None:
+        self.encoder = encoder
+        self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels)
+        self.K = self.trainer.K
+        self.group = group
+        self.logit_scale = -math.log(init_temperature)
+        self.max_logit_scale = -math.log(min_temperature)
+        self.fit_temperature = fit_temperature
+        if fit_temperature:
+            device = self.trainer.flat.device
+            self.temps = torch.full((1,), self.logit_scale, device=device, dtype=torch.float32)
+            self.temps_grad, self.temps_m, self.temps_v = (torch.zeros_like(self.temps) for _ in range(3))
+
+    def training_step(self, batch: Mapping[str, Any], _batch_idx: int = 0, optimize: bool = True) -> torch.Tensor:
+        K, tr = self.K, self.trainer
+        tr.zero_grad()
+        v_local = tr.encode_video(batch["video"])
+        t_local = tr.encode_text(batch["text"]["input_ids"])
+        n = v_local.shape[0]
+        if self.fit_temperature:
+            self.logit_scale = float(self.temps[0])
+        scale = math.exp(self.logit_scale)
+        # _step_end (:57-76): all_gather with sync_grads, then the loss on the global batch
+        v, off = _all_gather_rows(v_local, self.group)
+        t, _ = _all_gather_rows(t_local, self.group)
+        scores = K.sgemm(v, t, trans_b=True, alpha=scale)
+        loss, dscores = K.loss_fwd_bwd(scores, None, gscale=1.0)
+        if self.fit_temperature:  # scores = exp(logit_scale) * V T^T  =>  dL/d logit_scale = sum(dL/dscores * scores)
+            self.temps_grad[0] = (dscores * scores).sum()
+        tr.backward_text(K.sgemm(dscores[:, off:off + n], v, trans_a=True, alpha=scale))
+        tr.backward_video(K.sgemm(dscores[off:off + n], t, alpha=scale))
+        if optimize:
+            tr.optimizer_step(self.group)
+            if self.fit_temperature:
+                _adamw_scales_step(tr, self.temps, self.temps_grad, self.temps_m, self.temps_v, self.max_logit_scale)
+        return loss
+
+
 class TeacherStudentTrainingModule:
     """``TeacherStudentLightningModule`` training path without Lightning: :meth:`training_step` is
     ``training_step`` + ``training_step_end`` + ``backward`` + ``optimizer_step`` of the reference loop.
@@ -473,14 +536,4 @@ class TeacherStudentTrainingModule:
         return 2 * weighted_loss.reshape(()) + weight * through_targets
 
     def _temperature_step(self) -> None:
-        """AdamW on the two log-space scales with the trainer's hyper-parameters (one parameter group in the reference,
-        ``aligner/cli.py:126-134``), then the clamp of ``optimizer_step`` (video_text_module.py:93-97)."""
-        tr = self.trainer
-        b1, b2 = tr.betas
-        step = tr.step_count  # already advanced by ClipTrainer.optimizer_step
-        self.temps.mul_(1 - tr.lr * tr.weight_decay)
-        self.temps_m.mul_(b1).add_(self.temps_grad, alpha=1 - b1)
-        self.temps_v.mul_(b2).addcmul_(self.temps_grad, self.temps_grad, value=1 - b2)
-        denom = self.temps_v.sqrt() / (1 - b2 ** step) ** 0.5 + tr.eps
-        self.temps.addcdiv_(self.temps_m, denom, value=-tr.lr / (1 - b1 ** step))
-        self.temps.clamp_(max=self.max_logit_scale)
+        _adamw_scales_step(self.trainer, self.temps, self.temps_grad, self.temps_m, self.temps_v, self.max_logit_scale)

@@ -35,8 +35,8 @@ def test_compose_wise_with_package_placement():
 def test_missing_mandatory_values_are_reported():
     with pytest.raises(ValueError, match="Missing mandatory"):
         runner.compose(["command=evaluate"])
-    with pytest.raises(ValueError):
-        runner.main(["command=train", "encoder=clip_vit_b_16", "data=synthetic_msrvtt"])
+    with pytest.raises(ValueError, match="encoder map"):  # neither one encoder nor a student / teacher map
+        runner.train({"command": "train", "encoder": {"a": {"_target_": "x"}}, "data": {}})
 
 
 def test_instantiate_is_recursive_and_rejects_unfilled_slots():
@@ -193,3 +193,15 @@ def test_train_command_with_a_prompts_file(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     result = json.loads(out.stdout.strip().splitlines()[-1])
     assert result["step"] == 3 and result["loss/train"] == result["loss/train"]
+
+
+@pytest.mark.gpu
+def test_train_command_with_a_single_encoder():
+    """``command=train`` with one encoder (the reference fits its TextVideoRetrievalLightningModule: NCE on the batch,
+    logit scale trained and clamped, video_text_module.py:25-97)."""
+    cfg = runner.compose(["command=train", "encoder=clip_vit_b_16", "data=synthetic_msrvtt", "data.batch_size=16",
+                          "+trainer.max_steps=4", "+optimizer.lr=1e-4", "model.fit_temperature=true", *TINY])
+    result = runner.train(cfg)
+    assert result["step"] == 4 and result["loss/train"] == result["loss/train"]
+    assert all(x == x and x < 1e4 for x in result["losses"])  # finite on every step
+    assert 0.001 <= result["temperature"] <= 0.05 + 1e-6

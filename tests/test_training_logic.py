@@ -264,3 +264,47 @@ def test_fit_temperature_gradients_with_prompts_match_autograd():
         if p.grad is not None and name in module.trainer.g:
             err, scale = (module.trainer.g[name] - p.grad).abs().max().item(), p.grad.abs().max().item()
             assert err <= 3e-4 * scale + 1e-6, name
+
+
+def test_single_encoder_nce_training_matches_autograd():
+    """``VideoTextLightningModule`` training (video_text_module.py:25-97): NCE on ``exp(logit_scale) * V @ T.T`` with the
+    logit scale as a trained parameter, AdamW, clamp -- against torch.autograd + torch.optim.AdamW on the oracle."""
+    import math
+    from fitclip_b200.training import VideoTextTrainingModule
+    student, _ = make_models()
+    ref = oracle.RefClipVideoTextEncoder(copy.deepcopy(student))
+    ls = torch.nn.Parameter(torch.tensor([-math.log(0.05)]))
+    opt = torch.optim.AdamW(list(ref.model.parameters()) + [ls], lr=1e-3)
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    module = VideoTextTrainingModule(enc, lr=1e-3, kernels=TorchKernels())
+    for step in range(2):
+        full = make_batch(6, seed=20 + step)
+        batch = {"video": full["video_student"], "text": full["text_student"], "video_id": ["v"] * 6}
+        opt.zero_grad(set_to_none=True)
+        v, t = ref(batch["video"], batch["text"])
+        expect = oracle.ref_nce_loss(ls.exp() * v @ t.T)
+        expect.backward()
+        loss = module.training_step(batch, step, optimize=False)
+        assert torch.allclose(loss, expect.detach(), rtol=1e-4, atol=1e-5)
+        assert abs(float(module.temps_grad[0]) - float(ls.grad)) <= 2e-4 * abs(float(ls.grad)) + 1e-6
+        for name, p in ref.model.named_parameters():
+            if p.grad is not None:
+                err, scale = (module.trainer.g[name] - p.grad).abs().max().item(), p.grad.abs().max().item()
+                assert err <= 2e-4 * scale + 1e-6, name
+        # optimizer on identical gradients (see test_gradients_and_adamw_match_autograd), then the scale's own AdamW step
+        for name, p in ref.model.named_parameters():
+            if p.grad is not None:
+                module.trainer.g[name].copy_(p.grad)
+        module.temps_grad[0] = float(ls.grad)
+        opt.step()
+        module.trainer.optimizer_step()
+        from fitclip_b200.training import _adamw_scales_step
+        _adamw_scales_step(module.trainer, module.temps, module.temps_grad, module.temps_m, module.temps_v,
+                           module.max_logit_scale)
+        assert abs(float(module.temps[0]) - float(ls)) <= 1e-5
+        for name, p in ref.model.named_parameters():
+            assert torch.allclose(module.trainer.w[name], p.detach(), rtol=1e-5, atol=1e-6), name
+    # clamp (video_text_module.py:93-97)
+    module.temps.fill_(module.max_logit_scale + 2.0)
+    module.training_step(batch, 2)
+    assert float(module.temps[0]) <= module.max_logit_scale + 1e-6
