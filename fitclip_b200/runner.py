@@ -326,6 +326,8 @@ def train(cfg: Mapping[str, Any], device: Optional[torch.device] = None) -> Dict
     if cfg.get("prompts"):  # aligner/cli.py:117-121: a text file, one prompt per non-empty line
         with open(cfg["prompts"]) as file:
             extra["prompts"] = [line.strip() for line in file if line.strip()]
+    if cfg.get("trainer", {}).get("gradient_clip_val") is not None:  # config/trainer.yaml:39
+        extra["gradient_clip_val"] = float(cfg["trainer"]["gradient_clip_val"])
     model = instantiate(cfg["model"], encoder=encoders["student"], teacher=encoders["teacher"],
                         lr=float(opt.get("lr", 3e-6)), weight_decay=float(opt.get("weight_decay", 1e-2)), **extra)
     steps = int(cfg.get("trainer", {}).get("max_steps", 10))
@@ -352,7 +354,8 @@ def _train_single(cfg: Mapping[str, Any], device: Optional[torch.device] = None)
     model = VideoTextTrainingModule(encoder, init_temperature=float(mcfg.get("init_temperature", 0.05)),
                                     min_temperature=float(mcfg.get("min_temperature", 0.001)),
                                     fit_temperature=bool(mcfg.get("fit_temperature", True)),
-                                    lr=float(opt.get("lr", 3e-6)), weight_decay=float(opt.get("weight_decay", 1e-2)))
+                                    lr=float(opt.get("lr", 3e-6)), weight_decay=float(opt.get("weight_decay", 1e-2)),
+                                    gradient_clip_val=cfg.get("trainer", {}).get("gradient_clip_val"))
     steps = int(cfg.get("trainer", {}).get("max_steps", 10))
     losses = [model.training_step(batch, i) for i, batch in enumerate(data.train_batches(device, steps))]
     losses = [float(x) for x in losses]  # one device read-back at the end

@@ -100,8 +100,11 @@ class ClipTrainer:
 
     def __init__(self, model: B200Clip, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, kernels: Any = None, keep_layernorm: bool = True,
-                 keep_activation: bool = True) -> None:
+                 keep_activation: bool = True, gradient_clip_val: Optional[float] = None) -> None:
         self.model = model
+        # Lightning's Trainer(gradient_clip_val=...) (config/trainer.yaml:39, null in the reference's config): the global
+        # L2 norm of ALL gradients of the optimizer is brought down to this value before the step (clip_grad_norm_)
+        self.gradient_clip_val = gradient_clip_val
         self.keep_layernorm = keep_layernorm
         # keep QuickGELU(u) from the forward (+ 2 B per MLP-hidden element: 30 GB at 2048 frames of ViT-B/16, 133 GB peak)
         # instead of re-emitting it from the backward's pass over u: that pass then writes 2 B per element less
@@ -157,12 +160,22 @@ class ClipTrainer:
             flag.zero_()
             raise _lib.FitclipError(-3, "training step: token id out of range (text_embed clamped it to 0)")
 
-    def optimizer_step(self, group=None) -> None:
+    def optimizer_step(self, group=None, extra_grads: Sequence[torch.Tensor] = ()) -> None:
         """All-reduce(SUM) of the flat gradient across ``group`` (each rank holds the gradient of the GLOBAL-batch loss
-        through its own samples), then one fused AdamW launch and the weight-copy refresh."""
+        through its own samples), optional global-norm clipping (``extra_grads``: gradients of parameters that live outside
+        the flat buffer -- the logit scales -- which share the norm and the coefficient), then one fused AdamW launch and
+        the weight-copy refresh."""
         dist = torch.distributed
         if group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.grad, group=group)
+        if self.gradient_clip_val is not None:  # torch.nn.utils.clip_grad_norm_(params, max_norm), norm type 2
+            sq = self.grad.double().pow(2).sum()
+            for g in extra_grads:
+                sq = sq + g.double().pow(2).sum()
+            coef = (self.gradient_clip_val / (sq.sqrt() + 1e-6)).clamp(max=1.0).float()
+            self.grad.mul_(coef)
+            for g in extra_grads:
+                g.mul_(coef)
         self.step_count += 1
         self.K.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
                           self.eps, self.weight_decay, p_bf16=self.flat_act)
@@ -341,9 +354,10 @@ class VideoTextTrainingModule:
 
     def __init__(self, encoder, init_temperature: float = 0.05, min_temperature: float = 0.001,
                  fit_temperature: bool = True, lr: float = 3e-6, weight_decay: float = 1e-2, group=None,
-                 kernels: Any = None) -> None:
+                 kernels: Any = None, gradient_clip_val: Optional[float] = None) -> None:
         self.encoder = encoder
-        self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels)
+        self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels,
+                                   gradient_clip_val=gradient_clip_val)
         self.K = self.trainer.K
         self.group = group
         self.logit_scale = -math.log(init_temperature)
@@ -373,7 +387,7 @@ class VideoTextTrainingModule:
         tr.backward_text(K.sgemm(dscores[:, off:off + n], v, trans_a=True, alpha=scale))
         tr.backward_video(K.sgemm(dscores[off:off + n], t, alpha=scale))
         if optimize:
-            tr.optimizer_step(self.group)
+            tr.optimizer_step(self.group, extra_grads=[self.temps_grad] if self.fit_temperature else ())
             if self.fit_temperature:
                 _adamw_scales_step(tr, self.temps, self.temps_grad, self.temps_m, self.temps_v, self.max_logit_scale)
         return loss
@@ -395,9 +409,11 @@ class TeacherStudentTrainingModule:
                  labeled_dataset_loss_share: Optional[float] = None,
                  dataset_names: Sequence[str] = ("labeled", "unlabeled"), lr: float = 3e-6,
                  weight_decay: float = 1e-2, group=None, kernels: Any = None, fit_temperature: bool = False,
-                 min_temperature: float = 0.001, prompts: Optional[Sequence[str]] = None) -> None:
+                 min_temperature: float = 0.001, prompts: Optional[Sequence[str]] = None,
+                 gradient_clip_val: Optional[float] = None) -> None:
         self.encoder, self.teacher = encoder, teacher
-        self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels)
+        self.trainer = ClipTrainer(encoder.model, lr=lr, weight_decay=weight_decay, kernels=kernels,
+                                   gradient_clip_val=gradient_clip_val)
         self.K = self.trainer.K
         self.group = group
         self.logit_scale = -math.log(init_temperature)                # video_text_module.py:32
@@ -514,7 +530,7 @@ class TeacherStudentTrainingModule:
         tr.backward_text(dt)
         tr.backward_video(dv)
         if optimize:
-            tr.optimizer_step(self.group)
+            tr.optimizer_step(self.group, extra_grads=[self.temps_grad] if self.fit_temperature else ())
             if self.fit_temperature:
                 self._temperature_step()
         return total

@@ -308,3 +308,37 @@ def test_single_encoder_nce_training_matches_autograd():
     module.temps.fill_(module.max_logit_scale + 2.0)
     module.training_step(batch, 2)
     assert float(module.temps[0]) <= module.max_logit_scale + 1e-6
+
+
+def test_gradient_clipping_matches_clip_grad_norm():
+    """``Trainer(gradient_clip_val=...)`` (config/trainer.yaml:39): global L2 norm over every gradient of the optimizer, the
+    trained logit scale included -- against torch.nn.utils.clip_grad_norm_ on the oracle."""
+    import math
+    from fitclip_b200.training import VideoTextTrainingModule
+    student, _ = make_models()
+    ref = oracle.RefClipVideoTextEncoder(copy.deepcopy(student))
+    ls = torch.nn.Parameter(torch.tensor([-math.log(0.05)]))
+    full = make_batch(6, seed=33)
+    batch = {"video": full["video_student"], "text": full["text_student"]}
+    v, t = ref(batch["video"], batch["text"])
+    oracle.ref_nce_loss(ls.exp() * v @ t.T).backward()
+    params = [p for p in ref.model.parameters() if p.grad is not None] + [ls]
+    before = torch.sqrt(sum(p.grad.double().pow(2).sum() for p in params))
+    clip = 0.25 * float(before)
+    torch.nn.utils.clip_grad_norm_(params, clip)
+    enc = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    module = VideoTextTrainingModule(enc, lr=1e-3, kernels=TorchKernels(), gradient_clip_val=clip)
+    module.training_step(batch, 0)  # optimizer_step clips self.grad / temps_grad in place before AdamW
+    for name, p in ref.model.named_parameters():
+        if p.grad is not None:
+            err, scale = (module.trainer.g[name] - p.grad).abs().max().item(), p.grad.abs().max().item()
+            assert err <= 3e-4 * scale + 1e-7, name
+    assert abs(float(module.temps_grad[0]) - float(ls.grad)) <= 3e-4 * abs(float(ls.grad)) + 1e-7
+    after = torch.sqrt(module.trainer.grad.double().pow(2).sum() + module.temps_grad.double().pow(2).sum())
+    assert abs(float(after) - clip) <= 1e-3 * clip
+    # a threshold above the norm leaves the gradients alone
+    enc2 = B200ClipVideoTextEncoder(student.state_dict(), num_frames=2)
+    loose = VideoTextTrainingModule(enc2, lr=1e-3, kernels=TorchKernels(), gradient_clip_val=10 * float(before))
+    loose.training_step(batch, 0)
+    untouched = torch.sqrt(loose.trainer.grad.double().pow(2).sum() + loose.temps_grad.double().pow(2).sum())
+    assert abs(float(untouched) - float(before)) <= 1e-3 * float(before)
